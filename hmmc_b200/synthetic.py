@@ -1,0 +1,110 @@
+"""Seeded synthetic embeddings for tests, golden fixtures and bench.py.
+
+Everything is drawn with ``numpy.random.RandomState`` (the legacy MT19937
+stream is bit-stable across numpy versions and machines), so the container that
+generates ``tests/golden`` and the GPU box that checks against it see the same
+bytes.  Shapes follow the reference's batch layouts:
+``[b, D]`` for text / video embeddings and ``[b, F, D]`` for frame embeddings.
+"""
+import numpy as np
+
+
+def _randn(rs, *shape):
+    return rs.standard_normal(shape).astype(np.float32)
+
+
+def normalize_cols(x, eps=1e-12):
+    n = np.sqrt((x.astype(np.float64) ** 2).sum(axis=0, keepdims=True))
+    return (x / np.maximum(n, eps)).astype(np.float32)
+
+
+def finetune_inputs(B, F=12, D=512, seed=1, corr=0.0):
+    """text [B,D], video [B,D], frames [B,F,D] (modules/modeling.py:691-692)."""
+    rs = np.random.RandomState(seed)
+    t = _randn(rs, B, D)
+    v = _randn(rs, B, D)
+    fr = _randn(rs, B, F, D)
+    if corr:
+        v += corr * t
+        fr += (0.66 * corr) * t[:, None, :]
+    return t, v, fr
+
+
+PRETRAIN_Q_NAMES = ["v_fea", "frame_fea", "title_fea", "frame_pred", "frame_proj"]
+PRETRAIN_K_NAMES = ["v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k", "frame_proj_k"]
+QUEUE_NAMES = ["queue_v_cross_ng", "queue_frame_proj_ng", "queue_frame_cross_ng",
+               "queue_title_cross_ng", "queue_tag_cross_ng"]
+
+
+def pretrain_inputs(b, F=12, D=512, seed=2, corr=0.5):
+    """Query- and key-side embeddings of one pre-train step
+    (modules/modeling.py:347-378).  Keys are correlated with queries so the
+    positives are not lost in the noise."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    out["v_fea"] = _randn(rs, b, D)
+    out["frame_fea"] = _randn(rs, b, F, D)
+    out["title_fea"] = _randn(rs, b, D) + corr * out["v_fea"]
+    out["frame_pred"] = _randn(rs, b, F, D)
+    out["frame_proj"] = _randn(rs, b, F, D)
+    out["v_fea_k"] = _randn(rs, b, D) + corr * out["v_fea"]
+    out["frame_fea_k"] = _randn(rs, b, F, D) + corr * out["frame_fea"]
+    out["title_fea_k"] = _randn(rs, b, D) + corr * out["title_fea"]
+    out["tag_fea_k"] = _randn(rs, b, D)
+    out["frame_proj_k"] = _randn(rs, b, F, D) + corr * out["frame_pred"]
+    return out
+
+
+def queues(K, F=12, D=512, seed=3):
+    """The five negative queues in the state-dict layout ``[D, Kq]`` with
+    unit-norm columns (modules/modeling.py:138-149)."""
+    rs = np.random.RandomState(seed)
+    shapes = {"queue_v_cross_ng": K, "queue_frame_proj_ng": K * F,
+              "queue_frame_cross_ng": K * F, "queue_title_cross_ng": K,
+              "queue_tag_cross_ng": K}
+    return {n: normalize_cols(_randn(rs, D, shapes[n])) for n in QUEUE_NAMES}
+
+
+def eval_inputs(Nt, Nv, F=12, D=512, seed=4, per_video=None, corr=0.15):
+    """Text / video / frame embeddings of a retrieval eval set.
+
+    Square (``per_video is None``): text i matches video i (MSR-VTT 1k-A,
+    dataloaders/dataloader_msrvtt_retrieval.py:155-164).  Multi-sentence:
+    ``per_video`` captions per video, text s matches video ``gt[s]`` (VATEX,
+    dataloaders/dataloader_vatex_retrieval.py:77-89).  Returns
+    (T, V, Fr, gt, cut_off_points) with cut_off_points already shifted by -1 as
+    main_task_retrieval.py:380 does.
+    """
+    rs = np.random.RandomState(seed)
+    if per_video is None:
+        assert Nt == Nv
+        gt = np.arange(Nt, dtype=np.int64)
+        cut = None
+    else:
+        per = np.asarray(per_video, dtype=np.int64)
+        assert per.shape[0] == Nv and int(per.sum()) == Nt
+        gt = np.repeat(np.arange(Nv, dtype=np.int64), per)
+        cut = (np.cumsum(per) - 1).tolist()
+    T = _randn(rs, Nt, D)
+    V = _randn(rs, Nv, D)
+    Fr = _randn(rs, Nv, F, D)
+    # make the ground-truth pair stand out: the video side carries a copy of
+    # the mean of its captions
+    acc = np.zeros((Nv, D), dtype=np.float32)
+    np.add.at(acc, gt, T)
+    cnt = np.maximum(np.bincount(gt, minlength=Nv), 1).astype(np.float32)[:, None]
+    V += corr * acc / np.sqrt(cnt)
+    Fr += (0.66 * corr) * (acc / np.sqrt(cnt))[:, None, :]
+    return T, V, Fr, gt, cut
+
+
+def ema_tensors(seed=5, sizes=((513,), (64, 33), (7,), (1024, 96), (3, 5, 7), (1,)),
+                dtypes=("float32", "float16", "float32", "float16", "float32", "float32")):
+    """(param, param_k) pairs in mixed fp32 / fp16 like the CLIP weights after
+    convert_weights (modules/module_clip.py:506-527)."""
+    rs = np.random.RandomState(seed)
+    ps, pks = [], []
+    for shp, dt in zip(sizes, dtypes):
+        ps.append(_randn(rs, *shp).astype(dt))
+        pks.append(_randn(rs, *shp).astype(dt))
+    return ps, pks

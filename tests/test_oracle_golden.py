@@ -1,0 +1,193 @@
+"""Pin the numpy oracle (oracle/head_oracle.py) against outputs of the
+reference's own code (tests/golden/*.npz, written by oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+
+from hmmc_b200 import synthetic as syn
+from oracle import head_oracle as O
+
+KEYS = ["R1", "R5", "R10", "MR", "MeanR"]
+TVK = ["R1", "R5", "R10", "MedianR", "MeanR", "Std_Rank", "MR"]
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def test_metrics_square(golden):
+    g = golden("metrics")
+    rs = np.random.RandomState(0)
+    x = rs.randn(1000, 1000).astype(np.float32)
+    x[np.arange(1000), np.arange(1000)] += 2.0
+    a = O.compute_metrics(x)
+    b = O.compute_metrics(x.T)
+    assert [a[k] for k in KEYS] == list(g["sq_t2v"])
+    assert [b[k] for k in KEYS] == list(g["sq_v2t"])
+    # rank-count form reproduces the sort/where form exactly
+    assert O.metrics_from_ranks(O.ranks_square(x)) == a
+    ties = np.array([[1, 1, 0], [0, 2, 3], [0, 0, 5]], dtype=np.float32)
+    c = O.compute_metrics(ties)
+    assert [c[k] for k in KEYS] == list(g["ties"])
+
+
+def test_metrics_nonsquare_raises():
+    with pytest.raises(ValueError):
+        O.compute_metrics(np.zeros((20, 10), dtype=np.float32))
+
+
+def test_metrics_multi_sentence(golden):
+    g = golden("metrics")
+    rs = np.random.RandomState(int(g["ms_seed"]))
+    V = 50
+    per = rs.randint(1, 6, size=V)
+    assert (per == g["ms_per"]).all()
+    S = int(per.sum())
+    gt = np.repeat(np.arange(V), per)
+    sim = rs.randn(S, V).astype(np.float32)
+    sim[np.arange(S), gt] += 1.5
+    cut = (np.cumsum(per) - 1).tolist()
+    tv, vt = O.logging_rank(sim, True, cut)
+    assert [tv[k] for k in TVK] == list(g["ms_tv"])
+    assert [vt[k] for k in KEYS] == list(g["ms_vt"])
+    # integer-rank form
+    t2v, v2t = O.ranks_multi_sentence(sim, gt)
+    assert O.metrics_from_ranks(v2t) == vt
+    assert float(np.mean(t2v + 1)) == tv["MeanR"]
+
+
+def test_similarity(golden):
+    g = golden("similarity")
+    s2 = O.loose_similarity(g["q"], g["v"])
+    s3 = O.loose_similarity(g["q"], g["fr"])
+    assert s2.shape == g["s2"].shape and s3.shape == g["s3"].shape
+    np.testing.assert_allclose(s2, g["s2"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(s3, g["s3"], rtol=0, atol=2e-5)
+    assert abs(O.cross_en(g["s2"][:7, :7]) - float(g["ce"])) < 1e-5
+
+
+@pytest.mark.parametrize("B", [32, 256])
+def test_finetune(golden, B):
+    g = golden("finetune_B%d" % B)
+    t, v, fr = syn.finetune_inputs(B, seed=int(g["seed"]))
+    l32 = O.finetune_loss(t, v, fr)
+    assert abs(l32 - float(g["loss"])) / float(g["loss"]) < 2e-6
+    l64, dt, dv, dfr = O.finetune_loss_and_grads(t, v, fr)
+    assert abs(l64 - float(g["loss"])) / float(g["loss"]) < 2e-6
+    gn = [np.linalg.norm(dt), np.linalg.norm(dv), np.linalg.norm(dfr)]
+    np.testing.assert_allclose(gn, g["gnorm"], rtol=1e-4)   # the fp32 reference itself carries ~2e-5 noise at scale 100
+    assert _rel(dt[:g["dt"].shape[0]], g["dt"]) < 1e-4
+    assert _rel(dv[:g["dv"].shape[0]], g["dv"]) < 1e-4
+    assert _rel(dfr[:g["dfr"].shape[0]], g["dfr"]) < 1e-4
+
+
+def test_contrastive_small(golden):
+    g = golden("contrastive_small")
+    l = O.contrastive_loss(g["q"], g["k"], g["queue"], float(g["T"]))
+    assert abs(l - float(g["loss"])) < 2e-6
+    l64, dq = O.contrastive_loss_and_grad(g["q"], g["k"], g["queue"], float(g["T"]))
+    assert abs(l64 - float(g["loss"])) < 2e-6
+    assert _rel(dq, g["dq"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["small", "b32"])
+def test_pretrain(golden, tag):
+    g = golden("pretrain_" + tag)
+    b, F, D, K, T = int(g["b"]), int(g["F"]), int(g["D"]), int(g["K"]), float(g["T"])
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    qs = syn.queues(K, F=F, D=D, seed=3)
+    fam, vtm, ftm = O.pretrain_loss_parts(inp, qs, T)
+    assert abs(fam - float(g["fam"])) / float(g["fam"]) < 3e-6
+    assert abs(vtm - float(g["vtm"])) / float(g["vtm"]) < 3e-6
+    assert abs(ftm - float(g["ftm"])) / float(g["ftm"]) < 3e-6
+    loss, grads = O.pretrain_loss_and_grads(inp, qs, T)
+    assert abs(loss - float(g["loss"])) / float(g["loss"]) < 3e-6
+    for n in ("v_fea", "title_fea", "frame_fea", "frame_pred"):
+        ref = g["d_" + n]
+        assert _rel(grads[n][:ref.shape[0]], ref) < 3e-5, n
+        assert abs(np.linalg.norm(grads[n]) - float(g["gn_" + n])) / float(g["gn_" + n]) < 3e-5
+    # enqueue
+    ptr = O.dequeue_and_enqueue(qs, 0, inp["v_fea_k"], inp["tag_fea_k"], inp["title_fea_k"],
+                                inp["frame_fea_k"], inp["frame_proj_k"], K)
+    assert ptr == int(g["ptr"])
+    for n in syn.QUEUE_NAMES:
+        ref = g["after_" + n]
+        np.testing.assert_allclose(qs[n][:, :ref.shape[1]], ref, rtol=0, atol=1e-7)
+        if "sum_" + n in g.files:
+            np.testing.assert_allclose(qs[n].astype(np.float64).sum(axis=1), g["sum_" + n], rtol=0, atol=1e-5)
+
+
+def test_enqueue_wrap(golden):
+    g = golden("enqueue_wrap")
+    qs = syn.queues(16, F=4, D=64, seed=3)
+    ptr, ptrs = 0, []
+    for step in range(3):
+        k = syn.pretrain_inputs(8, F=4, D=64, seed=20 + step)
+        ptr = O.dequeue_and_enqueue(qs, ptr, k["v_fea_k"], k["tag_fea_k"], k["title_fea_k"],
+                                    k["frame_fea_k"], k["frame_proj_k"], 16)
+        ptrs.append(ptr)
+    assert ptrs == list(g["ptrs"])
+    for n in syn.QUEUE_NAMES:
+        np.testing.assert_allclose(qs[n], g["after_" + n], rtol=0, atol=1e-7)
+    with pytest.raises(ValueError):
+        k = syn.pretrain_inputs(12, F=4, D=64, seed=1)
+        O.dequeue_and_enqueue(qs, 8, k["v_fea_k"], k["tag_fea_k"], k["title_fea_k"],
+                              k["frame_fea_k"], k["frame_proj_k"], 16)
+
+
+def test_ema_bit_exact(golden):
+    g = golden("ema")
+    ps, pks = syn.ema_tensors()
+    for _ in range(int(g["steps"])):
+        pks = O.momentum_update(ps, pks, float(g["m"]))
+    for i, pk in enumerate(pks):
+        ref = g["out%d" % i]
+        assert pk.dtype == ref.dtype
+        assert np.array_equal(pk.view(np.uint8), ref.view(np.uint8)), i
+
+
+def test_eval_1k(golden):
+    g = golden("eval_1k")
+    T, V, Fr, gt, _ = syn.eval_inputs(1000, 1000, seed=int(g["seed"]))
+    k = int(g["top_frames"])
+    tl = lambda x: [x[i:i + 256] for i in range(0, x.shape[0], 256)]
+    a, b, c = O.run_on_single_gpu(tl(T), tl(V), [np.zeros_like(x) for x in tl(V)], tl(Fr), k)
+    sim = np.concatenate(a, 0)
+    simf = np.concatenate(c, 0)
+    assert bool(g["nan_title"]) and np.isnan(np.concatenate(b, 0)).all()
+    np.testing.assert_allclose(sim[:4], g["sim_rows"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(simf[:4], g["simf_rows"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(np.diag(sim), g["sim_diag"], rtol=0, atol=3e-5)
+    tot = sim + simf
+    tv, vt = O.logging_rank(tot, False, None)
+    assert [tv[k_] for k_ in KEYS] == list(g["tv"])
+    assert [vt[k_] for k_ in KEYS] == list(g["vt"])
+    assert (O.ranks_square(tot) == g["ranks_t2v"]).all()
+    assert (O.ranks_square(tot.T) == g["ranks_v2t"]).all()
+    np.testing.assert_allclose(O.eval_scores(T, V, Fr, k), tot, rtol=0, atol=1e-6)
+
+
+def test_eval_multi(golden):
+    g = golden("eval_multi")
+    per = g["per"]
+    T, V, Fr, gt, cut = syn.eval_inputs(int(per.sum()), 60, seed=int(g["seed"]), per_video=per)
+    tot = O.eval_scores(T, V, Fr, int(g["top_frames"]), tile=128)
+    np.testing.assert_allclose(tot, g["tot"], rtol=0, atol=3e-5)
+    tv, vt = O.logging_rank(g["tot"], True, cut)
+    assert [tv[k] for k in TVK] == list(g["tv"])
+    assert [vt[k] for k in KEYS] == list(g["vt"])
+    t2v, v2t = O.ranks_multi_sentence(g["tot"], gt)
+    assert O.metrics_from_ranks(v2t) == vt
+    assert float(np.mean(t2v + 1)) == tv["MeanR"]
+
+
+def test_dist_collect_contract():
+    rs = np.random.RandomState(3)
+    W, b = 4, 3
+    xs = [rs.randn(b, 5) for _ in range(W)]
+    full = O.dist_collect_emulated(xs)
+    assert full.shape == (W * b, 5) and np.array_equal(full[b:2 * b], xs[1])
+    grads = [rs.randn(W * b, 5) for _ in range(W)]
+    back = O.dist_collect_emulated_backward(grads, b)
+    np.testing.assert_allclose(back[2], sum(g[2 * b:3 * b] for g in grads))
