@@ -1,0 +1,331 @@
+// Fine-tune (hierarchical matching) head: loose_similarity, CrossEn and the fused
+// symmetric-CE loss over the text x video and the F text x frame similarity matrices.
+#include "common.cuh"
+
+namespace hmmc {
+
+// dx = (g - x_hat (x_hat . g)) / ||x||  for x_hat = x/||x|| (no eps, loose_similarity).
+// One warp per row; optional row remap of the *destination/source* x rows:
+//   src_row(r) = (r % remap_B) * remap_F + (r / remap_B - remap_skip)   when remap_B > 0
+// lets the gallery-ordered gradient rows (f*B + j) land in the [B,F,D] frame layout.
+__global__ void unnormalize_grad_kernel(const float* __restrict__ x, const float* __restrict__ ghat,
+                                        float* __restrict__ dx, int64_t R, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* xr = x + row * D;
+  const float* gr = ghat + row * D;
+  float ss = 0.f, xg = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = xr[d];
+    ss = fmaf(v, v, ss);
+    xg = fmaf(v, gr[d], xg);
+  }
+  ss = warp_sum(ss);
+  xg = warp_sum(xg);
+  const float n = sqrtf(ss);
+  const float proj = xg / (n * n);            // (x_hat . g) / ||x||  folded: x_hat*(x_hat.g) = x * (x.g)/n^2
+  for (int d = lane; d < D; d += 32) dx[row * D + d] = (gr[d] - xr[d] * proj) / n;
+}
+
+// ------------------------------------------------------------------ CrossEn
+// one block per row: lse_i = logsumexp(S[i,:]); row_loss[i] = (lse_i - S[i,i]) / B;
+// dS[i,j] = (exp(S[i,j]-lse_i) - [i==j]) / B
+__global__ void cross_en_row_kernel(const float* __restrict__ S, int64_t lds, int B, float* __restrict__ row_loss,
+                                    float* __restrict__ dS, int64_t ldds) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  const float* row = S + int64_t(i) * lds;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) m = fmaxf(m, row[j]);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) s += expf(row[j] - m);
+  s = block_sum(s, red);
+  const float lse = m + logf(s);
+  if (threadIdx.x == 0) row_loss[i] = (lse - row[i]) / float(B);
+  if (dS != nullptr) {
+    float* drow = dS + int64_t(i) * ldds;
+    for (int j = threadIdx.x; j < B; j += blockDim.x)
+      drow[j] = (expf(row[j] - lse) - (j == i ? 1.f : 0.f)) / float(B);
+  }
+}
+
+__global__ void sum_to_scalar_kernel(const float* __restrict__ v, int n, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + acc : acc;
+}
+
+// ------------------------------------------------------------------ fused fine-tune head
+// Gallery rows are ordered g = fp*B + j with fp = 0 the video embedding and fp = 1..F frame fp-1,
+// so the similarity matrix S_all [B, (1+F)*B] holds the 1+F square blocks side by side.
+__global__ void gallery_norm_kernel(const float* __restrict__ video, const float* __restrict__ frames, int B, int F,
+                                    int voff, int D, float* __restrict__ ghat) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= int64_t(voff + F) * B) return;
+  const int fp = int(g / B), j = int(g % B);
+  const float* x = (fp < voff) ? video + int64_t(j) * D : frames + (int64_t(j) * F + (fp - voff)) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = x[d]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float n = sqrtf(ss);
+  for (int d = lane; d < D; d += 32) ghat[g * D + d] = x[d] / n;
+}
+
+// row statistics: one block per text row i, loops over the 1+F blocks
+__global__ void symce_row_lse_kernel(const float* __restrict__ S, int B, int NB, float* __restrict__ lse_row) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  for (int fp = 0; fp < NB; ++fp) {
+    const float* row = S + int64_t(i) * NB * B + int64_t(fp) * B;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < B; j += blockDim.x) m = fmaxf(m, row[j]);
+    m = block_max(m, red);
+    float s = 0.f;
+    for (int j = threadIdx.x; j < B; j += blockDim.x) s += expf(row[j] - m);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) lse_row[fp * B + i] = m + logf(s);
+  }
+}
+
+// column statistics: block = 32 consecutive columns of S_all, 8 warps stride the rows
+__global__ void __launch_bounds__(256)
+symce_col_lse_kernel(const float* __restrict__ S, int B, int NB, float* __restrict__ lse_col) {
+  __shared__ float sm[8][32], ss[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ncol = int64_t(NB) * B;
+  const int64_t col = int64_t(blockIdx.x) * 32 + lane;
+  float m = -INFINITY, s = 0.f;
+  if (col < ncol) {
+    for (int i = warp; i < B; i += 8) {
+      const float v = S[int64_t(i) * ncol + col];
+      if (v > m) { s = s * expf(m - v) + 1.f; m = v; } else { s += expf(v - m); }
+    }
+  }
+  sm[warp][lane] = m;
+  ss[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && col < ncol) {
+    float M = sm[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) M = fmaxf(M, sm[w][lane]);
+    float Ssum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) Ssum += (sm[w][lane] == -INFINITY) ? 0.f : ss[w][lane] * expf(sm[w][lane] - M);
+    lse_col[col] = M + logf(Ssum);      // index fp*B + j == col
+  }
+}
+
+// loss terms and G = dL/dS in place:  G_ij = w_fp/B * (exp(S_ij - lse_row) + exp(S_ij - lse_col) - 2 [i==j])
+// block per row i; also the row's loss share  w_fp/B * (lse_row + lse_col - 2 S_ii)
+__global__ void symce_grad_kernel(float* __restrict__ S, int B, int NB, const float* __restrict__ lse_row,
+                                  const float* __restrict__ lse_col, int voff, float w0, float wf,
+                                  float* __restrict__ row_loss, int write_grad) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  const int64_t ncol = int64_t(NB) * B;
+  float* row = S + int64_t(i) * ncol;
+  float loss = 0.f;
+  for (int64_t c = threadIdx.x; c < ncol; c += blockDim.x) {
+    const int fp = int(c / B), j = int(c - int64_t(fp) * B);
+    const float w = ((fp < voff) ? w0 : wf) / float(B);
+    const float v = row[c];
+    const float lr = lse_row[fp * B + i], lc = lse_col[c];
+    if (j == i) loss += w * (lr + lc - 2.f * v);
+    if (write_grad) row[c] = w * (expf(v - lr) + expf(v - lc) - (j == i ? 2.f : 0.f));
+  }
+  loss = block_sum(loss, red);
+  if (threadIdx.x == 0) row_loss[i] = loss;
+}
+
+// scatter gallery-ordered gradient rows back: dvideo[j] = dG[0*B + j], dframes[j,f] = dG[(f+1)*B + j]
+__global__ void gallery_scatter_kernel(const float* __restrict__ dG, int B, int F, int voff, int D,
+                                       float* __restrict__ dvideo, float* __restrict__ dframes) {
+  const int64_t g = blockIdx.x;
+  const int fp = int(g / B), j = int(g % B);
+  float* dst = (fp < voff) ? dvideo + int64_t(j) * D : dframes + (int64_t(j) * F + (fp - voff)) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] = dG[g * D + d];
+}
+
+}  // namespace hmmc
+
+using namespace hmmc;
+
+extern "C" {
+
+size_t hmmc_similarity_workspace_bytes(int64_t Bt, int64_t Bv, int Fv, int D, int prec) {
+  Workspace ws(nullptr, 0);
+  const int planes = planes_of(prec);
+  const int64_t N = Bv * Fv;
+  if (prec == HMMC_PREC_FP32) {
+    ws.take<float>(size_t(Bt) * D);
+    ws.take<float>(size_t(N) * D);
+  } else {
+    ws.take<__nv_bfloat16>(size_t(Bt) * planes * D);
+    ws.take<__nv_bfloat16>(size_t(N) * planes * D);
+  }
+  // backward: normalised copies + two gradient buffers
+  Workspace wb(nullptr, 0);
+  wb.take<float>(size_t(Bt) * D);
+  wb.take<float>(size_t(N) * D);
+  wb.take<float>(size_t(Bt) * D);
+  wb.take<float>(size_t(N) * D);
+  return (ws.used > wb.used ? ws.used : wb.used) + 256;
+}
+
+int hmmc_loose_similarity_fwd(const float* seq, int64_t Bt, const float* vis, int64_t Bv, int Fv, int D, float scale,
+                              int prec, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HMMC_REQUIRE(seq && vis && out && Bt > 0 && Bv > 0 && Fv > 0 && D > 0, "loose_similarity: bad arguments");
+  HMMC_REQUIRE(prec >= 0 && prec <= 2, "loose_similarity: unknown precision %d", prec);
+  const int64_t N = Bv * Fv;
+  HMMC_REQUIRE(N < (int64_t(1) << 31) && Bt < (int64_t(1) << 31), "loose_similarity: tile too large");
+  Workspace ws(workspace, workspace_bytes);
+  int rc;
+  if (prec == HMMC_PREC_FP32) {
+    float* sh = ws.take<float>(size_t(Bt) * D);
+    float* vh = ws.take<float>(size_t(N) * D);
+    if (!ws.ok()) { set_error("loose_similarity: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
+    if ((rc = rownorm_pack(seq, Bt, D, D, 0.f, 1, sh, nullptr, nullptr, 0, st))) return rc;
+    if ((rc = rownorm_pack(vis, N, D, D, 0.f, 1, vh, nullptr, nullptr, 0, st))) return rc;
+    return gemm_f32(sh, D, 1, vh, D, 1, out, N, int(Bt), int(N), D, scale, st);
+  }
+  HMMC_REQUIRE(D % 64 == 0, "loose_similarity: tensor-core path needs D %% 64 == 0 (D=%d)", D);
+  const int planes = planes_of(prec);
+  __nv_bfloat16* sp = ws.take<__nv_bfloat16>(size_t(Bt) * planes * D);
+  __nv_bfloat16* vp = ws.take<__nv_bfloat16>(size_t(N) * planes * D);
+  if (!ws.ok()) { set_error("loose_similarity: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
+  if ((rc = rownorm_pack(seq, Bt, D, D, 0.f, planes, nullptr, nullptr, sp, int64_t(planes) * D, st))) return rc;
+  if ((rc = rownorm_pack(vis, N, D, D, 0.f, planes, nullptr, nullptr, vp, int64_t(planes) * D, st))) return rc;
+  return umma_gemm_store(sp, int64_t(planes) * D, vp, int64_t(planes) * D, out, N, 0, int(Bt), int(N), D, planes, 1,
+                         scale, st);
+}
+
+int hmmc_loose_similarity_bwd(const float* seq, int64_t Bt, const float* vis, int64_t Bv, int Fv, int D, float scale,
+                              const float* dout, float* dseq, float* dvis, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HMMC_REQUIRE(seq && vis && dout && Bt > 0 && Bv > 0 && Fv > 0 && D > 0, "loose_similarity_bwd: bad arguments");
+  const int64_t N = Bv * Fv;
+  Workspace ws(workspace, workspace_bytes);
+  float* sh = ws.take<float>(size_t(Bt) * D);
+  float* vh = ws.take<float>(size_t(N) * D);
+  float* gs = ws.take<float>(size_t(Bt) * D);
+  float* gv = ws.take<float>(size_t(N) * D);
+  if (!ws.ok()) { set_error("loose_similarity_bwd: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
+  int rc;
+  if ((rc = rownorm_pack(seq, Bt, D, D, 0.f, 1, sh, nullptr, nullptr, 0, st))) return rc;
+  if ((rc = rownorm_pack(vis, N, D, D, 0.f, 1, vh, nullptr, nullptr, 0, st))) return rc;
+  if (dseq != nullptr) {
+    // g_shat[i,d] = scale * sum_j dout[i,j] vhat[j,d]
+    if ((rc = gemm_f32(dout, N, 1, vh, 1, D, gs, D, int(Bt), D, int(N), scale, st))) return rc;
+    unnormalize_grad_kernel<<<unsigned((Bt + 7) / 8), 256, 0, st>>>(seq, gs, dseq, Bt, D);
+    HMMC_CHECK_LAUNCH();
+  }
+  if (dvis != nullptr) {
+    // g_vhat[j,d] = scale * sum_i dout[i,j] shat[i,d]
+    if ((rc = gemm_f32(dout, 1, N, sh, 1, D, gv, D, int(N), D, int(Bt), scale, st))) return rc;
+    unnormalize_grad_kernel<<<unsigned((N + 7) / 8), 256, 0, st>>>(vis, gv, dvis, N, D);
+    HMMC_CHECK_LAUNCH();
+  }
+  return HMMC_OK;
+}
+
+int hmmc_cross_en_fwd_bwd(const float* S, int64_t lds, int B, float* loss_out, float* dS, int64_t ldds,
+                          float* row_scratch, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HMMC_REQUIRE(S && loss_out && row_scratch && B > 0 && lds >= B, "cross_en: bad arguments");
+  cross_en_row_kernel<<<B, 256, 0, st>>>(S, lds, B, row_scratch, dS, ldds);
+  HMMC_CHECK_LAUNCH();
+  sum_to_scalar_kernel<<<1, 256, 0, st>>>(row_scratch, B, loss_out, 0);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+struct SymCeWs {
+  float *that, *ghat, *S, *lse_row, *lse_col, *row_loss, *gt, *gg;
+};
+static void symce_carve(Workspace& ws, SymCeWs& w, int B, int F, int D) {
+  const size_t NB = size_t(1 + F);
+  w.that = ws.take<float>(size_t(B) * D);
+  w.ghat = ws.take<float>(NB * B * D);
+  w.S = ws.take<float>(size_t(B) * NB * B);
+  w.lse_row = ws.take<float>(NB * B);
+  w.lse_col = ws.take<float>(NB * B);
+  w.row_loss = ws.take<float>(size_t(B));
+  w.gt = ws.take<float>(size_t(B) * D);
+  w.gg = ws.take<float>(NB * B * D);
+}
+
+size_t hmmc_sym_ce_workspace_bytes(int B, int F, int D, int prec) {
+  (void)prec;
+  Workspace ws(nullptr, 0);
+  SymCeWs w;
+  symce_carve(ws, w, B, F, D);
+  return ws.used + 256;
+}
+
+int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* frames, int B, int F, int D, float scale,
+                        float w_vtm, float w_ftm, int prec, float* loss_out, float* dtext, float* dvideo,
+                        float* dframes, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HMMC_REQUIRE(text && loss_out && B > 0 && D > 0 && F >= 0, "sym_ce: bad arguments");
+  const int voff = (video != nullptr) ? 1 : 0;   // video == NULL: frame_loss alone (modules/modeling.py:665-673)
+  HMMC_REQUIRE(voff + F > 0, "sym_ce: neither video nor frames given");
+  HMMC_REQUIRE(voff == 1 || dvideo == nullptr, "sym_ce: dvideo requested without video");
+  HMMC_REQUIRE(F == 0 || frames != nullptr, "sym_ce: frames is null but F=%d", F);
+  HMMC_REQUIRE(prec >= 0 && prec <= 2, "sym_ce: unknown precision %d", prec);
+  const int NB = voff + F;
+  Workspace ws(workspace, workspace_bytes);
+  SymCeWs w;
+  symce_carve(ws, w, B, F, D);
+  if (!ws.ok()) { set_error("sym_ce: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
+  const bool need_grad = dtext || dvideo || dframes;
+  int rc;
+  if ((rc = rownorm_pack(text, B, D, D, 0.f, 1, w.that, nullptr, nullptr, 0, st))) return rc;
+  gallery_norm_kernel<<<unsigned((int64_t(NB) * B + 7) / 8), 256, 0, st>>>(video, frames, B, F, voff, D, w.ghat);
+  HMMC_CHECK_LAUNCH();
+  const int NG = NB * B;
+  // S_all = scale * that . ghat^T   [B, NG]
+  if ((rc = gemm_f32(w.that, D, 1, w.ghat, D, 1, w.S, NG, B, NG, D, scale, st))) return rc;
+  symce_row_lse_kernel<<<B, 256, 0, st>>>(w.S, B, NB, w.lse_row);
+  HMMC_CHECK_LAUNCH();
+  symce_col_lse_kernel<<<unsigned((NG + 31) / 32), 256, 0, st>>>(w.S, B, NB, w.lse_col);
+  HMMC_CHECK_LAUNCH();
+  const float wf = (F > 0) ? w_ftm / float(F) : 0.f;
+  symce_grad_kernel<<<B, 256, 0, st>>>(w.S, B, NB, w.lse_row, w.lse_col, voff, w_vtm, wf, w.row_loss, need_grad ? 1 : 0);
+  HMMC_CHECK_LAUNCH();
+  sum_to_scalar_kernel<<<1, 256, 0, st>>>(w.row_loss, B, loss_out, 0);
+  HMMC_CHECK_LAUNCH();
+  if (!need_grad) return HMMC_OK;
+  if (dtext != nullptr) {
+    // g_that[i,d] = scale * sum_g G[i,g] ghat[g,d]
+    if ((rc = gemm_f32(w.S, NG, 1, w.ghat, 1, D, w.gt, D, B, D, NG, scale, st))) return rc;
+    unnormalize_grad_kernel<<<unsigned((B + 7) / 8), 256, 0, st>>>(text, w.gt, dtext, B, D);
+    HMMC_CHECK_LAUNCH();
+  }
+  if (dvideo != nullptr || dframes != nullptr) {
+    // g_ghat[g,d] = scale * sum_i G[i,g] that[i,d]
+    if ((rc = gemm_f32(w.S, 1, NG, w.that, 1, D, w.gg, D, NG, D, B, scale, st))) return rc;
+    // chain through the normalisation in gallery order (reuse ghat buffer for the raw rows is not
+    // possible, so un-normalise against the raw inputs row by row after scattering)
+    if (dvideo != nullptr) {
+      unnormalize_grad_kernel<<<unsigned((B + 7) / 8), 256, 0, st>>>(video, w.gg, dvideo, B, D);
+      HMMC_CHECK_LAUNCH();
+    }
+    if (dframes != nullptr && F > 0) {
+      // gather gallery-ordered g_hat rows into [B,F,D] order (into ghat, no longer needed), then un-normalise
+      gallery_scatter_kernel<<<unsigned(int64_t(NB) * B), 128, 0, st>>>(w.gg, B, F, voff, D, /*dvideo=*/w.ghat, /*dframes=*/w.ghat + int64_t(B) * D);
+      HMMC_CHECK_LAUNCH();
+      unnormalize_grad_kernel<<<unsigned((int64_t(B) * F + 7) / 8), 256, 0, st>>>(frames, w.ghat + int64_t(B) * D, dframes, int64_t(B) * F, D);
+      HMMC_CHECK_LAUNCH();
+    }
+  }
+  return HMMC_OK;
+}
+
+}  // extern "C"

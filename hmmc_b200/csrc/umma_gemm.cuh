@@ -1,0 +1,349 @@
+// tcgen05 / TMA GEMM engine:  acc[m,n] = sum_k A[m,k] * B[n,k]   (both operands K-major bf16)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma, M=128 x N=BN x K=16, fp32 accumulators in TMEM)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue      (tcgen05.ld: one accumulator row per thread -> fused epilogue)
+// Two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// The K loop runs over up to three "segments" (pairs of K offsets into the plane-packed
+// operands), which is how the BF16X3 mode (hi*hi + hi*lo + lo*hi) is expressed without
+// duplicating data, and over a [k-block) sub-range per tile for split-K.
+//
+// The epilogue is a functor (Epi) that sees 32 consecutive accumulator columns of one row
+// at a time; see the Epi* structs below.
+#pragma once
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace hmmc {
+
+struct GemmShape {
+  int M, N;                 // logical output extent (rows / columns beyond are masked)
+  int num_m_blk, num_n_blk, num_splits;
+  int num_seg;              // 1 or 3
+  int kb_per_seg;           // K / 64
+  int kb_per_split;         // k-blocks (over all segments) handled by one split
+  int a_k0[3], b_k0[3];     // element offsets of each segment on the packed K axis
+};
+
+constexpr int UMMA_BM = 128;
+constexpr int UMMA_BK = 64;
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int STAGES = (BN > 128) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = UMMA_BM * UMMA_BK * 2;
+  static constexpr uint32_t B_BYTES = BN * UMMA_BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(256, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmShape s, const typename Epi::Params ep) {
+  using Cfg = UmmaCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bar_base = ptx::smem_u32(bars);
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (STAGES + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(full_bar(i), 1);
+      ptx::mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull_bar(i), 1);
+      ptx::mbar_init(tempty_bar(i), 4);   // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = s.num_m_blk * s.num_n_blk;
+  const int num_tiles = tiles_mn * s.num_splits;
+  const int total_kb = s.num_seg * s.kb_per_seg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int mn = t - split * tiles_mn;
+        const int m_blk = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, total_kb);
+        for (int i = kb0; i < kb1; ++i) {
+          const int seg = i / s.kb_per_seg, kb = i - seg * s.kb_per_seg;
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          ptx::tma_load_2d(sa, &tmA, full_bar(stage), s.a_k0[seg] + kb * UMMA_BK, m_blk * UMMA_BM);
+          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), s.b_k0[seg] + kb * UMMA_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(UMMA_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, total_kb);
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int i = kb0; i < kb1; ++i) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < UMMA_BK / 16; ++k) {
+            // +32 bytes along K inside the 128-byte swizzle span = +2 in the (addr>>4) field
+            ptx::umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    Epi epi;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn;
+      const int mn = t - split * tiles_mn;
+      const int m_blk = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
+      const int row = m_blk * UMMA_BM + quad * 32 + lane;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      epi.begin_tile(ep, s, row, n_blk, split);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        ptx::tmem_ld_x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        epi.chunk(ep, s, row, n_blk * BN + c * 32, v);
+      }
+      if constexpr (BN % 32 != 0) {
+        float v[16];
+        ptx::tmem_ld_x16(taddr + (BN / 32) * 32, v);
+        ptx::tmem_ld_wait();
+        epi.chunk16(ep, s, row, n_blk * BN + (BN / 32) * 32, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      epi.end_tile(ep, s, row, n_blk, split);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ epilogues
+
+// C[split][m, n] = alpha * acc
+struct EpiStoreF32 {
+  struct Params {
+    float* C;
+    int64_t ldc;
+    int64_t split_stride;
+    float alpha;
+  };
+  float* out;
+  __device__ __forceinline__ void begin_tile(const Params& p, const GemmShape& s, int row, int n_blk, int split) {
+    out = p.C + int64_t(split) * p.split_stride + int64_t(row) * p.ldc;
+  }
+  __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
+    if (row >= s.M) return;
+    if (col0 + 32 <= s.N && (p.ldc & 3) == 0) {
+      float4* o = reinterpret_cast<float4*>(out + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha, v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < s.N) out[col0 + j] = v[j] * p.alpha;
+    }
+  }
+  __device__ __forceinline__ void chunk16(const Params& p, const GemmShape& s, int row, int col0, float (&v)[16]) {
+    if (row >= s.M) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < s.N) out[col0 + j] = v[j] * p.alpha;
+  }
+  __device__ __forceinline__ void end_tile(const Params&, const GemmShape&, int, int, int) {}
+};
+
+// InfoNCE negatives: e = exp2(acc*a2 - c2)  (= exp(l - c) with a2 = log2(e)/T, c2 = c*log2(e));
+// per-row partial sums -> rowsum_part[n_blk][row]; optional bf16 hi(/lo) planes of e -> E.
+// No logits are written.
+struct EpiInfoNCE {
+  struct Params {
+    float a2, c2;
+    float* rowsum_part;       // [num_n_blk, M]
+    __nv_bfloat16* E;         // [M, e_planes * N] or nullptr
+    int64_t ldE;
+    int e_planes;
+  };
+  float acc_sum;
+  __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int, int, int) { acc_sum = 0.f; }
+  __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      e[j] = ptx::ex2_approx(fmaf(v[j], p.a2, -p.c2));
+      if (col0 + j >= s.N) e[j] = 0.f;
+      acc_sum += e[j];
+    }
+    if (p.E != nullptr && row < s.M && col0 + 32 <= s.N) {
+      __nv_bfloat16* dst = p.E + int64_t(row) * p.ldE + col0;
+      uint32_t hi[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
+        hi[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      if (p.e_planes == 2) {
+        uint32_t lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&hi[j]);
+          __nv_bfloat162 l = __floats2bfloat162_rn(e[2 * j] - __low2float(h), e[2 * j + 1] - __high2float(h));
+          lo[j] = *reinterpret_cast<uint32_t*>(&l);
+        }
+        uint4* l4 = reinterpret_cast<uint4*>(dst + s.N);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
+    }
+  }
+  __device__ __forceinline__ void chunk16(const Params&, const GemmShape&, int, int, float (&)[16]) {}
+  __device__ __forceinline__ void end_tile(const Params& p, const GemmShape& s, int row, int n_blk, int) {
+    if (row < s.M) p.rowsum_part[int64_t(n_blk) * s.M + row] = acc_sum;
+  }
+};
+
+// ------------------------------------------------------------------ host side
+
+// bf16 row-major [rows, cols] (leading dimension ld elements) -> 2-D tensor map with a
+// [box_rows x 64] box and the 128-byte swizzle.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+static inline void fill_segments(GemmShape& s, int planes, int K) {
+  s.kb_per_seg = K / UMMA_BK;
+  if (planes == 2) {
+    s.num_seg = 3;   // hi*hi, hi*lo, lo*hi
+    s.a_k0[0] = 0; s.b_k0[0] = 0;
+    s.a_k0[1] = 0; s.b_k0[1] = K;
+    s.a_k0[2] = K; s.b_k0[2] = 0;
+  } else {
+    s.num_seg = 1;
+    s.a_k0[0] = s.b_k0[0] = 0;
+    s.a_k0[1] = s.b_k0[1] = s.a_k0[2] = s.b_k0[2] = 0;
+  }
+}
+
+template <int BN, class Epi>
+int launch_umma_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int planes,
+                     int splits, const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = UmmaCfg<BN>;
+  HMMC_REQUIRE(K % UMMA_BK == 0 && K > 0, "umma gemm: K=%d must be a positive multiple of %d", K, UMMA_BK);
+  HMMC_REQUIRE(planes == 1 || planes == 2, "umma gemm: planes must be 1 or 2");
+  HMMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "umma gemm: leading dimensions must be multiples of 8");
+  HMMC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+               "umma gemm: operands must be 16-byte aligned");
+  if (M <= 0 || N <= 0) return HMMC_OK;
+  GemmShape s;
+  s.M = M;
+  s.N = N;
+  s.num_m_blk = (M + UMMA_BM - 1) / UMMA_BM;
+  s.num_n_blk = (N + BN - 1) / BN;
+  fill_segments(s, planes, K);
+  const int total_kb = s.num_seg * s.kb_per_seg;
+  if (splits < 1) splits = 1;
+  if (splits > total_kb) splits = total_kb;
+  s.kb_per_split = (total_kb + splits - 1) / splits;
+  s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;   // every split gets >= 1 k-block
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, uint64_t(M), uint64_t(planes) * K, uint64_t(lda), UMMA_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, uint64_t(N), uint64_t(planes) * K, uint64_t(ldb), BN);
+  if (rc) return rc;
+  auto kern = umma_gemm_kernel<BN, Epi>;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    attr_set = true;
+  }
+  const int tiles = s.num_m_blk * s.num_n_blk * s.num_splits;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, s, ep);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+// number of split-K slices that fills the machine for an (M x N) output with BN-wide tiles
+static inline int pick_splits(int M, int N, int BN, int total_kb) {
+  const int tiles = ((M + UMMA_BM - 1) / UMMA_BM) * ((N + BN - 1) / BN);
+  int sp = sm_count() / (tiles > 0 ? tiles : 1);
+  if (sp < 1) sp = 1;
+  if (sp > 32) sp = 32;
+  if (sp > total_kb) sp = total_kb;
+  return sp;
+}
+
+}  // namespace hmmc

@@ -1,0 +1,473 @@
+"""Torch-facing wrappers of the C ABI: tensors in, tensors out, autograd where the
+reference differentiates.  Device memory and streams come from torch; all arithmetic
+happens in libhmmc_head.so on the caller's current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (PREC_BF16, PREC_BF16X3, PREC_FP32, PRECISIONS, POS_FRAME_NEIGHBOUR, POS_FRAMES_TO_ONE,
+                   POS_ONE_TO_FRAMES, POS_PAIR, HmmcError, hmmc_queue)
+
+DEFAULT_PRECISION = os.environ.get("HMMC_PRECISION", "bf16x3")
+
+
+def resolve_precision(p=None):
+    if p is None:
+        p = DEFAULT_PRECISION
+    if isinstance(p, str):
+        if p not in PRECISIONS:
+            raise ValueError("unknown precision %r (choose from %s)" % (p, sorted(PRECISIONS)))
+        return PRECISIONS[p]
+    return int(p)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f32c(t, name):
+    """fp32 contiguous CUDA view of ``t`` (the reference's encoders end in .float())."""
+    if not t.is_cuda:
+        raise HmmcError("%s must be a CUDA tensor: libhmmc_head has no CPU path" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_workspaces = {}
+
+
+def workspace(device, nbytes):
+    """One growing scratch buffer per device (all calls are stream-ordered)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def device_check():
+    _lib.check(_lib.load().hmmc_device_check(), "hmmc_device_check")
+
+
+# ----------------------------------------------------------------------------- primitives
+
+def rownorm_pack(x, eps, planes, want_xhat=False, want_packed=True):
+    lib = _lib.load()
+    x = _f32c(x, "x")
+    R, D = x.shape
+    xhat = torch.empty_like(x) if want_xhat else None
+    inv = torch.empty(R, dtype=torch.float32, device=x.device)
+    packed = torch.empty(R, planes * D, dtype=torch.bfloat16, device=x.device) if want_packed else None
+    _lib.check(lib.hmmc_rownorm_pack(_p(x), R, D, D, float(eps), planes, _p(xhat), _p(inv), _p(packed),
+                                     planes * D, _stream()), "hmmc_rownorm_pack")
+    return xhat, inv, packed
+
+
+def gemm_f32(A, B, alpha=1.0):
+    """C = alpha * A @ B.T for 2-D fp32 tensors of any strides (CUDA-core path)."""
+    lib = _lib.load()
+    M, K = A.shape
+    N = B.shape[0]
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.check(lib.hmmc_gemm_f32(_p(A), A.stride(0), A.stride(1), _p(B), B.stride(0), B.stride(1), _p(C), N,
+                                 M, N, K, float(alpha), _stream()), "hmmc_gemm_f32")
+    return C
+
+
+def umma_gemm_nt(Ap, Bp, K, planes, alpha=1.0):
+    """C = alpha * A . B^T on tcgen05 from plane-packed bf16 operands [rows, planes*K]."""
+    lib = _lib.load()
+    M, N = Ap.shape[0], Bp.shape[0]
+    C = torch.empty(M, N, dtype=torch.float32, device=Ap.device)
+    _lib.check(lib.hmmc_umma_gemm_nt(_p(Ap), Ap.stride(0), _p(Bp), Bp.stride(0), _p(C), N, M, N, K, planes,
+                                     float(alpha), _stream()), "hmmc_umma_gemm_nt")
+    return C
+
+
+# ----------------------------------------------------------------------------- queues
+
+class QueueState:
+    """Packed operand copies of one negative queue buffer ([D, Kq] fp32, the
+    reference's state-dict layout, modules/modeling.py:138-149)."""
+
+    def __init__(self, buf, planes):
+        assert buf.dim() == 2 and buf.dtype == torch.float32 and buf.is_cuda and buf.is_contiguous()
+        self.buf = buf
+        self.D, self.Kq = buf.shape
+        self.planes = planes
+        self.pack_kd = torch.empty(self.Kq, planes * self.D, dtype=torch.bfloat16, device=buf.device)
+        self.pack_dk = torch.empty(self.D, planes * self.Kq, dtype=torch.bfloat16, device=buf.device)
+        self.version = None
+        self.repack()
+
+    def struct(self):
+        return hmmc_queue(self.buf.data_ptr(), self.pack_kd.data_ptr(), self.pack_dk.data_ptr(), self.D,
+                          self.Kq, self.planes, 0)
+
+    def repack(self):
+        q = self.struct()
+        _lib.check(_lib.load().hmmc_queue_pack(ctypes.byref(q), _stream()), "hmmc_queue_pack")
+        self.version = self.buf._version
+
+    def fresh(self):
+        if self.buf._version != self.version:   # someone wrote the buffer through torch (load_state_dict, ...)
+            self.repack()
+        return self
+
+
+_queue_states = {}
+
+
+def queue_state(buf, prec):
+    """Packed copies for ``buf``; FP32 precision needs none."""
+    planes = 2 if prec == PREC_BF16X3 else 1
+    if prec == PREC_FP32:
+        return None
+    key = (buf.data_ptr(), tuple(buf.shape), planes)
+    st = _queue_states.get(key)
+    if st is None or st.buf is not buf:
+        if not buf.is_contiguous():
+            raise HmmcError("queue buffers must be contiguous [D, Kq] tensors")
+        st = QueueState(buf, planes)
+        _queue_states[key] = st
+    return st.fresh()
+
+
+def _queue_struct(buf, prec):
+    st = queue_state(buf, prec)
+    if st is not None:
+        return st.struct(), st
+    D, Kq = buf.shape
+    return hmmc_queue(buf.data_ptr(), 0, 0, D, Kq, 1, 0), None
+
+
+# ----------------------------------------------------------------------------- InfoNCE vs queue
+
+def infonce_raw(q2d, keys2d, pos_mode, b, Fq, Fk, queue_buf, temperature, weight, prec, need_grad):
+    """Returns (loss 0-d tensor, dq or None)."""
+    lib = _lib.load()
+    D = q2d.shape[1]
+    qs, keep = _queue_struct(queue_buf, prec)
+    R = b * Fq
+    nbytes = lib.hmmc_infonce_workspace_bytes(R, D, qs.Kq, prec)
+    ws = workspace(q2d.device, nbytes)
+    loss = torch.zeros((), dtype=torch.float32, device=q2d.device)
+    dq = torch.empty_like(q2d) if need_grad else None
+    _lib.check(lib.hmmc_infonce_queue_fwd_bwd(_p(q2d), _p(keys2d), pos_mode, b, Fq, Fk, D, ctypes.byref(qs),
+                                              float(temperature), float(weight), prec, _p(loss), _p(dq),
+                                              _p(ws), ws.numel(), _stream()), "hmmc_infonce_queue_fwd_bwd")
+    return loss, dq
+
+
+class _InfoNCEFn(torch.autograd.Function):
+    """loss = weight * sum over the positive terms of mean-CE([l+, l_neg]/T, 0); forward
+    and backward run in one pass (the gradient w.r.t. q is produced with the loss)."""
+
+    @staticmethod
+    def forward(ctx, q, keys, queue_buf, pos_mode, b, Fq, Fk, temperature, weight, prec):
+        q2d = _f32c(q, "q").reshape(b * Fq, -1)
+        k2d = _f32c(keys, "k").reshape(b * Fk, -1)
+        need = q.requires_grad
+        loss, dq = infonce_raw(q2d, k2d, pos_mode, b, Fq, Fk, queue_buf, temperature, weight, prec, need)
+        ctx.q_shape = q.shape
+        ctx.q_dtype = q.dtype
+        if need:
+            ctx.save_for_backward(dq)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dq,) = ctx.saved_tensors
+        gq = (dq * g).reshape(ctx.q_shape).to(ctx.q_dtype)
+        return gq, None, None, None, None, None, None, None, None, None
+
+
+def infonce(q, keys, queue_buf, pos_mode, b, Fq, Fk, temperature, weight=1.0, precision=None):
+    return _InfoNCEFn.apply(q, keys, queue_buf, pos_mode, b, Fq, Fk, float(temperature), float(weight),
+                            resolve_precision(precision))
+
+
+# ----------------------------------------------------------------------------- EMA / enqueue
+
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+class EmaTable:
+    """Device-side pointer table of the (param_k, param) pairs of _momentum_update."""
+
+    def __init__(self, pairs):
+        lib = _lib.load()
+        be = lib.hmmc_ema_block_elems()
+        pk_ptrs, p_ptrs, numels, dts, offs = [], [], [], [], [0]
+        dev = None
+        for p, pk in pairs:
+            if p.dtype not in _DT or pk.dtype != p.dtype:
+                raise HmmcError("EMA: unsupported / mismatching dtypes %s vs %s" % (p.dtype, pk.dtype))
+            if not (p.is_cuda and pk.is_cuda and p.is_contiguous() and pk.is_contiguous()):
+                raise HmmcError("EMA: parameters must be contiguous CUDA tensors")
+            if p.numel() == 0:
+                continue
+            dev = pk.device
+            pk_ptrs.append(pk.data_ptr())
+            p_ptrs.append(p.data_ptr())
+            numels.append(p.numel())
+            dts.append(_DT[p.dtype])
+            offs.append(offs[-1] + (p.numel() + be - 1) // be)
+        live = [(p, pk) for p, pk in pairs if p.numel()]
+        self.probe = [(live[i][0], live[i][1], live[i][0].data_ptr(), live[i][1].data_ptr())
+                      for i in sorted({0, len(live) // 2, len(live) - 1})] if live else []
+        self.n = len(numels)
+        self.total_blocks = offs[-1]
+        self.total_elems = sum(numels)
+        self.signature = (tuple(pk_ptrs), tuple(p_ptrs))
+        if self.n:
+            u64 = lambda v: torch.tensor(v, dtype=torch.int64).to(dev)   # pointers < 2^63
+            self.pk = u64(pk_ptrs)
+            self.p = u64(p_ptrs)
+            self.numels = u64(numels)
+            self.dtypes = torch.tensor(dts, dtype=torch.int32).to(dev)
+            self.offs = u64(offs)
+
+    def still_valid(self):
+        return all(p.data_ptr() == a and pk.data_ptr() == b for p, pk, a, b in self.probe)
+
+    def run(self, m):
+        if not self.n:
+            return
+        import numpy as np
+        m32 = float(np.float32(m))
+        omm32 = float(np.float32(1.0 - m))      # (1. - m) in python double, then fp32 (modeling.py:242)
+        _lib.check(_lib.load().hmmc_ema_multi(_p(self.pk), _p(self.p), _p(self.numels), _p(self.dtypes),
+                                              _p(self.offs), self.n, self.total_blocks, m32, omm32, _stream()),
+                   "hmmc_ema_multi")
+
+
+def pack_rows(tensors, out=None):
+    """[rows, w_i] blocks -> one [rows, sum w_i] fp32 buffer (send buffer of the all-gather)."""
+    lib = _lib.load()
+    ts = [_f32c(t, "block").reshape(t.shape[0], -1) for t in tensors]
+    rows = ts[0].shape[0]
+    widths = [t.shape[1] for t in ts]
+    if out is None:
+        out = torch.empty(rows, sum(widths), dtype=torch.float32, device=ts[0].device)
+    n = len(ts)
+    ptrs = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in ts])
+    ws = (ctypes.c_int32 * n)(*widths)
+    _lib.check(lib.hmmc_pack_rows(ptrs, ws, n, rows, _p(out), _stream()), "hmmc_pack_rows")
+    return out
+
+
+def unpack_rows(packed, widths):
+    lib = _lib.load()
+    rows = packed.shape[0]
+    outs = [torch.empty(rows, w, dtype=torch.float32, device=packed.device) for w in widths]
+    n = len(outs)
+    ptrs = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in outs])
+    ws = (ctypes.c_int32 * n)(*widths)
+    _lib.check(lib.hmmc_unpack_rows(_p(packed), ptrs, ws, n, rows, _stream()), "hmmc_unpack_rows")
+    return outs
+
+
+def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec):
+    """queue_bufs5 order: v, tag, title, frame_cross, frame_proj."""
+    lib = _lib.load()
+    arr = (hmmc_queue * 5)()
+    keep = []
+    for i, buf in enumerate(queue_bufs5):
+        qs, st = _queue_struct(buf, prec)
+        arr[i] = qs
+        keep.append(st)
+    _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _stream()),
+               "hmmc_enqueue_norm")
+    for st, buf in zip(keep, queue_bufs5):
+        if st is not None:
+            st.version = buf._version       # the kernel kept the packed copies in step
+
+
+# ----------------------------------------------------------------------------- fine-tune head
+
+def loose_similarity_raw(seq, vis, scale, prec):
+    lib = _lib.load()
+    Bt, D = seq.shape
+    if vis.dim() == 3:
+        Bv, Fv = vis.shape[0], vis.shape[1]
+    else:
+        Bv, Fv = vis.shape[0], 1
+    out = torch.empty(Bt, Bv * Fv, dtype=torch.float32, device=seq.device)
+    nbytes = lib.hmmc_similarity_workspace_bytes(Bt, Bv, Fv, D, prec)
+    ws = workspace(seq.device, nbytes)
+    _lib.check(lib.hmmc_loose_similarity_fwd(_p(seq), Bt, _p(vis), Bv, Fv, D, float(scale), prec, _p(out),
+                                             _p(ws), ws.numel(), _stream()), "hmmc_loose_similarity_fwd")
+    return out.view(Bt, Bv, Fv) if vis.dim() == 3 else out
+
+
+class _LooseSimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seq, vis, scale, prec):
+        s = _f32c(seq, "sequence_output")
+        v = _f32c(vis, "visual_output")
+        ctx.save_for_backward(s, v)
+        ctx.scale = scale
+        ctx.prec = prec
+        ctx.dtypes = (seq.dtype, vis.dtype)
+        return loose_similarity_raw(s, v, scale, prec)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        s, v = ctx.saved_tensors
+        Bt, D = s.shape
+        Bv, Fv = (v.shape[0], v.shape[1]) if v.dim() == 3 else (v.shape[0], 1)
+        g = _f32c(g, "grad").reshape(Bt, Bv * Fv)
+        ds = torch.empty_like(s) if ctx.needs_input_grad[0] else None
+        dv = torch.empty_like(v) if ctx.needs_input_grad[1] else None
+        nbytes = lib.hmmc_similarity_workspace_bytes(Bt, Bv, Fv, D, ctx.prec)
+        ws = workspace(s.device, nbytes)
+        _lib.check(lib.hmmc_loose_similarity_bwd(_p(s), Bt, _p(v), Bv, Fv, D, float(ctx.scale), _p(g), _p(ds),
+                                                 _p(dv), _p(ws), ws.numel(), _stream()),
+                   "hmmc_loose_similarity_bwd")
+        if ds is not None:
+            ds = ds.to(ctx.dtypes[0])
+        if dv is not None:
+            dv = dv.to(ctx.dtypes[1])
+        return ds, dv, None, None
+
+
+def loose_similarity(seq, vis, scale, precision=None):
+    return _LooseSimFn.apply(seq, vis, float(scale), resolve_precision(precision))
+
+
+class _CrossEnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sim):
+        lib = _lib.load()
+        if sim.dim() != 2 or sim.shape[0] != sim.shape[1]:
+            raise HmmcError("CrossEn expects a square similarity matrix, got %s" % (tuple(sim.shape),))
+        S = sim if (sim.is_cuda and sim.dtype == torch.float32 and sim.stride(1) == 1) else _f32c(sim, "sim_matrix")
+        B = S.shape[0]
+        loss = torch.empty((), dtype=torch.float32, device=S.device)
+        need = sim.requires_grad
+        dS = torch.empty(B, B, dtype=torch.float32, device=S.device) if need else None
+        scratch = torch.empty(B, dtype=torch.float32, device=S.device)
+        _lib.check(lib.hmmc_cross_en_fwd_bwd(_p(S), S.stride(0), B, _p(loss), _p(dS), B, _p(scratch), _stream()),
+                   "hmmc_cross_en_fwd_bwd")
+        if need:
+            ctx.save_for_backward(dS)
+        ctx.dtype = sim.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dS,) = ctx.saved_tensors
+        return (dS * g).to(ctx.dtype)
+
+
+def cross_en(sim):
+    return _CrossEnFn.apply(sim)
+
+
+def sym_ce_raw(text, video, frames, scale, w_vtm, w_ftm, prec, need_grad):
+    """Fused fine-tune head on gathered embeddings; returns (loss, dtext, dvideo, dframes)."""
+    lib = _lib.load()
+    B, D = text.shape
+    F = frames.shape[1] if frames is not None else 0
+    nbytes = lib.hmmc_sym_ce_workspace_bytes(B, F, D, prec)
+    ws = workspace(text.device, nbytes)
+    loss = torch.empty((), dtype=torch.float32, device=text.device)
+    dt = torch.empty_like(text) if need_grad else None
+    dv = torch.empty_like(video) if (need_grad and video is not None) else None
+    df = torch.empty_like(frames) if (need_grad and frames is not None) else None
+    _lib.check(lib.hmmc_sym_ce_fwd_bwd(_p(text), _p(video), _p(frames), B, F, D, float(scale), float(w_vtm),
+                                       float(w_ftm), prec, _p(loss), _p(dt), _p(dv), _p(df), _p(ws), ws.numel(),
+                                       _stream()), "hmmc_sym_ce_fwd_bwd")
+    return loss, dt, dv, df
+
+
+class _SymCeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, text, video, frames, scale, w_vtm, w_ftm, prec):
+        t = _f32c(text, "query_output")
+        v = _f32c(video, "visual_output") if video is not None else None
+        f = _f32c(frames, "frame_output") if frames is not None else None
+        need = any(x is not None and x.requires_grad for x in (text, video, frames))
+        loss, dt, dv, df = sym_ce_raw(t, v, f, scale, w_vtm, w_ftm, prec, need)
+        ctx.has = (video is not None, frames is not None)
+        if need:
+            ctx.save_for_backward(*[x for x in (dt, dv, df) if x is not None])
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        dt = saved.pop(0) * g
+        dv = saved.pop(0) * g if ctx.has[0] else None
+        df = saved.pop(0) * g if ctx.has[1] else None
+        return dt, dv, df, None, None, None, None
+
+
+def sym_ce(text, video, frames, scale, w_vtm, w_ftm, precision=None):
+    return _SymCeFn.apply(text, video, frames, float(scale), float(w_vtm), float(w_ftm),
+                          resolve_precision(precision))
+
+
+# ----------------------------------------------------------------------------- eval
+
+def sim_topk(text, video, frames, scale, top_k, precision=None, want_sim=True, want_fsim=True):
+    """(sim [Nt,Nv], fsim [Nt,Nv]) of one text block against one gallery block."""
+    lib = _lib.load()
+    prec = resolve_precision(precision)
+    text = _f32c(text, "text")
+    Nt, D = text.shape
+    video = _f32c(video, "video") if video is not None else None
+    frames = _f32c(frames, "frames") if frames is not None else None
+    Nv = video.shape[0] if video is not None else frames.shape[0]
+    F = frames.shape[1] if frames is not None else 0
+    sim = torch.empty(Nt, Nv, dtype=torch.float32, device=text.device) if (want_sim and video is not None) else None
+    fsim = torch.empty(Nt, Nv, dtype=torch.float32, device=text.device) if (want_fsim and frames is not None) else None
+    nbytes = lib.hmmc_sim_topk_workspace_bytes(Nt, Nv, F, D, prec)
+    ws = workspace(text.device, nbytes)
+    _lib.check(lib.hmmc_sim_topk_fwd(_p(text), Nt, _p(video), _p(frames), Nv, F, D, float(scale), int(top_k), prec,
+                                     _p(sim), _p(fsim), Nv, _p(ws), ws.numel(), _stream()), "hmmc_sim_topk_fwd")
+    return sim, fsim
+
+
+def rank_count(sim, gt=None, group_start=None, want_t2v=True, want_v2t=True):
+    """Integer rank vectors (int32, on the device) of a materialised similarity matrix."""
+    lib = _lib.load()
+    sim = _f32c(sim, "sim")
+    Nt, Nv = sim.shape
+    dev = sim.device
+    if gt is None:
+        if Nt != Nv:
+            raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,1)" % (Nt, Nv, Nt))
+        gt = torch.arange(Nt, dtype=torch.int32, device=dev)
+        group_start = torch.arange(Nv + 1, dtype=torch.int32, device=dev)
+    gt = gt.to(device=dev, dtype=torch.int32).contiguous()
+    group_start = group_start.to(device=dev, dtype=torch.int32).contiguous()
+    t2v = torch.empty(Nt, dtype=torch.int32, device=dev) if want_t2v else None
+    v2t = torch.empty(Nv, dtype=torch.int32, device=dev) if want_v2t else None
+    theta = torch.empty(Nv, dtype=torch.float32, device=dev)
+    _lib.check(lib.hmmc_rank_count(_p(sim), sim.stride(0), Nt, Nv, _p(gt), _p(group_start), _p(t2v), _p(v2t),
+                                   _p(theta), _stream()), "hmmc_rank_count")
+    return t2v, v2t
+
+
+def group_max(sim, group_start):
+    """tensor_video_to_text_sim on the device: out[j, g] = max_{s in g} sim[s, j]."""
+    lib = _lib.load()
+    sim = _f32c(sim, "sim")
+    Nt, Nv = sim.shape
+    G = group_start.numel() - 1
+    out = torch.empty(Nv, G, dtype=torch.float32, device=sim.device)
+    gs = group_start.to(device=sim.device, dtype=torch.int32).contiguous()
+    _lib.check(lib.hmmc_group_max(_p(sim), sim.stride(0), Nv, G, _p(gs), _p(out), _stream()), "hmmc_group_max")
+    return out

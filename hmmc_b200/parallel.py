@@ -1,0 +1,105 @@
+"""Process-group plumbing of the head: one process per GPU, torch.distributed (NCCL on
+the B200 box, gloo in the CPU tests).  The only exchanges of the path are
+
+  * the embedding all-gather of the fine-tune head and its SUM reduce-scatter backward
+    (modules/modeling.py:25-36, 698-700; the backward lives in diffdist==0.1 which is
+    not vendored -- contract: rank r receives the sum over ranks of gradient slice r);
+  * the key all-gather of the pre-train enqueue (modules/modeling.py:249-258);
+  * the [Nt] score / count exchange of the sharded-gallery eval.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _all_gather_into(out, x):
+    try:
+        dist.all_gather_into_tensor(out, x)
+    except (RuntimeError, NotImplementedError):      # backends without the flat variant
+        W = dist.get_world_size()
+        dist.all_gather(list(out.chunk(W, dim=0)), x)
+
+
+def _reduce_scatter_sum(out, g):
+    backend = dist.get_backend()
+    if backend == "nccl":
+        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
+    else:                                            # gloo has no reduce-scatter
+        g = g.clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        W, r = world()
+        b = g.shape[0] // W
+        out.copy_(g[r * b:(r + 1) * b])
+
+
+class _AllGatherCat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        W, _ = world()
+        x = x.contiguous()
+        out = x.new_empty((W * x.shape[0],) + tuple(x.shape[1:]))
+        _all_gather_into(out, x)
+        ctx.b = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        out = g.new_empty((ctx.b,) + tuple(g.shape[1:]))
+        _reduce_scatter_sum(out, g)
+        return out
+
+
+def all_gather_cat(x):
+    """Differentiable concat-all-gather on dim 0."""
+    W, _ = world()
+    if W == 1:
+        return x.contiguous()
+    return _AllGatherCat.apply(x)
+
+
+@torch.no_grad()
+def all_gather_rows(x):
+    """Plain all-gather of a [b, w] block -> [W*b, w] (keys for the enqueue; no gradient)."""
+    W, _ = world()
+    if W == 1:
+        return x
+    out = x.new_empty((W * x.shape[0],) + tuple(x.shape[1:]))
+    _all_gather_into(out, x.contiguous())
+    return out
+
+
+def shard_range(n, W=None, r=None):
+    """Contiguous [begin, end) slice of n items owned by rank r (gallery / text sharding)."""
+    if W is None:
+        W, r = world()
+    per = (n + W - 1) // W
+    lo = min(r * per, n)
+    return lo, min(lo + per, n)
+
+
+@torch.no_grad()
+def all_reduce_sum_(t):
+    W, _ = world()
+    if W > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+@torch.no_grad()
+def all_gather_varlen(x, counts):
+    """Concatenate per-rank 1-D blocks of different lengths (v2t ranks of the gallery shards)."""
+    W, r = world()
+    if W == 1:
+        return x
+    m = max(counts)
+    pad = x.new_zeros(m)
+    pad[:x.numel()] = x
+    out = x.new_empty(W * m)
+    _all_gather_into(out, pad)
+    return torch.cat([out[i * m:i * m + counts[i]] for i in range(W)])

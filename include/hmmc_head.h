@@ -1,0 +1,195 @@
+/*
+ * hmmc_head.h -- C ABI of libhmmc_head.so, the B200 (sm_100a) implementation of the
+ * HMMC hierarchical-matching contrastive head.
+ *
+ * The reference (cheetah003/HMMC) is pure Python / PyTorch: it has no FFI layer, its
+ * "interface" for this path is a handful of Python methods.  Each entry point below
+ * names the reference function (file:line, relative to the reference root) whose
+ * arithmetic it replaces; hmmc_b200/ (the Python host side) keeps the reference's
+ * method names and signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - no allocation, no global state except the last-error string: outputs and
+ *     workspaces are caller-allocated (sizes from the *_workspace_bytes helpers);
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*), nothing
+ *     synchronises;
+ *   - return value 0 = ok, negative = error (text from hmmc_last_error());
+ *   - matrices are row-major; "ld" = leading dimension in elements.
+ *
+ * Precision modes (`prec`): how the big contractions are carried out
+ *   HMMC_PREC_FP32   CUDA-core fp32 FMA (reference-grade, slow, no tensor cores)
+ *   HMMC_PREC_BF16   tcgen05 bf16 x bf16 -> fp32 (fast; ~1e-3 on logits)
+ *   HMMC_PREC_BF16X3 tcgen05 with operands split hi+lo in bf16, three products
+ *                    hi*hi + hi*lo + lo*hi accumulated in fp32 (~1e-6, fp32-parity)
+ */
+#ifndef HMMC_HEAD_H
+#define HMMC_HEAD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMMC_PREC_FP32 0
+#define HMMC_PREC_BF16 1
+#define HMMC_PREC_BF16X3 2
+
+#define HMMC_OK 0
+#define HMMC_ERR_ARG (-1)
+#define HMMC_ERR_CUDA (-2)
+#define HMMC_ERR_UNSUPPORTED (-3)
+#define HMMC_ERR_WORKSPACE (-4)
+
+/* positive-key layouts of hmmc_infonce_queue_fwd_bwd */
+#define HMMC_POS_PAIR 0          /* contrastive_loss(q, k, queue): key row = query row              */
+#define HMMC_POS_FRAME_NEIGHBOUR 1 /* frame_self_loss: query (n,f) vs keys (n,f+1) and (n,f-1)       */
+#define HMMC_POS_ONE_TO_FRAMES 2   /* frame_cross_loss 1st term: query n vs keys (n,0..F-1)          */
+#define HMMC_POS_FRAMES_TO_ONE 3   /* frame_cross_loss 2nd term: query (n,f) vs key n                */
+
+const char* hmmc_last_error(void);
+int hmmc_version(void);
+/* 0 when the current device is sm_100 (B200); HMMC_ERR_UNSUPPORTED otherwise. */
+int hmmc_device_check(void);
+
+/* ------------------------------------------------------------------ operands */
+
+/* Row L2-normalise x[R,D] and emit the GEMM operand planes.
+ *   eps > 0 : x / max(||x||, eps)   (F.normalize, modules/modeling.py:289,291,250-258)
+ *   eps = 0 : x / ||x||             (loose_similarity, modules/modeling.py:211,214)
+ * Any of the outputs may be NULL.  packed is bf16 [R, planes*D] (plane 0 = hi,
+ * plane 1 = lo = bf16(x_hat - hi)), row stride ld_packed elements. */
+int hmmc_rownorm_pack(const float* x, int64_t R, int D, int64_t ldx, float eps, int planes,
+                      float* xhat, float* inv_norm, void* packed, int64_t ld_packed, void* stream);
+
+/* C[M,N] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk], CUDA-core fp32. */
+int hmmc_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
+                  float* C, int64_t ldc, int M, int N, int K, float alpha, void* stream);
+
+/* C[M,N] = alpha * A[M,:] . B[N,:]  on tcgen05; A, B are bf16 plane-packed operands
+ * ([rows, planes*K], from hmmc_rownorm_pack).  planes = 1 -> one product, 2 -> three
+ * products (BF16X3).  K % 64 == 0; M, N arbitrary (edge tiles are masked). */
+int hmmc_umma_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                      int M, int N, int K, int planes, float alpha, void* stream);
+
+/* ------------------------------------------------------- pre-train head (MoCo) */
+
+/* A negative queue as the kernels see it.  `dk` is the reference's buffer
+ * (modules/modeling.py:138-149): fp32 [D, Kq], unit-norm columns.  pack_kd / pack_dk
+ * are derived bf16 operand copies kept in step by hmmc_queue_pack / hmmc_enqueue_norm:
+ *   pack_kd  [Kq, planes*D ]  (B operand of  S = q_hat . Q)
+ *   pack_dk  [D,  planes*Kq]  (B operand of  U = E . Q^T)
+ * They may be NULL when only HMMC_PREC_FP32 is used. */
+typedef struct {
+  float* dk;
+  void* pack_kd;
+  void* pack_dk;
+  int32_t D;
+  int32_t Kq;
+  int32_t planes;
+  int32_t reserved;
+} hmmc_queue;
+
+/* (Re)build pack_kd / pack_dk from dk (after init or load_state_dict). */
+int hmmc_queue_pack(const hmmc_queue* q, void* stream);
+
+size_t hmmc_infonce_workspace_bytes(int64_t R, int D, int Kq, int prec);
+
+/* Fused InfoNCE-vs-queue forward + backward for one query block.
+ * Replaces contrastive_loss (modules/modeling.py:286-313) and, through `pos_mode`,
+ * the loops of frame_self_loss (:315-323) and frame_cross_loss (:325-332):
+ *   loss_out[0] += weight * sum_terms mean_n [ log(e^{l+} + sum_j e^{l_nj}) - l+ ]
+ *   dq          =  d(that sum)/dq          (fp32 [R,D]; only q receives a gradient)
+ * q is [b*Fq, D] (row (n,f) = n*Fq+f), keys is [b*Fk, D]; both raw (un-normalised).
+ * dq may be NULL (forward only). */
+int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, int b, int Fq, int Fk, int D,
+                               const hmmc_queue* queue, float temperature, float weight, int prec,
+                               float* loss_out, float* dq, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
+/* _momentum_update (modules/modeling.py:238-242): p_k <- p_k*m + p*(1-m) for a table of
+ * tensors, each in its own dtype (0 = fp32, 1 = fp16, 2 = bf16), three separately
+ * rounded ops like the reference.  The three tables are device arrays of length n. */
+int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_t* numels,
+                   const int32_t* dtypes, const int64_t* block_offsets, int n, int64_t total_blocks,
+                   float m, float one_minus_m, void* stream);
+/* elements handled by one thread block of hmmc_ema_multi (for building block_offsets) */
+int hmmc_ema_block_elems(void);
+
+/* _dequeue_and_enqueue (modules/modeling.py:244-284) after the all-gather:
+ * L2-normalise (eps 1e-12) the gathered keys and write them as queue columns
+ * [ptr, ptr+B) (frame queues: columns [(ptr)*F, (ptr+B)*F), frame index fastest), in
+ * dk and in the packed copies; then ptr <- (ptr+B) % K on the device.
+ * `gathered` is the all-gather output [W][b][row_elems] with one rank's row =
+ * [v | tag | title | frame_fea(F*D) | frame_proj(F*D)]; queues order: v, tag, title,
+ * frame_cross (gets frame_fea), frame_proj.  queue_ptr is the int64[1] buffer.
+ * ptr_host is the host's copy of the pointer, used only for the bounds check the
+ * reference performs through slice assignment. */
+int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
+                      int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
+
+/* gather n row-blocks src_i[rows, width_i] into dst[rows, sum width_i] (the packed
+ * send buffer of the key / embedding all-gather) and the inverse. */
+int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows,
+                   float* dst, void* stream);
+int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int32_t* widths_host, int n,
+                     int64_t rows, void* stream);
+
+/* ---------------------------------------------------------- fine-tune head (HM) */
+
+/* loose_similarity (modules/modeling.py:207-229), forward.  vis is [Bv*Fv, D]
+ * (Fv = 1 for the 2-D case); out is [Bt, Bv*Fv] = [Bt,Bv,Fv] contiguous. */
+size_t hmmc_similarity_workspace_bytes(int64_t Bt, int64_t Bv, int Fv, int D, int prec);
+int hmmc_loose_similarity_fwd(const float* seq, int64_t Bt, const float* vis, int64_t Bv, int Fv, int D,
+                              float scale, int prec, float* out, void* workspace, size_t workspace_bytes,
+                              void* stream);
+/* backward of the above: dseq [Bt,D], dvis [Bv*Fv,D] from dout [Bt,Bv*Fv]. */
+int hmmc_loose_similarity_bwd(const float* seq, int64_t Bt, const float* vis, int64_t Bv, int Fv, int D,
+                              float scale, const float* dout, float* dseq, float* dvis, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* CrossEn.forward (modules/until_module.py:196-205) + its backward:
+ * loss_out[0] = -mean(diag(log_softmax(S, -1))), dS = (softmax - I)/B (NULL to skip). */
+int hmmc_cross_en_fwd_bwd(const float* S, int64_t lds, int B, float* loss_out, float* dS, int64_t ldds,
+                          float* row_scratch /* B floats */, void* stream);
+
+/* The whole fine-tune head after the gather (BirdModel.forward, modules/modeling.py:702-709
+ * with frame_loss :665-673): loss = w_vtm*(CE(S)+CE(S^T)) + w_ftm/F * sum_f (CE(S_f)+CE(S_f^T)).
+ * text [B,D], video [B,D], frames [B,F,D]; gradients may be NULL (forward only). */
+size_t hmmc_sym_ce_workspace_bytes(int B, int F, int D, int prec);
+int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* frames, int B, int F, int D,
+                        float scale, float w_vtm, float w_ftm, int prec, float* loss_out, float* dtext,
+                        float* dvideo, float* dframes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ eval */
+
+/* One (text tile x gallery tile) of _run_on_single_gpu (main_task_retrieval.py:321-357):
+ *   sim  [Nt,Nv] = s * t_hat . v_hat
+ *   fsim [Nt,Nv] = mean over the top_k frames of s * t_hat . f_hat   (torch.topk + mean)
+ * video [Nv,D], frames [Nv,F,D].  Either output may be NULL. */
+size_t hmmc_sim_topk_workspace_bytes(int64_t Nt, int64_t Nv, int F, int D, int prec);
+int hmmc_sim_topk_fwd(const float* text, int64_t Nt, const float* video, const float* frames, int64_t Nv,
+                      int F, int D, float scale, int top_k, int prec, float* sim, float* fsim, int64_t ld_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Rank counting on a materialised similarity matrix (metrics.py:12-39, 49-86):
+ *   t2v[s] = #{ j : sim[s,j] > sim[s,gt[s]] }                       (int32 [Nt])
+ *   v2t[j] = #{ g != j : max_{s in g} sim[s,j] > max_{s in group j} sim[s,j] }   (int32 [Nv])
+ * gt[s] = index of the video text s belongs to; texts of one video are contiguous
+ * and group_start[g] .. group_start[g+1] delimits them (int32 [Nv+1]).  NaN is
+ * treated as -inf in v2t (metrics.py:83).  Either output may be NULL. */
+int hmmc_rank_count(const float* sim, int64_t lds, int Nt, int Nv, const int32_t* gt,
+                    const int32_t* group_start, int32_t* t2v, int32_t* v2t, float* theta_scratch /* Nv floats */,
+                    void* stream);
+
+/* tensor_video_to_text_sim (metrics.py:79-86): out[j, g] = max_{s in group g} sim[s, j]
+ * (NaN -> -inf); out is [Nv, G] row-major, G < 65536. */
+int hmmc_group_max(const float* sim, int64_t lds, int Nv, int G, const int32_t* group_start, float* out,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMMC_HEAD_H */

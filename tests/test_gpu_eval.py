@@ -1,0 +1,114 @@
+import logging
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from hmmc_b200 import metrics as GM
+from hmmc_b200 import modeling, ops, retrieval
+from hmmc_b200 import synthetic as syn
+from oracle import head_oracle as O
+from gpu_util import cu, rel
+
+pytestmark = pytest.mark.gpu
+KEYS = ["R1", "R5", "R10", "MR", "MeanR"]
+TVK = ["R1", "R5", "R10", "MedianR", "MeanR", "Std_Rank", "MR"]
+LOG = logging.getLogger("test")
+
+
+def _model(prec, top_frames):
+    task = types.SimpleNamespace(local_rank=0, top_frames=top_frames, use_frame_fea=True, head_precision=prec)
+    return modeling.BirdModel(modeling.default_cross_config(), task)
+
+
+def test_compute_metrics_square_golden(golden):
+    g = golden("metrics")
+    rs = np.random.RandomState(0)
+    x = rs.randn(1000, 1000).astype(np.float32)
+    x[np.arange(1000), np.arange(1000)] += 2.0
+    a, b = GM.compute_metrics(x), GM.compute_metrics(x.T)
+    assert [a[k] for k in KEYS] == list(g["sq_t2v"]) and [b[k] for k in KEYS] == list(g["sq_v2t"])
+    t2v, v2t = ops.rank_count(cu(x))
+    assert np.array_equal(t2v.cpu().numpy(), O.ranks_square(x))
+    assert np.array_equal(v2t.cpu().numpy(), O.ranks_square(x.T))
+    with pytest.raises(ValueError):
+        GM.compute_metrics(np.zeros((20, 10), np.float32))
+
+
+def test_multi_sentence_metrics_golden(golden):
+    g = golden("metrics")
+    rs = np.random.RandomState(int(g["ms_seed"]))
+    V = 50
+    per = rs.randint(1, 6, size=V)
+    S = int(per.sum())
+    gt = np.repeat(np.arange(V), per)
+    sim = rs.randn(S, V).astype(np.float32)
+    sim[np.arange(S), gt] += 1.5
+    cut = (np.cumsum(per) - 1).tolist()
+    t2v, v2t = GM.multi_sentence_ranks(sim, cut)
+    rt, rv = O.ranks_multi_sentence(sim, gt)
+    assert np.array_equal(t2v, rt) and np.array_equal(v2t, rv)
+    tv = GM.t2v_metrics_from_ranks(t2v)
+    vt = GM.metrics_from_ranks(v2t)
+    assert [tv[k] for k in TVK] == list(g["ms_tv"]) and [vt[k] for k in KEYS] == list(g["ms_vt"])
+    assert GM.logging_rank(sim, True, cut, LOG) == tv
+    # the padded-cube entry points of the reference
+    sim3 = O.pad_multi_sentence(sim, cut)
+    tv3 = GM.tensor_text_to_video_metrics(sim3)
+    assert [tv3[k] for k in TVK] == list(g["ms_tv"])
+    v2tsim = GM.tensor_video_to_text_sim(sim3).cpu().numpy()
+    assert np.array_equal(v2tsim, O.tensor_video_to_text_sim(sim3))
+    vt3 = GM.compute_metrics(v2tsim)
+    assert [vt3[k] for k in KEYS] == list(g["ms_vt"])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
+def test_eval_1k(golden, prec):
+    """config 2: 1000 x 1000 x 12, top_frames 2, tiles of 256, through _run_on_single_gpu."""
+    g = golden("eval_1k")
+    T, V, Fr, gt, _ = syn.eval_inputs(1000, 1000, seed=int(g["seed"]))
+    m = _model(prec, int(g["top_frames"]))
+    tl = lambda x: [cu(x[i:i + 256]) for i in range(0, x.shape[0], 256)]
+    a, b, c = retrieval._run_on_single_gpu(m, tl(T), tl(V), [torch.zeros_like(x) for x in tl(V)], tl(Fr))
+    assert len(a) == len(b) == len(c) == 4 and a[0].shape == (256, 1000) and a[3].shape == (232, 1000)
+    sim = np.concatenate(a, 0)
+    simf = np.concatenate(c, 0)
+    assert np.isnan(np.concatenate(b, 0)).all() == bool(g["nan_title"])
+    atol = {"fp32": 4e-5, "bf16x3": 1e-4, "bf16": 0.15}[prec]
+    np.testing.assert_allclose(sim[:4], g["sim_rows"], rtol=0, atol=atol)
+    np.testing.assert_allclose(simf[:4], g["simf_rows"], rtol=0, atol=atol)
+    np.testing.assert_allclose(np.diag(sim), g["sim_diag"], rtol=0, atol=atol)
+    tot = sim + simf
+    # rank kernel is bit-exact on the matrix it is given
+    t2v, v2t = ops.rank_count(cu(tot))
+    assert np.array_equal(t2v.cpu().numpy(), O.ranks_square(tot))
+    assert np.array_equal(v2t.cpu().numpy(), O.ranks_square(tot.T))
+    tv = GM.logging_rank(tot, False, None, LOG)
+    if prec != "bf16":
+        # fp32-grade scores reproduce the reference's ranks and metrics exactly on this set
+        assert np.array_equal(t2v.cpu().numpy(), g["ranks_t2v"])
+        assert np.array_equal(v2t.cpu().numpy(), g["ranks_v2t"])
+        assert [tv[k] for k in KEYS] == list(g["tv"])
+    else:
+        assert np.mean(t2v.cpu().numpy() != g["ranks_t2v"]) < 0.02
+        assert abs(tv["R1"] - g["tv"][0]) <= 0.5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_eval_multi_sentence(golden, prec):
+    g = golden("eval_multi")
+    per = g["per"]
+    T, V, Fr, gt, cut = syn.eval_inputs(int(per.sum()), 60, seed=int(g["seed"]), per_video=per)
+    m = _model(prec, int(g["top_frames"]))
+    tv, vt = retrieval.eval_metrics(m, cu(T), cu(V), cu(Fr), True, cut)
+    sim = retrieval.similarity_matrix(m, cu(T), cu(V), cu(Fr)).cpu().numpy()
+    np.testing.assert_allclose(sim, g["tot"], rtol=0, atol=1e-4)
+    assert [tv[k] for k in TVK] == list(g["tv"]) and [vt[k] for k in KEYS] == list(g["vt"])
+
+
+def test_topk_bounds_are_loud():
+    m = _model("fp32", 13)
+    T, V, Fr, _, _ = syn.eval_inputs(8, 8, seed=1, D=64)
+    with pytest.raises(Exception):
+        ops.sim_topk(cu(T), cu(V), cu(Fr), 100.0, 13)

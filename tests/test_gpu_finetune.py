@@ -1,0 +1,88 @@
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from hmmc_b200 import modeling, ops
+from hmmc_b200 import synthetic as syn
+from oracle import head_oracle as O
+from gpu_util import TOL, cu, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(prec, top_frames=2):
+    task = types.SimpleNamespace(local_rank=0, top_frames=top_frames, use_frame_fea=True, head_precision=prec)
+    return modeling.BirdModel(modeling.default_cross_config(), task)
+
+
+@pytest.mark.parametrize("prec", ["fp32"])
+def test_loose_similarity_and_cross_en_golden(golden, prec):
+    g = golden("similarity")
+    m = _model(prec)
+    s2 = m.loose_similarity(cu(g["q"]), cu(g["v"]))
+    s3 = m.loose_similarity(cu(g["q"]), cu(g["fr"]))
+    assert tuple(s2.shape) == g["s2"].shape and tuple(s3.shape) == g["s3"].shape
+    np.testing.assert_allclose(s2.cpu().numpy(), g["s2"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(s3.cpu().numpy(), g["s3"], rtol=0, atol=3e-5)
+    ce = m.loss_fct(cu(g["s2"][:7, :7].copy()))
+    assert abs(float(ce) - float(g["ce"])) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_loose_similarity_tensor_core(prec):
+    rs = np.random.RandomState(3)
+    q = rs.randn(130, 512).astype(np.float32)
+    fr = rs.randn(40, 12, 512).astype(np.float32)
+    m = _model(prec)
+    s3 = m.loose_similarity(cu(q), cu(fr)).cpu().numpy()
+    ref = O.loose_similarity(q, fr, dtype=np.float64)
+    assert s3.shape == ref.shape == (130, 40, 12)
+    assert np.abs(s3 - ref).max() < (2e-4 if prec == "bf16x3" else 0.12)
+
+
+@pytest.mark.parametrize("B", [32, 256])
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_finetune_head(golden, B, prec):
+    g = golden("finetune_B%d" % B)
+    t, v, fr = syn.finetune_inputs(B, seed=int(g["seed"]))
+    m = _model(prec)
+    tt, tv, tf = cu(t, True), cu(v, True), cu(fr, True)
+    loss = m.head_loss(tt, tv, tf)
+    loss.backward()
+    ltol, gtol = TOL[prec]
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < ltol
+    _, dt, dv, dfr = O.finetune_loss_and_grads(t, v, fr)
+    assert rel(tt.grad.cpu().numpy(), dt) < gtol
+    assert rel(tv.grad.cpu().numpy(), dv) < gtol
+    assert rel(tf.grad.cpu().numpy(), dfr) < gtol
+    gd = g["dt"]
+    assert rel(tt.grad.cpu().numpy()[:gd.shape[0]], gd) < 1e-4
+
+
+def test_granular_path_equals_fused():
+    """frame_loss + loose_similarity + loss_fct composed as BirdModel.forward does
+    (modules/modeling.py:702-709) agree with the fused head, values and gradients."""
+    B = 48
+    t, v, fr = syn.finetune_inputs(B, seed=5)
+    m = _model("fp32")
+    a = [cu(t, True), cu(v, True), cu(fr, True)]
+    loss = 0.15 * m.frame_loss(a[0], a[2])
+    sim = m.loose_similarity(a[0], a[1])
+    loss = loss + 0.85 * (m.loss_fct(sim) + m.loss_fct(sim.T))
+    loss.backward()
+    b = [cu(t, True), cu(v, True), cu(fr, True)]
+    fused = m.head_loss(*b)
+    fused.backward()
+    assert abs(float(loss) - float(fused)) / float(fused) < 2e-6
+    for x, y in zip(a, b):
+        assert rel(x.grad.cpu().numpy(), y.grad.cpu().numpy()) < 1e-5
+
+
+def test_single_row_and_no_grad():
+    m = _model("fp32")
+    t, v, fr = syn.finetune_inputs(2, seed=9)
+    with torch.no_grad():
+        l = m.head_loss(cu(t), cu(v), cu(fr))
+    assert abs(float(l) - float(O.finetune_loss(t, v, fr))) < 1e-4

@@ -1,0 +1,159 @@
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from hmmc_b200 import modeling, ops
+from hmmc_b200 import synthetic as syn
+from oracle import head_oracle as O
+from gpu_util import TOL, cu, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(K, F, D, prec, T=0.07):
+    task = types.SimpleNamespace(local_rank=0, top_frames=3, contrast_momentum=0.99, contrast_temperature=T,
+                                 contrast_num_negative=K, max_frames=F, use_frame_fea=True, head_precision=prec)
+    m = modeling.BirdPreTrainedModel(modeling.default_cross_config(temporal_hidden_size=D), task).cuda()
+    return m
+
+
+def _load_queues(m, qs):
+    with torch.no_grad():
+        for n, x in qs.items():
+            getattr(m, n).copy_(torch.from_numpy(x))
+
+
+def test_contrastive_small_fp32(golden):
+    g = golden("contrastive_small")
+    m = _model(40, 1, 32, "fp32")
+    q = cu(g["q"], True)
+    loss = m.contrastive_loss(q, cu(g["k"]), cu(g["queue"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    assert rel(q.grad.cpu().numpy(), g["dq"]) < 2e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
+def test_pretrain_head_b32(golden, prec):
+    """config 1: b=32, F=12, D=512, K=1024, T=0.07 against the reference's own outputs."""
+    g = golden("pretrain_b32")
+    b, F, D, K, T = int(g["b"]), int(g["F"]), int(g["D"]), int(g["K"]), float(g["T"])
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    qs = syn.queues(K, F=F, D=D, seed=3)
+    m = _model(K, F, D, prec, T)
+    _load_queues(m, qs)
+    ltol, gtol = TOL[prec]
+    t = {n: cu(x, n in ("v_fea", "title_fea", "frame_fea", "frame_pred")) for n, x in inp.items()}
+    with torch.no_grad():
+        fam = float(m.frame_self_loss(t["frame_pred"], t["frame_proj_k"], m.queue_frame_proj_ng))
+        vtm = float(m.contrastive_loss(t["v_fea"], t["title_fea_k"], m.queue_title_cross_ng)
+                    + m.contrastive_loss(t["title_fea"], t["v_fea_k"], m.queue_v_cross_ng))
+        ftm = float(m.frame_cross_loss(t["frame_fea"], t["frame_fea_k"], m.queue_frame_cross_ng, t["title_fea"],
+                                       t["title_fea_k"], m.queue_title_cross_ng))
+    for got, name in ((fam, "fam"), (vtm, "vtm"), (ftm, "ftm")):
+        assert abs(got - float(g[name])) / float(g[name]) < ltol, (name, got, float(g[name]))
+    loss = m.head_loss(t["v_fea"], t["frame_fea"], t["title_fea"], t["frame_pred"], t["v_fea_k"], t["frame_fea_k"],
+                       t["title_fea_k"], t["tag_fea_k"], t["frame_proj_k"])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < ltol
+    _, ref = O.pretrain_loss_and_grads(inp, qs, T)            # fp64 oracle (pinned to the golden grads)
+    for n in ("v_fea", "title_fea", "frame_fea", "frame_pred"):
+        got = t[n].grad.cpu().numpy()
+        assert rel(got, ref[n]) < gtol, (n, rel(got, ref[n]))
+        gg = g["d_" + n]
+        assert rel(got[:gg.shape[0]], gg) < max(gtol, 1e-4), n
+    # enqueue happened inside head_loss: pointer and the first written columns
+    assert int(m.queue_ptr) == int(g["ptr"])
+    for n in syn.QUEUE_NAMES:
+        after = getattr(m, n).cpu().numpy()
+        refq = g["after_" + n]
+        np.testing.assert_allclose(after[:, :refq.shape[1]], refq, rtol=0, atol=2e-7)
+        np.testing.assert_allclose(after.astype(np.float64).sum(1), g["sum_" + n], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_enqueue_wrap_and_packed_copies(golden, prec):
+    g = golden("enqueue_wrap")
+    K, F, D = 16, 4, 64
+    m = _model(K, F, D, prec)
+    _load_queues(m, syn.queues(K, F=F, D=D, seed=3))
+    ptrs = []
+    for step in range(3):
+        k = syn.pretrain_inputs(8, F=F, D=D, seed=20 + step)
+        m._dequeue_and_enqueue(cu(k["v_fea_k"]), cu(k["tag_fea_k"]), cu(k["title_fea_k"]), cu(k["frame_fea_k"]),
+                               cu(k["frame_proj_k"]))
+        ptrs.append(int(m.queue_ptr))
+    assert ptrs == list(g["ptrs"])
+    for n in syn.QUEUE_NAMES:
+        np.testing.assert_allclose(getattr(m, n).cpu().numpy(), g["after_" + n], rtol=0, atol=2e-7)
+    if prec != "fp32":
+        # the packed operand copies written by the enqueue kernel equal a fresh re-pack
+        for buf in m._queue_buffers():
+            st = ops.queue_state(buf, ops.resolve_precision(prec))
+            kd, dk = st.pack_kd.clone(), st.pack_dk.clone()
+            st.repack()
+            assert torch.equal(kd, st.pack_kd) and torch.equal(dk, st.pack_dk)
+    # a batch that does not fit raises like the reference's slice assignment
+    k = syn.pretrain_inputs(12, F=F, D=D, seed=1)
+    with pytest.raises(Exception):
+        m._dequeue_and_enqueue(cu(k["v_fea_k"]), cu(k["tag_fea_k"]), cu(k["title_fea_k"]), cu(k["frame_fea_k"]),
+                               cu(k["frame_proj_k"]))
+
+
+def test_ema_bit_exact(golden):
+    g = golden("ema")
+    ps, pks = syn.ema_tensors()
+
+    class Mod(torch.nn.Module):
+        def __init__(self, xs):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(cu(x), requires_grad=False) for x in xs])
+    m = _model(16, 4, 64, "fp32")
+    a, b = Mod(ps), Mod(pks)
+    m.model_pairs = [[a, b]]
+    for _ in range(int(g["steps"])):
+        m._momentum_update()
+    for i, pk in enumerate(b.ps):
+        got = pk.detach().cpu().numpy()
+        ref = g["out%d" % i]
+        assert got.dtype == ref.dtype and np.array_equal(got.view(np.uint8), ref.view(np.uint8)), i
+    m.copy_params()
+    assert all(torch.equal(x, y) for x, y in zip(a.ps, b.ps))
+
+
+def test_ema_large_matches_oracle():
+    rs = np.random.RandomState(0)
+    n = 3 * 8192 + 77
+    p = rs.randn(n).astype(np.float32)
+    pk = rs.randn(n).astype(np.float32)
+    tp, tpk = cu(p), cu(pk)
+    tab = ops.EmaTable([(tp[1:], tpk[1:])])       # misaligned views take the scalar path
+    tab.run(0.99)
+    ref = O.momentum_update([p[1:]], [pk[1:]], 0.99)[0]
+    assert np.array_equal(tpk[1:].cpu().numpy().view(np.uint8), ref.view(np.uint8))
+
+
+def test_unsupported_temperature_is_loud():
+    m = _model(128, 2, 64, "fp32", T=0.001)
+    q = cu(np.random.RandomState(0).randn(4, 64).astype(np.float32))
+    with pytest.raises(Exception):
+        m.contrastive_loss(q, q, m.queue_v_cross_ng)
+
+
+def test_pretrain_head_small_fp32(golden):
+    g = golden("pretrain_small")
+    b, F, D, K, T = int(g["b"]), int(g["F"]), int(g["D"]), int(g["K"]), float(g["T"])
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    m = _model(K, F, D, "fp32", T)
+    _load_queues(m, syn.queues(K, F=F, D=D, seed=3))
+    t = {n: cu(x, n in ("v_fea", "title_fea", "frame_fea", "frame_pred")) for n, x in inp.items()}
+    loss = m.head_loss(t["v_fea"], t["frame_fea"], t["title_fea"], t["frame_pred"], t["v_fea_k"], t["frame_fea_k"],
+                       t["title_fea_k"], t["tag_fea_k"], t["frame_proj_k"])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-5
+    for n in ("v_fea", "title_fea", "frame_fea", "frame_pred"):
+        assert rel(t[n].grad.cpu().numpy(), g["d_" + n]) < 1e-4, n
+    for n in syn.QUEUE_NAMES:
+        np.testing.assert_allclose(getattr(m, n).cpu().numpy(), g["after_" + n], rtol=0, atol=2e-7)
