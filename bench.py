@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- HM+MoCo contrastive head on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU)
+    python bench.py --impl reference ...                      # the reference's CPU path (oracle port)
+
+One "step" of the default workload is the pre-train head of BASELINE.json config 4 on one
+rank: momentum EMA over the 172,325,632 key-encoder parameters, the FAM + VTM + FTM InfoNCE
+losses against the negative queues forward AND backward (b = 128 samples per GPU, 12 frames,
+dim 512, queue 1024, T 0.07), the key all-gather and the enqueue.  Ranks are data parallel
+(weak scaling); the only exchange is the key all-gather.  A retrieval leg (config 2: 1000 x 1000
+x 12 similarity + top-k frames + rank metrics) is timed after the main loop and reported in the
+same JSON line under "retrieval".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain"])
+    ap.add_argument("--precision", default=os.environ.get("HMMC_BENCH_PRECISION", "bf16"),
+                    choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--batch", type=int, default=128, help="samples per GPU")
+    ap.add_argument("--frames", type=int, default=12)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--queue", type=int, default=1024)
+    ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+FLOPS_ALGO = lambda b, F, D, K: 2 * 2.0 * D * b * (F * K * F + K * F + F * K + 2 * K)   # SURVEY.md §8d, fwd + bwd
+EMA_ELEMS = 172325632
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:   # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:   # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's torch port on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_pretrain_steps(args, max_seconds, min_steps=1, max_steps=10 ** 9, with_ema=True):
+    """Times oracle/torch_port.pretrain_step (the reference's op sequence) on all host cores.
+    Returns (ms per step, steps run, cores, sample description)."""
+    from hmmc_b200 import synthetic as syn
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b, F, D, K = args.batch, args.frames, args.dim, args.queue
+    inp_np = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    qs = {n: torch.from_numpy(x) for n, x in syn.queues(K, F=F, D=D, seed=3).items()}
+    ema = None
+    if with_ema:
+        sizes = syn.ema_param_numels()
+        big = torch.randn(sum(sizes))
+        bigk = torch.randn(sum(sizes))
+        ps = list(torch.split(big, sizes))
+        pks = [torch.nn.Parameter(x.clone(), requires_grad=False) for x in torch.split(bigk, sizes)]
+        ema = (ps, pks)
+    ptr = 0
+    times = []
+    t_all = time.perf_counter()
+    n = 0
+    while True:
+        inp = {k: torch.from_numpy(v).requires_grad_(k in ("v_fea", "title_fea", "frame_fea", "frame_pred"))
+               for k, v in inp_np.items()}
+        t0 = time.perf_counter()
+        _, ptr = P.pretrain_step(inp, qs, ptr, K, 0.07, ema=ema)
+        if ptr + b > K:
+            ptr = 0
+        times.append(time.perf_counter() - t0)
+        n += 1
+        if n >= max_steps or (n >= min_steps and time.perf_counter() - t_all > max_seconds):
+            break
+    use = times[1:] if len(times) > 2 else times          # first step pays allocator warm-up
+    ms = 1e3 * float(np.median(use))
+    sample = ("%d full steps of the same workload (b=%d, F=%d, D=%d, K=%d, EMA over %d params) on %d host threads, "
+              "median" % (n, b, F, D, K, EMA_ELEMS if with_ema else 0, cores))
+    return ms, n, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ms, n, cores, sample = cpu_pretrain_steps(args, max_seconds=120.0, min_steps=args.warmup + 1,
+                                              max_steps=args.warmup + args.steps)
+    value = args.batch / (ms / 1e3)
+    line = {"impl": "reference", "metric": "hm_moco_head_fwd_bwd_throughput", "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, max(n - 1, 0)), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is pure Python/PyTorch and absent on the GPU box: this arm times oracle/torch_port.py, "
+                    "an op-for-op torch restatement pinned to golden vectors generated from the reference"}
+    print(json.dumps(line))
+
+
+def workload_config(args, W):
+    return {"workload": "pretrain head step (BASELINE config 4): EMA(172.3M params) + FAM/VTM/FTM InfoNCE fwd+bwd + "
+                        "key all-gather + enqueue",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * W, "frames": args.frames, "dim": args.dim,
+            "queue": args.queue, "temperature": 0.07, "momentum": 0.99, "parallelism": "dp%d" % W,
+            "l2": "inputs > L2: every step streams the 2.07 GB EMA state through HBM (126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from hmmc_b200 import _lib, modeling, ops, retrieval
+    from hmmc_b200 import synthetic as syn
+
+    W = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if W > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.device_check()
+    lib = _lib.load()
+
+    b, F, D, K = args.batch, args.frames, args.dim, args.queue
+    if (b * W) > K or K % (b * W):
+        # the reference requires ptr + B <= K (no wrap inside a batch): grow the queue with the world
+        K = max(K, b * W)
+    task = types.SimpleNamespace(local_rank=local, top_frames=3, contrast_momentum=0.99, contrast_temperature=0.07,
+                                 contrast_num_negative=K, max_frames=F, use_frame_fea=True,
+                                 head_precision=args.precision)
+
+    class Params(torch.nn.Module):
+        def __init__(self, flat, sizes):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(x, requires_grad=False) for x in torch.split(flat, sizes)])
+
+    sizes = syn.ema_param_numels()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    enc = Params(torch.randn(sum(sizes), device=dev, generator=g), sizes)
+    enc_k = Params(torch.randn(sum(sizes), device=dev, generator=g), sizes)
+    model = modeling.BirdPreTrainedModel(modeling.default_cross_config(temporal_hidden_size=D), task).to(dev)
+    model.model_pairs = [[enc, enc_k]]
+    with torch.no_grad():
+        for n, x in syn.queues(K, F=F, D=D, seed=3).items():
+            getattr(model, n).copy_(torch.from_numpy(x))
+
+    inp_np = syn.pretrain_inputs(b, F=F, D=D, seed=100 + rank)
+    q_names = ("v_fea", "title_fea", "frame_fea", "frame_pred")
+    order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k",
+             "frame_proj_k"]
+    host = {n: torch.from_numpy(inp_np[n]).pin_memory() for n in order}
+    devt = {n: host[n].to(dev).requires_grad_(n in q_names) for n in order}
+    h2d_bytes = sum(host[n].numel() * 4 for n in order)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    ema_events, head_events = [], []
+
+    def step(inputs, timed):
+        for n in q_names:
+            inputs[n].grad = None
+        if timed:
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+        with torch.no_grad():
+            model._momentum_update()
+        if timed:
+            e1.record()
+        loss = model.head_loss(*[inputs[n] for n in order])
+        loss.backward()
+        if timed:
+            e2.record()
+            ema_events.append((e0, e1))
+            head_events.append((e1, e2))
+        return loss
+
+    def barrier():
+        if W > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(devt, False)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    clocks = ClockSampler(local)
+    launches0 = lib.hmmc_launch_count()
+    clocks.start()
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        step(devt, True)
+    t1.record()
+    barrier()
+    clk = clocks.stop()
+    launches = lib.hmmc_launch_count() - launches0
+    ms_total = t0.elapsed_time(t1)
+    ms_ema = float(np.mean([a.elapsed_time(c) for a, c in ema_events]))
+    ms_head = float(np.mean([a.elapsed_time(c) for a, c in head_events]))
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    e2e_steps = args.steps
+    barrier()
+    s0, s1 = ev(), ev()
+    s0.record()
+    for _ in range(e2e_steps):
+        ins = {n: host[n].to(dev, non_blocking=True).requires_grad_(n in q_names) for n in order}
+        loss = step(ins, False)
+        loss_host.copy_(loss.detach(), non_blocking=False)      # the reference reads float(loss) every step
+    s1.record()
+    barrier()
+    ms_e2e_total = s0.elapsed_time(s1)
+
+    def allmax(x):
+        if W == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total, ms_e2e_total = allmax(ms_total), allmax(ms_e2e_total)
+    ms_step = ms_total / args.steps
+    value = W * b / (ms_step / 1e3)
+    e2e_value = W * b / (ms_e2e_total / e2e_steps / 1e3)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:   # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    ema_bytes = 12.0 * EMA_ELEMS
+    ema_gbs = ema_bytes / (ms_ema * 1e-3) / 1e9
+    head_flops = FLOPS_ALGO(b, F, D, K)
+    head_tf = head_flops / (ms_head * 1e-3) / 1e12
+
+    line = {"metric": "hm_moco_head_fwd_bwd_throughput", "value": value, "unit": "samples/s", "n_gpus": W,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (fp32-parity split)",
+                                                                "fp32": "f32"}[args.precision],
+            "data": "synthetic", "config": workload_config(args, W),
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e_total / e2e_steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "ema_multi_kernel", "bound": "hbm", "achieved": ema_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ema_gbs / hbm_peak, "traffic": None,
+                         "algorithmic_bytes": ema_bytes, "ms": ms_ema, "peak_source": peak_src},
+            "roofline_head": {"kernels": "infonce fwd+bwd (5 query blocks: rownorm_pack, umma S-GEMM+exp epilogue, "
+                                         "umma U-GEMM, finish, reduce) + pack + enqueue",
+                              "bound": "tensor", "achieved": head_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                              "frac": head_tf / tf_peak, "algorithmic_flops": head_flops, "ms": ms_head,
+                              "peak_source": peak_src},
+            "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head}}
+
+    # ---- retrieval leg (config 2) on rank 0
+    if rank == 0 and not args.no_retrieval:
+        line["retrieval"] = retrieval_leg(args, dev)
+    if rank == 0 and not args.no_cpu_baseline:
+        ms, n, cores, sample = cpu_pretrain_steps(args, max_seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": b / (ms / 1e3), "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": sample, "ms_per_step": ms}
+    if rank == 0:
+        print(json.dumps(line))
+    if W > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def retrieval_leg(args, dev):
+    """config 2: 1000 texts x 1000 videos x 12 frames, top_frames 2: similarity + both rank directions."""
+    from hmmc_b200 import modeling, ops, retrieval
+    from hmmc_b200 import synthetic as syn
+    T, V, Fr, gt, _ = syn.eval_inputs(1000, 1000, seed=4)
+    task = types.SimpleNamespace(local_rank=0, top_frames=2, use_frame_fea=True, head_precision=args.precision)
+    m = modeling.BirdModel(modeling.default_cross_config(), task)
+    hT, hV, hF = [torch.from_numpy(x).pin_memory() for x in (T, V, Fr)]
+    dT, dV, dF = hT.to(dev), hV.to(dev), hF.to(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def dev_pass():
+        sim = retrieval.similarity_matrix(m, dT, dV, dF)
+        return ops.rank_count(sim)
+
+    for _ in range(3):
+        dev_pass()
+    torch.cuda.synchronize()
+    reps = 20
+    a, c = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        dev_pass()
+    c.record()
+    torch.cuda.synchronize()
+    ms_dev = a.elapsed_time(c) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sim = retrieval.similarity_matrix(m, hT.to(dev, non_blocking=True), hV.to(dev, non_blocking=True),
+                                          hF.to(dev, non_blocking=True))
+        t2v, v2t = ops.rank_count(sim)
+        r = (t2v.cpu(), v2t.cpu())
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / reps
+    from hmmc_b200 import metrics as GM
+    tv = GM.metrics_from_ranks(r[0].numpy())
+    out = {"workload": "BASELINE config 2: 1000 x 1000 x 12, top_frames 2, sim + top-k + t2v/v2t ranks",
+           "value": 1000.0 / (ms_dev / 1e3), "unit": "queries/s", "ms": ms_dev,
+           "e2e": {"value": 1000.0 / (ms_e2e / 1e3), "unit": "queries/s", "ms": ms_e2e,
+                   "h2d_bytes": int(4 * (T.size + V.size + Fr.size)), "d2h_bytes": 8000},
+           "R1": tv["R1"], "MeanR": tv["MeanR"]}
+    if not args.no_cpu_baseline:
+        from oracle import torch_port as P
+        torch.set_num_threads(os.cpu_count() or 1)
+        cT, cV, cF = torch.from_numpy(T), torch.from_numpy(V), torch.from_numpy(Fr)
+        P.eval_sim_and_rank(cT, cV, cF, 2)
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 or time.perf_counter() - t0 < 3.0:
+            P.eval_sim_and_rank(cT, cV, cF, 2)
+            n += 1
+        ms_cpu = 1e3 * (time.perf_counter() - t0) / n
+        out["cpu_baseline"] = {"value": 1000.0 / (ms_cpu / 1e3), "unit": "queries/s", "cores": os.cpu_count(),
+                               "kind": "port", "sample": "%d full passes of the same 1000x1000x12 set" % n}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,7 @@ class hmmc_queue(Structure):
 SIGNATURES = {
     "hmmc_last_error": (c_char_p, []),
     "hmmc_version": (c_int, []),
+    "hmmc_launch_count": (ctypes.c_ulonglong, []),
     "hmmc_device_check": (c_int, []),
     "hmmc_rownorm_pack": (c_int, [c_void_p, c_int64, c_int, c_int64, c_float, c_int, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),

@@ -11,6 +11,7 @@
 namespace hmmc {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define HMMC_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \
@@ -21,7 +22,12 @@ void set_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
-#define HMMC_CHECK_LAUNCH() HMMC_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through here (also feeds hmmc_launch_count())
+#define HMMC_CHECK_LAUNCH()                  \
+  do {                                       \
+    hmmc::count_launch();                    \
+    HMMC_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 #define HMMC_REQUIRE(cond, ...)          \
   do {                                   \

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "umma_gemm.cuh"
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
@@ -15,6 +16,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -188,6 +192,7 @@ extern "C" {
 
 const char* hmmc_last_error(void) { return g_err; }
 int hmmc_version(void) { return 100; }
+unsigned long long hmmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int hmmc_device_check(void) {
   int dev = 0;

@@ -108,3 +108,33 @@ def ema_tensors(seed=5, sizes=((513,), (64, 33), (7,), (1024, 96), (3, 5, 7), (1
         ps.append(_randn(rs, *shp).astype(dt))
         pks.append(_randn(rs, *shp).astype(dt))
     return ps, pks
+
+
+def ema_param_numels(total=172325632, count=362):
+    """Element counts of the 362 parameter tensors the reference's _momentum_update walks
+    (ViT-B/32 87.85 M, temporal transformer 12.63 M, CLIP text 63.43 M, two MLPs; SURVEY.md
+    §8 a10).  The shapes follow the transformer block pattern (qkv, out-proj, two MLP matrices,
+    biases and LayerNorms); a final filler tensor makes the total exact."""
+    sizes = []
+
+    def block(width, mlp):
+        sizes.extend([3 * width * width, 3 * width, width * width, width, width, width,
+                      width * mlp, mlp, mlp * width, width, width, width])
+    sizes.extend([768 * 3 * 32 * 32, 768, 50 * 768, 768, 768])        # ViT stem
+    for _ in range(12):
+        block(768, 3072)
+    sizes.extend([768, 768, 768 * 512])
+    sizes.extend([49408 * 512, 77 * 512])                               # CLIP text stem
+    for _ in range(12):
+        block(512, 2048)
+    sizes.extend([512, 512, 512 * 512])
+    sizes.extend([48 * 512])                                            # temporal transformer
+    for _ in range(4):
+        block(512, 2048)
+    for _ in range(2):                                                  # projector MLPs
+        sizes.extend([512 * 4096, 4096, 4096, 4096, 4096 * 512, 512])
+    sizes = sizes[:count - 1]
+    rest = total - sum(sizes)
+    assert rest > 0, rest
+    sizes.append(rest)
+    return sizes

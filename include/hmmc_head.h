@@ -51,6 +51,8 @@ extern "C" {
 
 const char* hmmc_last_error(void);
 int hmmc_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long hmmc_launch_count(void);
 /* 0 when the current device is sm_100 (B200); HMMC_ERR_UNSUPPORTED otherwise. */
 int hmmc_device_check(void);
 

@@ -191,3 +191,28 @@ def test_dist_collect_contract():
     grads = [rs.randn(W * b, 5) for _ in range(W)]
     back = O.dist_collect_emulated_backward(grads, b)
     np.testing.assert_allclose(back[2], sum(g[2 * b:3 * b] for g in grads))
+
+
+def test_torch_port(golden):
+    """The CPU-baseline port (oracle/torch_port.py) reproduces the reference's outputs."""
+    import torch
+    from oracle import torch_port as P
+    g = golden("pretrain_small")
+    b, F, D, K, T = int(g["b"]), int(g["F"]), int(g["D"]), int(g["K"]), float(g["T"])
+    inp = {n: torch.from_numpy(x).requires_grad_(n in ("v_fea", "title_fea", "frame_fea", "frame_pred"))
+           for n, x in syn.pretrain_inputs(b, F=F, D=D, seed=2).items()}
+    qs = {n: torch.from_numpy(x) for n, x in syn.queues(K, F=F, D=D, seed=3).items()}
+    loss, ptr = P.pretrain_step(inp, qs, 0, K, T)
+    assert abs(loss - float(g["loss"])) < 1e-5 and ptr == int(g["ptr"])
+    for n in ("v_fea", "title_fea", "frame_fea", "frame_pred"):
+        assert _rel(inp[n].grad.numpy(), g["d_" + n]) < 1e-5
+    for n in syn.QUEUE_NAMES:
+        np.testing.assert_allclose(qs[n].numpy(), g["after_" + n], rtol=0, atol=1e-7)
+    g = golden("finetune_B32")
+    t, v, fr = [torch.from_numpy(x).requires_grad_(True) for x in syn.finetune_inputs(32, seed=1)]
+    assert abs(P.finetune_step(t, v, fr) - float(g["loss"])) < 1e-4
+    assert _rel(t.grad.numpy(), g["dt"]) < 1e-5
+    g = golden("eval_1k")
+    Tn, Vn, Fn, _, _ = syn.eval_inputs(1000, 1000, seed=4)
+    sim, (tv, vt) = P.eval_sim_and_rank(torch.from_numpy(Tn), torch.from_numpy(Vn), torch.from_numpy(Fn), 2)
+    assert tv["R1"] == g["tv"][0] and vt["R1"] == g["vt"][0] and tv["MeanR"] == g["tv"][4]
