@@ -25,6 +25,12 @@ class hmmc_queue(Structure):
                 ("D", c_int32), ("Kq", c_int32), ("planes", c_int32), ("reserved", c_int32)]
 
 
+class hmmc_pretrain_io(Structure):
+    _fields_ = [(n, c_void_p) for n in ("v_fea", "title_fea", "frame_fea", "frame_pred", "v_fea_k", "title_fea_k",
+                                        "frame_fea_k", "frame_proj_k", "d_v_fea", "d_title_fea", "d_frame_fea",
+                                        "d_frame_pred")]
+
+
 # name -> (restype, argtypes); must list every symbol of include/hmmc_head.h
 SIGNATURES = {
     "hmmc_last_error": (c_char_p, []),
@@ -42,6 +48,13 @@ SIGNATURES = {
     "hmmc_infonce_queue_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            POINTER(hmmc_queue), c_float, c_float, c_int, c_void_p, c_void_p,
                                            c_void_p, c_size_t, c_void_p]),
+    "hmmc_pretrain_head_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "hmmc_pretrain_head_fwd_bwd": (c_int, [POINTER(hmmc_pretrain_io), c_int, c_int, c_int, POINTER(hmmc_queue),
+                                           POINTER(hmmc_queue), POINTER(hmmc_queue), POINTER(hmmc_queue), c_float,
+                                           c_float, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]),
+    "hmmc_enqueue_norm_direct": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         POINTER(hmmc_queue), c_void_p, c_int64, c_int, c_void_p]),
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),

@@ -54,126 +54,208 @@ __global__ void exp_rowsum_kernel(float* __restrict__ S, int64_t lds, int Kq, fl
   if (threadIdx.x == 0) rowsum[blockIdx.x] = acc;
 }
 
-// ------------------------------------------------------------------ finish kernel
-// One block per query row r = n*Fq + f.  Consumes the negatives' row sum S_r and
-// U_r = sum_j e_rj Q_j, evaluates the positive terms selected by pos_mode and writes the
-// per-row loss and dL/dq_r (SURVEY.md 8a').
-constexpr int FIN_THREADS = 128;
-constexpr int FIN_MAXE = 8;   // D <= FIN_THREADS * FIN_MAXE
+// ------------------------------------------------------------------ prep: normalise + pack several q tensors
+constexpr int MAX_GROUPS = 4;   // distinct query tensors of one fused call
+constexpr int MAX_BLOCKS = 6;   // (query tensor, queue) pairs = GEMM problems
 
-__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
-  a = warp_sum(a);
-  b = warp_sum(b);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) { red[w] = a; red[8 + w] = b; }
-  __syncthreads();
-  float ta = 0.f, tb = 0.f;
+struct PrepArgs {
+  const float* x[MAX_GROUPS];
+  float* xhat[MAX_GROUPS];              // fp32 normalised copy (FP32 path) or nullptr
+  __nv_bfloat16* packed[MAX_GROUPS];    // bf16 planes (tensor-core path) or nullptr
+  int row_begin[MAX_GROUPS + 1];
+  int n;
+};
+
+// one warp per row, all query tensors of the call in one launch (F.normalize, eps 1e-12)
+__global__ void prep_rows_kernel(PrepArgs a, int D, int planes) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.row_begin[a.n]) return;
+  int gi = 0;
 #pragma unroll
-  for (int i = 0; i < FIN_THREADS / 32; ++i) { ta += red[i]; tb += red[8 + i]; }
-  a = ta;
-  b = tb;
+  for (int i = 1; i < MAX_GROUPS; ++i)
+    if (i < a.n && row >= a.row_begin[i]) gi = i;
+  const int r = row - a.row_begin[gi];
+  const float* xr = a.x[gi] + int64_t(r) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = xr[d]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float n = fmaxf(sqrtf(ss), 1e-12f);
+  float* xh = a.xhat[gi];
+  __nv_bfloat16* pk = a.packed[gi];
+  for (int d = lane; d < D; d += 32) {
+    const float v = xr[d] / n;
+    if (xh != nullptr) xh[int64_t(r) * D + d] = v;
+    if (pk != nullptr) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      pk[int64_t(r) * planes * D + d] = hi;
+      if (planes == 2) pk[int64_t(r) * planes * D + D + d] = lo;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
-infonce_finish_kernel(const float* __restrict__ q, const float* __restrict__ keys, int pos_mode, int b, int Fq, int Fk,
-                      int D, const float* __restrict__ rowsum_part, int n_parts, int R,
-                      const float* __restrict__ U_part, int n_splits, int64_t split_stride, float invT, float cmax,
-                      float coef, float* __restrict__ dq, float* __restrict__ row_loss) {
-  __shared__ float red[32];
-  const int r = blockIdx.x;
-  const int n = r / Fq, f = r - n * Fq;
-  const int tid = threadIdx.x;
+// ------------------------------------------------------------------ finish kernel
+// One WARP per query row r = n*Fq + f of a query tensor.  For every (queue) contribution of
+// that tensor it consumes the negatives' row sum S_r and U_r = sum_j e_rj Q_j, evaluates the
+// positive terms selected by pos_mode, and writes the row's loss shares and dL/dq_r
+// (SURVEY.md 8a').  A tensor that is the query of two losses (title_fea: VTM and FTM) gets
+// both contributions here, so its gradient is written once.
+constexpr int FIN_MAXD = 2048;            // D <= 32 lanes * FIN_MAXE
+constexpr int FIN_MAXE = FIN_MAXD / 32;
 
-  float qv[FIN_MAXE], g[FIN_MAXE];
-  float ss = 0.f, dummy = 0.f;
+struct Contribution {
+  const float* keys;
+  const float* rowsum_part;   // [n_parts, rows]
+  const float* U_part;        // [n_splits][rows, D]
+  int64_t split_stride;
+  int pos_mode, Fk, n_parts, n_splits;
+  float coef;                 // weight / b
+  int kind;                   // loss slot (0 FAM, 1 VTM, 2 FTM)
+};
+struct RowGroup {
+  const float* q;
+  float* dq;                  // nullptr: forward only
+  int rows, Fq, ncontrib;
+  Contribution c[2];
+};
+struct FinishArgs {
+  RowGroup g[MAX_GROUPS];
+  int row_begin[MAX_GROUPS + 1];
+  int n;
+};
+
+template <int NE>   // elements per lane = D / 32 rounded up
+__global__ void __launch_bounds__(256)
+infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax,
+                      float* __restrict__ row_loss /* [3][total_rows] */) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int total_rows = a.row_begin[a.n];
+  if (row >= total_rows) return;
+  int gi = 0;
 #pragma unroll
-  for (int i = 0; i < FIN_MAXE; ++i) {
-    const int d = tid + i * FIN_THREADS;
-    qv[i] = (d < D) ? q[int64_t(r) * D + d] : 0.f;
+  for (int i = 1; i < MAX_GROUPS; ++i)
+    if (i < a.n && row >= a.row_begin[i]) gi = i;
+  const RowGroup& G = a.g[gi];
+  const int r = row - a.row_begin[gi];
+  const int n = r / G.Fq, f = r - n * G.Fq;
+
+  float qv[NE], g[NE];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const int d = lane + i * 32;
+    qv[i] = (d < D) ? G.q[int64_t(r) * D + d] : 0.f;
     g[i] = 0.f;
     ss = fmaf(qv[i], qv[i], ss);
   }
-  block_sum2(ss, dummy, red);
+  ss = warp_sum(ss);
   const float nq_raw = sqrtf(ss);
   const float nq = fmaxf(nq_raw, 1e-12f);
 #pragma unroll
-  for (int i = 0; i < FIN_MAXE; ++i) qv[i] = qv[i] / nq;   // q_hat
+  for (int i = 0; i < NE; ++i) qv[i] = qv[i] / nq;   // q_hat
 
-  // S_r
-  float S = 0.f;
-  for (int p = tid; p < n_parts; p += FIN_THREADS) S += rowsum_part[int64_t(p) * R + r];
-  dummy = 0.f;
-  block_sum2(S, dummy, red);
-
-  // positive terms
-  int nterm, kbase, kstep;
-  if (pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
-  else if (pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
-  else if (pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = Fk; kbase = n * Fk; kstep = 1; }
-  else { nterm = 1; kbase = n; kstep = 0; }
-
-  float loss = 0.f, sum_invZ = 0.f;
-  for (int t = 0; t < nterm; ++t) {
-    int kr = kbase + t * kstep;
-    if (pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
-      const int fk = (t == 0) ? f + 1 : f - 1;      // pairs (i, i+1) and (i+1, i) of frame_self_loss
-      if (fk < 0 || fk >= Fk) continue;             // block-uniform
-      kr = n * Fk + fk;
-    }
-    float kv[FIN_MAXE];
-    float kk = 0.f, qk = 0.f;
+  float loss_kind[3] = {0.f, 0.f, 0.f};
+  for (int ci = 0; ci < G.ncontrib; ++ci) {
+    const Contribution& C = G.c[ci];
+    // S_r: negatives' sum of exp(l - cmax)
+    float S = 0.f;
+    for (int p = lane; p < C.n_parts; p += 32) S += C.rowsum_part[int64_t(p) * G.rows + r];
+    S = warp_sum(S);
+    int nterm, kbase, kstep;
+    if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
+    else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
+    else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kbase = n * C.Fk; kstep = 1; }
+    else { nterm = 1; kbase = n; kstep = 0; }
+    float loss = 0.f, sum_invZ = 0.f;
+    float gk[NE];
 #pragma unroll
-    for (int i = 0; i < FIN_MAXE; ++i) {
-      const int d = tid + i * FIN_THREADS;
-      kv[i] = (d < D) ? keys[int64_t(kr) * D + d] : 0.f;
-      kk = fmaf(kv[i], kv[i], kk);
-      qk = fmaf(kv[i], qv[i], qk);
-    }
-    block_sum2(kk, qk, red);
-    const float nk = fmaxf(sqrtf(kk), 1e-12f);
-    const float lpos = (qk / nk) * invT;
-    const float epos = expf(lpos - cmax);
-    const float Z = epos + S;
-    loss += logf(Z) + cmax - lpos;
-    const float ppos = epos / Z;
-    sum_invZ += 1.0f / Z;
-    const float w = (ppos - 1.0f) / nk;
+    for (int i = 0; i < NE; ++i) gk[i] = 0.f;
+    for (int t = 0; t < nterm; ++t) {
+      int kr = kbase + t * kstep;
+      if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
+        const int fk = (t == 0) ? f + 1 : f - 1;      // pairs (i, i+1) and (i+1, i) of frame_self_loss
+        if (fk < 0 || fk >= C.Fk) continue;           // warp-uniform
+        kr = n * C.Fk + fk;
+      }
+      float kv[NE];
+      float kk = 0.f, qk = 0.f;
 #pragma unroll
-    for (int i = 0; i < FIN_MAXE; ++i) g[i] = fmaf(w, kv[i], g[i]);
+      for (int i = 0; i < NE; ++i) {
+        const int d = lane + i * 32;
+        kv[i] = (d < D) ? C.keys[int64_t(kr) * D + d] : 0.f;
+        kk = fmaf(kv[i], kv[i], kk);
+        qk = fmaf(kv[i], qv[i], qk);
+      }
+      kk = warp_sum(kk);
+      qk = warp_sum(qk);
+      const float nk = fmaxf(sqrtf(kk), 1e-12f);
+      const float lpos = (qk / nk) * invT;
+      const float epos = expf(lpos - cmax);
+      const float Z = epos + S;
+      loss += logf(Z) + cmax - lpos;
+      sum_invZ += 1.0f / Z;
+      const float w = (epos / Z - 1.0f) / nk;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) gk[i] = fmaf(w, kv[i], gk[i]);
+    }
+    loss_kind[C.kind] += C.coef * loss;
+    if (G.dq != nullptr) {
+      // g_hat += coef/T * (sum_t (p+ - 1) k_hat_t + (sum_t 1/Z_t) U_r)
+      const float scale = C.coef * invT;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int d = lane + i * 32;
+        float u = 0.f;
+        if (d < D)
+          for (int sidx = 0; sidx < C.n_splits; ++sidx) u += C.U_part[int64_t(sidx) * C.split_stride + int64_t(r) * D + d];
+        g[i] += scale * fmaf(sum_invZ, u, gk[i]);
+      }
+    }
   }
-  if (tid == 0) row_loss[r] = coef * loss;
-  if (dq == nullptr) return;
-
-  // g_hat = coef/T * (sum_t (p+ - 1) k_hat_t + (sum_t 1/Z_t) U_r);   dq = (g_hat - q_hat (q_hat.g_hat)) / ||q||
-  const float scale = coef * invT;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) row_loss[int64_t(k) * total_rows + row] = loss_kind[k];
+  }
+  if (G.dq == nullptr) return;
+  // dq = (g_hat - q_hat (q_hat . g_hat)) / ||q||
   float qg = 0.f;
 #pragma unroll
-  for (int i = 0; i < FIN_MAXE; ++i) {
-    const int d = tid + i * FIN_THREADS;
-    float u = 0.f;
-    if (d < D)
-      for (int sidx = 0; sidx < n_splits; ++sidx) u += U_part[int64_t(sidx) * split_stride + int64_t(r) * D + d];
-    g[i] = scale * fmaf(sum_invZ, u, g[i]);
-    qg = fmaf(qv[i], g[i], qg);
-  }
-  dummy = 0.f;
-  block_sum2(qg, dummy, red);
+  for (int i = 0; i < NE; ++i) qg = fmaf(qv[i], g[i], qg);
+  qg = warp_sum(qg);
   const bool clamped = nq_raw < 1e-12f;   // F.normalize clamps: q_hat = q/eps is then linear in q
 #pragma unroll
-  for (int i = 0; i < FIN_MAXE; ++i) {
-    const int d = tid + i * FIN_THREADS;
-    if (d < D) dq[int64_t(r) * D + d] = clamped ? g[i] / nq : (g[i] - qv[i] * qg) / nq;
+  for (int i = 0; i < NE; ++i) {
+    const int d = lane + i * 32;
+    if (d < D) G.dq[int64_t(r) * D + d] = clamped ? g[i] / nq : (g[i] - qv[i] * qg) / nq;
   }
 }
 
-// loss_out[0] += sum_r row_loss[r], fixed summation order (deterministic)
-__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int R, float* __restrict__ loss_out) {
+// per-kind sums in a fixed order (deterministic); kind_out[k] (+)= sum_r row_loss[k][r]
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total_rows, float* __restrict__ kind_out,
+                                   int accumulate) {
   __shared__ float red[32];
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) acc += row_loss[i];
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) loss_out[0] += acc;
+  for (int k = 0; k < 3; ++k) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < total_rows; i += blockDim.x) acc += row_loss[int64_t(k) * total_rows + i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) kind_out[k] = accumulate ? kind_out[k] + acc : acc;
+    __syncthreads();
+  }
+}
+
+__global__ void add_scalar_kernel(float* __restrict__ out, const float* __restrict__ kinds) {
+  out[0] += kinds[0] + kinds[1] + kinds[2];
+}
+// losses_out = [total, FAM, VTM, FTM]; the slots arrive weighted (w * loss), report them unweighted too
+__global__ void head_losses_kernel(float* __restrict__ out, const float* __restrict__ kinds, float w_fam, float w_vtm,
+                                   float w_ftm, int use_frame_fea) {
+  const float fam = kinds[0], vtm = kinds[1], ftm = use_frame_fea ? kinds[2] : 0.f;
+  out[0] = fam + vtm + ftm;
+  out[1] = (w_fam != 0.f) ? fam / w_fam : 0.f;
+  out[2] = (w_vtm != 0.f) ? vtm / w_vtm : 0.f;
+  out[3] = (w_ftm != 0.f) ? ftm / w_ftm : 0.f;
 }
 
 // ------------------------------------------------------------------ EMA
@@ -249,32 +331,34 @@ struct EnqueueArgs {
   float* dk[5];
   __nv_bfloat16* pack_kd[5];
   __nv_bfloat16* pack_dk[5];
-  int Kq[5];        // columns of each queue
-  int mult[5];      // columns per sample: 1 or F
-  int src_off[5];   // element offset of the queue's block inside one gathered row
+  const float* src[5];      // first sample of this queue's keys
+  int64_t src_stride[5];    // elements between consecutive samples
+  int Kq[5];                // columns of each queue
+  int mult[5];              // columns per sample: 1 or F
   int planes;
 };
 
-// Block = 32 consecutive queue columns of one queue.  Phase 1: one warp per 4 columns computes
-// 1/max(||x||,1e-12).  Phase 2: 32(d) x 32(col) tiles go through shared memory so the [D,Kq]
-// layouts are written 32 columns (128 B) at a time.
+constexpr int ENQ_DCHUNK = 128;
+
+// Block = 32 consecutive queue columns x ENQ_DCHUNK embedding dims of one queue.  Phase 1: one warp
+// per 4 columns computes max(||x||,1e-12) over the full vector.  Phase 2: 32(d) x 32(col) tiles go
+// through shared memory so the [D,Kq] layouts are written 32 columns (128 B) at a time.
 __global__ void __launch_bounds__(256)
-enqueue_kernel(const float* __restrict__ gathered, int nsamples, int F, int D, int row_elems, EnqueueArgs a,
-               const int64_t* __restrict__ queue_ptr) {
-  __shared__ float inv[32];
+enqueue_kernel(int nsamples, int D, EnqueueArgs a, int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
+  __shared__ float nrm[32];
   __shared__ float tile[32][33];
-  const int qi = blockIdx.y;
+  const int qi = blockIdx.z;
   const int mult = a.mult[qi];
   const int ncols = nsamples * mult;
   const int c0 = blockIdx.x * 32;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) queue_ptr[0] = new_ptr;
   if (c0 >= ncols) return;
-  const int ptr = int(queue_ptr[0]);
   const int Kq = a.Kq[qi];
   const int col_base = ptr * mult;       // first destination column
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto src_of = [&](int c) -> const float* {     // c = local column = sample*mult + f
     const int smp = c / mult, f = c - smp * mult;
-    return gathered + int64_t(smp) * row_elems + a.src_off[qi] + int64_t(f) * D;
+    return a.src[qi] + int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
   };
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + warp * 4 + i;
@@ -284,20 +368,22 @@ enqueue_kernel(const float* __restrict__ gathered, int nsamples, int F, int D, i
       for (int d = lane; d < D; d += 32) { const float v = x[d]; ss = fmaf(v, v, ss); }
     }
     ss = warp_sum(ss);
-    if (lane == 0) inv[warp * 4 + i] = fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) nrm[warp * 4 + i] = fmaxf(sqrtf(ss), 1e-12f);
   }
   __syncthreads();
   const int planes = a.planes;
   float* dk = a.dk[qi];
   __nv_bfloat16* pkd = a.pack_kd[qi];
   __nv_bfloat16* pdk = a.pack_dk[qi];
-  for (int d0 = 0; d0 < D; d0 += 32) {
+  const int dbeg = blockIdx.y * ENQ_DCHUNK;
+  const int dend = min(dbeg + ENQ_DCHUNK, D);
+  for (int d0 = dbeg; d0 < dend; d0 += 32) {
     // read: warp w handles columns w, w+8, ..; lane = d
     for (int cc = warp; cc < 32; cc += 8) {
       const int c = c0 + cc, d = d0 + lane;
       float v = 0.f;
-      if (c < ncols && d < D) {
-        v = src_of(c)[d] / inv[cc];
+      if (c < ncols && d < dend) {
+        v = src_of(c)[d] / nrm[cc];
         if (pkd != nullptr) {
           __nv_bfloat16 hi, lo;
           split_bf16(v, hi, lo);
@@ -312,7 +398,7 @@ enqueue_kernel(const float* __restrict__ gathered, int nsamples, int F, int D, i
     // write transposed: warp w handles d = w, w+8, ..; lane = column
     for (int dd = warp; dd < 32; dd += 8) {
       const int d = d0 + dd, c = c0 + lane;
-      if (d < D && c < ncols) {
+      if (d < dend && c < ncols) {
         const float v = tile[lane][dd];
         dk[int64_t(d) * Kq + col_base + c] = v;
         if (pdk != nullptr) {
@@ -328,10 +414,6 @@ enqueue_kernel(const float* __restrict__ gathered, int nsamples, int F, int D, i
   }
 }
 
-__global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K) {
-  queue_ptr[0] = (queue_ptr[0] + B) % K;
-}
-
 // ------------------------------------------------------------------ pack / unpack rows
 struct RowPackArgs {
   uint64_t ptrs[8];
@@ -344,13 +426,11 @@ struct RowPackArgs {
 template <bool PACK>
 __global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_t rows) {
   const int64_t row = blockIdx.x;
-  float* prow = packed + row * a.total;
-  for (int t = 0; t < a.n; ++t) {
-    float* x = reinterpret_cast<float*>(a.ptrs[t]) + row * a.widths[t];
-    float* y = prow + a.offs[t];
-    for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
-      if (PACK) y[i] = x[i]; else x[i] = y[i];
-    }
+  const int t = blockIdx.y;
+  float* x = reinterpret_cast<float*>(a.ptrs[t]) + row * a.widths[t];
+  float* y = packed + row * a.total + a.offs[t];
+  for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
+    if (PACK) y[i] = x[i]; else x[i] = y[i];
   }
 }
 
@@ -385,140 +465,308 @@ int hmmc_queue_pack(const hmmc_queue* q, void* stream) {
   return HMMC_OK;
 }
 
-static int infonce_bn(int Kq) { return (Kq % 256 == 0) ? 256 : 128; }
+}  // extern "C"
 
-struct InfoNCEPlan {
-  int planes, bn1, nparts, splits2, bn2;
+namespace hmmc {
+// ---------------------------------------------------------------------------------------
+// Generic fused InfoNCE driver: several query tensors ("groups"), each contracted against one
+// or two queues ("blocks" = GEMM problems), in a fixed number of launches:
+//   prep_rows (1) -> S-GEMM + exp/rowsum/E epilogue (1, grouped) -> U-GEMM (1, grouped, split-K)
+//   -> finish (1) -> loss reduce (1)
+struct BlockDesc {
+  int group;                 // which query tensor
+  const float* keys;
+  int pos_mode, Fk;
+  const hmmc_queue* queue;
+  float coef;                // weight / b
+  int kind;                  // loss slot
 };
-static InfoNCEPlan infonce_plan(int64_t R, int D, int Kq, int prec) {
-  InfoNCEPlan p;
-  p.planes = planes_of(prec);
-  if (prec == HMMC_PREC_FP32) {
-    p.bn1 = p.bn2 = 0;
-    p.nparts = 1;
-    p.splits2 = 1;
-  } else {
-    p.bn1 = infonce_bn(Kq);
-    p.nparts = (Kq + p.bn1 - 1) / p.bn1;
-    p.bn2 = (D % 256 == 0) ? 256 : 128;
-    const int nseg = (p.planes == 2) ? 3 : 1;
-    p.splits2 = pick_splits(int(R), D, p.bn2, nseg * (Kq / UMMA_BK));
-  }
-  return p;
-}
+struct GroupDesc {
+  const float* q;
+  float* dq;
+  int rows, Fq;
+};
 
-struct InfoNCEWs {
-  float* qhat;
-  __nv_bfloat16* qpack;
-  float* rowsum_part;
-  void* E;
-  float* U_part;
+struct InfoNCELayout {       // workspace carving shared by the size query and the run
   float* row_loss;
+  float* xhat[MAX_GROUPS];
+  __nv_bfloat16* packed[MAX_GROUPS];
+  float* rowsum_part[MAX_BLOCKS];
+  void* E[MAX_BLOCKS];
+  float* U_part[MAX_BLOCKS];
+  int nparts[MAX_BLOCKS], splits[MAX_BLOCKS], nsplits_eff[MAX_BLOCKS];
+  int bn1, bn2;
 };
-static void infonce_carve(Workspace& ws, InfoNCEWs& w, const InfoNCEPlan& p, int64_t R, int D, int Kq, int prec) {
-  w.row_loss = ws.take<float>(size_t(R));
-  w.rowsum_part = ws.take<float>(size_t(p.nparts) * R);
-  w.U_part = ws.take<float>(size_t(p.splits2) * R * D);
-  if (prec == HMMC_PREC_FP32) {
-    w.qhat = ws.take<float>(size_t(R) * D);
-    w.qpack = nullptr;
-    w.E = ws.take<float>(size_t(R) * Kq);
-  } else {
-    w.qhat = nullptr;
-    w.qpack = ws.take<__nv_bfloat16>(size_t(R) * p.planes * D);
-    w.E = ws.take<__nv_bfloat16>(size_t(R) * p.planes * Kq);
+
+static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* groups, int ng, const int* blk_group,
+                           const int* blk_Kq, int nb, int D, int prec, bool need_grad) {
+  const int planes = planes_of(prec);
+  int total_rows = 0;
+  for (int i = 0; i < ng; ++i) total_rows += groups[i].rows;
+  L.row_loss = ws.take<float>(size_t(3) * total_rows);
+  for (int i = 0; i < ng; ++i) {
+    L.xhat[i] = (prec == HMMC_PREC_FP32) ? ws.take<float>(size_t(groups[i].rows) * D) : nullptr;
+    L.packed[i] = (prec != HMMC_PREC_FP32) ? ws.take<__nv_bfloat16>(size_t(groups[i].rows) * planes * D) : nullptr;
+  }
+  L.bn1 = 256;
+  for (int k = 0; k < nb; ++k)
+    if (blk_Kq[k] % 256 != 0) L.bn1 = 128;
+  L.bn2 = (D % 256 == 0) ? 256 : 128;
+  // split-K of the U-GEMMs: aim at ~2 waves of equally sized units over the whole group
+  const int nseg = (planes == 2) ? 3 : 1;
+  double work = 0;
+  for (int k = 0; k < nb; ++k) {
+    const int R = groups[blk_group[k]].rows;
+    work += double((R + UMMA_BM - 1) / UMMA_BM) * ((D + L.bn2 - 1) / L.bn2) * nseg * (blk_Kq[k] / UMMA_BK);
+  }
+  int unit_kb = int(work / (2.0 * sm_count())) + 1;
+  if (unit_kb < 8) unit_kb = 8;
+  for (int k = 0; k < nb; ++k) {
+    const int R = groups[blk_group[k]].rows;
+    const int Kq = blk_Kq[k];
+    if (prec == HMMC_PREC_FP32) {
+      L.nparts[k] = 1;
+      L.splits[k] = L.nsplits_eff[k] = 1;
+      L.rowsum_part[k] = ws.take<float>(size_t(R));
+      L.E[k] = ws.take<float>(size_t(R) * Kq);
+    } else {
+      L.nparts[k] = (Kq + L.bn1 - 1) / L.bn1;
+      const int total_kb = nseg * (Kq / UMMA_BK);
+      int sp = (total_kb + unit_kb - 1) / unit_kb;
+      if (sp > 32) sp = 32;
+      L.splits[k] = sp;
+      L.nsplits_eff[k] = effective_splits(Kq, planes, sp);
+      L.rowsum_part[k] = ws.take<float>(size_t(L.nparts[k]) * R);
+      L.E[k] = need_grad ? ws.take<__nv_bfloat16>(size_t(R) * planes * Kq) : nullptr;
+    }
+    L.U_part[k] = need_grad ? ws.take<float>(size_t(L.nsplits_eff[k]) * R * D) : nullptr;
   }
 }
+
+template <int NE>
+static void launch_finish(const FinishArgs& fa, int total_rows, int D, float invT, float cmax, float* row_loss,
+                          cudaStream_t st) {
+  infonce_finish_kernel<NE><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
+}
+
+static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
+                       int prec, float* kind_out, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+  HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
+  HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
+  HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
+  // constant-max log-sum-exp: all logits lie in [-1/T, 1/T]; exp(-2/T) must stay a normal fp32
+  HMMC_REQUIRE(temperature >= 0.025f, "infonce: temperature %g < 0.025 is not supported by the constant-max LSE",
+               temperature);
+  const int planes = planes_of(prec);
+  bool need_grad = false;
+  for (int i = 0; i < ng; ++i) need_grad = need_grad || groups[i].dq != nullptr;
+  int blk_group[MAX_BLOCKS], blk_Kq[MAX_BLOCKS];
+  for (int k = 0; k < nb; ++k) {
+    const hmmc_queue* q = blocks[k].queue;
+    HMMC_REQUIRE(q != nullptr && q->dk != nullptr && q->D == D, "infonce: queue %d has D=%d, embeddings D=%d", k, q ? q->D : -1, D);
+    blk_group[k] = blocks[k].group;
+    blk_Kq[k] = q->Kq;
+    if (prec != HMMC_PREC_FP32) {
+      HMMC_REQUIRE(q->pack_kd && q->pack_dk, "infonce: queue has no packed operands (call hmmc_queue_pack)");
+      HMMC_REQUIRE(q->planes == planes, "infonce: queue packed with %d planes, precision needs %d", q->planes, planes);
+      HMMC_REQUIRE(D % UMMA_BK == 0 && q->Kq % 128 == 0,
+                   "infonce: tensor-core path needs D %% 64 == 0 and Kq %% 128 == 0 (D=%d Kq=%d)", D, q->Kq);
+    }
+  }
+  Workspace ws(workspace, workspace_bytes);
+  InfoNCELayout L;
+  infonce_layout(ws, L, groups, ng, blk_group, blk_Kq, nb, D, prec, need_grad);
+  if (!ws.ok()) {
+    set_error("infonce: workspace too small: need %zu bytes, got %zu", ws.used, workspace_bytes);
+    return HMMC_ERR_WORKSPACE;
+  }
+  const float invT = 1.0f / temperature, cmax = invT;
+  // 1. normalise (+ pack) every query tensor
+  PrepArgs pa;
+  pa.n = ng;
+  pa.row_begin[0] = 0;
+  for (int i = 0; i < MAX_GROUPS; ++i) {
+    const int k = i < ng ? i : 0;
+    pa.x[i] = groups[k].q;
+    pa.xhat[i] = L.xhat[k];
+    pa.packed[i] = L.packed[k];
+    pa.row_begin[i + 1] = pa.row_begin[i] + (i < ng ? groups[i].rows : 0);
+  }
+  const int total_rows = pa.row_begin[ng];
+  prep_rows_kernel<<<(total_rows + 7) / 8, 256, 0, st>>>(pa, D, planes);
+  HMMC_CHECK_LAUNCH();
+  int rc;
+  if (prec == HMMC_PREC_FP32) {
+    for (int k = 0; k < nb; ++k) {
+      const GroupDesc& G = groups[blocks[k].group];
+      const int Kq = blk_Kq[k];
+      float* S = static_cast<float*>(L.E[k]);
+      if ((rc = gemm_f32(L.xhat[blocks[k].group], D, 1, blocks[k].queue->dk, 1, Kq, S, Kq, G.rows, Kq, D, 1.0f, st))) return rc;
+      exp_rowsum_kernel<<<G.rows, 256, 0, st>>>(S, Kq, Kq, invT, cmax, L.rowsum_part[k]);
+      HMMC_CHECK_LAUNCH();
+      if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
+    }
+  } else {
+    const float LOG2E = 1.4426950408889634f;
+    GemmProblem<EpiInfoNCE> p1[MAX_BLOCKS];
+    GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
+    for (int k = 0; k < nb; ++k) {
+      const GroupDesc& G = groups[blocks[k].group];
+      const int Kq = blk_Kq[k];
+      EpiInfoNCE::Params e1;
+      e1.a2 = invT * LOG2E;
+      e1.c2 = cmax * LOG2E;
+      e1.rowsum_part = L.rowsum_part[k];
+      e1.E = static_cast<__nv_bfloat16*>(L.E[k]);
+      e1.ldE = int64_t(planes) * Kq;
+      e1.e_planes = planes;
+      p1[k] = GemmProblem<EpiInfoNCE>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
+                                      int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1};
+      EpiStoreF32::Params e2{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
+      p2[k] = GemmProblem<EpiStoreF32>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
+                                       G.rows, D, Kq, planes, L.splits[k], e2};
+    }
+    rc = (L.bn1 == 256) ? launch_umma_grouped<256, EpiInfoNCE>(p1, nb, st) : launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st);
+    if (rc) return rc;
+    if (need_grad) {
+      rc = (L.bn2 == 256) ? launch_umma_grouped<256, EpiStoreF32>(p2, nb, st) : launch_umma_grouped<128, EpiStoreF32>(p2, nb, st);
+      if (rc) return rc;
+    }
+  }
+  // 4. positives, loss, gradient
+  FinishArgs fa;
+  fa.n = ng;
+  fa.row_begin[0] = 0;
+  for (int i = 0; i < MAX_GROUPS; ++i) {
+    const int gi = i < ng ? i : 0;
+    RowGroup& R = fa.g[i];
+    R.q = groups[gi].q;
+    R.dq = groups[gi].dq;
+    R.rows = groups[gi].rows;
+    R.Fq = groups[gi].Fq;
+    R.ncontrib = 0;
+    fa.row_begin[i + 1] = fa.row_begin[i] + (i < ng ? groups[i].rows : 0);
+  }
+  for (int k = 0; k < nb; ++k) {
+    RowGroup& R = fa.g[blocks[k].group];
+    HMMC_REQUIRE(R.ncontrib < 2, "infonce: a query tensor may feed at most two queues");
+    Contribution& C = R.c[R.ncontrib++];
+    C.keys = blocks[k].keys;
+    C.rowsum_part = L.rowsum_part[k];
+    C.U_part = L.U_part[k];
+    C.split_stride = int64_t(R.rows) * D;
+    C.pos_mode = blocks[k].pos_mode;
+    C.Fk = blocks[k].Fk;
+    C.n_parts = L.nparts[k];
+    C.n_splits = L.nsplits_eff[k];
+    C.coef = blocks[k].coef;
+    C.kind = blocks[k].kind;
+  }
+  for (int i = 0; i < MAX_GROUPS; ++i)
+    if (fa.g[i].ncontrib < 2) fa.g[i].c[1] = fa.g[i].c[0];
+  const int ne = (D + 31) / 32;
+  if (ne <= 4) launch_finish<4>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  else if (ne <= 16) launch_finish<16>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  else if (ne <= 32) launch_finish<32>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  else launch_finish<FIN_MAXE>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  HMMC_CHECK_LAUNCH();
+  loss_reduce_kernel<<<1, 256, 0, st>>>(L.row_loss, total_rows, kind_out, accumulate);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+static int check_pos_mode(int pos_mode, int Fq, int Fk) {
+  HMMC_REQUIRE(pos_mode >= 0 && pos_mode <= 3, "infonce: unknown pos_mode %d", pos_mode);
+  if (pos_mode == HMMC_POS_PAIR) HMMC_REQUIRE(Fq == Fk, "infonce: PAIR needs Fq == Fk");
+  if (pos_mode == HMMC_POS_FRAME_NEIGHBOUR) HMMC_REQUIRE(Fq == Fk && Fq >= 2, "infonce: FRAME_NEIGHBOUR needs Fq == Fk >= 2");
+  if (pos_mode == HMMC_POS_ONE_TO_FRAMES) HMMC_REQUIRE(Fq == 1, "infonce: ONE_TO_FRAMES needs Fq == 1");
+  if (pos_mode == HMMC_POS_FRAMES_TO_ONE) HMMC_REQUIRE(Fk == 1, "infonce: FRAMES_TO_ONE needs Fk == 1");
+  return HMMC_OK;
+}
+
+}  // namespace hmmc
+
+extern "C" {
 
 size_t hmmc_infonce_workspace_bytes(int64_t R, int D, int Kq, int prec) {
   Workspace ws(nullptr, 0);
-  InfoNCEWs w;
-  infonce_carve(ws, w, infonce_plan(R, D, Kq, prec), R, D, Kq, prec);
-  return ws.used + 256;
+  InfoNCELayout L;
+  GroupDesc g{nullptr, nullptr, int(R), 1};
+  int bg = 0, bk = Kq;
+  infonce_layout(ws, L, &g, 1, &bg, &bk, 1, D, prec, true);
+  return ws.used + 1024;
 }
 
 int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, int b, int Fq, int Fk, int D,
                                const hmmc_queue* queue, float temperature, float weight, int prec, float* loss_out,
                                float* dq, void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   HMMC_REQUIRE(q && keys && queue && loss_out, "infonce: null argument");
   HMMC_REQUIRE(b > 0 && Fq > 0 && Fk > 0 && D > 0, "infonce: bad sizes b=%d Fq=%d Fk=%d D=%d", b, Fq, Fk, D);
-  HMMC_REQUIRE(D <= FIN_THREADS * FIN_MAXE, "infonce: D=%d exceeds the supported %d", D, FIN_THREADS * FIN_MAXE);
-  HMMC_REQUIRE(queue->D == D, "infonce: queue D=%d but embeddings D=%d", queue->D, D);
-  HMMC_REQUIRE(pos_mode >= 0 && pos_mode <= 3, "infonce: unknown pos_mode %d", pos_mode);
-  HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
-  if (pos_mode == HMMC_POS_PAIR) HMMC_REQUIRE(Fq == Fk, "infonce: PAIR needs Fq == Fk");
-  if (pos_mode == HMMC_POS_FRAME_NEIGHBOUR) HMMC_REQUIRE(Fq == Fk && Fq >= 2, "infonce: FRAME_NEIGHBOUR needs Fq == Fk >= 2");
-  if (pos_mode == HMMC_POS_ONE_TO_FRAMES) HMMC_REQUIRE(Fq == 1, "infonce: ONE_TO_FRAMES needs Fq == 1");
-  if (pos_mode == HMMC_POS_FRAMES_TO_ONE) HMMC_REQUIRE(Fk == 1, "infonce: FRAMES_TO_ONE needs Fk == 1");
-  // constant-max log-sum-exp: all logits lie in [-1/T, 1/T]; exp(-2/T) must stay a normal fp32
-  HMMC_REQUIRE(temperature >= 0.025f, "infonce: temperature %g < 0.025 is not supported by the constant-max LSE", temperature);
-  const int Kq = queue->Kq;
-  const int64_t R = int64_t(b) * Fq;
-  const InfoNCEPlan plan = infonce_plan(R, D, Kq, prec);
-  Workspace ws(workspace, workspace_bytes);
-  InfoNCEWs w;
-  infonce_carve(ws, w, plan, R, D, Kq, prec);
-  if (!ws.ok()) {
-    set_error("infonce: workspace too small: need %zu bytes, got %zu", ws.used, workspace_bytes);
-    return HMMC_ERR_WORKSPACE;
-  }
-  const float invT = 1.0f / temperature;
-  const float cmax = invT;
-  const bool need_grad = dq != nullptr;
-  int rc;
-  if (prec == HMMC_PREC_FP32) {
-    rc = rownorm_pack(q, R, D, D, 1e-12f, 1, w.qhat, nullptr, nullptr, 0, st);
-    if (rc) return rc;
-    float* S = static_cast<float*>(w.E);
-    rc = gemm_f32(w.qhat, D, 1, queue->dk, 1, Kq, S, Kq, int(R), Kq, D, 1.0f, st);
-    if (rc) return rc;
-    exp_rowsum_kernel<<<unsigned(R), 256, 0, st>>>(S, Kq, Kq, invT, cmax, w.rowsum_part);
-    HMMC_CHECK_LAUNCH();
-    if (need_grad) {
-      rc = gemm_f32(S, Kq, 1, queue->dk, Kq, 1, w.U_part, D, int(R), D, Kq, 1.0f, st);
-      if (rc) return rc;
-    }
-  } else {
-    HMMC_REQUIRE(queue->pack_kd && queue->pack_dk, "infonce: queue has no packed operands (call hmmc_queue_pack)");
-    HMMC_REQUIRE(queue->planes == plan.planes, "infonce: queue packed with %d planes, precision needs %d", queue->planes, plan.planes);
-    HMMC_REQUIRE(D % UMMA_BK == 0 && Kq % 128 == 0, "infonce: tensor-core path needs D %% 64 == 0 and Kq %% 128 == 0 (D=%d Kq=%d)", D, Kq);
-    rc = rownorm_pack(q, R, D, D, 1e-12f, plan.planes, nullptr, nullptr, w.qpack, int64_t(plan.planes) * D, st);
-    if (rc) return rc;
-    const float LOG2E = 1.4426950408889634f;
-    EpiInfoNCE::Params ep;
-    ep.a2 = invT * LOG2E;
-    ep.c2 = cmax * LOG2E;
-    ep.rowsum_part = w.rowsum_part;
-    ep.E = need_grad ? static_cast<__nv_bfloat16*>(w.E) : nullptr;
-    ep.ldE = int64_t(plan.planes) * Kq;
-    ep.e_planes = plan.planes;
-    if (plan.bn1 == 256)
-      rc = launch_umma_gemm<256, EpiInfoNCE>(w.qpack, int64_t(plan.planes) * D, queue->pack_kd, int64_t(plan.planes) * D,
-                                             int(R), Kq, D, plan.planes, 1, ep, st);
-    else
-      rc = launch_umma_gemm<128, EpiInfoNCE>(w.qpack, int64_t(plan.planes) * D, queue->pack_kd, int64_t(plan.planes) * D,
-                                             int(R), Kq, D, plan.planes, 1, ep, st);
-    if (rc) return rc;
-    if (need_grad) {
-      rc = umma_gemm_store(w.E, int64_t(plan.planes) * Kq, queue->pack_dk, int64_t(plan.planes) * Kq, w.U_part, D,
-                           R * D, int(R), D, Kq, plan.planes, plan.splits2, 1.0f, st);
-      if (rc) return rc;
-    }
-  }
-  // how many split-K partials umma_gemm_store really produced (mirrors launch_umma_gemm)
-  int n_splits = 1;
-  if (prec != HMMC_PREC_FP32) {
-    const int total_kb = ((plan.planes == 2) ? 3 : 1) * (Kq / UMMA_BK);
-    int sp = plan.splits2 < 1 ? 1 : (plan.splits2 > total_kb ? total_kb : plan.splits2);
-    const int per = (total_kb + sp - 1) / sp;
-    n_splits = (total_kb + per - 1) / per;
-  }
-  infonce_finish_kernel<<<unsigned(R), FIN_THREADS, 0, st>>>(q, keys, pos_mode, b, Fq, Fk, D, w.rowsum_part, plan.nparts,
-                                                           int(R), w.U_part, n_splits, R * D, invT, cmax,
-                                                           weight / float(b), dq, w.row_loss);
+  int rc = check_pos_mode(pos_mode, Fq, Fk);
+  if (rc) return rc;
+  // the three loss slots of the generic driver live at the head of the workspace
+  HMMC_REQUIRE(workspace != nullptr && workspace_bytes >= 1024, "infonce: workspace too small");
+  float* kinds = static_cast<float*>(workspace);
+  GroupDesc g{q, dq, b * Fq, Fq};
+  BlockDesc blk{0, keys, pos_mode, Fk, queue, weight / float(b), 0};
+  rc = run_infonce(&g, 1, &blk, 1, b, D, temperature, prec, kinds, 0, static_cast<char*>(workspace) + 1024,
+                   workspace_bytes - 1024, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  add_scalar_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_out, kinds);
   HMMC_CHECK_LAUNCH();
-  loss_reduce_kernel<<<1, 256, 0, st>>>(w.row_loss, int(R), loss_out);
+  return HMMC_OK;
+}
+
+size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec) {
+  Workspace ws(nullptr, 0);
+  InfoNCELayout L;
+  GroupDesc g[4] = {{nullptr, nullptr, b * F, F}, {nullptr, nullptr, b, 1}, {nullptr, nullptr, b, 1}, {nullptr, nullptr, b * F, F}};
+  const int bg[5] = {0, 1, 2, 2, 3};
+  const int bk[5] = {K * F, K, K, K * F, K};
+  infonce_layout(ws, L, g, 4, bg, bk, 5, D, prec, true);
+  return ws.used + 1024;
+}
+
+int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
+                               const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
+                               const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
+                               float w_ftm, int use_frame_fea, int prec, float* losses_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  HMMC_REQUIRE(io && q_v && q_title && q_frame_proj && q_frame_cross && losses_out, "pretrain_head: null argument");
+  HMMC_REQUIRE(io->v_fea && io->title_fea && io->frame_fea && io->frame_pred && io->v_fea_k && io->title_fea_k &&
+               io->frame_fea_k && io->frame_proj_k, "pretrain_head: null embedding pointer");
+  HMMC_REQUIRE(b > 0 && F >= 2 && D > 0, "pretrain_head: bad sizes b=%d F=%d D=%d", b, F, D);
+  HMMC_REQUIRE(workspace != nullptr && workspace_bytes >= 1024, "pretrain_head: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // query tensors: 0 frame_pred, 1 v_fea, 2 title_fea, 3 frame_fea
+  GroupDesc groups[4] = {{io->frame_pred, io->d_frame_pred, b * F, F},
+                         {io->v_fea, io->d_v_fea, b, 1},
+                         {io->title_fea, io->d_title_fea, b, 1},
+                         {io->frame_fea, io->d_frame_fea, b * F, F}};
+  const float fb = float(b);
+  BlockDesc blocks[5] = {
+      // FAM, frame_self_loss(frame_pred, frame_proj_k, queue_frame_proj_ng)        modules/modeling.py:385
+      {0, io->frame_proj_k, HMMC_POS_FRAME_NEIGHBOUR, F, q_frame_proj, 1.0f / float(F - 1) / fb, 0},
+      // VTM, contrastive_loss(v_fea, title_fea_k, queue_title) + (title_fea, v_fea_k, queue_v)   :387-388
+      {1, io->title_fea_k, HMMC_POS_PAIR, 1, q_title, 1.0f / fb, 1},
+      {2, io->v_fea_k, HMMC_POS_PAIR, 1, q_v, 1.0f / fb, 1},
+      // FTM, frame_cross_loss(frame_fea, frame_fea_k, queue_frame_cross, title_fea, title_fea_k, queue_title)  :398
+      {2, io->frame_fea_k, HMMC_POS_ONE_TO_FRAMES, F, q_frame_cross, 1.0f / float(F) / fb, 2},
+      {3, io->title_fea_k, HMMC_POS_FRAMES_TO_ONE, 1, q_title, 1.0f / float(F) / fb, 2}};
+  // gradients carry the loss weights: scale each block's coefficient (the loss slots stay unweighted
+  // only when all three weights are applied afterwards, so slots are reported weighted = w * loss)
+  const float wk[3] = {w_fam, w_vtm, w_ftm};
+  int nb = use_frame_fea ? 5 : 3;
+  int ng = use_frame_fea ? 4 : 3;
+  for (int k = 0; k < nb; ++k) blocks[k].coef *= wk[blocks[k].kind];
+  float* kinds = static_cast<float*>(workspace);
+  int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, kinds, 0, static_cast<char*>(workspace) + 1024,
+                       workspace_bytes - 1024, st);
+  if (rc) return rc;
+  if (!use_frame_fea && io->d_frame_fea != nullptr)
+    HMMC_CHECK_CUDA(cudaMemsetAsync(io->d_frame_fea, 0, sizeof(float) * size_t(b) * F * D, st));
+  head_losses_kernel<<<1, 1, 0, st>>>(losses_out, kinds, w_fam, w_vtm, w_ftm, use_frame_fea);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -536,37 +784,50 @@ int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_
   return HMMC_OK;
 }
 
-int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5, int64_t* queue_ptr,
-                      int64_t ptr_host, int K, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  HMMC_REQUIRE(gathered && queues5 && queue_ptr, "enqueue: null argument");
-  const int B = W * b;
+static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
+                          const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, cudaStream_t st) {
+  HMMC_REQUIRE(queues5 && queue_ptr, "enqueue: null argument");
   // the reference's slice assignment raises when the batch does not fit (modules/modeling.py:273-280)
   HMMC_REQUIRE(ptr_host >= 0 && ptr_host + B <= K, "enqueue: ptr %lld + batch %d exceeds queue size %d",
                (long long)ptr_host, B, K);
   EnqueueArgs a;
   const int mult[5] = {1, 1, 1, F, F};
-  const int off[5] = {0, D, 2 * D, 3 * D, 3 * D + F * D};
   a.planes = queues5[0].planes;
   for (int i = 0; i < 5; ++i) {
     const hmmc_queue& q = queues5[i];
     HMMC_REQUIRE(q.dk != nullptr && q.D == D && q.Kq == K * mult[i], "enqueue: queue %d has shape [%d,%d], expected [%d,%d]",
                  i, q.D, q.Kq, D, K * mult[i]);
     HMMC_REQUIRE(q.planes == a.planes, "enqueue: queues disagree on planes");
+    HMMC_REQUIRE(src5[i] != nullptr, "enqueue: null key tensor %d", i);
     a.dk[i] = q.dk;
     a.pack_kd[i] = static_cast<__nv_bfloat16*>(q.pack_kd);
     a.pack_dk[i] = static_cast<__nv_bfloat16*>(q.pack_dk);
     a.Kq[i] = q.Kq;
     a.mult[i] = mult[i];
-    a.src_off[i] = off[i];
+    a.src[i] = src5[i];
+    a.src_stride[i] = stride5[i];
   }
-  const int row_elems = (3 + 2 * F) * D;
-  dim3 grid((B * F + 31) / 32, 5);
-  enqueue_kernel<<<grid, 256, 0, st>>>(gathered, B, F, D, row_elems, a, queue_ptr);
-  HMMC_CHECK_LAUNCH();
-  advance_ptr_kernel<<<1, 1, 0, st>>>(queue_ptr, B, K);
+  dim3 grid((B * F + 31) / 32, (D + ENQ_DCHUNK - 1) / ENQ_DCHUNK, 5);
+  enqueue_kernel<<<grid, 256, 0, st>>>(B, D, a, queue_ptr, int(ptr_host), int((ptr_host + B) % K));
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
+}
+
+int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5, int64_t* queue_ptr,
+                      int64_t ptr_host, int K, void* stream) {
+  HMMC_REQUIRE(gathered != nullptr, "enqueue: null gathered buffer");
+  const int64_t row = int64_t(3 + 2 * F) * D;
+  const float* src[5] = {gathered, gathered + D, gathered + 2 * D, gathered + 3 * D, gathered + 3 * D + int64_t(F) * D};
+  const int64_t stride[5] = {row, row, row, row, row};
+  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, static_cast<cudaStream_t>(stream));
+}
+
+int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
+                             const float* frame_proj_k, int B, int F, int D, const hmmc_queue* queues5,
+                             int64_t* queue_ptr, int64_t ptr_host, int K, void* stream) {
+  const float* src[5] = {v_k, tag_k, title_k, frame_fea_k, frame_proj_k};
+  const int64_t stride[5] = {D, D, D, int64_t(F) * D, int64_t(F) * D};
+  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, static_cast<cudaStream_t>(stream));
 }
 
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows, float* dst,
@@ -575,7 +836,7 @@ int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, in
   int rc = build_rowpack(a, src_ptrs_host, widths_host, n);
   if (rc) return rc;
   if (rows <= 0) return HMMC_OK;
-  rowpack_kernel<true><<<unsigned(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, rows);
+  rowpack_kernel<true><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, rows);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -586,7 +847,7 @@ int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int3
   int rc = build_rowpack(a, dst_ptrs_host, widths_host, n);
   if (rc) return rc;
   if (rows <= 0) return HMMC_OK;
-  rowpack_kernel<false><<<unsigned(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, const_cast<float*>(src), rows);
+  rowpack_kernel<false><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, const_cast<float*>(src), rows);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }

@@ -44,10 +44,36 @@ struct UmmaCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
 
+constexpr int UMMA_MAX_PROBLEMS = 6;
+
+// Tensor maps of a grouped launch (kept in kernel-parameter space: TMA reads them from there).
+struct TmapSet {
+  CUtensorMap a[UMMA_MAX_PROBLEMS];
+  CUtensorMap b[UMMA_MAX_PROBLEMS];
+};
+
+// A grouped launch = up to UMMA_MAX_PROBLEMS independent GEMMs sharing one persistent grid.
+// Tiles are numbered problem after problem; CTA c works on tiles c, c+grid, c+2*grid, ...
+template <class Epi>
+struct GroupedArgs {
+  int num_problems;
+  int tile_begin[UMMA_MAX_PROBLEMS + 1];
+  GemmShape shape[UMMA_MAX_PROBLEMS];
+  typename Epi::Params ep[UMMA_MAX_PROBLEMS];
+};
+
+template <class Epi>
+__device__ __forceinline__ int find_problem(const GroupedArgs<Epi>& g, int t) {
+  int p = 0;
+#pragma unroll
+  for (int i = 1; i < UMMA_MAX_PROBLEMS; ++i)
+    if (i < g.num_problems && t >= g.tile_begin[i]) p = i;
+  return p;
+}
+
 template <int BN, class Epi>
 __global__ void __launch_bounds__(256, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmShape s, const typename Epi::Params ep) {
+umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ GroupedArgs<Epi> g) {
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -65,8 +91,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
+    for (int p = 0; p < g.num_problems; ++p) {
+      ptx::prefetch_tmap(&tm.a[p]);
+      ptx::prefetch_tmap(&tm.b[p]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -89,27 +117,31 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = s.num_m_blk * s.num_n_blk;
-  const int num_tiles = tiles_mn * s.num_splits;
-  const int total_kb = s.num_seg * s.kb_per_seg;
+  const int num_tiles = g.tile_begin[g.num_problems];
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = t / tiles_mn;
-        const int mn = t - split * tiles_mn;
+        const int p = find_problem(g, t);
+        const GemmShape& s = g.shape[p];
+        const int tl = t - g.tile_begin[p];
+        const int tiles_mn = s.num_m_blk * s.num_n_blk;
+        const int split = tl / tiles_mn;
+        const int mn = tl - split * tiles_mn;
         const int m_blk = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
         const int kb0 = split * s.kb_per_split;
-        const int kb1 = min(kb0 + s.kb_per_split, total_kb);
+        const int kb1 = min(kb0 + s.kb_per_split, s.num_seg * s.kb_per_seg);
         for (int i = kb0; i < kb1; ++i) {
           const int seg = i / s.kb_per_seg, kb = i - seg * s.kb_per_seg;
+          const int ak = (seg == 0 ? s.a_k0[0] : (seg == 1 ? s.a_k0[1] : s.a_k0[2])) + kb * UMMA_BK;
+          const int bk = (seg == 0 ? s.b_k0[0] : (seg == 1 ? s.b_k0[1] : s.b_k0[2])) + kb * UMMA_BK;
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           ptx::mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          ptx::tma_load_2d(sa, &tmA, full_bar(stage), s.a_k0[seg] + kb * UMMA_BK, m_blk * UMMA_BM);
-          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), s.b_k0[seg] + kb * UMMA_BK, n_blk * BN);
+          ptx::tma_load_2d(sa, &tm.a[p], full_bar(stage), ak, m_blk * UMMA_BM);
+          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tm.b[p], full_bar(stage), bk, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -122,9 +154,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = t / tiles_mn;
+        const int p = find_problem(g, t);
+        const GemmShape& s = g.shape[p];
+        const int split = (t - g.tile_begin[p]) / (s.num_m_blk * s.num_n_blk);
         const int kb0 = split * s.kb_per_split;
-        const int kb1 = min(kb0 + s.kb_per_split, total_kb);
+        const int kb1 = min(kb0 + s.kb_per_split, s.num_seg * s.kb_per_seg);
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
@@ -152,8 +186,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc_phase = 0;
     Epi epi;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int split = t / tiles_mn;
-      const int mn = t - split * tiles_mn;
+      const int p = find_problem(g, t);
+      const GemmShape& s = g.shape[p];
+      const typename Epi::Params& ep = g.ep[p];
+      const int tl = t - g.tile_begin[p];
+      const int tiles_mn = s.num_m_blk * s.num_n_blk;
+      const int split = tl / tiles_mn;
+      const int mn = tl - split * tiles_mn;
       const int m_blk = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
       const int row = m_blk * UMMA_BM + quad * 32 + lane;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
@@ -297,43 +336,80 @@ static inline void fill_segments(GemmShape& s, int planes, int K) {
   }
 }
 
+// One problem of a grouped launch as the host describes it.
+template <class Epi>
+struct GemmProblem {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  int M, N, K, planes, splits;
+  typename Epi::Params ep;
+};
+
+template <int BN, class Epi>
+int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t stream) {
+  using Cfg = UmmaCfg<BN>;
+  HMMC_REQUIRE(n >= 1 && n <= UMMA_MAX_PROBLEMS, "umma gemm: %d problems (max %d)", n, UMMA_MAX_PROBLEMS);
+  TmapSet tm;
+  GroupedArgs<Epi> g;
+  g.num_problems = 0;
+  g.tile_begin[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmProblem<Epi>& pr = probs[i];
+    HMMC_REQUIRE(pr.K % UMMA_BK == 0 && pr.K > 0, "umma gemm: K=%d must be a positive multiple of %d", pr.K, UMMA_BK);
+    HMMC_REQUIRE(pr.planes == 1 || pr.planes == 2, "umma gemm: planes must be 1 or 2");
+    HMMC_REQUIRE(pr.lda % 8 == 0 && pr.ldb % 8 == 0, "umma gemm: leading dimensions must be multiples of 8");
+    HMMC_REQUIRE((reinterpret_cast<uintptr_t>(pr.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.B) & 15) == 0,
+                 "umma gemm: operands must be 16-byte aligned");
+    if (pr.M <= 0 || pr.N <= 0) continue;
+    const int k = g.num_problems;
+    GemmShape& s = g.shape[k];
+    s.M = pr.M;
+    s.N = pr.N;
+    s.num_m_blk = (pr.M + UMMA_BM - 1) / UMMA_BM;
+    s.num_n_blk = (pr.N + BN - 1) / BN;
+    fill_segments(s, pr.planes, pr.K);
+    const int total_kb = s.num_seg * s.kb_per_seg;
+    int splits = pr.splits < 1 ? 1 : (pr.splits > total_kb ? total_kb : pr.splits);
+    s.kb_per_split = (total_kb + splits - 1) / splits;
+    s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;   // every split gets >= 1 k-block
+    int rc = make_tmap_bf16(&tm.a[k], pr.A, uint64_t(pr.M), uint64_t(pr.planes) * pr.K, uint64_t(pr.lda), UMMA_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tm.b[k], pr.B, uint64_t(pr.N), uint64_t(pr.planes) * pr.K, uint64_t(pr.ldb), BN);
+    if (rc) return rc;
+    g.ep[k] = pr.ep;
+    g.tile_begin[k + 1] = g.tile_begin[k] + s.num_m_blk * s.num_n_blk * s.num_splits;
+    g.num_problems = k + 1;
+  }
+  if (g.num_problems == 0) return HMMC_OK;
+  for (int k = g.num_problems; k < UMMA_MAX_PROBLEMS; ++k) {
+    g.tile_begin[k + 1] = g.tile_begin[g.num_problems];
+    tm.a[k] = tm.a[0];
+    tm.b[k] = tm.b[0];
+    g.shape[k] = g.shape[0];
+    g.ep[k] = g.ep[0];
+  }
+  auto kern = umma_gemm_kernel<BN, Epi>;
+  HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+  const int tiles = g.tile_begin[g.num_problems];
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tm, g);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+// number of split-K partials launch_umma_grouped will produce for a request of `splits`
+static inline int effective_splits(int K, int planes, int splits) {
+  const int total_kb = ((planes == 2) ? 3 : 1) * (K / UMMA_BK);
+  int sp = splits < 1 ? 1 : (splits > total_kb ? total_kb : splits);
+  const int per = (total_kb + sp - 1) / sp;
+  return (total_kb + per - 1) / per;
+}
+
 template <int BN, class Epi>
 int launch_umma_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int planes,
                      int splits, const typename Epi::Params& ep, cudaStream_t stream) {
-  using Cfg = UmmaCfg<BN>;
-  HMMC_REQUIRE(K % UMMA_BK == 0 && K > 0, "umma gemm: K=%d must be a positive multiple of %d", K, UMMA_BK);
-  HMMC_REQUIRE(planes == 1 || planes == 2, "umma gemm: planes must be 1 or 2");
-  HMMC_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "umma gemm: leading dimensions must be multiples of 8");
-  HMMC_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-               "umma gemm: operands must be 16-byte aligned");
-  if (M <= 0 || N <= 0) return HMMC_OK;
-  GemmShape s;
-  s.M = M;
-  s.N = N;
-  s.num_m_blk = (M + UMMA_BM - 1) / UMMA_BM;
-  s.num_n_blk = (N + BN - 1) / BN;
-  fill_segments(s, planes, K);
-  const int total_kb = s.num_seg * s.kb_per_seg;
-  if (splits < 1) splits = 1;
-  if (splits > total_kb) splits = total_kb;
-  s.kb_per_split = (total_kb + splits - 1) / splits;
-  s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;   // every split gets >= 1 k-block
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16(&tmA, A, uint64_t(M), uint64_t(planes) * K, uint64_t(lda), UMMA_BM);
-  if (rc) return rc;
-  rc = make_tmap_bf16(&tmB, B, uint64_t(N), uint64_t(planes) * K, uint64_t(ldb), BN);
-  if (rc) return rc;
-  auto kern = umma_gemm_kernel<BN, Epi>;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-    attr_set = true;
-  }
-  const int tiles = s.num_m_blk * s.num_n_blk * s.num_splits;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, s, ep);
-  HMMC_CHECK_LAUNCH();
-  return HMMC_OK;
+  GemmProblem<Epi> pr{A, lda, B, ldb, M, N, K, planes, splits, ep};
+  return launch_umma_grouped<BN, Epi>(&pr, 1, stream);
 }
 
 // number of split-K slices that fills the machine for an (M x N) output with BN-wide tiles

@@ -159,17 +159,22 @@ class ContrastiveHeadMixin:
         frame_proj_k = frame_proj_k.reshape(b, -1, D)
         F = frame_fea_k.shape[1]
         K = self.contrast_num_negative
-        # one packed all-gather instead of five (the only exchange of the pre-train head)
-        send = ops.pack_rows([v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D), title_fea_k.reshape(b, D),
-                              frame_fea_k, frame_proj_k])
-        gathered = parallel.all_gather_rows(send)
-        W = gathered.shape[0] // b
+        W, _ = parallel.world()
+        direct = gathered = None
+        if W == 1:
+            direct = [ops._f32c(t, "key") for t in (v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D),
+                                                    title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k)]
+        else:
+            # one packed all-gather instead of five (the only exchange of the pre-train head)
+            send = ops.pack_rows([v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D), title_fea_k.reshape(b, D),
+                                  frame_fea_k, frame_proj_k])
+            gathered = parallel.all_gather_rows(send)
         ver = self.queue_ptr._version
         if getattr(self, "_hmmc_ptr", None) is None or self._hmmc_ptr[1] != ver:
             self._hmmc_ptr = (int(self.queue_ptr), ver)        # one sync, then tracked on the host
         ptr = self._hmmc_ptr[0]
         ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, ptr, K,
-                    ops.resolve_precision(self.head_precision))
+                    ops.resolve_precision(self.head_precision), direct=direct)
         self._hmmc_ptr = ((ptr + W * b) % K, self.queue_ptr._version)
 
 
@@ -221,18 +226,19 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
     def head_loss(self, v_fea, frame_fea, title_fea, frame_pred, v_fea_k, frame_fea_k, title_fea_k, tag_fea_k,
                   frame_proj_k, loss_MLM=None):
         """modules/modeling.py:385-424 for dataset != "bird" (the only reachable branch)."""
-        loss_FAM = self.frame_self_loss(frame_pred, frame_proj_k, self.queue_frame_proj_ng)
-        loss_VTM = self.contrastive_loss(v_fea, title_fea_k, self.queue_title_cross_ng) \
-            + self.contrastive_loss(title_fea, v_fea_k, self.queue_v_cross_ng)
-        loss_FTM = 0.
-        if self.task_config.use_frame_fea:
-            loss_FTM = self.frame_cross_loss(frame_fea, frame_fea_k, self.queue_frame_cross_ng, title_fea,
-                                             title_fea_k, self.queue_title_cross_ng)
+        b = v_fea.shape[0]
+        D = v_fea.shape[-1]
+        total, parts = ops.pretrain_head(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
+                                         v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k,
+                                         self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
+                                         self.queue_frame_cross_ng, self.contrast_temperature, self.weight_FAM,
+                                         self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
+                                         self.head_precision)
+        self.last_loss_parts = parts            # [FAM, VTM, FTM], device tensor (the reference logs them)
         self._dequeue_and_enqueue(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         if loss_MLM is None:
-            loss_MLM = 0.
-        return self.weight_FAM * loss_FAM + self.weight_VTM * loss_VTM + self.weight_FTM * loss_FTM \
-            + self.weight_MLM * loss_MLM
+            return total
+        return total + self.weight_MLM * loss_MLM
 
     def forward(self, video_data, video_frame, tag_ids, tag_mask, title_ids, title_mask, global_step):
         tag_ids = tag_ids.view(-1, tag_ids.shape[-1])

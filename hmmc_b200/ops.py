@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (PREC_BF16, PREC_BF16X3, PREC_FP32, PRECISIONS, POS_FRAME_NEIGHBOUR, POS_FRAMES_TO_ONE,
-                   POS_ONE_TO_FRAMES, POS_PAIR, HmmcError, hmmc_queue)
+                   POS_ONE_TO_FRAMES, POS_PAIR, HmmcError, hmmc_pretrain_io, hmmc_queue)
 
 DEFAULT_PRECISION = os.environ.get("HMMC_PRECISION", "bf16x3")
 
@@ -196,6 +196,55 @@ def infonce(q, keys, queue_buf, pos_mode, b, Fq, Fk, temperature, weight=1.0, pr
                             resolve_precision(precision))
 
 
+class _PretrainHeadFn(torch.autograd.Function):
+    """w_fam*FAM + w_vtm*VTM + w_ftm*FTM of the pre-train head, forward and backward in one C
+    call (five launches).  Returns (total, parts[3]); only ``total`` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k,
+                q_v, q_title, q_frame_proj, q_frame_cross, temperature, w_fam, w_vtm, w_ftm, use_frame_fea, prec):
+        lib = _lib.load()
+        b, F, D = frame_fea.shape
+        qin = [v_fea, title_fea, frame_fea, frame_pred]
+        t = [_f32c(x, "embedding") for x in qin + [v_fea_k, title_fea_k, frame_fea_k, frame_proj_k]]
+        need = [x.requires_grad for x in qin]
+        any_grad = any(need)
+        grads = [torch.empty_like(x) if any_grad else None for x in t[:4]]
+        io = hmmc_pretrain_io(*[x.data_ptr() for x in t], *[(g.data_ptr() if g is not None else 0) for g in grads])
+        structs = [_queue_struct(qb, prec) for qb in (q_v, q_title, q_frame_proj, q_frame_cross)]
+        K = q_v.shape[1]
+        nbytes = lib.hmmc_pretrain_head_workspace_bytes(b, F, D, K, prec)
+        ws = workspace(t[0].device, nbytes)
+        losses = torch.empty(4, dtype=torch.float32, device=t[0].device)
+        _lib.check(lib.hmmc_pretrain_head_fwd_bwd(ctypes.byref(io), b, F, D, *[ctypes.byref(s[0]) for s in structs],
+                                                  float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
+                                                  int(bool(use_frame_fea)), prec, _p(losses), _p(ws), ws.numel(),
+                                                  _stream()), "hmmc_pretrain_head_fwd_bwd")
+        ctx.need = need
+        ctx.meta = [(x.shape, x.dtype) for x in qin]
+        if any_grad:
+            ctx.save_for_backward(*grads)
+        total, parts = losses[0], losses[1:]
+        ctx.mark_non_differentiable(parts)
+        return total, parts
+
+    @staticmethod
+    def backward(ctx, g, _gparts):
+        grads = list(ctx.saved_tensors)
+        scaled = torch._foreach_mul(grads, g)
+        out = [scaled[i].reshape(ctx.meta[i][0]).to(ctx.meta[i][1]) if ctx.need[i] else None for i in range(4)]
+        return tuple(out) + (None,) * 14
+
+
+def pretrain_head(v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k,
+                  q_v, q_title, q_frame_proj, q_frame_cross, temperature, w_fam, w_vtm, w_ftm, use_frame_fea=True,
+                  precision=None):
+    return _PretrainHeadFn.apply(v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k,
+                                 frame_proj_k, q_v, q_title, q_frame_proj, q_frame_cross, float(temperature),
+                                 float(w_fam), float(w_vtm), float(w_ftm), bool(use_frame_fea),
+                                 resolve_precision(precision))
+
+
 # ----------------------------------------------------------------------------- EMA / enqueue
 
 _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
@@ -277,8 +326,9 @@ def unpack_rows(packed, widths):
     return outs
 
 
-def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec):
-    """queue_bufs5 order: v, tag, title, frame_cross, frame_proj."""
+def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None):
+    """queue_bufs5 order: v, tag, title, frame_cross, frame_proj.  ``direct`` = the five key
+    tensors themselves (single process: no gather, no packed copy)."""
     lib = _lib.load()
     arr = (hmmc_queue * 5)()
     keep = []
@@ -286,8 +336,12 @@ def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec):
         qs, st = _queue_struct(buf, prec)
         arr[i] = qs
         keep.append(st)
-    _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _stream()),
-               "hmmc_enqueue_norm")
+    if direct is not None:
+        _lib.check(lib.hmmc_enqueue_norm_direct(*[_p(t) for t in direct], W * b, F, D, arr, _p(queue_ptr),
+                                                int(ptr_host), K, _stream()), "hmmc_enqueue_norm_direct")
+    else:
+        _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _stream()),
+                   "hmmc_enqueue_norm")
     for st, buf in zip(keep, queue_bufs5):
         if st is not None:
             st.version = buf._version       # the kernel kept the packed copies in step

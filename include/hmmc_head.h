@@ -111,6 +111,35 @@ int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, 
                                float* loss_out, float* dq, void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* The whole pre-train head loss of BirdPreTrainedModel.forward (modules/modeling.py:385-400,424;
+ * dataset != "bird"), forward and backward in five launches:
+ *   losses_out[0] = w_fam*FAM + w_vtm*VTM + w_ftm*FTM,  losses_out[1..3] = FAM, VTM, FTM
+ *   FAM = frame_self_loss(frame_pred, frame_proj_k, q_frame_proj)
+ *   VTM = contrastive_loss(v_fea, title_fea_k, q_title) + contrastive_loss(title_fea, v_fea_k, q_v)
+ *   FTM = frame_cross_loss(frame_fea, frame_fea_k, q_frame_cross, title_fea, title_fea_k, q_title)
+ * and d(losses_out[0])/d{v_fea, title_fea, frame_fea, frame_pred} (all four NULL = forward only).
+ * [b,D] / [b,F,D] fp32 contiguous tensors. */
+typedef struct {
+  const float* v_fea;
+  const float* title_fea;
+  const float* frame_fea;
+  const float* frame_pred;
+  const float* v_fea_k;
+  const float* title_fea_k;
+  const float* frame_fea_k;
+  const float* frame_proj_k;
+  float* d_v_fea;
+  float* d_title_fea;
+  float* d_frame_fea;
+  float* d_frame_pred;
+} hmmc_pretrain_io;
+size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec);
+int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
+                               const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
+                               const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
+                               float w_ftm, int use_frame_fea, int prec, float* losses_out, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* _momentum_update (modules/modeling.py:238-242): p_k <- p_k*m + p*(1-m) for a table of
  * tensors, each in its own dtype (0 = fp32, 1 = fp16, 2 = bf16), three separately
  * rounded ops like the reference.  The three tables are device arrays of length n. */
@@ -127,10 +156,17 @@ int hmmc_ema_block_elems(void);
  * `gathered` is the all-gather output [W][b][row_elems] with one rank's row =
  * [v | tag | title | frame_fea(F*D) | frame_proj(F*D)]; queues order: v, tag, title,
  * frame_cross (gets frame_fea), frame_proj.  queue_ptr is the int64[1] buffer.
- * ptr_host is the host's copy of the pointer, used only for the bounds check the
- * reference performs through slice assignment. */
+ * ptr_host is the host's copy of the pointer (the kernel takes it by value: no device
+ * read, no sync); it also drives the bounds check the reference performs through slice
+ * assignment.  The kernel stores (ptr_host + B) % K into queue_ptr. */
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
                       int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
+
+/* Same, reading the five key tensors in place ([B,D] x3, [B,F,D] x2, contiguous): the
+ * single-process case needs no gather and no packed copy. */
+int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
+                             const float* frame_proj_k, int B, int F, int D, const hmmc_queue* queues5,
+                             int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
 
 /* gather n row-blocks src_i[rows, width_i] into dst[rows, sum width_i] (the packed
  * send buffer of the key / embedding all-gather) and the inverse. */

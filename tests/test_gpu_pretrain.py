@@ -58,6 +58,9 @@ def test_pretrain_head_b32(golden, prec):
                        t["title_fea_k"], t["tag_fea_k"], t["frame_proj_k"])
     loss.backward()
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < ltol
+    parts = m.last_loss_parts.cpu().numpy()                   # fused head reports FAM, VTM, FTM too
+    for got, name in zip(parts, ("fam", "vtm", "ftm")):
+        assert abs(got - float(g[name])) / float(g[name]) < ltol, (name, got)
     _, ref = O.pretrain_loss_and_grads(inp, qs, T)            # fp64 oracle (pinned to the golden grads)
     for n in ("v_fea", "title_fea", "frame_fea", "frame_pred"):
         got = t[n].grad.cpu().numpy()
@@ -157,3 +160,36 @@ def test_pretrain_head_small_fp32(golden):
         assert rel(t[n].grad.cpu().numpy(), g["d_" + n]) < 1e-4, n
     for n in syn.QUEUE_NAMES:
         np.testing.assert_allclose(getattr(m, n).cpu().numpy(), g["after_" + n], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_fused_head_equals_granular_calls(prec):
+    """The one-call head equals the reference-style composition of frame_self_loss /
+    contrastive_loss / frame_cross_loss (modules/modeling.py:385-400), values and gradients;
+    also without --use_frame_fea."""
+    b, F, D, K = 24, 5, 128, 256
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=31)
+    qs = syn.queues(K, F=F, D=D, seed=32)
+    names = ("v_fea", "title_fea", "frame_fea", "frame_pred")
+    for use_frames in (True, False):
+        m = _model(K, F, D, prec)
+        m.task_config.use_frame_fea = use_frames
+        _load_queues(m, qs)
+        a = {n: cu(x, n in names) for n, x in inp.items()}
+        fam = m.frame_self_loss(a["frame_pred"], a["frame_proj_k"], m.queue_frame_proj_ng)
+        vtm = m.contrastive_loss(a["v_fea"], a["title_fea_k"], m.queue_title_cross_ng) \
+            + m.contrastive_loss(a["title_fea"], a["v_fea_k"], m.queue_v_cross_ng)
+        ftm = m.frame_cross_loss(a["frame_fea"], a["frame_fea_k"], m.queue_frame_cross_ng, a["title_fea"],
+                                 a["title_fea_k"], m.queue_title_cross_ng) if use_frames else 0.0
+        l1 = 0.05 * fam + 0.45 * vtm + 0.45 * ftm
+        l1.backward()
+        c = {n: cu(x, n in names) for n, x in inp.items()}
+        l2 = m.head_loss(c["v_fea"], c["frame_fea"], c["title_fea"], c["frame_pred"], c["v_fea_k"], c["frame_fea_k"],
+                         c["title_fea_k"], c["tag_fea_k"], c["frame_proj_k"])
+        l2.backward()
+        assert abs(float(l1) - float(l2)) / float(l1) < 3e-6
+        for n in names:
+            if n == "frame_fea" and not use_frames:
+                assert a[n].grad is None and float(c[n].grad.abs().max()) == 0.0
+                continue
+            assert rel(c[n].grad.cpu().numpy(), a[n].grad.cpu().numpy()) < 1e-5, n
