@@ -126,7 +126,7 @@ struct FinishArgs {
 };
 
 template <int NE>   // elements per lane = D / 32 rounded up
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NE <= 16) ? 3 : 1)
 infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax,
                       float* __restrict__ row_loss /* [3][total_rows] */) {
   const int lane = threadIdx.x & 31;
@@ -160,18 +160,21 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
   for (int ci = 0; ci < G.ncontrib; ++ci) {
     const Contribution& C = G.c[ci];
     // S_r: negatives' sum of exp(l - cmax)
-    float S = 0.f;
-    for (int p = lane; p < C.n_parts; p += 32) S += C.rowsum_part[int64_t(p) * G.rows + r];
-    S = warp_sum(S);
+    float S = 0.f, S1 = 0.f;
+    for (int p = lane; p < C.n_parts; p += 64) {
+      const float a0 = C.rowsum_part[int64_t(p) * G.rows + r];
+      const float a1 = (p + 32 < C.n_parts) ? C.rowsum_part[int64_t(p + 32) * G.rows + r] : 0.f;
+      S += a0;
+      S1 += a1;
+    }
+    S = warp_sum(S + S1);
     int nterm, kbase, kstep;
     if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
     else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
     else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kbase = n * C.Fk; kstep = 1; }
     else { nterm = 1; kbase = n; kstep = 0; }
     float loss = 0.f, sum_invZ = 0.f;
-    float gk[NE];
-#pragma unroll
-    for (int i = 0; i < NE; ++i) gk[i] = 0.f;
+    const float scale = C.coef * invT;
     for (int t = 0; t < nterm; ++t) {
       int kr = kbase + t * kstep;
       if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
@@ -184,7 +187,10 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
 #pragma unroll
       for (int i = 0; i < NE; ++i) {
         const int d = lane + i * 32;
-        kv[i] = (d < D) ? C.keys[int64_t(kr) * D + d] : 0.f;
+        kv[i] = (d < D) ? __ldg(C.keys + int64_t(kr) * D + d) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
         kk = fmaf(kv[i], kv[i], kk);
         qk = fmaf(kv[i], qv[i], qk);
       }
@@ -196,21 +202,25 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
       const float Z = epos + S;
       loss += logf(Z) + cmax - lpos;
       sum_invZ += 1.0f / Z;
-      const float w = (epos / Z - 1.0f) / nk;
+      // g_hat += coef/T * (p+ - 1) k_hat_t
+      const float w = scale * (epos / Z - 1.0f) / nk;
 #pragma unroll
-      for (int i = 0; i < NE; ++i) gk[i] = fmaf(w, kv[i], gk[i]);
+      for (int i = 0; i < NE; ++i) g[i] = fmaf(w, kv[i], g[i]);
     }
     loss_kind[C.kind] += C.coef * loss;
     if (G.dq != nullptr) {
-      // g_hat += coef/T * (sum_t (p+ - 1) k_hat_t + (sum_t 1/Z_t) U_r)
-      const float scale = C.coef * invT;
+      // g_hat += coef/T * (sum_t 1/Z_t) U_r ;  U_r = sum over the split-K partials (loads batched per split)
+      const float wu = scale * sum_invZ;
+      for (int sidx = 0; sidx < C.n_splits; ++sidx) {
+        const float* up = C.U_part + int64_t(sidx) * C.split_stride + int64_t(r) * D;
+        float u[NE];
 #pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        const int d = lane + i * 32;
-        float u = 0.f;
-        if (d < D)
-          for (int sidx = 0; sidx < C.n_splits; ++sidx) u += C.U_part[int64_t(sidx) * C.split_stride + int64_t(r) * D + d];
-        g[i] += scale * fmaf(sum_invZ, u, gk[i]);
+        for (int i = 0; i < NE; ++i) {
+          const int d = lane + i * 32;
+          u[i] = (d < D) ? __ldg(up + d) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NE; ++i) g[i] = fmaf(wu, u[i], g[i]);
       }
     }
   }
@@ -237,8 +247,16 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total
                                    int accumulate) {
   __shared__ float red[32];
   for (int k = 0; k < 3; ++k) {
+    const float* v = row_loss + int64_t(k) * total_rows;
     float acc = 0.f;
-    for (int i = threadIdx.x; i < total_rows; i += blockDim.x) acc += row_loss[int64_t(k) * total_rows + i];
+    for (int i = threadIdx.x; i < total_rows; i += 4 * blockDim.x) {
+      const int i1 = i + blockDim.x, i2 = i + 2 * blockDim.x, i3 = i + 3 * blockDim.x;
+      const float a0 = v[i];
+      const float a1 = i1 < total_rows ? v[i1] : 0.f;
+      const float a2 = i2 < total_rows ? v[i2] : 0.f;
+      const float a3 = i3 < total_rows ? v[i3] : 0.f;
+      acc += (a0 + a1) + (a2 + a3);
+    }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) kind_out[k] = accumulate ? kind_out[k] + acc : acc;
     __syncthreads();
@@ -432,6 +450,28 @@ __global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_
   for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
     if (PACK) y[i] = x[i]; else x[i] = y[i];
   }
+}
+
+struct ScaleArgs {
+  float* ptrs[8];
+  int64_t numels[8];
+  int n;
+};
+// x_t *= scale[0] for up to 8 tensors (backward of the fused heads: the gradients were produced
+// with the loss, the upstream gradient arrives later)
+__global__ void scale_tensors_kernel(ScaleArgs a, const float* __restrict__ scale) {
+  const float s = scale[0];
+  float* x = a.ptrs[blockIdx.y];
+  const int64_t n = a.numels[blockIdx.y];
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x4[i] = v;
+  }
+  for (int64_t i = n4 * 4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    x[i] *= s;
 }
 
 static int build_rowpack(RowPackArgs& a, const uint64_t* ptrs, const int32_t* widths, int n) {
@@ -671,7 +711,7 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
   else if (ne <= 32) launch_finish<32>(fa, total_rows, D, invT, cmax, L.row_loss, st);
   else launch_finish<FIN_MAXE>(fa, total_rows, D, invT, cmax, L.row_loss, st);
   HMMC_CHECK_LAUNCH();
-  loss_reduce_kernel<<<1, 256, 0, st>>>(L.row_loss, total_rows, kind_out, accumulate);
+  loss_reduce_kernel<<<1, 1024, 0, st>>>(L.row_loss, total_rows, kind_out, accumulate);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -828,6 +868,25 @@ int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* 
   const float* src[5] = {v_k, tag_k, title_k, frame_fea_k, frame_proj_k};
   const int64_t stride[5] = {D, D, D, int64_t(F) * D, int64_t(F) * D};
   return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, static_cast<cudaStream_t>(stream));
+}
+
+int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, int n, const float* scale, void* stream) {
+  HMMC_REQUIRE(ptrs_host && numels_host && scale && n >= 1 && n <= 8, "scale_tensors: bad arguments");
+  ScaleArgs a;
+  a.n = n;
+  int64_t mx = 0;
+  for (int i = 0; i < n; ++i) {
+    a.ptrs[i] = reinterpret_cast<float*>(ptrs_host[i]);
+    a.numels[i] = numels_host[i];
+    mx = numels_host[i] > mx ? numels_host[i] : mx;
+  }
+  if (mx <= 0) return HMMC_OK;
+  int gx = int((mx / 4 + 255) / 256);
+  if (gx < 1) gx = 1;
+  if (gx > 4 * sm_count()) gx = 4 * sm_count();
+  scale_tensors_kernel<<<dim3(gx, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, scale);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
 }
 
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows, float* dst,

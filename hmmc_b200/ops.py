@@ -196,6 +196,20 @@ def infonce(q, keys, queue_buf, pos_mode, b, Fq, Fk, temperature, weight=1.0, pr
                             resolve_precision(precision))
 
 
+def scale_inplace(tensors, g):
+    """t *= g for every tensor (g: 0-d device tensor), one launch."""
+    lib = _lib.load()
+    ts = [t for t in tensors if t is not None and t.numel()]
+    if not ts:
+        return tensors
+    g = g.reshape(()).to(device=ts[0].device, dtype=torch.float32)
+    n = len(ts)
+    ptrs = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in ts])
+    nums = (ctypes.c_int64 * n)(*[t.numel() for t in ts])
+    _lib.check(lib.hmmc_scale_tensors(ptrs, nums, n, _p(g), _stream()), "hmmc_scale_tensors")
+    return tensors
+
+
 class _PretrainHeadFn(torch.autograd.Function):
     """w_fam*FAM + w_vtm*VTM + w_ftm*FTM of the pre-train head, forward and backward in one C
     call (five launches).  Returns (total, parts[3]); only ``total`` is differentiable."""
@@ -231,8 +245,11 @@ class _PretrainHeadFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _gparts):
         grads = list(ctx.saved_tensors)
-        scaled = torch._foreach_mul(grads, g)
-        out = [scaled[i].reshape(ctx.meta[i][0]).to(ctx.meta[i][1]) if ctx.need[i] else None for i in range(4)]
+        if getattr(ctx, "consumed", False):
+            raise HmmcError("the fused head's gradients were already consumed (retain_graph is not supported)")
+        ctx.consumed = True
+        scale_inplace([grads[i] for i in range(4) if ctx.need[i]], g)      # in place: the buffers are ours
+        out = [grads[i].reshape(ctx.meta[i][0]).to(ctx.meta[i][1]) if ctx.need[i] else None for i in range(4)]
         return tuple(out) + (None,) * 14
 
 

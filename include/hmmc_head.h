@@ -168,6 +168,11 @@ int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* 
                              const float* frame_proj_k, int B, int F, int D, const hmmc_queue* queues5,
                              int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
 
+/* x_t *= scale[0] (device scalar) for up to 8 fp32 tensors in one launch: applies the upstream
+ * gradient to the gradients the fused heads produced together with the loss. */
+int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, int n, const float* scale,
+                       void* stream);
+
 /* gather n row-blocks src_i[rows, width_i] into dst[rows, sum width_i] (the packed
  * send buffer of the key / embedding all-gather) and the inverse. */
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows,
