@@ -77,6 +77,14 @@ SIGNATURES = {
                                   c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "hmmc_rank_count": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    "hmmc_eval_fused_supported": (c_int, [c_int, c_int, c_int]),
+    "hmmc_eval_pack_text": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "hmmc_eval_pack_gallery": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hmmc_eval_gt_scores": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_int, c_int,
+                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "hmmc_eval_theta": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "hmmc_eval_fused_rank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hmmc_group_max": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -1,0 +1,481 @@
+// Large-gallery retrieval eval without materialising the similarity matrix (BASELINE config 5).
+//
+//   score[s, j] = scale * t_hat_s . v_hat_j  +  mean of the top_k of { scale * t_hat_s . f_hat_{j,f} }_f
+//   t2v_cnt[s]  = #{ j != gt(s) : score[s, j] > score[s, gt(s)] }
+//   v2t_cnt[j]  = #{ groups g != j : max_{s in g} score[s, j] > theta_j },  theta_j = max_{s in group j} score[s, j]
+//
+// (the multi-sentence ranks of metrics.py:49-86; a square set is the special case of one caption per
+// video).  The gallery is packed as 1+F consecutive rows per video (video embedding, then its frames)
+// so one 128 x 208 accumulator tile (F = 12: 16 videos x 13 columns) holds everything the top-k
+// pooling of 16 videos needs in ONE thread's row: no shuffles, no logits in HBM.
+//
+// Texts are packed group-aligned: the captions of one video never straddle a 128-row tile, so the
+// "any caption of group g beats theta_j" reduction stays inside one CTA tile.
+//
+// Same warp roles and TMA / tcgen05 pipeline as umma_gemm.cuh; the scheduling differs: a CTA owns
+// M tiles (128 captions) and sweeps all gallery tiles for each, so all CTAs walk the gallery in
+// step and every gallery tile is fetched from HBM once and then served from L2, and each thread
+// keeps its caption's t2v count in a register for the whole sweep.
+#include "common.cuh"
+#include "umma_gemm.cuh"
+
+namespace hmmc {
+
+constexpr int EV_F = 12;                    // frames per video handled by the fused path
+constexpr int EV_COLS = 1 + EV_F;           // accumulator columns per video
+constexpr int EV_VPT = 16;                  // videos per tile
+constexpr int EV_BN = EV_COLS * EV_VPT;     // 208
+constexpr int EV_MAXK = 4;                  // top_frames supported by the fused path
+
+struct EvalArgs {
+  int num_m_blk, num_n_blk;       // caption tiles (128 rows) and gallery tiles (16 videos)
+  int Nv_local;                   // videos in this shard
+  int num_seg, kb_per_seg;
+  int a_k0[3], b_k0[3];
+  float scale;
+  int top_k;
+  int mode;                       // 0: ground-truth scores on the listed tiles, 1: counting sweep
+  int video_base;                 // global index of this shard's first video
+  const int32_t* grp;             // [Nt_pad] global video id each packed caption belongs to, -1 = padding
+  float* gt_score;                // [Nt_pad] score[s, gt(s)] (mode 0 writes, mode 1 reads)
+  const float* theta;             // [Nv_local] (mode 1)
+  int32_t* t2v_cnt;               // [Nt_pad] (mode 1, plain store)
+  int32_t* v2t_cnt;               // [Nv_local] (mode 1, atomics)
+  const int2* diag_tiles;         // mode 0: (m_blk, n_blk) pairs
+  int n_diag_tiles;
+};
+
+// OR-reduction of a predicate over the 128 epilogue threads (named barrier 1); also a barrier.
+__device__ __forceinline__ int epi_bar_or(int pred) {
+  int r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %1, 0;\n\t"
+      "bar.red.or.pred q, 1, 128, p;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"(pred)
+      : "memory");
+  return r;
+}
+
+// finalise one video from its 13 accumulator values
+struct VideoAcc {
+  float vsim;
+  float best[EV_MAXK];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < EV_MAXK; ++i) best[i] = -INFINITY;
+  }
+  __device__ __forceinline__ void push(float x, int k) {
+#pragma unroll
+    for (int i = 0; i < EV_MAXK; ++i) {
+      if (i < k && x > best[i]) { const float t = best[i]; best[i] = x; x = t; }
+    }
+  }
+  __device__ __forceinline__ float score(int k) const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < EV_MAXK; ++i) if (i < k) s += best[i];
+    return vsim + s / float(k);
+  }
+};
+
+__global__ void __launch_bounds__(256, 1)
+eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ EvalArgs a) {
+  using Cfg = UmmaCfg<EV_BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bar_base = ptx::smem_u32(bars);
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (STAGES + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  // epilogue scratch: per-row hit masks (double buffered), group ids, per-tile video counters
+  __shared__ uint32_t s_mask[2][128];
+  __shared__ int32_t s_grp[128];
+  __shared__ int32_t s_cnt[2][EV_VPT];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(full_bar(i), 1);
+      ptx::mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull_bar(i), 1);
+      ptx::mbar_init(tempty_bar(i), 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_kb = a.num_seg * a.kb_per_seg;
+  // tile enumeration shared by the three roles
+  //   mode 1: for (m = blockIdx.x; m < num_m_blk; m += gridDim.x) for (n = 0; n < num_n_blk; ++n)
+  //   mode 0: for (t = blockIdx.x; t < n_diag_tiles; t += gridDim.x) (m, n) = diag_tiles[t]
+  const long long tiles_per_cta =
+      (a.mode == 1) ? (long long)((a.num_m_blk - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)) * a.num_n_blk
+                    : (long long)((a.n_diag_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x));
+  auto tile_of = [&](long long i, int& m_blk, int& n_blk) {
+    if (a.mode == 1) {
+      m_blk = int(blockIdx.x) + int(i / a.num_n_blk) * int(gridDim.x);
+      n_blk = int(i % a.num_n_blk);
+    } else {
+      const int2 t = a.diag_tiles[int(blockIdx.x) + int(i) * int(gridDim.x)];
+      m_blk = t.x;
+      n_blk = t.y;
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long i = 0; i < tiles_per_cta; ++i) {
+        int m_blk, n_blk;
+        tile_of(i, m_blk, n_blk);
+        for (int kbi = 0; kbi < total_kb; ++kbi) {
+          const int seg = kbi / a.kb_per_seg, kb = kbi - seg * a.kb_per_seg;
+          const int ak = (seg == 0 ? a.a_k0[0] : (seg == 1 ? a.a_k0[1] : a.a_k0[2])) + kb * UMMA_BK;
+          const int bk = (seg == 0 ? a.b_k0[0] : (seg == 1 ? a.b_k0[1] : a.b_k0[2])) + kb * UMMA_BK;
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          ptx::tma_load_2d(sa, &tmA, full_bar(stage), ak, m_blk * UMMA_BM);
+          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), bk, n_blk * EV_BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(UMMA_BM, EV_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long i = 0; i < tiles_per_cta; ++i) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kbi = 0; kbi < total_kb; ++kbi) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < UMMA_BK / 16; ++k)
+            ptx::umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kbi > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int trow = quad * 32 + lane;          // row inside the tile = epilogue thread id
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_m = -1;
+    int my_grp = -1;
+    float my_gt = 0.f;
+    int my_cnt = 0;
+    int buf = 0;
+    const int k = a.top_k;
+    for (long long i = 0; i < tiles_per_cta; ++i) {
+      int m_blk, n_blk;
+      tile_of(i, m_blk, n_blk);
+      const int row = m_blk * UMMA_BM + trow;
+      if (m_blk != cur_m) {
+        if (a.mode == 1 && cur_m >= 0) a.t2v_cnt[cur_m * UMMA_BM + trow] = my_cnt;
+        cur_m = m_blk;
+        my_cnt = 0;
+        my_grp = a.grp[row];
+        if (a.mode == 1) {
+          my_gt = a.gt_score[row];
+          // publish the tile's group ids for the cross-row reduction (all 128 epilogue threads)
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          s_grp[trow] = my_grp;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      const int v0 = n_blk * EV_VPT;             // first local video of this tile
+      uint32_t mask = 0;
+      VideoAcc va;
+      va.reset();
+      va.vsim = 0.f;
+      // walk the 208 columns in order; column c belongs to video c / 13, member c % 13
+      auto consume = [&](float x, int c) {
+        const int mem = c % EV_COLS;
+        const float sx = x * a.scale;
+        if (mem == 0) { va.reset(); va.vsim = sx; } else { va.push(sx, k); }
+        if (mem == EV_COLS - 1) {
+          const int vl = c / EV_COLS;             // video inside the tile
+          const int vloc = v0 + vl;               // local video index
+          const float sc = va.score(k);
+          const bool own = (my_grp == a.video_base + vloc);
+          if (a.mode == 0) {
+            if (own && my_grp >= 0 && vloc < a.Nv_local) a.gt_score[row] = sc;
+          } else if (my_grp >= 0 && vloc < a.Nv_local && !own) {
+            my_cnt += (sc > my_gt) ? 1 : 0;
+            if (sc > a.theta[vloc]) mask |= (1u << vl);
+          }
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < EV_BN / 32; ++c) {
+        float v[32];
+        ptx::tmem_ld_x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) consume(v[j], c * 32 + j);
+      }
+      {
+        float v[16];
+        ptx::tmem_ld_x16(taddr + (EV_BN / 32) * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) consume(v[j], (EV_BN / 32) * 32 + j);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+
+      if (a.mode == 1) {
+        // v2t: count, per video of this tile, the caption GROUPS with at least one hit.
+        // Skip the exchange entirely when no thread of the tile saw a hit (the common case).
+        s_mask[buf][trow] = mask;
+        if (trow < EV_VPT) s_cnt[buf][trow] = 0;
+        const int any = epi_bar_or(mask != 0 ? 1 : 0);
+        if (any) {
+          const bool head = (my_grp >= 0) && (trow == 0 || s_grp[trow - 1] != my_grp);
+          if (head) {
+            uint32_t m = 0;
+            for (int t = trow; t < 128 && s_grp[t] == my_grp; ++t) m |= s_mask[buf][t];
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              atomicAdd(&s_cnt[buf][b], 1);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (trow < EV_VPT) {
+            const int c = s_cnt[buf][trow];
+            if (c != 0 && v0 + trow < a.Nv_local) atomicAdd(&a.v2t_cnt[v0 + trow], c);
+          }
+        }
+        buf ^= 1;
+      }
+    }
+    if (a.mode == 1 && cur_m >= 0) a.t2v_cnt[cur_m * UMMA_BM + trow] = my_cnt;
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ packing
+// texts: packed row i takes source row src_row[i] (or zeros when src_row[i] < 0), L2-normalised without eps
+__global__ void eval_pack_text_kernel(const float* __restrict__ text, const int32_t* __restrict__ src_row, int64_t rows,
+                                      int D, int planes, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t ldp = int64_t(planes) * D;
+  const int sr = src_row[r];
+  if (sr < 0) {
+    for (int d = lane; d < planes * D; d += 32) out[r * ldp + d] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float* x = text + int64_t(sr) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = x[d]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float n = sqrtf(ss);
+  for (int d = lane; d < D; d += 32) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(x[d] / n, hi, lo);
+    out[r * ldp + d] = hi;
+    if (planes == 2) out[r * ldp + D + d] = lo;
+  }
+}
+
+// gallery: row v*(1+F)+0 = video v, rows v*(1+F)+1+f = frame f of video v; rows beyond Nv are zeros
+__global__ void eval_pack_gallery_kernel(const float* __restrict__ video, const float* __restrict__ frames, int64_t Nv,
+                                         int64_t rows_pad, int F, int D, int planes, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_pad) return;
+  const int64_t ldp = int64_t(planes) * D;
+  const int64_t v = r / (1 + F);
+  const int mem = int(r - v * (1 + F));
+  if (v >= Nv) {
+    for (int d = lane; d < planes * D; d += 32) out[r * ldp + d] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float* x = (mem == 0) ? video + v * D : frames + (v * F + (mem - 1)) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float t = x[d]; ss = fmaf(t, t, ss); }
+  ss = warp_sum(ss);
+  const float n = sqrtf(ss);
+  for (int d = lane; d < D; d += 32) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(x[d] / n, hi, lo);
+    out[r * ldp + d] = hi;
+    if (planes == 2) out[r * ldp + D + d] = lo;
+  }
+}
+
+// theta[j] = max over the packed captions of local video j of gt_score (a group's captions are contiguous)
+__global__ void eval_theta_kernel(const float* __restrict__ gt_score, const int32_t* __restrict__ group_start_packed,
+                                  const int32_t* __restrict__ group_count, int Nv_local, float* __restrict__ theta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Nv_local) return;
+  float m = -INFINITY;
+  const int s0 = group_start_packed[j];
+  for (int s = s0; s < s0 + group_count[j]; ++s) m = fmaxf(m, gt_score[s]);
+  theta[j] = m;
+}
+
+}  // namespace hmmc
+
+using namespace hmmc;
+
+extern "C" {
+
+int hmmc_eval_fused_supported(int F, int D, int top_k) {
+  return (F == EV_F && D % UMMA_BK == 0 && top_k >= 1 && top_k <= EV_MAXK) ? 1 : 0;
+}
+
+int hmmc_eval_pack_text(const float* text, const int32_t* src_row, int64_t rows_pad, int D, int prec, void* out,
+                        void* stream) {
+  HMMC_REQUIRE(text && src_row && out && rows_pad > 0 && rows_pad % UMMA_BM == 0, "eval_pack_text: bad arguments");
+  HMMC_REQUIRE(prec == HMMC_PREC_BF16 || prec == HMMC_PREC_BF16X3, "eval_pack_text: tensor-core precisions only");
+  eval_pack_text_kernel<<<unsigned((rows_pad + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      text, src_row, rows_pad, D, planes_of(prec), static_cast<__nv_bfloat16*>(out));
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_eval_pack_gallery(const float* video, const float* frames, int64_t Nv, int F, int D, int prec, void* out,
+                           void* stream) {
+  HMMC_REQUIRE(video && frames && out && Nv > 0, "eval_pack_gallery: bad arguments");
+  HMMC_REQUIRE(F == EV_F, "eval_pack_gallery: the fused path handles F = %d frames (got %d)", EV_F, F);
+  HMMC_REQUIRE(prec == HMMC_PREC_BF16 || prec == HMMC_PREC_BF16X3, "eval_pack_gallery: tensor-core precisions only");
+  const int64_t nblk = (Nv + EV_VPT - 1) / EV_VPT;
+  const int64_t rows_pad = nblk * EV_BN;
+  eval_pack_gallery_kernel<<<unsigned((rows_pad + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      video, frames, Nv, rows_pad, F, D, planes_of(prec), static_cast<__nv_bfloat16*>(out));
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+static int eval_launch(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
+                       int prec, EvalArgs& a, cudaStream_t st) {
+  HMMC_REQUIRE(text_packed && gallery_packed, "eval: null operand");
+  HMMC_REQUIRE(Nt_pad > 0 && Nt_pad % UMMA_BM == 0, "eval: Nt_pad must be a positive multiple of %d", UMMA_BM);
+  HMMC_REQUIRE(D % UMMA_BK == 0, "eval: D %% 64 != 0");
+  HMMC_REQUIRE(prec == HMMC_PREC_BF16 || prec == HMMC_PREC_BF16X3, "eval: tensor-core precisions only");
+  HMMC_REQUIRE(a.top_k >= 1 && a.top_k <= EV_MAXK, "eval: fused path supports 1 <= top_k <= %d", EV_MAXK);
+  const int planes = planes_of(prec);
+  a.num_m_blk = int(Nt_pad / UMMA_BM);
+  a.num_n_blk = int((Nv_local + EV_VPT - 1) / EV_VPT);
+  a.Nv_local = int(Nv_local);
+  GemmShape s;
+  fill_segments(s, planes, D);
+  a.num_seg = s.num_seg;
+  a.kb_per_seg = s.kb_per_seg;
+  for (int i = 0; i < 3; ++i) { a.a_k0[i] = s.a_k0[i]; a.b_k0[i] = s.b_k0[i]; }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, text_packed, uint64_t(Nt_pad), uint64_t(planes) * D, uint64_t(planes) * D, UMMA_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, gallery_packed, uint64_t(a.num_n_blk) * EV_BN, uint64_t(planes) * D, uint64_t(planes) * D, EV_BN);
+  if (rc) return rc;
+  using Cfg = UmmaCfg<EV_BN>;
+  HMMC_CHECK_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+  const int work = (a.mode == 1) ? a.num_m_blk : a.n_diag_tiles;
+  if (work <= 0) return HMMC_OK;
+  const int grid = work < sm_count() ? work : sm_count();
+  eval_rank_kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_eval_gt_scores(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
+                        int prec, float scale, int top_k, int video_base, const int32_t* grp,
+                        const int32_t* diag_tiles, int n_diag_tiles, float* gt_score, void* stream) {
+  HMMC_REQUIRE(grp && gt_score && (n_diag_tiles == 0 || diag_tiles), "eval_gt_scores: null argument");
+  EvalArgs a{};
+  a.scale = scale;
+  a.top_k = top_k;
+  a.mode = 0;
+  a.video_base = video_base;
+  a.grp = grp;
+  a.gt_score = gt_score;
+  a.diag_tiles = reinterpret_cast<const int2*>(diag_tiles);
+  a.n_diag_tiles = n_diag_tiles;
+  return eval_launch(text_packed, gallery_packed, Nt_pad, Nv_local, D, prec, a, static_cast<cudaStream_t>(stream));
+}
+
+int hmmc_eval_theta(const float* gt_score, const int32_t* group_start_packed, const int32_t* group_count, int Nv_local,
+                    float* theta, void* stream) {
+  HMMC_REQUIRE(gt_score && group_start_packed && group_count && theta && Nv_local > 0, "eval_theta: bad arguments");
+  eval_theta_kernel<<<(Nv_local + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      gt_score, group_start_packed, group_count, Nv_local, theta);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_eval_fused_rank(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
+                         int prec, float scale, int top_k, int video_base, const int32_t* grp, const float* gt_score,
+                         const float* theta, int32_t* t2v_cnt, int32_t* v2t_cnt, void* stream) {
+  HMMC_REQUIRE(grp && gt_score && theta && t2v_cnt && v2t_cnt, "eval_fused_rank: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HMMC_CHECK_CUDA(cudaMemsetAsync(v2t_cnt, 0, sizeof(int32_t) * size_t(Nv_local), st));
+  EvalArgs a{};
+  a.scale = scale;
+  a.top_k = top_k;
+  a.mode = 1;
+  a.video_base = video_base;
+  a.grp = grp;
+  a.gt_score = const_cast<float*>(gt_score);
+  a.theta = theta;
+  a.t2v_cnt = t2v_cnt;
+  a.v2t_cnt = v2t_cnt;
+  return eval_launch(text_packed, gallery_packed, Nt_pad, Nv_local, D, prec, a, st);
+}
+
+}  // extern "C"

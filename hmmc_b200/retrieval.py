@@ -61,3 +61,118 @@ def eval_metrics(model, text, video, frames, multi_sentence_=False, cut_off_poin
         return M.t2v_metrics_from_ranks(t2v), M.metrics_from_ranks(v2t)
     t2v, v2t = ops.rank_count(sim)
     return M.metrics_from_ranks(t2v.cpu().numpy()), M.metrics_from_ranks(v2t.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# Large-gallery eval (BASELINE config 5): fused similarity + top-k + rank counting, gallery sharded
+# over the ranks of the process group.  The [Nt, Nv] matrix never exists.
+# ---------------------------------------------------------------------------------------------
+
+def pack_caption_groups(per_video, tile=128):
+    """Lay the captions out group-aligned: the captions of one video are contiguous and never
+    straddle a ``tile``-row boundary.  ``per_video[j]`` = number of captions of video j (captions
+    are ordered by video, as the reference's multi-sentence loaders produce them).
+    Returns (src_row [Nt_pad] int32 with -1 padding, grp [Nt_pad] int32, group_start [Nv] int32)."""
+    per = np.asarray(per_video, dtype=np.int64)
+    if per.size and per.max() > tile:
+        raise ValueError("the fused eval path needs <= %d captions per video (got %d)" % (tile, per.max()))
+    Nv = per.size
+    starts = np.empty(Nv, dtype=np.int64)
+    if Nv and (per == per[0]).all():
+        g = int(per[0])
+        per_tile = tile // g
+        j = np.arange(Nv, dtype=np.int64)
+        starts = (j // per_tile) * tile + (j % per_tile) * g
+    else:
+        pos = 0
+        for j in range(Nv):
+            c = int(per[j])
+            if (pos % tile) + c > tile:
+                pos = (pos // tile + 1) * tile
+            starts[j] = pos
+            pos += c
+    total = int(starts[-1] + per[-1]) if Nv else 0
+    Nt_pad = max(tile, (total + tile - 1) // tile * tile)
+    src_row = np.full(Nt_pad, -1, dtype=np.int32)
+    grp = np.full(Nt_pad, -1, dtype=np.int32)
+    first = np.concatenate([[0], np.cumsum(per)[:-1]]) if Nv else np.zeros(0, np.int64)
+    idx = np.repeat(starts - first, per) + np.arange(int(per.sum()), dtype=np.int64)   # packed position of caption s
+    src_row[idx] = np.arange(int(per.sum()), dtype=np.int32)
+    grp[idx] = np.repeat(np.arange(Nv, dtype=np.int32), per)
+    return src_row, grp, starts.astype(np.int32)
+
+
+def fused_eval_ranks(text, video_local, frames_local, per_video, scale=100.0, top_k=2, precision="bf16",
+                     video_range=None):
+    """Integer ranks of a (possibly sharded) retrieval eval without materialising the matrix.
+
+    text [Nt, D] (replicated on every rank, captions ordered by video), video_local [Nv_loc, D] /
+    frames_local [Nv_loc, F, D] = this rank's gallery shard = videos ``video_range`` (default:
+    parallel.shard_range(Nv)), per_video [Nv] caption counts of ALL videos.
+    Returns (t2v ranks [Nt] int32 tensor, v2t ranks [Nv] int32 tensor), identical on every rank.
+    """
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    prec = ops.resolve_precision(precision)
+    if prec == ops.PREC_FP32:
+        raise ops.HmmcError("fused eval runs on tensor cores: precision must be bf16 or bf16x3")
+    per = np.asarray(per_video, dtype=np.int64)
+    Nv = per.size
+    W, rank = parallel.world()
+    lo, hi = video_range if video_range is not None else parallel.shard_range(Nv, W, rank)
+    text = ops._f32c(text, "text")
+    video_local = ops._f32c(video_local, "video")
+    frames_local = ops._f32c(frames_local, "frames")
+    Nt, D = text.shape
+    F = frames_local.shape[1]
+    Nv_loc = hi - lo
+    assert video_local.shape[0] == Nv_loc and int(per.sum()) == Nt
+    if not lib.hmmc_eval_fused_supported(F, D, int(top_k)):
+        raise ops.HmmcError("fused eval supports F=12, D %% 64 == 0, top_k <= 4 (got F=%d D=%d k=%d)" % (F, D, top_k))
+    dev = text.device
+    planes = 2 if prec == ops.PREC_BF16X3 else 1
+    st = ops._stream
+    src_row, grp, gstart = pack_caption_groups(per)
+    Nt_pad = src_row.size
+    d_src = torch.from_numpy(src_row).to(dev)
+    d_grp = torch.from_numpy(grp).to(dev)
+    tp = torch.empty(Nt_pad, planes * D, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.hmmc_eval_pack_text(ops._p(text), ops._p(d_src), Nt_pad, D, prec, ops._p(tp), st()), "eval_pack_text")
+    n_blk = (Nv_loc + 15) // 16
+    gp = torch.empty(max(n_blk, 1) * 16 * (1 + F), planes * D, dtype=torch.bfloat16, device=dev)
+    gt_score = torch.zeros(Nt_pad, dtype=torch.float32, device=dev)
+    t2v = torch.zeros(Nt_pad, dtype=torch.int32, device=dev)
+    v2t_loc = torch.zeros(max(Nv_loc, 1), dtype=torch.int32, device=dev)
+    if Nv_loc > 0:
+        _lib.check(lib.hmmc_eval_pack_gallery(ops._p(video_local), ops._p(frames_local), Nv_loc, F, D, prec, ops._p(gp),
+                                              st()), "eval_pack_gallery")
+        # diagonal tiles: (caption tile m, gallery tile n) pairs that contain a ground-truth pair of this shard
+        m_of = (gstart[lo:hi].astype(np.int64)) // 128
+        n_of = (np.arange(lo, hi, dtype=np.int64) - lo) // 16
+        pairs = np.unique(np.stack([m_of, n_of], axis=1), axis=0).astype(np.int32)
+        d_pairs = torch.from_numpy(np.ascontiguousarray(pairs)).to(dev)
+        _lib.check(lib.hmmc_eval_gt_scores(ops._p(tp), ops._p(gp), Nt_pad, Nv_loc, D, prec, float(scale), int(top_k),
+                                           int(lo), ops._p(d_grp), ops._p(d_pairs), int(pairs.shape[0]),
+                                           ops._p(gt_score), st()), "eval_gt_scores")
+    parallel.all_reduce_sum_(gt_score)          # each caption's score is produced by exactly one shard
+    if Nv_loc > 0:
+        d_gs = torch.from_numpy(np.ascontiguousarray(gstart[lo:hi])).to(dev)
+        d_gc = torch.from_numpy(per[lo:hi].astype(np.int32)).to(dev)
+        theta = torch.empty(Nv_loc, dtype=torch.float32, device=dev)
+        _lib.check(lib.hmmc_eval_theta(ops._p(gt_score), ops._p(d_gs), ops._p(d_gc), Nv_loc, ops._p(theta), st()),
+                   "eval_theta")
+        _lib.check(lib.hmmc_eval_fused_rank(ops._p(tp), ops._p(gp), Nt_pad, Nv_loc, D, prec, float(scale), int(top_k),
+                                            int(lo), ops._p(d_grp), ops._p(gt_score), ops._p(theta), ops._p(t2v),
+                                            ops._p(v2t_loc), st()), "eval_fused_rank")
+    parallel.all_reduce_sum_(t2v)
+    counts = [parallel.shard_range(Nv, W, r) for r in range(W)] if video_range is None else None
+    if W > 1 and counts is not None:
+        v2t = parallel.all_gather_varlen(v2t_loc[:Nv_loc], [b - a for a, b in counts])
+    else:
+        v2t = v2t_loc[:Nv_loc]
+    valid = torch.from_numpy(np.nonzero(src_row >= 0)[0]).to(dev)
+    order = torch.from_numpy(src_row[src_row >= 0].astype(np.int64)).to(dev)
+    t2v_out = torch.empty(Nt, dtype=torch.int32, device=dev)
+    t2v_out[order] = t2v[valid]
+    return t2v_out, v2t

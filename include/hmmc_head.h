@@ -227,6 +227,33 @@ int hmmc_rank_count(const float* sim, int64_t lds, int Nt, int Nv, const int32_t
                     const int32_t* group_start, int32_t* t2v, int32_t* v2t, float* theta_scratch /* Nv floats */,
                     void* stream);
 
+/* ---- large-gallery eval without materialising the matrix (BASELINE config 5) --------------
+ *   score[s,j] = scale*t_hat_s.v_hat_j + mean top_k_f scale*t_hat_s.f_hat_jf
+ *   t2v_cnt[s] = #{ j != gt(s) : score[s,j] > score[s,gt(s)] }
+ *   v2t_cnt[j] = #{ groups g != j : max_{s in g} score[s,j] > theta_j },  theta_j = max_{s in group j} score[s,j]
+ * i.e. the multi-sentence ranks of metrics.py:49-86 (a square set = one caption per video), for
+ * THIS rank's gallery shard (videos [video_base, video_base + Nv_local)).
+ * Packed operands: texts [Nt_pad, planes*D] bf16, Nt_pad % 128 == 0, packed row i = text
+ * src_row[i] (-1 = zero padding) with the captions of one video contiguous and never straddling a
+ * 128-row tile; gallery [ceil(Nv/16)*16*(1+F), planes*D] with 1+F rows per video.
+ * grp[i] = global video id of packed caption i (-1 = padding).
+ * Driver (hmmc_b200/retrieval.py): pack -> gt_scores on the diagonal tiles -> (all-reduce) ->
+ * theta -> counting sweep -> (all-reduce t2v_cnt). */
+int hmmc_eval_fused_supported(int F, int D, int top_k);
+int hmmc_eval_pack_text(const float* text, const int32_t* src_row, int64_t rows_pad, int D, int prec, void* out,
+                        void* stream);
+int hmmc_eval_pack_gallery(const float* video, const float* frames, int64_t Nv, int F, int D, int prec, void* out,
+                           void* stream);
+int hmmc_eval_gt_scores(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
+                        int prec, float scale, int top_k, int video_base, const int32_t* grp,
+                        const int32_t* diag_tiles /* (m_blk, n_blk) pairs */, int n_diag_tiles, float* gt_score,
+                        void* stream);
+int hmmc_eval_theta(const float* gt_score, const int32_t* group_start_packed, const int32_t* group_count, int Nv_local,
+                    float* theta, void* stream);
+int hmmc_eval_fused_rank(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
+                         int prec, float scale, int top_k, int video_base, const int32_t* grp, const float* gt_score,
+                         const float* theta, int32_t* t2v_cnt, int32_t* v2t_cnt, void* stream);
+
 /* tensor_video_to_text_sim (metrics.py:79-86): out[j, g] = max_{s in group g} sim[s, j]
  * (NaN -> -inf); out is [Nv, G] row-major, G < 65536. */
 int hmmc_group_max(const float* sim, int64_t lds, int Nv, int G, const int32_t* group_start, float* out,
