@@ -5,6 +5,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace hmmc {
 
@@ -180,6 +181,8 @@ int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, floa
                     int64_t split_stride, int M, int N, int K, int planes, int splits, float alpha,
                     cudaStream_t st) {
   EpiStoreF32::Params ep{C, ldc, split_stride, alpha};
+  static const char* force = getenv("HMMC_FORCE_BN");   // tuning aid (tools/gemm_bench.py)
+  if (force != nullptr && atoi(force) == 128) return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
   if (N % 256 == 0 || N > 1024) return launch_umma_gemm<256, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
   return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
 }

@@ -39,7 +39,9 @@ struct UmmaCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;
-  static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t EPI_STAGE_BYTES = 32 * 144;   // per epilogue warp: 32 rows x (128 + 16 pad) bytes
+  static constexpr size_t SMEM_BYTES =
+      size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -185,6 +187,10 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi;
+    // per-warp staging buffer: accumulator rows go through shared memory so that global stores
+    // are whole 64/128-byte row segments instead of 16 bytes per thread on 32 different lines
+    epi.stage = smem + size_t(STAGES) * Cfg::STAGE_BYTES + 256 + size_t(quad) * Cfg::EPI_STAGE_BYTES;
+    epi.lane = lane;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int p = find_problem(g, t);
       const GemmShape& s = g.shape[p];
@@ -238,28 +244,49 @@ struct EpiStoreF32 {
     int64_t split_stride;
     float alpha;
   };
-  float* out;
+  uint8_t* stage;
+  int lane;
+  float* tile_out;   // &C[split][row of lane 0 of this warp, 0]
+  int row0;
+  bool vec_ok;
   __device__ __forceinline__ void begin_tile(const Params& p, const GemmShape& s, int row, int n_blk, int split) {
-    out = p.C + int64_t(split) * p.split_stride + int64_t(row) * p.ldc;
+    row0 = row - lane;
+    tile_out = p.C + int64_t(split) * p.split_stride + int64_t(row0) * p.ldc;
+    vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.split_stride & 3) == 0);
   }
   __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
-    if (row >= s.M) return;
-    if (col0 + 32 <= s.N && (p.ldc & 3) == 0) {
-      float4* o = reinterpret_cast<float4*>(out + col0);
+    float* st = reinterpret_cast<float*>(stage);
+    float4* srow = reinterpret_cast<float4*>(st + lane * 36);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha, v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
-    } else {
+    for (int j = 0; j < 8; ++j)
+      srow[j] = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha, v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
+    __syncwarp();
+    const int c4 = (lane & 7) * 4;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < s.N) out[col0 + j] = v[j] * p.alpha;
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const float4 x = *reinterpret_cast<const float4*>(st + r * 36 + c4);
+      const int grow = row0 + r, gcol = col0 + c4;
+      if (grow < s.M) {
+        float* o = tile_out + int64_t(r) * p.ldc + gcol;
+        if (vec_ok && gcol + 3 < s.N) {
+          *reinterpret_cast<float4*>(o) = x;
+        } else {
+          if (gcol < s.N) o[0] = x.x;
+          if (gcol + 1 < s.N) o[1] = x.y;
+          if (gcol + 2 < s.N) o[2] = x.z;
+          if (gcol + 3 < s.N) o[3] = x.w;
+        }
+      }
     }
+    __syncwarp();
   }
   __device__ __forceinline__ void chunk16(const Params& p, const GemmShape& s, int row, int col0, float (&v)[16]) {
     if (row >= s.M) return;
+    float* o = tile_out + int64_t(lane) * p.ldc;
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < s.N) out[col0 + j] = v[j] * p.alpha;
+      if (col0 + j < s.N) o[col0 + j] = v[j] * p.alpha;
   }
   __device__ __forceinline__ void end_tile(const Params&, const GemmShape&, int, int, int) {}
 };
@@ -275,8 +302,30 @@ struct EpiInfoNCE {
     int64_t ldE;
     int e_planes;
   };
+  uint8_t* stage;
+  int lane;
   float acc_sum;
-  __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int, int, int) { acc_sum = 0.f; }
+  int row0;
+  __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int row, int, int) {
+    acc_sum = 0.f;
+    row0 = row - lane;
+  }
+  // write one bf16 plane of this warp's 32 x 32 chunk: rows staged at an 80-byte pitch, then each
+  // instruction stores eight 64-byte row segments
+  __device__ __forceinline__ void store_plane(const uint32_t (&w)[16], __nv_bfloat16* base, int64_t ldE, int col0, int M) {
+    uint4* srow = reinterpret_cast<uint4*>(stage + lane * 80);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) srow[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    __syncwarp();
+    const int c = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + (lane >> 2);
+      const uint4 x = *reinterpret_cast<const uint4*>(stage + r * 80 + c * 16);
+      if (row0 + r < M) *reinterpret_cast<uint4*>(base + int64_t(row0 + r) * ldE + col0 + c * 8) = x;
+    }
+    __syncwarp();
+  }
   __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
     float e[32];
 #pragma unroll
@@ -285,17 +334,14 @@ struct EpiInfoNCE {
       if (col0 + j >= s.N) e[j] = 0.f;
       acc_sum += e[j];
     }
-    if (p.E != nullptr && row < s.M && col0 + 32 <= s.N) {
-      __nv_bfloat16* dst = p.E + int64_t(row) * p.ldE + col0;
+    if (p.E != nullptr && col0 + 32 <= s.N) {     // warp-uniform
       uint32_t hi[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
         hi[j] = *reinterpret_cast<uint32_t*>(&h);
       }
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) d4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      store_plane(hi, p.E, p.ldE, col0, s.M);
       if (p.e_planes == 2) {
         uint32_t lo[16];
 #pragma unroll
@@ -304,9 +350,7 @@ struct EpiInfoNCE {
           __nv_bfloat162 l = __floats2bfloat162_rn(e[2 * j] - __low2float(h), e[2 * j + 1] - __high2float(h));
           lo[j] = *reinterpret_cast<uint32_t*>(&l);
         }
-        uint4* l4 = reinterpret_cast<uint4*>(dst + s.N);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        store_plane(lo, p.E + s.N, p.ldE, col0, s.M);
       }
     }
   }
