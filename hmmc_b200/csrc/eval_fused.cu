@@ -39,20 +39,20 @@ struct EvalArgs {
   const int32_t* grp;             // [Nt_pad] global video id each packed caption belongs to, -1 = padding
   float* gt_score;                // [Nt_pad] score[s, gt(s)] (mode 0 writes, mode 1 reads)
   const float* theta;             // [Nv_local] (mode 1)
-  int32_t* t2v_cnt;               // [Nt_pad] (mode 1, plain store)
+  int32_t* t2v_cnt;               // [Nt_pad] (mode 1, one atomic per row half per caption tile)
   int32_t* v2t_cnt;               // [Nv_local] (mode 1, atomics)
   const int2* diag_tiles;         // mode 0: (m_blk, n_blk) pairs
   int n_diag_tiles;
 };
 
-// OR-reduction of a predicate over the 128 epilogue threads (named barrier 1); also a barrier.
+// OR-reduction of a predicate over the 256 epilogue threads (named barrier 1); also a barrier.
 __device__ __forceinline__ int epi_bar_or(int pred) {
   int r;
   asm volatile(
       "{\n\t"
       ".reg .pred p, q;\n\t"
       "setp.ne.b32 p, %1, 0;\n\t"
-      "bar.red.or.pred q, 1, 128, p;\n\t"
+      "bar.red.or.pred q, 1, 256, p;\n\t"
       "selp.b32 %0, 1, 0, q;\n\t"
       "}\n"
       : "=r"(r)
@@ -61,29 +61,39 @@ __device__ __forceinline__ int epi_bar_or(int pred) {
   return r;
 }
 
-// finalise one video from its 13 accumulator values
+// running top-K of a video's frame similarities: branch-free insertion with min/max
+template <int K>
 struct VideoAcc {
   float vsim;
-  float best[EV_MAXK];
+  float best[K];
   __device__ __forceinline__ void reset() {
 #pragma unroll
-    for (int i = 0; i < EV_MAXK; ++i) best[i] = -INFINITY;
+    for (int i = 0; i < K; ++i) best[i] = -INFINITY;
   }
-  __device__ __forceinline__ void push(float x, int k) {
+  __device__ __forceinline__ void push(float x) {
 #pragma unroll
-    for (int i = 0; i < EV_MAXK; ++i) {
-      if (i < k && x > best[i]) { const float t = best[i]; best[i] = x; x = t; }
+    for (int i = 0; i < K; ++i) {
+      const float lo = fminf(best[i], x);
+      best[i] = fmaxf(best[i], x);
+      x = lo;
     }
   }
-  __device__ __forceinline__ float score(int k) const {
+  // scale > 0 commutes with max and mean: one multiply per video instead of one per column
+  __device__ __forceinline__ float score(float scale) const {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < EV_MAXK; ++i) if (i < k) s += best[i];
-    return vsim + s / float(k);
+    for (int i = 0; i < K; ++i) s += best[i] * scale;        // descending order, like torch.topk(...).mean
+    return vsim * scale + s / float(K);
   }
 };
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int EV_EPI_WARPS = 8;
+constexpr int EV_THREADS = (4 + EV_EPI_WARPS) * 32;
+constexpr int EV_HALF_COLS = EV_BN / 2;      // 104 columns = 8 videos per epilogue warp
+constexpr int EV_HALF_VID = EV_VPT / 2;
+
+template <int K>
+__global__ void __launch_bounds__(EV_THREADS, 1)
 eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ EvalArgs a) {
   using Cfg = UmmaCfg<EV_BN>;
@@ -99,7 +109,7 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   // epilogue scratch: per-row hit masks (double buffered), group ids, per-tile video counters
-  __shared__ uint32_t s_mask[2][128];
+  __shared__ uint32_t s_mask[2][2][128];     // [buffer][column half][row]
   __shared__ int32_t s_grp[128];
   __shared__ int32_t s_cnt[2][EV_VPT];
 
@@ -117,7 +127,7 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar(i), 1);
-      ptx::mbar_init(tempty_bar(i), 4);
+      ptx::mbar_init(tempty_bar(i), EV_EPI_WARPS);
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -198,7 +208,8 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;
-    const int trow = quad * 32 + lane;          // row inside the tile = epilogue thread id
+    const int half = (warp - 4) >> 2;           // videos [8*half, 8*half+8) of each tile
+    const int trow = quad * 32 + lane;          // row inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_m = -1;
@@ -206,41 +217,39 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float my_gt = 0.f;
     int my_cnt = 0;
     int buf = 0;
-    const int k = a.top_k;
     for (long long i = 0; i < tiles_per_cta; ++i) {
       int m_blk, n_blk;
       tile_of(i, m_blk, n_blk);
       const int row = m_blk * UMMA_BM + trow;
       if (m_blk != cur_m) {
-        if (a.mode == 1 && cur_m >= 0) a.t2v_cnt[cur_m * UMMA_BM + trow] = my_cnt;
+        if (a.mode == 1 && cur_m >= 0 && my_cnt != 0) atomicAdd(&a.t2v_cnt[cur_m * UMMA_BM + trow], my_cnt);
         cur_m = m_blk;
         my_cnt = 0;
         my_grp = a.grp[row];
         if (a.mode == 1) {
           my_gt = a.gt_score[row];
-          // publish the tile's group ids for the cross-row reduction (all 128 epilogue threads)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          s_grp[trow] = my_grp;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          // publish the tile's group ids for the cross-row reduction (all 256 epilogue threads)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0) s_grp[trow] = my_grp;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
       }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      const int v0 = n_blk * EV_VPT;             // first local video of this tile
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * EV_HALF_COLS;
+      const int v0 = n_blk * EV_VPT + half * EV_HALF_VID;     // first local video of this warp's columns
       uint32_t mask = 0;
-      VideoAcc va;
+      VideoAcc<K> va;
       va.reset();
       va.vsim = 0.f;
-      // walk the 208 columns in order; column c belongs to video c / 13, member c % 13
+      // walk this warp's 104 columns in order; local column c belongs to video c / 13, member c % 13
       auto consume = [&](float x, int c) {
         const int mem = c % EV_COLS;
-        const float sx = x * a.scale;
-        if (mem == 0) { va.reset(); va.vsim = sx; } else { va.push(sx, k); }
+        if (mem == 0) { va.reset(); va.vsim = x; } else { va.push(x); }
         if (mem == EV_COLS - 1) {
-          const int vl = c / EV_COLS;             // video inside the tile
+          const int vl = c / EV_COLS;             // video inside this warp's half
           const int vloc = v0 + vl;               // local video index
-          const float sc = va.score(k);
+          const float sc = va.score(a.scale);
           const bool own = (my_grp == a.video_base + vloc);
           if (a.mode == 0) {
             if (own && my_grp >= 0 && vloc < a.Nv_local) a.gt_score[row] = sc;
@@ -251,7 +260,7 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
 #pragma unroll
-      for (int c = 0; c < EV_BN / 32; ++c) {
+      for (int c = 0; c < EV_HALF_COLS / 32; ++c) {
         float v[32];
         ptx::tmem_ld_x32(taddr + c * 32, v);
         ptx::tmem_ld_wait();
@@ -259,11 +268,11 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 32; ++j) consume(v[j], c * 32 + j);
       }
       {
-        float v[16];
-        ptx::tmem_ld_x16(taddr + (EV_BN / 32) * 32, v);
+        float v[8];
+        ptx::tmem_ld_x8(taddr + (EV_HALF_COLS / 32) * 32, v);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) consume(v[j], (EV_BN / 32) * 32 + j);
+        for (int j = 0; j < 8; ++j) consume(v[j], (EV_HALF_COLS / 32) * 32 + j);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -273,30 +282,32 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (a.mode == 1) {
         // v2t: count, per video of this tile, the caption GROUPS with at least one hit.
         // Skip the exchange entirely when no thread of the tile saw a hit (the common case).
-        s_mask[buf][trow] = mask;
-        if (trow < EV_VPT) s_cnt[buf][trow] = 0;
+        s_mask[buf][half][trow] = mask;
+        if (half == 0 && trow < EV_VPT) s_cnt[buf][trow] = 0;
         const int any = epi_bar_or(mask != 0 ? 1 : 0);
         if (any) {
-          const bool head = (my_grp >= 0) && (trow == 0 || s_grp[trow - 1] != my_grp);
+          const bool head = (half == 0) && (my_grp >= 0) && (trow == 0 || s_grp[trow - 1] != my_grp);
           if (head) {
             uint32_t m = 0;
-            for (int t = trow; t < 128 && s_grp[t] == my_grp; ++t) m |= s_mask[buf][t];
+            for (int t = trow; t < 128 && s_grp[t] == my_grp; ++t)
+              m |= s_mask[buf][0][t] | (s_mask[buf][1][t] << EV_HALF_VID);
             while (m) {
               const int b = __ffs(m) - 1;
               m &= m - 1;
               atomicAdd(&s_cnt[buf][b], 1);
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (trow < EV_VPT) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0 && trow < EV_VPT) {
             const int c = s_cnt[buf][trow];
-            if (c != 0 && v0 + trow < a.Nv_local) atomicAdd(&a.v2t_cnt[v0 + trow], c);
+            const int vloc = n_blk * EV_VPT + trow;
+            if (c != 0 && vloc < a.Nv_local) atomicAdd(&a.v2t_cnt[vloc], c);
           }
         }
         buf ^= 1;
       }
     }
-    if (a.mode == 1 && cur_m >= 0) a.t2v_cnt[cur_m * UMMA_BM + trow] = my_cnt;
+    if (a.mode == 1 && cur_m >= 0 && my_cnt != 0) atomicAdd(&a.t2v_cnt[cur_m * UMMA_BM + trow], my_cnt);
   }
 
   ptx::tc_fence_before();
@@ -425,13 +436,21 @@ static int eval_launch(const void* text_packed, const void* gallery_packed, int6
   rc = make_tmap_bf16(&tmB, gallery_packed, uint64_t(a.num_n_blk) * EV_BN, uint64_t(planes) * D, uint64_t(planes) * D, EV_BN);
   if (rc) return rc;
   using Cfg = UmmaCfg<EV_BN>;
-  HMMC_CHECK_CUDA(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
   const int work = (a.mode == 1) ? a.num_m_blk : a.n_diag_tiles;
   if (work <= 0) return HMMC_OK;
   const int grid = work < sm_count() ? work : sm_count();
-  eval_rank_kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
-  HMMC_CHECK_LAUNCH();
-  return HMMC_OK;
+  auto launch = [&](auto kern) -> int {
+    HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    kern<<<grid, EV_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
+    HMMC_CHECK_LAUNCH();
+    return HMMC_OK;
+  };
+  switch (a.top_k) {
+    case 1: return launch(eval_rank_kernel<1>);
+    case 2: return launch(eval_rank_kernel<2>);
+    case 3: return launch(eval_rank_kernel<3>);
+    default: return launch(eval_rank_kernel<4>);
+  }
 }
 
 int hmmc_eval_gt_scores(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
@@ -465,6 +484,7 @@ int hmmc_eval_fused_rank(const void* text_packed, const void* gallery_packed, in
   HMMC_REQUIRE(grp && gt_score && theta && t2v_cnt && v2t_cnt, "eval_fused_rank: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HMMC_CHECK_CUDA(cudaMemsetAsync(v2t_cnt, 0, sizeof(int32_t) * size_t(Nv_local), st));
+  HMMC_CHECK_CUDA(cudaMemsetAsync(t2v_cnt, 0, sizeof(int32_t) * size_t(Nt_pad), st));
   EvalArgs a{};
   a.scale = scale;
   a.top_k = top_k;

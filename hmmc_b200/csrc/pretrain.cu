@@ -570,7 +570,7 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
       L.rowsum_part[k] = ws.take<float>(size_t(R));
       L.E[k] = ws.take<float>(size_t(R) * Kq);
     } else {
-      L.nparts[k] = (Kq + L.bn1 - 1) / L.bn1;
+      L.nparts[k] = 2 * ((Kq + L.bn1 - 1) / L.bn1);     // two epilogue halves per tile
       const int total_kb = nseg * (Kq / UMMA_BK);
       int sp = (total_kb + unit_kb - 1) / unit_kb;
       if (sp > 32) sp = 32;

@@ -4,7 +4,8 @@
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma, M=128 x N=BN x K=16, fp32 accumulators in TMEM)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue      (tcgen05.ld: one accumulator row per thread -> fused epilogue)
+//   warps 4..11   : epilogue      (tcgen05.ld: one accumulator row per thread -> fused epilogue;
+//                                  two warps per TMEM lane quadrant, each takes half of the columns)
 // Two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // The K loop runs over up to three "segments" (pairs of K offsets into the plane-packed
@@ -30,6 +31,8 @@ struct GemmShape {
 
 constexpr int UMMA_BM = 128;
 constexpr int UMMA_BK = 64;
+constexpr int UMMA_EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, half the columns each
+constexpr int UMMA_THREADS = (4 + UMMA_EPI_WARPS) * 32;
 
 template <int BN>
 struct UmmaCfg {
@@ -39,9 +42,9 @@ struct UmmaCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;
-  static constexpr uint32_t EPI_STAGE_BYTES = 32 * 144;   // per epilogue warp: 32 rows x (128 + 16 pad) bytes
+  static constexpr uint32_t EPI_STAGE_BYTES = 32 * 80;    // per epilogue warp: 32 rows x (64 + 16 pad) bytes
   static constexpr size_t SMEM_BYTES =
-      size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * EPI_STAGE_BYTES;
+      size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + UMMA_EPI_WARPS * EPI_STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -74,7 +77,7 @@ __device__ __forceinline__ int find_problem(const GroupedArgs<Epi>& g, int t) {
 }
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ GroupedArgs<Epi> g) {
   using Cfg = UmmaCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -105,7 +108,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar(i), 1);
-      ptx::mbar_init(tempty_bar(i), 4);   // one arrival per epilogue warp
+      ptx::mbar_init(tempty_bar(i), UMMA_EPI_WARPS);   // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -184,12 +187,15 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;           // which half of the tile's columns
+    constexpr int HALF_N = BN / 2;
+    static_assert(HALF_N % 32 == 0, "epilogue halves must be whole 32-column chunks");
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi;
     // per-warp staging buffer: accumulator rows go through shared memory so that global stores
-    // are whole 64/128-byte row segments instead of 16 bytes per thread on 32 different lines
-    epi.stage = smem + size_t(STAGES) * Cfg::STAGE_BYTES + 256 + size_t(quad) * Cfg::EPI_STAGE_BYTES;
+    // are whole 64-byte row segments instead of 16 bytes per thread on 32 different lines
+    epi.stage = smem + size_t(STAGES) * Cfg::STAGE_BYTES + 256 + size_t(warp - 4) * Cfg::EPI_STAGE_BYTES;
     epi.lane = lane;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int p = find_problem(g, t);
@@ -203,25 +209,19 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
       const int row = m_blk * UMMA_BM + quad * 32 + lane;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * HALF_N;
       epi.begin_tile(ep, s, row, n_blk, split);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < HALF_N / 32; ++c) {
         float v[32];
         ptx::tmem_ld_x32(taddr + c * 32, v);
         ptx::tmem_ld_wait();
-        epi.chunk(ep, s, row, n_blk * BN + c * 32, v);
-      }
-      if constexpr (BN % 32 != 0) {
-        float v[16];
-        ptx::tmem_ld_x16(taddr + (BN / 32) * 32, v);
-        ptx::tmem_ld_wait();
-        epi.chunk16(ep, s, row, n_blk * BN + (BN / 32) * 32, v);
+        epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
-      epi.end_tile(ep, s, row, n_blk, split);
+      epi.end_tile(ep, s, row, n_blk * 2 + half, split);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -255,31 +255,36 @@ struct EpiStoreF32 {
     vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.split_stride & 3) == 0);
   }
   __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
-    float* st = reinterpret_cast<float*>(stage);
-    float4* srow = reinterpret_cast<float4*>(st + lane * 36);
+    // two 16-column halves: rows staged at an 80-byte pitch, then each instruction stores eight
+    // 64-byte row segments
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      srow[j] = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha, v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
-    __syncwarp();
-    const int c4 = (lane & 7) * 4;
+    for (int h = 0; h < 2; ++h) {
+      float4* srow = reinterpret_cast<float4*>(stage + lane * 80);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = i * 4 + (lane >> 3);
-      const float4 x = *reinterpret_cast<const float4*>(st + r * 36 + c4);
-      const int grow = row0 + r, gcol = col0 + c4;
-      if (grow < s.M) {
-        float* o = tile_out + int64_t(r) * p.ldc + gcol;
-        if (vec_ok && gcol + 3 < s.N) {
-          *reinterpret_cast<float4*>(o) = x;
-        } else {
-          if (gcol < s.N) o[0] = x.x;
-          if (gcol + 1 < s.N) o[1] = x.y;
-          if (gcol + 2 < s.N) o[2] = x.z;
-          if (gcol + 3 < s.N) o[3] = x.w;
+      for (int j = 0; j < 4; ++j)
+        srow[j] = make_float4(v[16 * h + 4 * j] * p.alpha, v[16 * h + 4 * j + 1] * p.alpha,
+                              v[16 * h + 4 * j + 2] * p.alpha, v[16 * h + 4 * j + 3] * p.alpha);
+      __syncwarp();
+      const int c4 = (lane & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        const float4 x = *reinterpret_cast<const float4*>(stage + r * 80 + c4 * 4);
+        const int grow = row0 + r, gcol = col0 + 16 * h + c4;
+        if (grow < s.M) {
+          float* o = tile_out + int64_t(r) * p.ldc + gcol;
+          if (vec_ok && gcol + 3 < s.N) {
+            *reinterpret_cast<float4*>(o) = x;
+          } else {
+            if (gcol < s.N) o[0] = x.x;
+            if (gcol + 1 < s.N) o[1] = x.y;
+            if (gcol + 2 < s.N) o[2] = x.z;
+            if (gcol + 3 < s.N) o[3] = x.w;
+          }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
   __device__ __forceinline__ void chunk16(const Params& p, const GemmShape& s, int row, int col0, float (&v)[16]) {
     if (row >= s.M) return;
@@ -292,12 +297,12 @@ struct EpiStoreF32 {
 };
 
 // InfoNCE negatives: e = exp2(acc*a2 - c2)  (= exp(l - c) with a2 = log2(e)/T, c2 = c*log2(e));
-// per-row partial sums -> rowsum_part[n_blk][row]; optional bf16 hi(/lo) planes of e -> E.
+// per-row partial sums -> rowsum_part[2*n_blk + half][row]; optional bf16 hi(/lo) planes of e -> E.
 // No logits are written.
 struct EpiInfoNCE {
   struct Params {
     float a2, c2;
-    float* rowsum_part;       // [num_n_blk, M]
+    float* rowsum_part;       // [2 * num_n_blk, M]: one partial per epilogue half-tile
     __nv_bfloat16* E;         // [M, e_planes * N] or nullptr
     int64_t ldE;
     int e_planes;
@@ -436,7 +441,7 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
   HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
   const int tiles = g.tile_begin[g.num_problems];
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tm, g);
+  kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, g);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
