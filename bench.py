@@ -193,8 +193,8 @@ def gallery_data(Nv, cap, D, F, lo, hi, dev):
         if a < c:
             acc = t.view(b1 - b0, cap, D).sum(1) / cap ** 0.5
             fr = torch.randn(b1 - b0, F, D, device=dev, generator=g)
-            V[a - lo:c - lo] = (v + 0.15 * acc)[a - b0:c - b0]
-            Fr[a - lo:c - lo] = (fr + 0.10 * acc[:, None, :])[a - b0:c - b0]
+            V[a - lo:c - lo] = (v + 1.5 * acc)[a - b0:c - b0]          # strong enough to stand out of 1e5 distractors
+            Fr[a - lo:c - lo] = (fr + 1.0 * acc[:, None, :])[a - b0:c - b0]
     return T, V, Fr
 
 
@@ -402,8 +402,26 @@ def main():
     barrier()
     s0, s1 = ev(), ev()
     s0.record()
-    for _ in range(e2e_steps):
-        ins = {n: host[n].to(dev, non_blocking=True).requires_grad_(n in q_names) for n in order}
+    copy_stream = torch.cuda.Stream()
+
+    def upload():
+        # this step's inputs, host (pinned) -> device, on a side stream so the copy of step i+1
+        # overlaps the kernels of step i (a data loader's prefetch); the compute stream waits for it
+        with torch.cuda.stream(copy_stream):
+            t = {n: host[n].to(dev, non_blocking=True) for n in order}
+            e = torch.cuda.Event()
+            e.record(copy_stream)
+        return t, e
+
+    nxt = upload()
+    for i in range(e2e_steps):
+        cur, ready = nxt
+        if i + 1 < e2e_steps:
+            nxt = upload()
+        torch.cuda.current_stream().wait_event(ready)
+        ins = {n: cur[n].requires_grad_(n in q_names) for n in order}
+        for t in cur.values():
+            t.record_stream(torch.cuda.current_stream())
         loss = step(ins, False)
         loss_host.copy_(loss.detach(), non_blocking=False)      # the reference reads float(loss) every step
     s1.record()
@@ -445,7 +463,9 @@ def main():
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "ema_multi_kernel", "bound": "hbm", "achieved": ema_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ema_gbs / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": ema_gbs / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_head_kernels.md
+                         "traffic": 1378661000 + 646582528,
                          "algorithmic_bytes": ema_bytes, "ms": ms_ema, "peak_source": peak_src},
             "roofline_head": {"kernels": "infonce fwd+bwd (5 query blocks: rownorm_pack, umma S-GEMM+exp epilogue, "
                                          "umma U-GEMM, finish, reduce) + pack + enqueue",

@@ -152,23 +152,27 @@ class ContrastiveHeadMixin:
                 self.queue_frame_cross_ng, self.queue_frame_proj_ng]
 
     @torch.no_grad()
-    def _dequeue_and_enqueue(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+    def _gather_keys_async(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+        """Start the exchange of _dequeue_and_enqueue (modules/modeling.py:249-258): ONE packed
+        all-gather instead of five.  Returns a handle for _enqueue_gathered."""
         b = v_fea_k.shape[0]
         D = v_fea_k.shape[-1]
         frame_fea_k = frame_fea_k.reshape(b, -1, D)
         frame_proj_k = frame_proj_k.reshape(b, -1, D)
         F = frame_fea_k.shape[1]
-        K = self.contrast_num_negative
         W, _ = parallel.world()
-        direct = gathered = None
+        keys = [v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k]
         if W == 1:
-            direct = [ops._f32c(t, "key") for t in (v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D),
-                                                    title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k)]
-        else:
-            # one packed all-gather instead of five (the only exchange of the pre-train head)
-            send = ops.pack_rows([v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D), title_fea_k.reshape(b, D),
-                                  frame_fea_k, frame_proj_k])
-            gathered = parallel.all_gather_rows(send)
+            return (W, b, F, D, [ops._f32c(t, "key") for t in keys], None, lambda: None)
+        send = ops.pack_rows(keys)
+        gathered, wait = parallel.all_gather_rows_async(send)
+        return (W, b, F, D, None, gathered, wait)
+
+    @torch.no_grad()
+    def _enqueue_gathered(self, handle):
+        W, b, F, D, direct, gathered, wait = handle
+        K = self.contrast_num_negative
+        wait()
         ver = self.queue_ptr._version
         if getattr(self, "_hmmc_ptr", None) is None or self._hmmc_ptr[1] != ver:
             self._hmmc_ptr = (int(self.queue_ptr), ver)        # one sync, then tracked on the host
@@ -176,6 +180,10 @@ class ContrastiveHeadMixin:
         ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, ptr, K,
                     ops.resolve_precision(self.head_precision), direct=direct)
         self._hmmc_ptr = ((ptr + W * b) % K, self.queue_ptr._version)
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+        self._enqueue_gathered(self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k))
 
 
 def _register_queues(mod, D, K, F):
@@ -228,6 +236,8 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
         """modules/modeling.py:385-424 for dataset != "bird" (the only reachable branch)."""
         b = v_fea.shape[0]
         D = v_fea.shape[-1]
+        # the key exchange does not depend on the loss: start it first, enqueue after the loss kernels
+        pending = self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         total, parts = ops.pretrain_head(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
                                          v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k,
                                          self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
@@ -235,7 +245,7 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
                                          self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
                                          self.head_precision)
         self.last_loss_parts = parts            # [FAM, VTM, FTM], device tensor (the reference logs them)
-        self._dequeue_and_enqueue(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+        self._enqueue_gathered(pending)
         if loss_MLM is None:
             return total
         return total + self.weight_MLM * loss_MLM

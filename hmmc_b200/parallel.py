@@ -74,6 +74,21 @@ def all_gather_rows(x):
     return out
 
 
+@torch.no_grad()
+def all_gather_rows_async(x):
+    """Start the all-gather of a [b, w] block and return (out, wait): the collective runs on
+    NCCL's stream while the caller keeps launching kernels; call wait() before reading out."""
+    W, _ = world()
+    if W == 1:
+        return x, (lambda: None)
+    out = x.new_empty((W * x.shape[0],) + tuple(x.shape[1:]))
+    try:
+        work = dist.all_gather_into_tensor(out, x.contiguous(), async_op=True)
+    except (RuntimeError, NotImplementedError):
+        work = dist.all_gather(list(out.chunk(W, dim=0)), x.contiguous(), async_op=True)
+    return out, work.wait
+
+
 def shard_range(n, W=None, r=None):
     """Contiguous [begin, end) slice of n items owned by rank r (gallery / text sharding)."""
     if W is None:
