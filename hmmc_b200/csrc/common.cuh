@@ -123,4 +123,9 @@ int rownorm_pack(const float* x, int64_t R, int D, int64_t ldx, float eps, int p
 int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                     int64_t split_stride, int M, int N, int K, int planes, int splits, float alpha,
                     cudaStream_t st);
+// number of split-K partials umma_gemm_store(splits) really writes
+int umma_effective_splits(int K, int planes, int splits);
+// src [rows, cols] fp32 -> straight [rows, planes*cols] and transposed [cols, planes*rows] bf16 plane
+// packs (either output may be null); defined in pretrain.cu
+int pack_dual(const float* src, int rows, int cols, int planes, void* straight, void* transposed, cudaStream_t st);
 }  // namespace hmmc

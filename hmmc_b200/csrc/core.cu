@@ -187,6 +187,8 @@ int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, floa
   return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
 }
 
+int umma_effective_splits(int K, int planes, int splits) { return effective_splits(K, planes, splits); }
+
 }  // namespace hmmc
 
 using namespace hmmc;

@@ -38,6 +38,16 @@ __global__ void queue_pack_kernel(const float* __restrict__ dk, __nv_bfloat16* _
   }
 }
 
+int pack_dual(const float* src, int rows, int cols, int planes, void* straight, void* transposed, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return HMMC_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  // queue_pack_kernel with dk = src (D = rows, Kq = cols): pack_dk = straight, pack_kd = transposed
+  queue_pack_kernel<<<grid, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(transposed),
+                                          static_cast<__nv_bfloat16*>(straight), rows, cols, planes);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
 // ------------------------------------------------------------------ FP32 path helpers
 // E = exp(S/T - c) in place, row sums -> rowsum[r]
 __global__ void exp_rowsum_kernel(float* __restrict__ S, int64_t lds, int Kq, float invT, float c,
