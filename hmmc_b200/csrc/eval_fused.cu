@@ -43,6 +43,7 @@ struct EvalArgs {
   int32_t* v2t_cnt;               // [Nv_local] (mode 1, atomics)
   const int2* diag_tiles;         // mode 0: (m_blk, n_blk) pairs
   int n_diag_tiles;
+  int panel_n_blk;                // mode 1: gallery tiles per L2-resident panel
 };
 
 // OR-reduction of a predicate over the 256 epilogue threads (named barrier 1); also a barrier.
@@ -143,15 +144,33 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int total_kb = a.num_seg * a.kb_per_seg;
   // tile enumeration shared by the three roles
-  //   mode 1: for (m = blockIdx.x; m < num_m_blk; m += gridDim.x) for (n = 0; n < num_n_blk; ++n)
+  //   mode 1: the gallery is swept in panels small enough to stay in L2 while every CTA runs all
+  //           of its caption tiles against the panel:
+  //             for (panel) for (m = blockIdx.x; m < num_m_blk; m += gridDim.x) for (n in panel)
   //   mode 0: for (t = blockIdx.x; t < n_diag_tiles; t += gridDim.x) (m, n) = diag_tiles[t]
+  const int my_m = (a.num_m_blk - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   const long long tiles_per_cta =
-      (a.mode == 1) ? (long long)((a.num_m_blk - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x)) * a.num_n_blk
+      (a.mode == 1) ? (long long)my_m * a.num_n_blk
                     : (long long)((a.n_diag_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x));
+  const int NP = a.panel_n_blk;
+  const long long full_span = (long long)my_m * NP * (a.num_n_blk / (NP > 0 ? NP : 1));
+  const int rem_n = (NP > 0) ? a.num_n_blk % NP : 0;
   auto tile_of = [&](long long i, int& m_blk, int& n_blk) {
     if (a.mode == 1) {
-      m_blk = int(blockIdx.x) + int(i / a.num_n_blk) * int(gridDim.x);
-      n_blk = int(i % a.num_n_blk);
+      int mi, nj;
+      if (i < full_span) {
+        const long long per_panel = (long long)my_m * NP;
+        const int pnl = int(i / per_panel);
+        const int r = int(i - pnl * per_panel);
+        mi = r / NP;
+        nj = pnl * NP + (r - mi * NP);
+      } else {
+        const int r = int(i - full_span);
+        mi = r / rem_n;
+        nj = (a.num_n_blk - rem_n) + (r - mi * rem_n);
+      }
+      m_blk = int(blockIdx.x) + mi * int(gridDim.x);
+      n_blk = nj;
     } else {
       const int2 t = a.diag_tiles[int(blockIdx.x) + int(i) * int(gridDim.x)];
       m_blk = t.x;
@@ -495,6 +514,13 @@ int hmmc_eval_fused_rank(const void* text_packed, const void* gallery_packed, in
   a.theta = theta;
   a.t2v_cnt = t2v_cnt;
   a.v2t_cnt = v2t_cnt;
+  // panel = as many gallery tiles as fit comfortably in L2 next to the live caption tiles (~48 MB)
+  {
+    const int64_t tile_bytes = int64_t(EV_BN) * planes_of(prec) * D * 2;
+    int np = int((int64_t(48) << 20) / tile_bytes);
+    if (np < 8) np = 8;
+    a.panel_n_blk = np;
+  }
   return eval_launch(text_packed, gallery_packed, Nt_pad, Nv_local, D, prec, a, st);
 }
 

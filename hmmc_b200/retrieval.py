@@ -133,10 +133,8 @@ def fused_eval_ranks(text, video_local, frames_local, per_video, scale=100.0, to
     dev = text.device
     planes = 2 if prec == ops.PREC_BF16X3 else 1
     st = ops._stream
-    src_row, grp, gstart = pack_caption_groups(per)
-    Nt_pad = src_row.size
-    d_src = torch.from_numpy(src_row).to(dev)
-    d_grp = torch.from_numpy(grp).to(dev)
+    plan = _eval_plan(per, lo, hi, dev)
+    Nt_pad, d_src, d_grp = plan["Nt_pad"], plan["d_src"], plan["d_grp"]
     tp = torch.empty(Nt_pad, planes * D, dtype=torch.bfloat16, device=dev)
     _lib.check(lib.hmmc_eval_pack_text(ops._p(text), ops._p(d_src), Nt_pad, D, prec, ops._p(tp), st()), "eval_pack_text")
     n_blk = (Nv_loc + 15) // 16
@@ -147,20 +145,14 @@ def fused_eval_ranks(text, video_local, frames_local, per_video, scale=100.0, to
     if Nv_loc > 0:
         _lib.check(lib.hmmc_eval_pack_gallery(ops._p(video_local), ops._p(frames_local), Nv_loc, F, D, prec, ops._p(gp),
                                               st()), "eval_pack_gallery")
-        # diagonal tiles: (caption tile m, gallery tile n) pairs that contain a ground-truth pair of this shard
-        m_of = (gstart[lo:hi].astype(np.int64)) // 128
-        n_of = (np.arange(lo, hi, dtype=np.int64) - lo) // 16
-        pairs = np.unique(np.stack([m_of, n_of], axis=1), axis=0).astype(np.int32)
-        d_pairs = torch.from_numpy(np.ascontiguousarray(pairs)).to(dev)
         _lib.check(lib.hmmc_eval_gt_scores(ops._p(tp), ops._p(gp), Nt_pad, Nv_loc, D, prec, float(scale), int(top_k),
-                                           int(lo), ops._p(d_grp), ops._p(d_pairs), int(pairs.shape[0]),
+                                           int(lo), ops._p(d_grp), ops._p(plan["d_pairs"]), plan["n_pairs"],
                                            ops._p(gt_score), st()), "eval_gt_scores")
     parallel.all_reduce_sum_(gt_score)          # each caption's score is produced by exactly one shard
     if Nv_loc > 0:
-        d_gs = torch.from_numpy(np.ascontiguousarray(gstart[lo:hi])).to(dev)
-        d_gc = torch.from_numpy(per[lo:hi].astype(np.int32)).to(dev)
         theta = torch.empty(Nv_loc, dtype=torch.float32, device=dev)
-        _lib.check(lib.hmmc_eval_theta(ops._p(gt_score), ops._p(d_gs), ops._p(d_gc), Nv_loc, ops._p(theta), st()),
+        _lib.check(lib.hmmc_eval_theta(ops._p(gt_score), ops._p(plan["d_gs"]), ops._p(plan["d_gc"]), Nv_loc,
+                                       ops._p(theta), st()),
                    "eval_theta")
         _lib.check(lib.hmmc_eval_fused_rank(ops._p(tp), ops._p(gp), Nt_pad, Nv_loc, D, prec, float(scale), int(top_k),
                                             int(lo), ops._p(d_grp), ops._p(gt_score), ops._p(theta), ops._p(t2v),
@@ -171,8 +163,37 @@ def fused_eval_ranks(text, video_local, frames_local, per_video, scale=100.0, to
         v2t = parallel.all_gather_varlen(v2t_loc[:Nv_loc], [b - a for a, b in counts])
     else:
         v2t = v2t_loc[:Nv_loc]
-    valid = torch.from_numpy(np.nonzero(src_row >= 0)[0]).to(dev)
-    order = torch.from_numpy(src_row[src_row >= 0].astype(np.int64)).to(dev)
     t2v_out = torch.empty(Nt, dtype=torch.int32, device=dev)
-    t2v_out[order] = t2v[valid]
+    t2v_out[plan["d_order"]] = t2v[plan["d_valid"]]
     return t2v_out, v2t
+
+
+_eval_plans = {}
+
+
+def _eval_plan(per, lo, hi, dev):
+    """Index arrays of one (caption layout, gallery shard): built once per eval set, like the
+    reference builds cut_off_points once per dataset."""
+    key = (hash(per.tobytes()), per.size, lo, hi, str(dev))
+    plan = _eval_plans.get(key)
+    if plan is not None:
+        return plan
+    src_row, grp, gstart = pack_caption_groups(per)
+    plan = {"Nt_pad": int(src_row.size),
+            "d_src": torch.from_numpy(src_row).to(dev), "d_grp": torch.from_numpy(grp).to(dev),
+            "d_valid": torch.from_numpy(np.nonzero(src_row >= 0)[0]).to(dev),
+            "d_order": torch.from_numpy(src_row[src_row >= 0].astype(np.int64)).to(dev),
+            "n_pairs": 0, "d_pairs": None, "d_gs": None, "d_gc": None}
+    if hi > lo:
+        # diagonal tiles: (caption tile m, gallery tile n) pairs that contain a ground-truth pair of this shard
+        m_of = (gstart[lo:hi].astype(np.int64)) // 128
+        n_of = (np.arange(lo, hi, dtype=np.int64) - lo) // 16
+        pairs = np.unique(np.stack([m_of, n_of], axis=1), axis=0).astype(np.int32)
+        plan["d_pairs"] = torch.from_numpy(np.ascontiguousarray(pairs)).to(dev)
+        plan["n_pairs"] = int(pairs.shape[0])
+        plan["d_gs"] = torch.from_numpy(np.ascontiguousarray(gstart[lo:hi])).to(dev)
+        plan["d_gc"] = torch.from_numpy(per[lo:hi].astype(np.int32)).to(dev)
+    if len(_eval_plans) > 16:
+        _eval_plans.clear()
+    _eval_plans[key] = plan
+    return plan
