@@ -198,19 +198,11 @@ def gallery_data(Nv, cap, D, F, lo, hi, dev):
     return T, V, Fr
 
 
-def run_gallery(args):
-    """BASELINE config 5: Nt captions x Nv videos x 12 frames, gallery sharded over the ranks,
-    fused similarity + top-k frames + t2v / v2t rank counting (no matrix)."""
+def gallery_core(args, W, rank, local, dev, steps, warmup):
+    """One timed config-5 run on an initialised process group; returns the result dict (all
+    ranks must call it: the gallery is sharded over them)."""
     import torch.distributed as dist
     from hmmc_b200 import _lib, metrics as GM, modeling, ops, parallel, retrieval
-    W = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if W > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ops.device_check()
     lib = _lib.load()
     Nv, D, F, k = args.videos, args.dim, args.frames, 3
     cap = max(1, args.texts // Nv)
@@ -224,14 +216,13 @@ def run_gallery(args):
     def one():
         return retrieval.fused_eval_ranks(T, V, Fr, per, 100.0, k, prec)
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, warmup)):
         t2v, v2t = one()
     if W > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks = ClockSampler(local)
     clocks.start()
-    steps = max(1, args.steps)
     l0 = lib.hmmc_launch_count()
     a, c = ev(), ev()
     a.record()
@@ -271,26 +262,44 @@ def run_gallery(args):
     tf = flops / W / (ms * 1e-3) / 1e12
     tv = GM.t2v_metrics_from_ranks(t2v.cpu().numpy())
     vt = GM.metrics_from_ranks(v2t.cpu().numpy())
+    del T, V, Fr
+    torch.cuda.empty_cache()
+    return {"metric": "retrieval_sim_rank_throughput", "value": Nt / (ms / 1e3), "unit": "queries/s", "n_gpus": W,
+            "steps": steps, "warmup": max(1, warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+            "config": {"workload": "large-gallery retrieval (BASELINE config 5): fused sim + top-k frames + t2v/v2t ranks",
+                       "texts": Nt, "videos": Nv, "frames": F, "dim": D, "top_frames": k, "captions_per_video": cap,
+                       "parallelism": "gallery sharded x%d" % W,
+                       "l2": "inputs > L2: packed captions %.2f GB + gallery shard %.2f GB" %
+                             (Nt * D * 2e-9 * (2 if prec == "bf16x3" else 1),
+                              (hi - lo) * 13 * D * 2e-9 * (2 if prec == "bf16x3" else 1))},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": Nt / (ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "embeddings are produced on the device by the encoders; ranks stay on the device"},
+            "roofline": {"kernel": "eval_rank_kernel", "bound": "tensor", "achieved": tf, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+                         "algorithmic_flops_per_gpu": flops / W,
+                         "note": "per GPU; includes packing, ground-truth pass and collectives (whole pass timed)"},
+            "checks": {"sampled_t2v_vs_materialised_mismatches": sample_mismatch, "sampled": int(idx.numel()),
+                       "t2v_rank_sum": int(t2v.long().sum()), "v2t_rank_sum": int(v2t.long().sum())},
+            "metrics": {"t2v_R1": tv["R1"], "t2v_MeanR": tv["MeanR"], "v2t_R1": vt["R1"], "v2t_MeanR": vt["MeanR"]}}
+
+
+def run_gallery(args):
+    """BASELINE config 5: Nt captions x Nv videos x 12 frames, gallery sharded over the ranks,
+    fused similarity + top-k frames + t2v / v2t rank counting (no matrix)."""
+    import torch.distributed as dist
+    from hmmc_b200 import ops
+    W = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if W > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.device_check()
+    line = gallery_core(args, W, rank, local, dev, max(1, args.steps), max(1, min(args.warmup, 2)))
     if rank == 0:
-        line = {"metric": "retrieval_sim_rank_throughput", "value": Nt / (ms / 1e3), "unit": "queries/s", "n_gpus": W,
-                "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": prec, "data": "synthetic",
-                "config": {"workload": "large-gallery retrieval (BASELINE config 5): fused sim + top-k frames + t2v/v2t ranks",
-                           "texts": Nt, "videos": Nv, "frames": F, "dim": D, "top_frames": k, "captions_per_video": cap,
-                           "parallelism": "gallery sharded x%d" % W,
-                           "l2": "inputs > L2: packed captions %.2f GB + gallery shard %.2f GB" %
-                                 (Nt * D * 2e-9 * (2 if prec == "bf16x3" else 1),
-                                  (hi - lo) * 13 * D * 2e-9 * (2 if prec == "bf16x3" else 1))},
-                "clocks": clk, "gpu_launches": int(launches),
-                "e2e": {"value": Nt / (ms / 1e3), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                        "note": "embeddings are produced on the device by the encoders; ranks stay on the device"},
-                "roofline": {"kernel": "eval_rank_kernel", "bound": "tensor", "achieved": tf, "peak": tf_peak,
-                             "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
-                             "algorithmic_flops_per_gpu": flops / W,
-                             "note": "per GPU; includes packing, ground-truth pass and collectives (whole pass timed)"},
-                "checks": {"sampled_t2v_vs_materialised_mismatches": sample_mismatch, "sampled": int(idx.numel()),
-                           "t2v_rank_sum": int(t2v.long().sum()), "v2t_rank_sum": int(v2t.long().sum())},
-                "metrics": {"t2v_R1": tv["R1"], "t2v_MeanR": tv["MeanR"], "v2t_R1": vt["R1"], "v2t_MeanR": vt["MeanR"]}}
         print(json.dumps(line))
     if W > 1:
         dist.barrier()
@@ -488,9 +497,18 @@ def main():
                               "peak_source": peak_src},
             "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head}}
 
-    # ---- retrieval leg (config 2) on rank 0
+    # ---- retrieval legs: config 2 on rank 0; config 5 (gallery sharded over all ranks)
     if rank == 0 and not args.no_retrieval:
         line["retrieval"] = retrieval_leg(args, dev)
+    if not args.no_retrieval:
+        del enc, enc_k, model
+        torch.cuda.empty_cache()
+        try:
+            big = gallery_core(args, W, rank, local, dev, 2, 1)
+            line["retrieval_large"] = {k: big[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "roofline",
+                                                           "checks", "metrics", "clocks")}
+        except Exception as e:   # noqa: BLE001
+            line["retrieval_large"] = {"error": repr(e)[:300]}
     if rank == 0 and not args.no_cpu_baseline:
         ms, n, cores, sample = cpu_pretrain_steps(args, max_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": b / (ms / 1e3), "unit": "samples/s", "cores": cores, "kind": "port",
