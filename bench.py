@@ -402,6 +402,18 @@ def main():
     clk = clocks.stop()
     launches = lib.hmmc_launch_count() - launches0
     ms_total = t0.elapsed_time(t1)
+    detail = None
+    if os.environ.get("HMMC_BENCH_DETAIL"):
+        # separate short run with CUDA events inside head_loss: pack+gather launch | loss kernels | wait+enqueue
+        model._hmmc_marks = []
+        for _ in range(20):
+            step(devt, False)
+        torch.cuda.synchronize()
+        mk = model._hmmc_marks
+        model._hmmc_marks = None
+        seg = np.array([[mk[4 * i + j].elapsed_time(mk[4 * i + j + 1]) for j in range(3)] for i in range(20)])
+        detail = dict(zip(["pack_and_gather_launch_ms", "loss_fwd_bwd_ms", "gather_wait_and_enqueue_ms"],
+                          [float(x) for x in seg[5:].mean(0)]))
     ms_ema = float(np.mean([a.elapsed_time(c) for a, c in ema_events]))
     ms_head = float(np.mean([a.elapsed_time(c) for a, c in head_events]))
 
@@ -495,7 +507,7 @@ def main():
                               "bound": "tensor", "achieved": head_tf, "peak": tf_peak, "unit": "TFLOP/s",
                               "frac": head_tf / tf_peak, "algorithmic_flops": head_flops, "ms": ms_head,
                               "peak_source": peak_src},
-            "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head}}
+            "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head, "head_detail": detail}}
 
     # ---- retrieval legs: config 2 on rank 0; config 5 (gallery sharded over all ranks)
     if rank == 0 and not args.no_retrieval:

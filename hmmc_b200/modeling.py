@@ -186,6 +186,12 @@ class ContrastiveHeadMixin:
         self._enqueue_gathered(self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k))
 
 
+def _event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
 def _register_queues(mod, D, K, F):
     """Queue buffers exactly as modules/modeling.py:138-151 creates them."""
     shapes = [("queue_v_cross_ng", K), ("queue_frame_proj_ng", K * F), ("queue_frame_cross_ng", K * F),
@@ -237,7 +243,11 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
         b = v_fea.shape[0]
         D = v_fea.shape[-1]
         # the key exchange does not depend on the loss: start it first, enqueue after the loss kernels
+        marks = getattr(self, "_hmmc_marks", None)          # optional CUDA-event breakdown (bench.py)
+        mark = (lambda: marks.append(_event())) if marks is not None else (lambda: None)
+        mark()
         pending = self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+        mark()
         total, parts = ops.pretrain_head(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
                                          v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k,
                                          self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
@@ -245,7 +255,9 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
                                          self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
                                          self.head_precision)
         self.last_loss_parts = parts            # [FAM, VTM, FTM], device tensor (the reference logs them)
+        mark()
         self._enqueue_gathered(pending)
+        mark()
         if loss_MLM is None:
             return total
         return total + self.weight_MLM * loss_MLM
