@@ -395,8 +395,10 @@ def main():
     barrier()
     t0, t1 = ev(), ev()
     t0.record()
+    cpu_t0 = time.perf_counter()
     for _ in range(args.steps):
         step(devt, True)
+    cpu_issue_ms = 1e3 * (time.perf_counter() - cpu_t0) / args.steps     # host time to ISSUE one step (no sync)
     t1.record()
     barrier()
     clk = clocks.stop()
@@ -507,7 +509,8 @@ def main():
                               "bound": "tensor", "achieved": head_tf, "peak": tf_peak, "unit": "TFLOP/s",
                               "frac": head_tf / tf_peak, "algorithmic_flops": head_flops, "ms": ms_head,
                               "peak_source": peak_src},
-            "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head, "head_detail": detail}}
+            "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head, "head_detail": detail,
+                             "host_issue_per_step": cpu_issue_ms}}
 
     # ---- retrieval legs: config 2 on rank 0; config 5 (gallery sharded over all ranks)
     if rank == 0 and not args.no_retrieval:
