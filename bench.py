@@ -43,11 +43,15 @@ def parse():
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--queue", type=int, default=1024)
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
 
+# kernels of this library in one step: ema, prep, S-GEMM, U-GEMM, finish, loss reduce, head losses,
+# enqueue (+ pointer advance under graph capture), scale; + pack_rows when the keys are gathered
+LAUNCHES_PER_STEP = lambda W: 10 + (1 if W > 1 else 0)
 FLOPS_ALGO = lambda b, F, D, K: 2 * 2.0 * D * b * (F * K * F + K * F + F * K + 2 * K)   # SURVEY.md §8d, fwd + bwd
 EMA_ELEMS = 172325632
 
@@ -355,8 +359,19 @@ def main():
     order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k",
              "frame_proj_k"]
     host = {n: torch.from_numpy(inp_np[n]).pin_memory() for n in order}
-    devt = {n: host[n].to(dev).requires_grad_(n in q_names) for n in order}
-    h2d_bytes = sum(host[n].numel() * 4 for n in order)
+    sizes_in = [host[n].numel() for n in order]
+    packed_host = torch.cat([host[n].reshape(-1) for n in order]).pin_memory()
+    static_in = packed_host.to(dev)                       # the step's inputs live here (one H2D copy per step in e2e)
+
+    def views(buf):
+        out, off = {}, 0
+        for n, k in zip(order, sizes_in):
+            out[n] = buf[off:off + k].view(host[n].shape).detach().requires_grad_(n in q_names)
+            off += k
+        return out
+
+    devt = views(static_in)
+    h2d_bytes = packed_host.numel() * 4
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     ema_events, head_events = [], []
@@ -388,6 +403,23 @@ def main():
         step(devt, False)
     barrier()
 
+    # One step = a fixed sequence of launches: capture it once, replay it (hmmc_b200/graphs.py).
+    graphed = None
+    graph_note = "eager (--no-graph)"
+    if not args.no_graph:
+        try:
+            from hmmc_b200.graphs import GraphedStep
+            graphed = GraphedStep(lambda: step(devt, False))
+            graph_note = "cuda graph replay"
+        except Exception as e:   # noqa: BLE001
+            graphed = None
+            graph_note = "eager (graph capture failed: %s)" % repr(e)[:200]
+            torch.cuda.synchronize()
+    run_step = (lambda: graphed.replay()) if graphed is not None else (lambda: step(devt, False))
+    for _ in range(3):
+        run_step()
+    barrier()
+
     # ---- timed region 1: inputs resident in HBM
     clocks = ClockSampler(local)
     launches0 = lib.hmmc_launch_count()
@@ -397,12 +429,18 @@ def main():
     t0.record()
     cpu_t0 = time.perf_counter()
     for _ in range(args.steps):
-        step(devt, True)
+        run_step()
     cpu_issue_ms = 1e3 * (time.perf_counter() - cpu_t0) / args.steps     # host time to ISSUE one step (no sync)
     t1.record()
     barrier()
     clk = clocks.stop()
     launches = lib.hmmc_launch_count() - launches0
+    if graphed is not None:
+        launches = LAUNCHES_PER_STEP(W) * args.steps      # a replay re-runs the captured launches
+    # per-kernel timing for the roofline: a short eager run right after, events around the EMA launch
+    for _ in range(20):
+        step(devt, True)
+    barrier()
     ms_total = t0.elapsed_time(t1)
     detail = None
     if os.environ.get("HMMC_BENCH_DETAIL"):
@@ -422,29 +460,21 @@ def main():
     # ---- timed region 2: end to end through the public API with host buffers.
     # Every step: ONE host->device copy of the step's packed inputs from pinned memory (on a copy
     # stream, so step i+1's upload overlaps step i's kernels, like a prefetching data loader), the
-    # step itself through BirdPreTrainedModel.head_loss + backward, and a device->host copy of the
-    # loss into pinned memory.  The timed region ends with a full synchronise.
-    sizes_in = [host[n].numel() for n in order]
-    packed_host = torch.cat([host[n].reshape(-1) for n in order]).pin_memory()
+    # step itself (BirdPreTrainedModel._momentum_update + head_loss + backward, replayed as a graph
+    # when available), and a device->host copy of the loss into pinned memory.  The timed region
+    # ends with a full synchronise.
     e2e_steps = args.steps
     loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream()
-    dbuf = [torch.empty_like(packed_host, device=dev) for _ in range(2)]
+    dbuf = [torch.empty_like(static_in) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
     def upload(i):
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[i % 2])          # the step that last used this buffer is done
+            copy_stream.wait_event(freed[i % 2])          # the step that last read this buffer is done
             dbuf[i % 2].copy_(packed_host, non_blocking=True)
             ready[i % 2].record(copy_stream)
-
-    def views(buf):
-        out, off = {}, 0
-        for n, k in zip(order, sizes_in):
-            out[n] = buf[off:off + k].view(host[n].shape).requires_grad_(n in q_names)
-            off += k
-        return out
 
     for e in freed:
         e.record()
@@ -456,8 +486,9 @@ def main():
         if i + 1 < e2e_steps:
             upload(i + 1)
         torch.cuda.current_stream().wait_event(ready[i % 2])
-        loss = step(views(dbuf[i % 2]), False)
+        static_in.copy_(dbuf[i % 2], non_blocking=True)   # into the step's static inputs
         freed[i % 2].record()
+        loss = run_step()
         loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
     s1.record()
     barrier()
@@ -510,7 +541,9 @@ def main():
                               "frac": head_tf / tf_peak, "algorithmic_flops": head_flops, "ms": ms_head,
                               "peak_source": peak_src},
             "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head, "head_detail": detail,
-                             "host_issue_per_step": cpu_issue_ms}}
+                             "host_issue_per_step": cpu_issue_ms,
+                             "note": "ema / head: eager run with CUDA events right after the timed region"},
+            "issue_mode": graph_note}
 
     # ---- retrieval legs: config 2 on rank 0; config 5 (gallery sharded over all ranks)
     if rank == 0 and not args.no_retrieval:

@@ -371,6 +371,9 @@ constexpr int ENQ_DCHUNK = 128;
 // Block = 32 consecutive queue columns x ENQ_DCHUNK embedding dims of one queue.  Phase 1: one warp
 // per 4 columns computes max(||x||,1e-12) over the full vector.  Phase 2: 32(d) x 32(col) tiles go
 // through shared memory so the [D,Kq] layouts are written 32 columns (128 B) at a time.
+// ptr >= 0: the host-tracked pointer (block 0 stores new_ptr);  ptr < 0: read the pointer from
+// queue_ptr[0] on the device (CUDA-graph replay: no host value can be baked in) and leave the
+// advance to advance_ptr_kernel.
 __global__ void __launch_bounds__(256)
 enqueue_kernel(int nsamples, int D, EnqueueArgs a, int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
   __shared__ float nrm[32];
@@ -379,7 +382,11 @@ enqueue_kernel(int nsamples, int D, EnqueueArgs a, int64_t* __restrict__ queue_p
   const int mult = a.mult[qi];
   const int ncols = nsamples * mult;
   const int c0 = blockIdx.x * 32;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) queue_ptr[0] = new_ptr;
+  if (ptr >= 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) queue_ptr[0] = new_ptr;
+  } else {
+    ptr = int(queue_ptr[0]);
+  }
   if (c0 >= ncols) return;
   const int Kq = a.Kq[qi];
   const int col_base = ptr * mult;       // first destination column
@@ -834,12 +841,17 @@ int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_
   return HMMC_OK;
 }
 
+__global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K) { queue_ptr[0] = (queue_ptr[0] + B) % K; }
+
 static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
                           const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, cudaStream_t st) {
   HMMC_REQUIRE(queues5 && queue_ptr, "enqueue: null argument");
   // the reference's slice assignment raises when the batch does not fit (modules/modeling.py:273-280)
-  HMMC_REQUIRE(ptr_host >= 0 && ptr_host + B <= K, "enqueue: ptr %lld + batch %d exceeds queue size %d",
-               (long long)ptr_host, B, K);
+  const bool device_ptr = ptr_host < 0;     // pointer lives on the device only (graph replay)
+  if (device_ptr)
+    HMMC_REQUIRE(B <= K && K % B == 0, "enqueue (device pointer): queue size %d must be a multiple of the batch %d", K, B);
+  else
+    HMMC_REQUIRE(ptr_host + B <= K, "enqueue: ptr %lld + batch %d exceeds queue size %d", (long long)ptr_host, B, K);
   EnqueueArgs a;
   const int mult[5] = {1, 1, 1, F, F};
   a.planes = queues5[0].planes;
@@ -858,8 +870,13 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
     a.src_stride[i] = stride5[i];
   }
   dim3 grid((B * F + 31) / 32, (D + ENQ_DCHUNK - 1) / ENQ_DCHUNK, 5);
-  enqueue_kernel<<<grid, 256, 0, st>>>(B, D, a, queue_ptr, int(ptr_host), int((ptr_host + B) % K));
+  enqueue_kernel<<<grid, 256, 0, st>>>(B, D, a, queue_ptr, device_ptr ? -1 : int(ptr_host),
+                                       device_ptr ? 0 : int((ptr_host + B) % K));
   HMMC_CHECK_LAUNCH();
+  if (device_ptr) {
+    advance_ptr_kernel<<<1, 1, 0, st>>>(queue_ptr, B, K);
+    HMMC_CHECK_LAUNCH();
+  }
   return HMMC_OK;
 }
 

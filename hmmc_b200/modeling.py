@@ -173,6 +173,14 @@ class ContrastiveHeadMixin:
         W, b, F, D, direct, gathered, wait = handle
         K = self.contrast_num_negative
         wait()
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: the pointer is read and advanced on the device at every replay
+            if K % (W * b) != 0:
+                raise ValueError("graph capture of the enqueue needs K %% (world*batch) == 0 (K=%d, B=%d)" % (K, W * b))
+            ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, -1, K,
+                        ops.resolve_precision(self.head_precision), direct=direct)
+            self._hmmc_ptr = None          # host copy is stale after replays: re-read on the next eager call
+            return
         ver = self.queue_ptr._version
         if getattr(self, "_hmmc_ptr", None) is None or self._hmmc_ptr[1] != ver:
             self._hmmc_ptr = (int(self.queue_ptr), ver)        # one sync, then tracked on the host

@@ -158,7 +158,10 @@ int hmmc_ema_block_elems(void);
  * frame_cross (gets frame_fea), frame_proj.  queue_ptr is the int64[1] buffer.
  * ptr_host is the host's copy of the pointer (the kernel takes it by value: no device
  * read, no sync); it also drives the bounds check the reference performs through slice
- * assignment.  The kernel stores (ptr_host + B) % K into queue_ptr. */
+ * assignment.  The kernel stores (ptr_host + B) % K into queue_ptr.
+ * ptr_host = -1: the pointer is read and advanced on the device (CUDA-graph capture / replay,
+ * where no host value may be baked into the launch); requires K % B == 0 and a pointer that
+ * is a multiple of B, like the reference's own no-wrap condition. */
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
                       int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
 
