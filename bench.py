@@ -406,10 +406,16 @@ def main():
     # One step = a fixed sequence of launches: capture it once, replay it (hmmc_b200/graphs.py).
     graphed = None
     graph_note = "eager (--no-graph)"
-    if not args.no_graph:
+    dbg = (lambda m: print("[bench r%d] %s" % (rank, m), file=sys.stderr, flush=True)) if os.environ.get("HMMC_BENCH_DEBUG") else (lambda m: None)
+    want_graph = not args.no_graph and (W == 1 or os.environ.get("HMMC_GRAPH_MULTI") == "1")
+    if not args.no_graph and not want_graph:
+        graph_note = "eager (graph replay across ranks is opt-in: HMMC_GRAPH_MULTI=1)"
+    if want_graph:
         try:
             from hmmc_b200.graphs import GraphedStep
+            dbg("capturing")
             graphed = GraphedStep(lambda: step(devt, False))
+            dbg("captured")
             graph_note = "cuda graph replay"
         except Exception as e:   # noqa: BLE001
             graphed = None
@@ -418,7 +424,9 @@ def main():
     run_step = (lambda: graphed.replay()) if graphed is not None else (lambda: step(devt, False))
     for _ in range(3):
         run_step()
+    dbg("replayed 3")
     barrier()
+    dbg("barrier ok")
 
     # ---- timed region 1: inputs resident in HBM
     clocks = ClockSampler(local)
@@ -437,10 +445,12 @@ def main():
     launches = lib.hmmc_launch_count() - launches0
     if graphed is not None:
         launches = LAUNCHES_PER_STEP(W) * args.steps      # a replay re-runs the captured launches
+    dbg("timed region 1 done")
     # per-kernel timing for the roofline: a short eager run right after, events around the EMA launch
     for _ in range(20):
         step(devt, True)
     barrier()
+    dbg("eager breakdown done")
     ms_total = t0.elapsed_time(t1)
     detail = None
     if os.environ.get("HMMC_BENCH_DETAIL"):

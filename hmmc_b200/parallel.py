@@ -7,6 +7,8 @@ the B200 box, gloo in the CPU tests).  The only exchanges of the path are
   * the key all-gather of the pre-train enqueue (modules/modeling.py:249-258);
   * the [Nt] score / count exchange of the sharded-gallery eval.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -82,6 +84,9 @@ def all_gather_rows_async(x):
     if W == 1:
         return x, (lambda: None)
     out = x.new_empty((W * x.shape[0],) + tuple(x.shape[1:]))
+    if os.environ.get("HMMC_SYNC_GATHER") == "1":
+        _all_gather_into(out, x.contiguous())
+        return out, (lambda: None)
     try:
         work = dist.all_gather_into_tensor(out, x.contiguous(), async_op=True)
     except (RuntimeError, NotImplementedError):
