@@ -407,9 +407,7 @@ def main():
     graphed = None
     graph_note = "eager (--no-graph)"
     dbg = (lambda m: print("[bench r%d] %s" % (rank, m), file=sys.stderr, flush=True)) if os.environ.get("HMMC_BENCH_DEBUG") else (lambda m: None)
-    want_graph = not args.no_graph and (W == 1 or os.environ.get("HMMC_GRAPH_MULTI") == "1")
-    if not args.no_graph and not want_graph:
-        graph_note = "eager (graph replay across ranks is opt-in: HMMC_GRAPH_MULTI=1)"
+    want_graph = not args.no_graph
     if want_graph:
         try:
             from hmmc_b200.graphs import GraphedStep
@@ -528,6 +526,8 @@ def main():
     ema_bytes = 12.0 * EMA_ELEMS
     ema_gbs = ema_bytes / (ms_ema * 1e-3) / 1e9
     head_flops = FLOPS_ALGO(b, F, D, K)
+    if graphed is not None:
+        ms_head = max(ms_step - ms_ema, 1e-6)      # replayed step minus the EMA kernel (events cannot sit inside a replay)
     head_tf = head_flops / (ms_head * 1e-3) / 1e12
 
     line = {"metric": "hm_moco_head_fwd_bwd_throughput", "value": value, "unit": "samples/s", "n_gpus": W,
@@ -572,9 +572,16 @@ def main():
         line["cpu_baseline"] = {"value": b / (ms / 1e3), "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": sample, "ms_per_step": ms}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if W > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if graphed is not None:
+            # a captured graph that contains NCCL work keeps the communicator busy at teardown
+            # (destroy_process_group never returns): drop the graph and leave without the destroy
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
