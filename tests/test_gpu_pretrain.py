@@ -193,3 +193,54 @@ def test_fused_head_equals_granular_calls(prec):
                 assert a[n].grad is None and float(c[n].grad.abs().max()) == 0.0
                 continue
             assert rel(c[n].grad.cpu().numpy(), a[n].grad.cpu().numpy()) < 1e-5, n
+
+
+def test_graphed_step_matches_eager():
+    """Replaying the captured step (hmmc_b200/graphs.py) leaves the same queues, pointer, momentum
+    parameters, loss and gradients as issuing it from Python."""
+    from hmmc_b200.graphs import GraphedStep
+    b, F, D, K = 16, 12, 128, 64
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=41)
+    qs = syn.queues(K, F=F, D=D, seed=42)
+    names = ("v_fea", "title_fea", "frame_fea", "frame_pred")
+    order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k",
+             "frame_proj_k"]
+
+    class Enc(torch.nn.Module):
+        def __init__(self, seed):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.w = torch.nn.Parameter(torch.randn(1000, generator=g).cuda(), requires_grad=False)
+
+    def make():
+        m = _model(K, F, D, "bf16x3")
+        _load_queues(m, qs)
+        m.model_pairs = [[Enc(1), Enc(2)]]
+        t = {n: cu(x, n in names) for n, x in inp.items()}
+
+        def step():
+            for n in names:
+                t[n].grad = None
+            with torch.no_grad():
+                m._momentum_update()
+            loss = m.head_loss(*[t[n] for n in order])
+            loss.backward()
+            return loss
+        return m, t, step
+
+    m1, t1, step1 = make()
+    m2, t2, step2 = make()
+    n_warm, n_run = 3, 5          # GraphedStep runs 3 warm-up steps + 1 capture pass (capture does not execute)
+    g = GraphedStep(step2, warmup=n_warm)
+    for _ in range(n_run):
+        l2 = g.replay()
+    for _ in range(n_warm + n_run):
+        l1 = step1()
+    torch.cuda.synchronize()
+    assert int(m1.queue_ptr) == int(m2.queue_ptr) == ((n_warm + n_run) * b) % K
+    assert float(l1) == float(l2)
+    for n in syn.QUEUE_NAMES:
+        assert torch.equal(getattr(m1, n), getattr(m2, n)), n
+    assert torch.equal(m1.model_pairs[0][1].w, m2.model_pairs[0][1].w)
+    for n in names:
+        assert torch.equal(t1[n].grad, t2[n].grad), n
