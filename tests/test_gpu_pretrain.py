@@ -199,7 +199,7 @@ def test_graphed_step_matches_eager():
     """Replaying the captured step (hmmc_b200/graphs.py) leaves the same queues, pointer, momentum
     parameters, loss and gradients as issuing it from Python."""
     from hmmc_b200.graphs import GraphedStep
-    b, F, D, K = 16, 12, 128, 64
+    b, F, D, K = 16, 12, 128, 128
     inp = syn.pretrain_inputs(b, F=F, D=D, seed=41)
     qs = syn.queues(K, F=F, D=D, seed=42)
     names = ("v_fea", "title_fea", "frame_fea", "frame_pred")
