@@ -136,7 +136,7 @@ struct FinishArgs {
 };
 
 template <int NE>   // elements per lane = D / 32 rounded up
-__global__ void __launch_bounds__(256, (NE <= 16) ? 3 : 1)
+__global__ void __launch_bounds__(256, (NE <= 16) ? 2 : 1)
 infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax,
                       float* __restrict__ row_loss /* [3][total_rows] */) {
   const int lane = threadIdx.x & 31;
@@ -221,16 +221,20 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
     if (G.dq != nullptr) {
       // g_hat += coef/T * (sum_t 1/Z_t) U_r ;  U_r = sum over the split-K partials (loads batched per split)
       const float wu = scale * sum_invZ;
-      for (int sidx = 0; sidx < C.n_splits; ++sidx) {
-        const float* up = C.U_part + int64_t(sidx) * C.split_stride + int64_t(r) * D;
-        float u[NE];
+      // two splits per iteration: 2*NE independent loads in flight per lane
+      for (int sidx = 0; sidx < C.n_splits; sidx += 2) {
+        const float* up0 = C.U_part + int64_t(sidx) * C.split_stride + int64_t(r) * D;
+        const bool two = sidx + 1 < C.n_splits;
+        const float* up1 = two ? up0 + C.split_stride : up0;
+        float u0[NE], u1[NE];
 #pragma unroll
         for (int i = 0; i < NE; ++i) {
           const int d = lane + i * 32;
-          u[i] = (d < D) ? __ldg(up + d) : 0.f;
+          u0[i] = (d < D) ? __ldg(up0 + d) : 0.f;
+          u1[i] = (d < D && two) ? __ldg(up1 + d) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < NE; ++i) g[i] = fmaf(wu, u[i], g[i]);
+        for (int i = 0; i < NE; ++i) g[i] = fmaf(wu, u0[i] + u1[i], g[i]);
       }
     }
   }
