@@ -2,6 +2,7 @@
 // momentum EMA and the pack/unpack helpers of the key all-gather.
 #include "common.cuh"
 #include "umma_gemm.cuh"
+#include <stdlib.h>
 
 namespace hmmc {
 
@@ -135,8 +136,8 @@ struct FinishArgs {
   int n;
 };
 
-template <int NE>   // elements per lane = D / 32 rounded up
-__global__ void __launch_bounds__(256, (NE <= 16) ? 2 : 1)
+template <int NE, int OCC>   // NE = elements per lane = D / 32 rounded up; OCC = blocks per SM to compile for
+__global__ void __launch_bounds__(256, OCC)
 infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax,
                       float* __restrict__ row_loss /* [3][total_rows] */) {
   const int lane = threadIdx.x & 31;
@@ -573,6 +574,8 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   for (int k = 0; k < nb; ++k)
     if (blk_Kq[k] % 256 != 0) L.bn1 = 128;
   L.bn2 = (D % 256 == 0) ? 256 : 128;
+  static const int force_bn2 = tune_int("HMMC_U_BN", 0);
+  if (force_bn2 == 128) L.bn2 = 128;
   // split-K of the U-GEMMs: aim at ~2 waves of equally sized units over the whole group
   const int nseg = (planes == 2) ? 3 : 1;
   double work = 0;
@@ -580,7 +583,8 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
     const int R = groups[blk_group[k]].rows;
     work += double((R + UMMA_BM - 1) / UMMA_BM) * ((D + L.bn2 - 1) / L.bn2) * nseg * (blk_Kq[k] / UMMA_BK);
   }
-  int unit_kb = int(work / (2.0 * sm_count())) + 1;
+  static const int waves10 = tune_int("HMMC_U_WAVES10", 20);      // tuning aid: target waves x 10
+  int unit_kb = int(work / (0.1 * waves10 * sm_count())) + 1;
   if (unit_kb < 8) unit_kb = 8;
   for (int k = 0; k < nb; ++k) {
     const int R = groups[blk_group[k]].rows;
@@ -604,10 +608,19 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   }
 }
 
+static int tune_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 template <int NE>
 static void launch_finish(const FinishArgs& fa, int total_rows, int D, float invT, float cmax, float* row_loss,
                           cudaStream_t st) {
-  infonce_finish_kernel<NE><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
+  static const int occ = tune_int("HMMC_FIN_OCC", 2);
+  if (NE <= 16 && occ >= 3)
+    infonce_finish_kernel<NE, (NE <= 16 ? 3 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
+  else
+    infonce_finish_kernel<NE, (NE <= 16 ? 2 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
 }
 
 static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
