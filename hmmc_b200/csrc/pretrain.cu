@@ -535,6 +535,11 @@ namespace hmmc {
 // or two queues ("blocks" = GEMM problems), in a fixed number of launches:
 //   prep_rows (1) -> S-GEMM + exp/rowsum/E epilogue (1, grouped) -> U-GEMM (1, grouped, split-K)
 //   -> finish (1) -> loss reduce (1)
+static int tune_int(const char* name, int dflt) {     // tuning aids (tools/head_bench.py)
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 struct BlockDesc {
   int group;                 // which query tensor
   const float* keys;
@@ -606,11 +611,6 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
     }
     L.U_part[k] = need_grad ? ws.take<float>(size_t(L.nsplits_eff[k]) * R * D) : nullptr;
   }
-}
-
-static int tune_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
 }
 
 template <int NE>
