@@ -18,6 +18,7 @@
 // keeps its caption's t2v count in a register for the whole sweep.
 #include "common.cuh"
 #include "umma_gemm.cuh"
+#include <stdlib.h>
 
 namespace hmmc {
 
@@ -92,6 +93,80 @@ constexpr int EV_EPI_WARPS = 8;
 constexpr int EV_THREADS = (4 + EV_EPI_WARPS) * 32;
 constexpr int EV_HALF_COLS = EV_BN / 2;      // 104 columns = 8 videos per epilogue warp
 constexpr int EV_HALF_VID = EV_VPT / 2;
+
+// One epilogue warp's share of a tile: walk its 104 accumulator columns (8 videos x 13) in order,
+// pool each video (video sim + mean of the top-K frame sims), update the caption's t2v count and
+// return the bit mask of videos whose score beats theta (v2t candidates).
+template <int K>
+__device__ __forceinline__ uint32_t eval_tile_columns(const EvalArgs& a, uint32_t taddr, int row, int n_blk, int half,
+                                                      int my_grp, float my_gt, int& my_cnt) {
+  const int v0 = n_blk * EV_VPT + half * EV_HALF_VID;     // first local video of this warp's columns
+  uint32_t mask = 0;
+  VideoAcc<K> va;
+  va.reset();
+  va.vsim = 0.f;
+  auto consume = [&](float x, int c) {
+    const int mem = c % EV_COLS;
+    if (mem == 0) { va.reset(); va.vsim = x; } else { va.push(x); }
+    if (mem == EV_COLS - 1) {
+      const int vl = c / EV_COLS;             // video inside this warp's half
+      const int vloc = v0 + vl;               // local video index
+      const float sc = va.score(a.scale);
+      const bool own = (my_grp == a.video_base + vloc);
+      if (a.mode == 0) {
+        if (own && my_grp >= 0 && vloc < a.Nv_local) a.gt_score[row] = sc;
+      } else if (my_grp >= 0 && vloc < a.Nv_local && !own) {
+        my_cnt += (sc > my_gt) ? 1 : 0;
+        if (sc > a.theta[vloc]) mask |= (1u << vl);
+      }
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < EV_HALF_COLS / 32; ++c) {
+    float v[32];
+    ptx::tmem_ld_x32(taddr + c * 32, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) consume(v[j], c * 32 + j);
+  }
+  {
+    float v[8];
+    ptx::tmem_ld_x8(taddr + (EV_HALF_COLS / 32) * 32, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) consume(v[j], (EV_HALF_COLS / 32) * 32 + j);
+  }
+  return mask;
+}
+
+// v2t: count, per video of this tile, the caption GROUPS with at least one hit (all 256 epilogue
+// threads of the CTA take part).  The exchange is skipped when no thread saw a hit (the common case).
+__device__ __forceinline__ void eval_tile_v2t(const EvalArgs& a, uint32_t mask, int buf, int trow, int half, int n_blk,
+                                              int my_grp, uint32_t (*s_mask)[2][128], const int32_t* s_grp,
+                                              int32_t (*s_cnt)[EV_VPT]) {
+  s_mask[buf][half][trow] = mask;
+  if (half == 0 && trow < EV_VPT) s_cnt[buf][trow] = 0;
+  const int any = epi_bar_or(mask != 0 ? 1 : 0);
+  if (any) {
+    const bool head = (half == 0) && (my_grp >= 0) && (trow == 0 || s_grp[trow - 1] != my_grp);
+    if (head) {
+      uint32_t m = 0;
+      for (int t = trow; t < 128 && s_grp[t] == my_grp; ++t)
+        m |= s_mask[buf][0][t] | (s_mask[buf][1][t] << EV_HALF_VID);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        atomicAdd(&s_cnt[buf][b], 1);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (half == 0 && trow < EV_VPT) {
+      const int c = s_cnt[buf][trow];
+      const int vloc = n_blk * EV_VPT + trow;
+      if (c != 0 && vloc < a.Nv_local) atomicAdd(&a.v2t_cnt[vloc], c);
+    }
+  }
+}
 
 template <int K>
 __global__ void __launch_bounds__(EV_THREADS, 1)
@@ -256,73 +331,13 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * EV_HALF_COLS;
-      const int v0 = n_blk * EV_VPT + half * EV_HALF_VID;     // first local video of this warp's columns
-      uint32_t mask = 0;
-      VideoAcc<K> va;
-      va.reset();
-      va.vsim = 0.f;
-      // walk this warp's 104 columns in order; local column c belongs to video c / 13, member c % 13
-      auto consume = [&](float x, int c) {
-        const int mem = c % EV_COLS;
-        if (mem == 0) { va.reset(); va.vsim = x; } else { va.push(x); }
-        if (mem == EV_COLS - 1) {
-          const int vl = c / EV_COLS;             // video inside this warp's half
-          const int vloc = v0 + vl;               // local video index
-          const float sc = va.score(a.scale);
-          const bool own = (my_grp == a.video_base + vloc);
-          if (a.mode == 0) {
-            if (own && my_grp >= 0 && vloc < a.Nv_local) a.gt_score[row] = sc;
-          } else if (my_grp >= 0 && vloc < a.Nv_local && !own) {
-            my_cnt += (sc > my_gt) ? 1 : 0;
-            if (sc > a.theta[vloc]) mask |= (1u << vl);
-          }
-        }
-      };
-#pragma unroll
-      for (int c = 0; c < EV_HALF_COLS / 32; ++c) {
-        float v[32];
-        ptx::tmem_ld_x32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) consume(v[j], c * 32 + j);
-      }
-      {
-        float v[8];
-        ptx::tmem_ld_x8(taddr + (EV_HALF_COLS / 32) * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) consume(v[j], (EV_HALF_COLS / 32) * 32 + j);
-      }
+      const uint32_t mask = eval_tile_columns<K>(a, taddr, row, n_blk, half, my_grp, my_gt, my_cnt);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-
       if (a.mode == 1) {
-        // v2t: count, per video of this tile, the caption GROUPS with at least one hit.
-        // Skip the exchange entirely when no thread of the tile saw a hit (the common case).
-        s_mask[buf][half][trow] = mask;
-        if (half == 0 && trow < EV_VPT) s_cnt[buf][trow] = 0;
-        const int any = epi_bar_or(mask != 0 ? 1 : 0);
-        if (any) {
-          const bool head = (half == 0) && (my_grp >= 0) && (trow == 0 || s_grp[trow - 1] != my_grp);
-          if (head) {
-            uint32_t m = 0;
-            for (int t = trow; t < 128 && s_grp[t] == my_grp; ++t)
-              m |= s_mask[buf][0][t] | (s_mask[buf][1][t] << EV_HALF_VID);
-            while (m) {
-              const int b = __ffs(m) - 1;
-              m &= m - 1;
-              atomicAdd(&s_cnt[buf][b], 1);
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (half == 0 && trow < EV_VPT) {
-            const int c = s_cnt[buf][trow];
-            const int vloc = n_blk * EV_VPT + trow;
-            if (c != 0 && vloc < a.Nv_local) atomicAdd(&a.v2t_cnt[vloc], c);
-          }
-        }
+        eval_tile_v2t(a, mask, buf, trow, half, n_blk, my_grp, s_mask, s_grp, s_cnt);
         buf ^= 1;
       }
     }
@@ -334,6 +349,188 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ CTA-pair, caption-stationary sweep
+// Counting sweep (mode 1, one bf16 plane) on CTA pairs: tcgen05 cta_group::2, M = 256 captions per
+// pair (128 per CTA), N = 208.  Each CTA keeps ITS caption tile (128 x D bf16, 128 KB at D = 512)
+// resident in shared memory for a whole gallery panel, and streams only HALF of every gallery tile
+// (104 rows, 13 KB per k-block): the L2 -> SM traffic per tile drops from 336 KB to 104 KB.
+//   warp 0 lane 0 (both CTAs) : TMA producer; completion bytes land on the leader's barriers
+//   warp 1 lane 0 (leader)    : tcgen05.mma.cta_group::2 issuer; commits are multicast to both CTAs
+//   warp 2 (both)             : TMEM allocation (cta_group::2)
+//   warps 4..11 (both)        : epilogue over the CTA's own 128 accumulator rows
+constexpr int EVP_STAGES = 6;
+constexpr uint32_t EVP_B_BYTES = (EV_BN / 2) * UMMA_BK * 2;      // 104 rows x 128 B = 13 KB
+constexpr uint32_t EVP_A_SLICE = UMMA_BM * UMMA_BK * 2;          // 16 KB per 64-wide k-block
+constexpr int EVP_MAX_KB = 8;                                    // D <= 512
+constexpr size_t EVP_SMEM_BYTES = size_t(EVP_MAX_KB) * EVP_A_SLICE + size_t(EVP_STAGES) * EVP_B_BYTES + 1024 + 256;
+static_assert(EVP_B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
+
+template <int K>
+__global__ void __launch_bounds__(EV_THREADS, 1)
+eval_rank_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                      const __grid_constant__ EvalArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_base = ptx::smem_u32(smem);
+  const uint32_t b_base = a_base + EVP_MAX_KB * EVP_A_SLICE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(EVP_MAX_KB) * EVP_A_SLICE + size_t(EVP_STAGES) * EVP_B_BYTES);
+  const uint32_t bar_base = ptx::smem_u32(bars);
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (EVP_STAGES + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * EVP_STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * EVP_STAGES + 2 + i); };
+  const uint32_t afull_bar = bar_base + 8u * (2 * EVP_STAGES + 4);
+  const uint32_t aempty_bar = bar_base + 8u * (2 * EVP_STAGES + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * EVP_STAGES + 6);
+  __shared__ uint32_t s_mask[2][2][128];
+  __shared__ int32_t s_grp[128];
+  __shared__ int32_t s_cnt[2][EV_VPT];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = ptx::cluster_ctarank();        // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  constexpr uint32_t TMEM_COLS = 512, ACC_STRIDE = 256;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmBh);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < EVP_STAGES; ++i) {
+      ptx::mbar_init(full_bar(i), 1);       // leader's producer arrives once; bytes come from both CTAs
+      ptx::mbar_init(empty_bar(i), 1);      // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull_bar(i), 1);
+      ptx::mbar_init(tempty_bar(i), 2 * EV_EPI_WARPS);   // epilogue warps of BOTH CTAs (used on the leader)
+    }
+    ptx::mbar_init(afull_bar, 1);
+    ptx::mbar_init(aempty_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                  // barriers of both CTAs initialised before any remote signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kbs = a.kb_per_seg;                                     // one plane: K / 64
+  const int num_m2 = (a.num_m_blk + 1) / 2;                         // 256-caption super tiles
+  const int my_m2 = (num_m2 - pair + num_pairs - 1) / num_pairs;
+  const int NP = a.panel_n_blk;
+  const int num_panels = (a.num_n_blk + NP - 1) / NP;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int pnl = 0; pnl < num_panels; ++pnl) {
+        const int n0 = pnl * NP, n1 = min(n0 + NP, a.num_n_blk);
+        for (int mi = 0; mi < my_m2; ++mi) {
+          const int m_blk = (pair + mi * num_pairs) * 2 + int(cta);
+          // caption tile: wait until the MMAs of the previous block have released it, then load all k-blocks
+          ptx::mbar_wait(aempty_bar, aphase ^ 1u);
+          if (cta == 0) ptx::mbar_expect_tx(afull_bar, 2u * kbs * EVP_A_SLICE);
+          for (int kb = 0; kb < kbs; ++kb)
+            ptx::tma_load_2d_pair(a_base + kb * EVP_A_SLICE, &tmA, afull_bar, kb * UMMA_BK, m_blk * UMMA_BM);
+          aphase ^= 1u;
+          for (int n = n0; n < n1; ++n) {
+            for (int kb = 0; kb < kbs; ++kb) {
+              ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (cta == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * EVP_B_BYTES);
+              ptx::tma_load_2d_pair(b_base + stage * EVP_B_BYTES, &tmBh, full_bar(stage), kb * UMMA_BK,
+                                    n * EV_BN + int(cta) * (EV_BN / 2));
+              if (++stage == EVP_STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * UMMA_BM, EV_BN);
+      int stage = 0;
+      uint32_t phase = 0, aphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pnl = 0; pnl < num_panels; ++pnl) {
+        const int n0 = pnl * NP, n1 = min(n0 + NP, a.num_n_blk);
+        for (int mi = 0; mi < my_m2; ++mi) {
+          ptx::mbar_wait(afull_bar, aphase);
+          aphase ^= 1u;
+          ptx::tc_fence_after();
+          for (int n = n0; n < n1; ++n) {
+            ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+            for (int kb = 0; kb < kbs; ++kb) {
+              ptx::mbar_wait(full_bar(stage), phase);
+              ptx::tc_fence_after();
+              const uint64_t adesc = ptx::umma_desc_k_sw128(a_base + kb * EVP_A_SLICE);
+              const uint64_t bdesc = ptx::umma_desc_k_sw128(b_base + stage * EVP_B_BYTES);
+#pragma unroll
+              for (int k = 0; k < UMMA_BK / 16; ++k)
+                ptx::umma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              ptx::umma_commit_pair(empty_bar(stage));
+              if (++stage == EVP_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            ptx::umma_commit_pair(tfull_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          }
+          ptx::umma_commit_pair(aempty_bar);       // caption tiles of both CTAs may be overwritten
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int trow = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    for (int pnl = 0; pnl < num_panels; ++pnl) {
+      const int n0 = pnl * NP, n1 = min(n0 + NP, a.num_n_blk);
+      for (int mi = 0; mi < my_m2; ++mi) {
+        const int m_blk = (pair + mi * num_pairs) * 2 + int(cta);
+        const bool live = m_blk < a.num_m_blk;                     // odd tile count: the last pair has one idle CTA
+        const int row = m_blk * UMMA_BM + trow;
+        const int my_grp = live ? a.grp[row] : -1;
+        const float my_gt = live ? a.gt_score[row] : 0.f;
+        int my_cnt = 0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) s_grp[trow] = my_grp;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int n = n0; n < n1; ++n) {
+          ptx::mbar_wait(tfull_bar(acc), acc_phase);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * EV_HALF_COLS;
+          const uint32_t mask = eval_tile_columns<K>(a, taddr, row, n, half, my_grp, my_gt, my_cnt);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA thread waits on it
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          eval_tile_v2t(a, mask, buf, trow, half, n, my_grp, s_mask, s_grp, s_cnt);
+          buf ^= 1;
+        }
+        if (live && my_cnt != 0) atomicAdd(&a.t2v_cnt[row], my_cnt);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                  // nobody leaves while the peer may still signal or read
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -457,6 +654,40 @@ static int eval_launch(const void* text_packed, const void* gallery_packed, int6
   using Cfg = UmmaCfg<EV_BN>;
   const int work = (a.mode == 1) ? a.num_m_blk : a.n_diag_tiles;
   if (work <= 0) return HMMC_OK;
+  // counting sweep in one bf16 plane: CTA pairs with the caption tile resident in shared memory
+  static const char* no_pair = getenv("HMMC_EVAL_NO_PAIR");
+  if (a.mode == 1 && planes == 1 && D / UMMA_BK <= EVP_MAX_KB && no_pair == nullptr) {
+    CUtensorMap tmBh;
+    rc = make_tmap_bf16(&tmBh, gallery_packed, uint64_t(a.num_n_blk) * EV_BN, uint64_t(D), uint64_t(D), EV_BN / 2);
+    if (rc) return rc;
+    const int num_m2 = (a.num_m_blk + 1) / 2;
+    int pairs = sm_count() / 2;
+    if (pairs > num_m2) pairs = num_m2;
+    auto launch_pair = [&](auto kern) -> int {
+      HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EVP_SMEM_BYTES)));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(EV_THREADS);
+      cfg.dynamicSmemBytes = EVP_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      count_launch();
+      HMMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmBh, a));
+      return HMMC_OK;
+    };
+    switch (a.top_k) {
+      case 1: return launch_pair(eval_rank_pair_kernel<1>);
+      case 2: return launch_pair(eval_rank_pair_kernel<2>);
+      case 3: return launch_pair(eval_rank_pair_kernel<3>);
+      default: return launch_pair(eval_rank_pair_kernel<4>);
+    }
+  }
   const int grid = work < sm_count() ? work : sm_count();
   auto launch = [&](auto kern) -> int {
     HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
