@@ -471,6 +471,410 @@ enqueue_kernel(int nsamples, int D, EnqueueArgs a, int64_t* __restrict__ queue_p
   }
 }
 
+// ------------------------------------------------------------------ pack / unpack rows
+struct RowPackArgs {
+  uint64_t ptrs[8];
+  int widths[8];
+  int offs[8];
+  int n;
+  int total;
+};
+
+template <bool PACK>
+__global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_t rows) {
+  const int64_t row = blockIdx.x;
+  const int t = blockIdx.y;
+  float* x = reinterpret_cast<float*>(a.ptrs[t]) + row * a.widths[t];
+  float* y = packed + row * a.total + a.offs[t];
+  for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
+    if (PACK) y[i] = x[i]; else x[i] = y[i];
+  }
+}
+
+struct ScaleArgs {
+  float* ptrs[8];
+  int64_t numels[8];
+  int n;
+};
+// x_t *= scale[0] for up to 8 tensors (backward of the fused heads: the gradients were produced
+// with the loss, the upstream gradient arrives later)
+__global__ void scale_tensors_kernel(ScaleArgs a, const float* __restrict__ scale) {
+  const float s = scale[0];
+  float* x = a.ptrs[blockIdx.y];
+  const int64_t n = a.numels[blockIdx.y];
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x4[i] = v;
+  }
+  for (int64_t i = n4 * 4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    x[i] *= s;
+}
+
+static int build_rowpack(RowPackArgs& a, const uint64_t* ptrs, const int32_t* widths, int n) {
+  HMMC_REQUIRE(n >= 1 && n <= 8, "pack_rows: between 1 and 8 blocks, got %d", n);
+  a.n = n;
+  int off = 0;
+  for (int i = 0; i < n; ++i) {
+    a.ptrs[i] = ptrs[i];
+    a.widths[i] = widths[i];
+    a.offs[i] = off;
+    off += widths[i];
+  }
+  a.total = off;
+  return HMMC_OK;
+}
+
+}  // namespace hmmc
+
+using namespace hmmc;
+
+extern "C" {
+
+int hmmc_queue_pack(const hmmc_queue* q, void* stream) {
+  HMMC_REQUIRE(q != nullptr && q->dk != nullptr && q->D > 0 && q->Kq > 0, "queue_pack: bad queue");
+  HMMC_REQUIRE(q->planes == 1 || q->planes == 2, "queue_pack: planes must be 1 or 2");
+  if (q->pack_kd == nullptr && q->pack_dk == nullptr) return HMMC_OK;
+  dim3 grid((q->Kq + 31) / 32, (q->D + 31) / 32);
+  queue_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q->dk, static_cast<__nv_bfloat16*>(q->pack_kd), static_cast<__nv_bfloat16*>(q->pack_dk), q->D, q->Kq, q->planes);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+}  // extern "C"
+
+namespace hmmc {
+// ---------------------------------------------------------------------------------------
+// Generic fused InfoNCE driver: several query tensors ("groups"), each contracted against one
+// or two queues ("blocks" = GEMM problems), in a fixed number of launches:
+//   prep_rows (1) -> S-GEMM + exp/rowsum/E epilogue (1, grouped) -> U-GEMM (1, grouped, split-K)
+//   -> finish (1) -> loss reduce (1)
+static int tune_int(const char* name, int dflt) {     // tuning aids (tools/head_bench.py)
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+struct BlockDesc {
+  int group;                 // which query tensor
+  const float* keys;
+  int pos_mode, Fk;
+  const hmmc_queue* queue;
+  float coef;                // weight / b
+  int kind;                  // loss slot
+};
+struct GroupDesc {
+  const float* q;
+  float* dq;
+  int rows, Fq;
+};
+
+struct InfoNCELayout {       // workspace carving shared by the size query and the run
+  float* row_loss;
+  float* xhat[MAX_GROUPS];
+  __nv_bfloat16* packed[MAX_GROUPS];
+  float* rowsum_part[MAX_BLOCKS];
+  void* E[MAX_BLOCKS];
+  float* U_part[MAX_BLOCKS];
+  int nparts[MAX_BLOCKS], splits[MAX_BLOCKS], nsplits_eff[MAX_BLOCKS];
+  int bn1, bn2;
+};
+
+static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* groups, int ng, const int* blk_group,
+                           const int* blk_Kq, int nb, int D, int prec, bool need_grad) {
+  const int planes = planes_of(prec);
+  int total_rows = 0;
+  for (int i = 0; i < ng; ++i) total_rows += groups[i].rows;
+  L.row_loss = ws.take<float>(size_t(3) * total_rows);
+  for (int i = 0; i < ng; ++i) {
+    L.xhat[i] = (prec == HMMC_PREC_FP32) ? ws.take<float>(size_t(groups[i].rows) * D) : nullptr;
+    L.packed[i] = (prec != HMMC_PREC_FP32) ? ws.take<__nv_bfloat16>(size_t(groups[i].rows) * planes * D) : nullptr;
+  }
+  L.bn1 = 256;
+  for (int k = 0; k < nb; ++k)
+    if (blk_Kq[k] % 256 != 0) L.bn1 = 128;
+  L.bn2 = (D % 256 == 0) ? 256 : 128;
+  static const int force_bn2 = tune_int("HMMC_U_BN", 0);
+  if (force_bn2 == 128) L.bn2 = 128;
+  // split-K of the U-GEMMs: aim at ~2 waves of equally sized units over the whole group
+  const int nseg = (planes == 2) ? 3 : 1;
+  double work = 0;
+  for (int k = 0; k < nb; ++k) {
+    const int R = groups[blk_group[k]].rows;
+    work += double((R + UMMA_BM - 1) / UMMA_BM) * ((D + L.bn2 - 1) / L.bn2) * nseg * (blk_Kq[k] / UMMA_BK);
+  }
+  static const int waves10 = tune_int("HMMC_U_WAVES10", 20);      // tuning aid: target waves x 10
+  int unit_kb = int(work / (0.1 * waves10 * sm_count())) + 1;
+  if (unit_kb < 8) unit_kb = 8;
+  for (int k = 0; k < nb; ++k) {
+    const int R = groups[blk_group[k]].rows;
+    const int Kq = blk_Kq[k];
+    if (prec == HMMC_PREC_FP32) {
+      L.nparts[k] = 1;
+      L.splits[k] = L.nsplits_eff[k] = 1;
+      L.rowsum_part[k] = ws.take<float>(size_t(R));
+      L.E[k] = ws.take<float>(size_t(R) * Kq);
+    } else {
+      L.nparts[k] = 2 * ((Kq + L.bn1 - 1) / L.bn1);     // two epilogue halves per tile
+      const int total_kb = nseg * (Kq / UMMA_BK);
+      int sp = (total_kb + unit_kb - 1) / unit_kb;
+      if (sp > 32) sp = 32;
+      L.splits[k] = sp;
+      L.nsplits_eff[k] = effective_splits(Kq, planes, sp);
+      L.rowsum_part[k] = ws.take<float>(size_t(L.nparts[k]) * R);
+      L.E[k] = need_grad ? ws.take<__nv_bfloat16>(size_t(R) * planes * Kq) : nullptr;
+    }
+    L.U_part[k] = need_grad ? ws.take<float>(size_t(L.nsplits_eff[k]) * R * D) : nullptr;
+  }
+}
+
+template <int NE>
+static void launch_finish(const FinishArgs& fa, int total_rows, int D, float invT, float cmax, float* row_loss,
+                          cudaStream_t st) {
+  static const int occ = tune_int("HMMC_FIN_OCC", 2);
+  if (NE <= 16 && occ >= 3)
+    infonce_finish_kernel<NE, (NE <= 16 ? 3 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
+  else
+    infonce_finish_kernel<NE, (NE <= 16 ? 2 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
+}
+
+static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
+                       int prec, float* kind_out, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+  HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
+  HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
+  HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
+  // constant-max log-sum-exp: all logits lie in [-1/T, 1/T]; exp(-2/T) must stay a normal fp32
+  HMMC_REQUIRE(temperature >= 0.025f, "infonce: temperature %g < 0.025 is not supported by the constant-max LSE",
+               temperature);
+  const int planes = planes_of(prec);
+  bool need_grad = false;
+  for (int i = 0; i < ng; ++i) need_grad = need_grad || groups[i].dq != nullptr;
+  int blk_group[MAX_BLOCKS], blk_Kq[MAX_BLOCKS];
+  for (int k = 0; k < nb; ++k) {
+    const hmmc_queue* q = blocks[k].queue;
+    HMMC_REQUIRE(q != nullptr && q->dk != nullptr && q->D == D, "infonce: queue %d has D=%d, embeddings D=%d", k, q ? q->D : -1, D);
+    blk_group[k] = blocks[k].group;
+    blk_Kq[k] = q->Kq;
+    if (prec != HMMC_PREC_FP32) {
+      HMMC_REQUIRE(q->pack_kd && q->pack_dk, "infonce: queue has no packed operands (call hmmc_queue_pack)");
+      HMMC_REQUIRE(q->planes == planes, "infonce: queue packed with %d planes, precision needs %d", q->planes, planes);
+      HMMC_REQUIRE(D % UMMA_BK == 0 && q->Kq % 128 == 0,
+                   "infonce: tensor-core path needs D %% 64 == 0 and Kq %% 128 == 0 (D=%d Kq=%d)", D, q->Kq);
+    }
+  }
+  Workspace ws(workspace, workspace_bytes);
+  InfoNCELayout L;
+  infonce_layout(ws, L, groups, ng, blk_group, blk_Kq, nb, D, prec, need_grad);
+  if (!ws.ok()) {
+    set_error("infonce: workspace too small: need %zu bytes, got %zu", ws.used, workspace_bytes);
+    return HMMC_ERR_WORKSPACE;
+  }
+  const float invT = 1.0f / temperature, cmax = invT;
+  // 1. normalise (+ pack) every query tensor
+  PrepArgs pa;
+  pa.n = ng;
+  pa.row_begin[0] = 0;
+  for (int i = 0; i < MAX_GROUPS; ++i) {
+    const int k = i < ng ? i : 0;
+    pa.x[i] = groups[k].q;
+    pa.xhat[i] = L.xhat[k];
+    pa.packed[i] = L.packed[k];
+    pa.row_begin[i + 1] = pa.row_begin[i] + (i < ng ? groups[i].rows : 0);
+  }
+  const int total_rows = pa.row_begin[ng];
+  prep_rows_kernel<<<(total_rows + 7) / 8, 256, 0, st>>>(pa, D, planes);
+  HMMC_CHECK_LAUNCH();
+  int rc;
+  if (prec == HMMC_PREC_FP32) {
+    for (int k = 0; k < nb; ++k) {
+      const GroupDesc& G = groups[blocks[k].group];
+      const int Kq = blk_Kq[k];
+      float* S = static_cast<float*>(L.E[k]);
+      if ((rc = gemm_f32(L.xhat[blocks[k].group], D, 1, blocks[k].queue->dk, 1, Kq, S, Kq, G.rows, Kq, D, 1.0f, st))) return rc;
+      exp_rowsum_kernel<<<G.rows, 256, 0, st>>>(S, Kq, Kq, invT, cmax, L.rowsum_part[k]);
+      HMMC_CHECK_LAUNCH();
+      if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
+    }
+  } else {
+    const float LOG2E = 1.4426950408889634f;
+    GemmProblem<EpiInfoNCE> p1[MAX_BLOCKS];
+    GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
+    for (int k = 0; k < nb; ++k) {
+      const GroupDesc& G = groups[blocks[k].group];
+      const int Kq = blk_Kq[k];
+      EpiInfoNCE::Params e1;
+      e1.a2 = invT * LOG2E;
+      e1.c2 = cmax * LOG2E;
+      e1.rowsum_part = L.rowsum_part[k];
+      e1.E = static_cast<__nv_bfloat16*>(L.E[k]);
+      e1.ldE = int64_t(planes) * Kq;
+      e1.e_planes = planes;
+      p1[k] = GemmProblem<EpiInfoNCE>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
+                                      int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1};
+      EpiStoreF32::Params e2{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
+      p2[k] = GemmProblem<EpiStoreF32>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
+                                       G.rows, D, Kq, planes, L.splits[k], e2};
+    }
+    rc = (L.bn1 == 256) ? launch_umma_grouped<256, EpiInfoNCE>(p1, nb, st) : launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st);
+    if (rc) return rc;
+    if (need_grad) {
+      rc = (L.bn2 == 256) ? launch_umma_grouped<256, EpiStoreF32>(p2, nb, st) : launch_umma_grouped<128, EpiStoreF32>(p2, nb, st);
+      if (rc) return rc;
+    }
+  }
+  // 4. positives, loss, gradient
+  FinishArgs fa;
+  fa.n = ng;
+  fa.row_begin[0] = 0;
+  for (int i = 0; i < MAX_GROUPS; ++i) {
+    const int gi = i < ng ? i : 0;
+    RowGroup& R = fa.g[i];
+    R.q = groups[gi].q;
+    R.dq = groups[gi].dq;
+    R.rows = groups[gi].rows;
+    R.Fq = groups[gi].Fq;
+    R.ncontrib = 0;
+    fa.row_begin[i + 1] = fa.row_begin[i] + (i < ng ? groups[i].rows : 0);
+  }
+  for (int k = 0; k < nb; ++k) {
+    RowGroup& R = fa.g[blocks[k].group];
+    HMMC_REQUIRE(R.ncontrib < 2, "infonce: a query tensor may feed at most two queues");
+    Contribution& C = R.c[R.ncontrib++];
+    C.keys = blocks[k].keys;
+    C.rowsum_part = L.rowsum_part[k];
+    C.U_part = L.U_part[k];
+    C.split_stride = int64_t(R.rows) * D;
+    C.pos_mode = blocks[k].pos_mode;
+    C.Fk = blocks[k].Fk;
+    C.n_parts = L.nparts[k];
+    C.n_splits = L.nsplits_eff[k];
+    C.coef = blocks[k].coef;
+    C.kind = blocks[k].kind;
+  }
+  for (int i = 0; i < MAX_GROUPS; ++i)
+    if (fa.g[i].ncontrib < 2) fa.g[i].c[1] = fa.g[i].c[0];
+  const int ne = (D + 31) / 32;
+  if (ne <= 4) launch_finish<4>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  else if (ne <= 16) launch_finish<16>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  else if (ne <= 32) launch_finish<32>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  else launch_finish<FIN_MAXE>(fa, total_rows, D, invT, cmax, L.row_loss, st);
+  HMMC_CHECK_LAUNCH();
+  loss_reduce_kernel<<<1, 1024, 0, st>>>(L.row_loss, total_rows, kind_out, accumulate);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+static int check_pos_mode(int pos_mode, int Fq, int Fk) {
+  HMMC_REQUIRE(pos_mode >= 0 && pos_mode <= 3, "infonce: unknown pos_mode %d", pos_mode);
+  if (pos_mode == HMMC_POS_PAIR) HMMC_REQUIRE(Fq == Fk, "infonce: PAIR needs Fq == Fk");
+  if (pos_mode == HMMC_POS_FRAME_NEIGHBOUR) HMMC_REQUIRE(Fq == Fk && Fq >= 2, "infonce: FRAME_NEIGHBOUR needs Fq == Fk >= 2");
+  if (pos_mode == HMMC_POS_ONE_TO_FRAMES) HMMC_REQUIRE(Fq == 1, "infonce: ONE_TO_FRAMES needs Fq == 1");
+  if (pos_mode == HMMC_POS_FRAMES_TO_ONE) HMMC_REQUIRE(Fk == 1, "infonce: FRAMES_TO_ONE needs Fk == 1");
+  return HMMC_OK;
+}
+
+}  // namespace hmmc
+
+extern "C" {
+
+size_t hmmc_infonce_workspace_bytes(int64_t R, int D, int Kq, int prec) {
+  Workspace ws(nullptr, 0);
+  InfoNCELayout L;
+  GroupDesc g{nullptr, nullptr, int(R), 1};
+  int bg = 0, bk = Kq;
+  infonce_layout(ws, L, &g, 1, &bg, &bk, 1, D, prec, true);
+  return ws.used + 1024;
+}
+
+int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, int b, int Fq, int Fk, int D,
+                               const hmmc_queue* queue, float temperature, float weight, int prec, float* loss_out,
+                               float* dq, void* workspace, size_t workspace_bytes, void* stream) {
+  HMMC_REQUIRE(q && keys && queue && loss_out, "infonce: null argument");
+  HMMC_REQUIRE(b > 0 && Fq > 0 && Fk > 0 && D > 0, "infonce: bad sizes b=%d Fq=%d Fk=%d D=%d", b, Fq, Fk, D);
+  int rc = check_pos_mode(pos_mode, Fq, Fk);
+  if (rc) return rc;
+  // the three loss slots of the generic driver live at the head of the workspace
+  HMMC_REQUIRE(workspace != nullptr && workspace_bytes >= 1024, "infonce: workspace too small");
+  float* kinds = static_cast<float*>(workspace);
+  GroupDesc g{q, dq, b * Fq, Fq};
+  BlockDesc blk{0, keys, pos_mode, Fk, queue, weight / float(b), 0};
+  rc = run_infonce(&g, 1, &blk, 1, b, D, temperature, prec, kinds, 0, static_cast<char*>(workspace) + 1024,
+                   workspace_bytes - 1024, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  add_scalar_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_out, kinds);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec) {
+  Workspace ws(nullptr, 0);
+  InfoNCELayout L;
+  GroupDesc g[4] = {{nullptr, nullptr, b * F, F}, {nullptr, nullptr, b, 1}, {nullptr, nullptr, b, 1}, {nullptr, nullptr, b * F, F}};
+  const int bg[5] = {0, 1, 2, 2, 3};
+  const int bk[5] = {K * F, K, K, K * F, K};
+  infonce_layout(ws, L, g, 4, bg, bk, 5, D, prec, true);
+  return ws.used + 1024;
+}
+
+int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
+                               const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
+                               const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
+                               float w_ftm, int use_frame_fea, int prec, float* losses_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  HMMC_REQUIRE(io && q_v && q_title && q_frame_proj && q_frame_cross && losses_out, "pretrain_head: null argument");
+  HMMC_REQUIRE(io->v_fea && io->title_fea && io->frame_fea && io->frame_pred && io->v_fea_k && io->title_fea_k &&
+               io->frame_fea_k && io->frame_proj_k, "pretrain_head: null embedding pointer");
+  HMMC_REQUIRE(b > 0 && F >= 2 && D > 0, "pretrain_head: bad sizes b=%d F=%d D=%d", b, F, D);
+  HMMC_REQUIRE(workspace != nullptr && workspace_bytes >= 1024, "pretrain_head: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // query tensors: 0 frame_pred, 1 v_fea, 2 title_fea, 3 frame_fea
+  GroupDesc groups[4] = {{io->frame_pred, io->d_frame_pred, b * F, F},
+                         {io->v_fea, io->d_v_fea, b, 1},
+                         {io->title_fea, io->d_title_fea, b, 1},
+                         {io->frame_fea, io->d_frame_fea, b * F, F}};
+  const float fb = float(b);
+  BlockDesc blocks[5] = {
+      // FAM, frame_self_loss(frame_pred, frame_proj_k, queue_frame_proj_ng)        modules/modeling.py:385
+      {0, io->frame_proj_k, HMMC_POS_FRAME_NEIGHBOUR, F, q_frame_proj, 1.0f / float(F - 1) / fb, 0},
+      // VTM, contrastive_loss(v_fea, title_fea_k, queue_title) + (title_fea, v_fea_k, queue_v)   :387-388
+      {1, io->title_fea_k, HMMC_POS_PAIR, 1, q_title, 1.0f / fb, 1},
+      {2, io->v_fea_k, HMMC_POS_PAIR, 1, q_v, 1.0f / fb, 1},
+      // FTM, frame_cross_loss(frame_fea, frame_fea_k, queue_frame_cross, title_fea, title_fea_k, queue_title)  :398
+      {2, io->frame_fea_k, HMMC_POS_ONE_TO_FRAMES, F, q_frame_cross, 1.0f / float(F) / fb, 2},
+      {3, io->title_fea_k, HMMC_POS_FRAMES_TO_ONE, 1, q_title, 1.0f / float(F) / fb, 2}};
+  // gradients carry the loss weights: scale each block's coefficient (the loss slots stay unweighted
+  // only when all three weights are applied afterwards, so slots are reported weighted = w * loss)
+  const float wk[3] = {w_fam, w_vtm, w_ftm};
+  int nb = use_frame_fea ? 5 : 3;
+  int ng = use_frame_fea ? 4 : 3;
+  for (int k = 0; k < nb; ++k) blocks[k].coef *= wk[blocks[k].kind];
+  float* kinds = static_cast<float*>(workspace);
+  int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, kinds, 0, static_cast<char*>(workspace) + 1024,
+                       workspace_bytes - 1024, st);
+  if (rc) return rc;
+  if (!use_frame_fea && io->d_frame_fea != nullptr)
+    HMMC_CHECK_CUDA(cudaMemsetAsync(io->d_frame_fea, 0, sizeof(float) * size_t(b) * F * D, st));
+  head_losses_kernel<<<1, 1, 0, st>>>(losses_out, kinds, w_fam, w_vtm, w_ftm, use_frame_fea);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_ema_block_elems(void) { return EMA_BLOCK_ELEMS; }
+
+int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_t* numels, const int32_t* dtypes,
+                   const int64_t* block_offsets, int n, int64_t total_blocks, float m, float one_minus_m, void* stream) {
+  HMMC_REQUIRE(pk_ptrs && p_ptrs && numels && dtypes && block_offsets, "ema_multi: null table");
+  if (n <= 0 || total_blocks <= 0) return HMMC_OK;
+  HMMC_REQUIRE(total_blocks < (int64_t(1) << 31), "ema_multi: too many blocks");
+  ema_multi_kernel<<<unsigned(total_blocks), EMA_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      pk_ptrs, p_ptrs, numels, dtypes, block_offsets, n, m, one_minus_m);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
 __global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K) { queue_ptr[0] = (queue_ptr[0] + B) % K; }
 
 static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
