@@ -6,6 +6,11 @@
 
 namespace hmmc {
 
+static int tune_int(const char* name, int dflt) {     // tuning aids (tools/*_bench.py)
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 // ------------------------------------------------------------------ queue packing
 // dk [D,Kq] fp32  ->  pack_kd [Kq, planes*D] and pack_dk [D, planes*Kq] (bf16 hi / lo planes).
 // 32x32 tile transpose through shared memory so both global sides stay coalesced.
@@ -382,7 +387,7 @@ constexpr int ENQ_DCHUNK = 128;
 // advance to advance_ptr_kernel.
 template <int CB>
 __global__ void __launch_bounds__(256)
-enqueue_kernel(int nsamples, int D, EnqueueArgs a, int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
+enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
   __shared__ float nrm[CB];
   __shared__ float tile[CB][33];
   const int qi = blockIdx.z;
@@ -426,8 +431,8 @@ enqueue_kernel(int nsamples, int D, EnqueueArgs a, int64_t* __restrict__ queue_p
   float* dk = a.dk[qi];
   __nv_bfloat16* pkd = a.pack_kd[qi];
   __nv_bfloat16* pdk = a.pack_dk[qi];
-  const int dbeg = blockIdx.y * ENQ_DCHUNK;
-  const int dend = min(dbeg + ENQ_DCHUNK, D);
+  const int dbeg = blockIdx.y * dchunk;
+  const int dend = min(dbeg + dchunk, D);
   for (int d0 = dbeg; d0 < dend; d0 += 32) {
     // read: warp w handles columns w, w+8, ..; lane = d
 #pragma unroll 4
@@ -552,11 +557,6 @@ namespace hmmc {
 // or two queues ("blocks" = GEMM problems), in a fixed number of launches:
 //   prep_rows (1) -> S-GEMM + exp/rowsum/E epilogue (1, grouped) -> U-GEMM (1, grouped, split-K)
 //   -> finish (1) -> loss reduce (1)
-static int tune_int(const char* name, int dflt) {     // tuning aids (tools/head_bench.py)
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 struct BlockDesc {
   int group;                 // which query tensor
   const float* keys;
@@ -903,14 +903,17 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
     a.src[i] = src5[i];
     a.src_stride[i] = stride5[i];
   }
-  const int dchunks = (D + ENQ_DCHUNK - 1) / ENQ_DCHUNK;
+  static const int dchunk_env = tune_int("HMMC_ENQ_DCHUNK", 0);
+  static const int cb_env = tune_int("HMMC_ENQ_CB", 32);
+  const int dchunk = dchunk_env > 0 ? dchunk_env : ENQ_DCHUNK;
+  const int dchunks = (D + dchunk - 1) / dchunk;
   const int p_arg = device_ptr ? -1 : int(ptr_host), np_arg = device_ptr ? 0 : int((ptr_host + B) % K);
-  if (B * F >= 4096) {
+  if (cb_env == 128) {
     dim3 grid((B * F + 127) / 128, dchunks, 5);
-    enqueue_kernel<128><<<grid, 256, 0, st>>>(B, D, a, queue_ptr, p_arg, np_arg);
+    enqueue_kernel<128><<<grid, 256, 0, st>>>(B, D, dchunk, a, queue_ptr, p_arg, np_arg);
   } else {
     dim3 grid((B * F + 31) / 32, dchunks, 5);
-    enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, a, queue_ptr, p_arg, np_arg);
+    enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, dchunk, a, queue_ptr, p_arg, np_arg);
   }
   HMMC_CHECK_LAUNCH();
   if (device_ptr) {
