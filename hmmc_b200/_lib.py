@@ -54,12 +54,12 @@ SIGNATURES = {
                                            c_float, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
     "hmmc_enqueue_norm_direct": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                         POINTER(hmmc_queue), c_void_p, c_int64, c_int, c_void_p]),
+                                         POINTER(hmmc_queue), c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
     "hmmc_enqueue_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_queue), c_void_p, c_int64,
-                                  c_int, c_void_p]),
+                                  c_int, c_void_p, c_void_p]),
     "hmmc_scale_tensors": (c_int, [POINTER(c_uint64), POINTER(c_int64), c_int, c_void_p, c_void_p]),
     "hmmc_pack_rows": (c_int, [POINTER(c_uint64), POINTER(c_int32), c_int, c_int64, c_void_p, c_void_p]),
     "hmmc_unpack_rows": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_int32), c_int, c_int64, c_void_p]),

@@ -373,6 +373,7 @@ struct EnqueueArgs {
   int64_t src_stride[5];    // elements between consecutive samples
   int Kq[5];                // columns of each queue
   int mult[5];              // columns per sample: 1 or F
+  int norm_off[5];          // offset of each queue's norms in the scratch array
   int planes;
 };
 
@@ -385,9 +386,26 @@ constexpr int ENQ_DCHUNK = 128;
 // ptr >= 0: the host-tracked pointer (block 0 stores new_ptr);  ptr < 0: read the pointer from
 // queue_ptr[0] on the device (CUDA-graph replay: no host value can be baked in) and leave the
 // advance to advance_ptr_kernel.
+// max(||x||, 1e-12) of every key vector of the five queues, one warp per vector;
+// norms[qi][c] with c = sample*mult + f, queue qi starting at norm_off[qi]
+__global__ void key_norms_kernel(int nsamples, int D, EnqueueArgs a, float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.y;
+  const int mult = a.mult[qi];
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= nsamples * mult) return;
+  const int smp = c / mult, f = c - smp * mult;
+  const float* x = a.src[qi] + int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = x[d]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) norms[a.norm_off[qi] + c] = fmaxf(sqrtf(ss), 1e-12f);
+}
+
 template <int CB>
 __global__ void __launch_bounds__(256)
-enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
+enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __restrict__ norms,
+               int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
   __shared__ float nrm[CB];
   __shared__ float tile[CB][33];
   const int qi = blockIdx.z;
@@ -407,23 +425,27 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, int64_t* __restri
     const int smp = c / mult, f = c - smp * mult;
     return a.src[qi] + int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
   };
-  constexpr int CPW = CB / 8;                    // columns per warp
-  for (int i = 0; i < CPW; i += 2) {             // two vectors at a time: more loads in flight
-    const int ca = c0 + warp * CPW + i, cb = ca + 1;
-    float sa = 0.f, sb = 0.f;
-    const float* xa = (ca < ncols) ? src_of(ca) : nullptr;
-    const float* xb = (cb < ncols && i + 1 < CPW) ? src_of(cb) : nullptr;
-    for (int d = lane; d < D; d += 32) {
-      const float va = xa ? xa[d] : 0.f;
-      const float vb = xb ? xb[d] : 0.f;
-      sa = fmaf(va, va, sa);
-      sb = fmaf(vb, vb, sb);
-    }
-    sa = warp_sum(sa);
-    sb = warp_sum(sb);
-    if (lane == 0) {
-      nrm[warp * CPW + i] = fmaxf(sqrtf(sa), 1e-12f);
-      if (i + 1 < CPW) nrm[warp * CPW + i + 1] = fmaxf(sqrtf(sb), 1e-12f);
+  if (norms != nullptr) {
+    for (int cc = threadIdx.x; cc < CB; cc += blockDim.x) nrm[cc] = (c0 + cc < ncols) ? norms[a.norm_off[qi] + c0 + cc] : 1.f;
+  } else {
+    constexpr int CPW = CB / 8;                    // columns per warp
+    for (int i = 0; i < CPW; i += 2) {             // two vectors at a time: more loads in flight
+      const int ca = c0 + warp * CPW + i, cb = ca + 1;
+      float sa = 0.f, sb = 0.f;
+      const float* xa = (ca < ncols) ? src_of(ca) : nullptr;
+      const float* xb = (cb < ncols && i + 1 < CPW) ? src_of(cb) : nullptr;
+      for (int d = lane; d < D; d += 32) {
+        const float va = xa ? xa[d] : 0.f;
+        const float vb = xb ? xb[d] : 0.f;
+        sa = fmaf(va, va, sa);
+        sb = fmaf(vb, vb, sb);
+      }
+      sa = warp_sum(sa);
+      sb = warp_sum(sb);
+      if (lane == 0) {
+        nrm[warp * CPW + i] = fmaxf(sqrtf(sa), 1e-12f);
+        if (i + 1 < CPW) nrm[warp * CPW + i + 1] = fmaxf(sqrtf(sb), 1e-12f);
+      }
     }
   }
   __syncthreads();
@@ -878,7 +900,8 @@ int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_
 __global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K) { queue_ptr[0] = (queue_ptr[0] + B) % K; }
 
 static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
-                          const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, cudaStream_t st) {
+                          const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch,
+                          cudaStream_t st) {
   HMMC_REQUIRE(queues5 && queue_ptr, "enqueue: null argument");
   // the reference's slice assignment raises when the batch does not fit (modules/modeling.py:273-280)
   const bool device_ptr = ptr_host < 0;     // pointer lives on the device only (graph replay)
@@ -902,18 +925,24 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
     a.mult[i] = mult[i];
     a.src[i] = src5[i];
     a.src_stride[i] = stride5[i];
+    a.norm_off[i] = (i == 0) ? 0 : a.norm_off[i - 1] + B * mult[i - 1];
+  }
+  if (scratch != nullptr) {
+    // norms once (one warp per key vector) so the transposing kernel can use small, numerous blocks
+    key_norms_kernel<<<dim3((B * F + 7) / 8, 5), 256, 0, st>>>(B, D, a, scratch);
+    HMMC_CHECK_LAUNCH();
   }
   static const int dchunk_env = tune_int("HMMC_ENQ_DCHUNK", 0);
   static const int cb_env = tune_int("HMMC_ENQ_CB", 32);
-  const int dchunk = dchunk_env > 0 ? dchunk_env : ENQ_DCHUNK;
+  const int dchunk = dchunk_env > 0 ? dchunk_env : (scratch != nullptr ? 64 : ENQ_DCHUNK);
   const int dchunks = (D + dchunk - 1) / dchunk;
   const int p_arg = device_ptr ? -1 : int(ptr_host), np_arg = device_ptr ? 0 : int((ptr_host + B) % K);
   if (cb_env == 128) {
     dim3 grid((B * F + 127) / 128, dchunks, 5);
-    enqueue_kernel<128><<<grid, 256, 0, st>>>(B, D, dchunk, a, queue_ptr, p_arg, np_arg);
+    enqueue_kernel<128><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg);
   } else {
     dim3 grid((B * F + 31) / 32, dchunks, 5);
-    enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, dchunk, a, queue_ptr, p_arg, np_arg);
+    enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg);
   }
   HMMC_CHECK_LAUNCH();
   if (device_ptr) {
@@ -924,20 +953,21 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
 }
 
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5, int64_t* queue_ptr,
-                      int64_t ptr_host, int K, void* stream) {
+                      int64_t ptr_host, int K, float* scratch, void* stream) {
   HMMC_REQUIRE(gathered != nullptr, "enqueue: null gathered buffer");
   const int64_t row = int64_t(3 + 2 * F) * D;
   const float* src[5] = {gathered, gathered + D, gathered + 2 * D, gathered + 3 * D, gathered + 3 * D + int64_t(F) * D};
   const int64_t stride[5] = {row, row, row, row, row};
-  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, static_cast<cudaStream_t>(stream));
+  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, scratch,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
                              const float* frame_proj_k, int B, int F, int D, const hmmc_queue* queues5,
-                             int64_t* queue_ptr, int64_t ptr_host, int K, void* stream) {
+                             int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch, void* stream) {
   const float* src[5] = {v_k, tag_k, title_k, frame_fea_k, frame_proj_k};
   const int64_t stride[5] = {D, D, D, int64_t(F) * D, int64_t(F) * D};
-  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, static_cast<cudaStream_t>(stream));
+  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, static_cast<cudaStream_t>(stream));
 }
 
 int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, int n, const float* scale, void* stream) {

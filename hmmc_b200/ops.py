@@ -353,12 +353,14 @@ def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, dir
         qs, st = _queue_struct(buf, prec)
         arr[i] = qs
         keep.append(st)
+    dev = queue_bufs5[0].device
+    scratch = torch.empty((3 + 2 * F) * W * b, dtype=torch.float32, device=dev)     # key norms
     if direct is not None:
         _lib.check(lib.hmmc_enqueue_norm_direct(*[_p(t) for t in direct], W * b, F, D, arr, _p(queue_ptr),
-                                                int(ptr_host), K, _stream()), "hmmc_enqueue_norm_direct")
+                                                int(ptr_host), K, _p(scratch), _stream()), "hmmc_enqueue_norm_direct")
     else:
-        _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _stream()),
-                   "hmmc_enqueue_norm")
+        _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _p(scratch),
+                                         _stream()), "hmmc_enqueue_norm")
     for st, buf in zip(keep, queue_bufs5):
         if st is not None:
             st.version = buf._version       # the kernel kept the packed copies in step

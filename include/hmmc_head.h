@@ -163,13 +163,14 @@ int hmmc_ema_block_elems(void);
  * where no host value may be baked into the launch); requires K % B == 0 and a pointer that
  * is a multiple of B, like the reference's own no-wrap condition. */
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
-                      int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
+                      int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch /* (3+2F)*W*b floats, or NULL */,
+                      void* stream);
 
 /* Same, reading the five key tensors in place ([B,D] x3, [B,F,D] x2, contiguous): the
  * single-process case needs no gather and no packed copy. */
 int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
                              const float* frame_proj_k, int B, int F, int D, const hmmc_queue* queues5,
-                             int64_t* queue_ptr, int64_t ptr_host, int K, void* stream);
+                             int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch, void* stream);
 
 /* x_t *= scale[0] (device scalar) for up to 8 fp32 tensors in one launch: applies the upstream
  * gradient to the gradients the fused heads produced together with the loss. */
