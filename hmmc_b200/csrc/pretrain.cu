@@ -406,7 +406,8 @@ template <int CB>
 __global__ void __launch_bounds__(256)
 enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __restrict__ norms,
                int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
-  __shared__ float nrm[CB];
+  __shared__ float inv[CB];            // 1 / max(||x||, 1e-12) of the block's key vectors
+  __shared__ int64_t soff[CB];         // element offset of each key vector in its source tensor
   __shared__ float tile[CB][33];
   const int qi = blockIdx.z;
   const int mult = a.mult[qi];
@@ -421,31 +422,25 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __re
   const int Kq = a.Kq[qi];
   const int col_base = ptr * mult;       // first destination column
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto src_of = [&](int c) -> const float* {     // c = local column = sample*mult + f
+  const float* src = a.src[qi];
+  for (int cc = threadIdx.x; cc < CB; cc += blockDim.x) {
+    const int c = min(c0 + cc, ncols - 1);         // c = local column = sample*mult + f
     const int smp = c / mult, f = c - smp * mult;
-    return a.src[qi] + int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
-  };
+    soff[cc] = int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
+  }
+  __syncthreads();
   if (norms != nullptr) {
-    for (int cc = threadIdx.x; cc < CB; cc += blockDim.x) nrm[cc] = (c0 + cc < ncols) ? norms[a.norm_off[qi] + c0 + cc] : 1.f;
+    for (int cc = threadIdx.x; cc < CB; cc += blockDim.x)
+      inv[cc] = (c0 + cc < ncols) ? 1.0f / norms[a.norm_off[qi] + c0 + cc] : 0.f;
   } else {
-    constexpr int CPW = CB / 8;                    // columns per warp
-    for (int i = 0; i < CPW; i += 2) {             // two vectors at a time: more loads in flight
-      const int ca = c0 + warp * CPW + i, cb = ca + 1;
-      float sa = 0.f, sb = 0.f;
-      const float* xa = (ca < ncols) ? src_of(ca) : nullptr;
-      const float* xb = (cb < ncols && i + 1 < CPW) ? src_of(cb) : nullptr;
-      for (int d = lane; d < D; d += 32) {
-        const float va = xa ? xa[d] : 0.f;
-        const float vb = xb ? xb[d] : 0.f;
-        sa = fmaf(va, va, sa);
-        sb = fmaf(vb, vb, sb);
+    for (int cc = warp; cc < CB; cc += 8) {
+      float ss = 0.f;
+      if (c0 + cc < ncols) {
+        const float* x = src + soff[cc];
+        for (int d = lane; d < D; d += 32) { const float v = x[d]; ss = fmaf(v, v, ss); }
       }
-      sa = warp_sum(sa);
-      sb = warp_sum(sb);
-      if (lane == 0) {
-        nrm[warp * CPW + i] = fmaxf(sqrtf(sa), 1e-12f);
-        if (i + 1 < CPW) nrm[warp * CPW + i + 1] = fmaxf(sqrtf(sb), 1e-12f);
-      }
+      ss = warp_sum(ss);
+      if (lane == 0) inv[cc] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
     }
   }
   __syncthreads();
@@ -456,13 +451,13 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __re
   const int dbeg = blockIdx.y * dchunk;
   const int dend = min(dbeg + dchunk, D);
   for (int d0 = dbeg; d0 < dend; d0 += 32) {
-    // read: warp w handles columns w, w+8, ..; lane = d
+    // read: warp w handles columns w, w+8, ..; lane = d.  x * (1/n): within 1 ulp of F.normalize's x / n
 #pragma unroll 4
     for (int cc = warp; cc < CB; cc += 8) {
       const int c = c0 + cc, d = d0 + lane;
       float v = 0.f;
       if (c < ncols && d < dend) {
-        v = src_of(c)[d] / nrm[cc];
+        v = src[soff[cc] + d] * inv[cc];
         if (pkd != nullptr) {
           __nv_bfloat16 hi, lo;
           split_bf16(v, hi, lo);
