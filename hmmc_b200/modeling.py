@@ -194,6 +194,19 @@ class ContrastiveHeadMixin:
         self._enqueue_gathered(self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k))
 
 
+def patch_reference_classes(*classes):
+    """Install the B200 head on the reference's own model classes: every method
+    of ContrastiveHeadMixin replaces the class's method of the same name; classes that own the
+    negative queues also get the fused ``head_loss``."""
+    for cls in classes:
+        for name, fn in vars(ContrastiveHeadMixin).items():
+            if callable(fn) and not name.startswith("__"):
+                setattr(cls, name, fn)
+        if hasattr(cls, "_dequeue_and_enqueue") and cls.__name__ == "BirdPreTrainedModel":
+            cls.head_loss = BirdPreTrainedModel.head_loss
+    return classes
+
+
 def _event():
     e = torch.cuda.Event(enable_timing=True)
     e.record()
