@@ -96,11 +96,11 @@ __global__ void prep_rows_kernel(PrepArgs a, int D, int planes) {
   float ss = 0.f;
   for (int d = lane; d < D; d += 32) { const float v = xr[d]; ss = fmaf(v, v, ss); }
   ss = warp_sum(ss);
-  const float n = fmaxf(sqrtf(ss), 1e-12f);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);     // x * (1/n): within 1 ulp of F.normalize's x / n
   float* xh = a.xhat[gi];
   __nv_bfloat16* pk = a.packed[gi];
   for (int d = lane; d < D; d += 32) {
-    const float v = xr[d] / n;
+    const float v = xr[d] * inv;
     if (xh != nullptr) xh[int64_t(r) * D + d] = v;
     if (pk != nullptr) {
       __nv_bfloat16 hi, lo;
@@ -262,10 +262,19 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
   }
 }
 
-// per-kind sums in a fixed order (deterministic); kind_out[k] (+)= sum_r row_loss[k][r]
-__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total_rows, float* __restrict__ kind_out,
-                                   int accumulate) {
+// Per-kind sums in a fixed order (deterministic) and the final scalars, one launch:
+//   mode 0: out[0] += fam + vtm + ftm                     (hmmc_infonce_queue_fwd_bwd)
+//   mode 1: out[0..3] = total, FAM, VTM, FTM; the slots arrive weighted (w * loss) and are
+//           reported unweighted as well               (hmmc_pretrain_head_fwd_bwd)
+struct LossFinal {
+  float* out;
+  int mode;
+  float w_fam, w_vtm, w_ftm;
+  int use_frame_fea;
+};
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total_rows, LossFinal f) {
   __shared__ float red[32];
+  __shared__ float kinds[3];
   for (int k = 0; k < 3; ++k) {
     const float* v = row_loss + int64_t(k) * total_rows;
     float acc = 0.f;
@@ -278,22 +287,19 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total
       acc += (a0 + a1) + (a2 + a3);
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) kind_out[k] = accumulate ? kind_out[k] + acc : acc;
+    if (threadIdx.x == 0) kinds[k] = acc;
     __syncthreads();
   }
-}
-
-__global__ void add_scalar_kernel(float* __restrict__ out, const float* __restrict__ kinds) {
-  out[0] += kinds[0] + kinds[1] + kinds[2];
-}
-// losses_out = [total, FAM, VTM, FTM]; the slots arrive weighted (w * loss), report them unweighted too
-__global__ void head_losses_kernel(float* __restrict__ out, const float* __restrict__ kinds, float w_fam, float w_vtm,
-                                   float w_ftm, int use_frame_fea) {
-  const float fam = kinds[0], vtm = kinds[1], ftm = use_frame_fea ? kinds[2] : 0.f;
-  out[0] = fam + vtm + ftm;
-  out[1] = (w_fam != 0.f) ? fam / w_fam : 0.f;
-  out[2] = (w_vtm != 0.f) ? vtm / w_vtm : 0.f;
-  out[3] = (w_ftm != 0.f) ? ftm / w_ftm : 0.f;
+  if (threadIdx.x != 0) return;
+  if (f.mode == 0) {
+    f.out[0] += kinds[0] + kinds[1] + kinds[2];
+  } else {
+    const float fam = kinds[0], vtm = kinds[1], ftm = f.use_frame_fea ? kinds[2] : 0.f;
+    f.out[0] = fam + vtm + ftm;
+    f.out[1] = (f.w_fam != 0.f) ? fam / f.w_fam : 0.f;
+    f.out[2] = (f.w_vtm != 0.f) ? vtm / f.w_vtm : 0.f;
+    f.out[3] = (f.w_ftm != 0.f) ? ftm / f.w_ftm : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------ EMA
@@ -522,6 +528,7 @@ struct ScaleArgs {
 // with the loss, the upstream gradient arrives later)
 __global__ void scale_tensors_kernel(ScaleArgs a, const float* __restrict__ scale) {
   const float s = scale[0];
+  if (s == 1.0f) return;               // loss.backward() with no upstream scaling: nothing to do
   float* x = a.ptrs[blockIdx.y];
   const int64_t n = a.numels[blockIdx.y];
   const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
@@ -658,8 +665,7 @@ static void launch_finish(const FinishArgs& fa, int total_rows, int D, float inv
 }
 
 static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
-                       int prec, float* kind_out, int accumulate, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st) {
+                       int prec, const LossFinal& fin, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
   HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
   HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
@@ -779,7 +785,7 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
   else if (ne <= 32) launch_finish<32>(fa, total_rows, D, invT, cmax, L.row_loss, st);
   else launch_finish<FIN_MAXE>(fa, total_rows, D, invT, cmax, L.row_loss, st);
   HMMC_CHECK_LAUNCH();
-  loss_reduce_kernel<<<1, 1024, 0, st>>>(L.row_loss, total_rows, kind_out, accumulate);
+  loss_reduce_kernel<<<1, 1024, 0, st>>>(L.row_loss, total_rows, fin);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -813,17 +819,12 @@ int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, 
   HMMC_REQUIRE(b > 0 && Fq > 0 && Fk > 0 && D > 0, "infonce: bad sizes b=%d Fq=%d Fk=%d D=%d", b, Fq, Fk, D);
   int rc = check_pos_mode(pos_mode, Fq, Fk);
   if (rc) return rc;
-  // the three loss slots of the generic driver live at the head of the workspace
-  HMMC_REQUIRE(workspace != nullptr && workspace_bytes >= 1024, "infonce: workspace too small");
-  float* kinds = static_cast<float*>(workspace);
+  HMMC_REQUIRE(workspace != nullptr, "infonce: null workspace");
   GroupDesc g{q, dq, b * Fq, Fq};
   BlockDesc blk{0, keys, pos_mode, Fk, queue, weight / float(b), 0};
-  rc = run_infonce(&g, 1, &blk, 1, b, D, temperature, prec, kinds, 0, static_cast<char*>(workspace) + 1024,
-                   workspace_bytes - 1024, static_cast<cudaStream_t>(stream));
-  if (rc) return rc;
-  add_scalar_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_out, kinds);
-  HMMC_CHECK_LAUNCH();
-  return HMMC_OK;
+  LossFinal fin{loss_out, 0, 0.f, 0.f, 0.f, 1};
+  return run_infonce(&g, 1, &blk, 1, b, D, temperature, prec, fin, workspace, workspace_bytes,
+                     static_cast<cudaStream_t>(stream));
 }
 
 size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec) {
@@ -845,7 +846,7 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
   HMMC_REQUIRE(io->v_fea && io->title_fea && io->frame_fea && io->frame_pred && io->v_fea_k && io->title_fea_k &&
                io->frame_fea_k && io->frame_proj_k, "pretrain_head: null embedding pointer");
   HMMC_REQUIRE(b > 0 && F >= 2 && D > 0, "pretrain_head: bad sizes b=%d F=%d D=%d", b, F, D);
-  HMMC_REQUIRE(workspace != nullptr && workspace_bytes >= 1024, "pretrain_head: workspace too small");
+  HMMC_REQUIRE(workspace != nullptr, "pretrain_head: null workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // query tensors: 0 frame_pred, 1 v_fea, 2 title_fea, 3 frame_fea
   GroupDesc groups[4] = {{io->frame_pred, io->d_frame_pred, b * F, F},
@@ -868,14 +869,11 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
   int nb = use_frame_fea ? 5 : 3;
   int ng = use_frame_fea ? 4 : 3;
   for (int k = 0; k < nb; ++k) blocks[k].coef *= wk[blocks[k].kind];
-  float* kinds = static_cast<float*>(workspace);
-  int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, kinds, 0, static_cast<char*>(workspace) + 1024,
-                       workspace_bytes - 1024, st);
+  LossFinal fin{losses_out, 1, w_fam, w_vtm, w_ftm, use_frame_fea};
+  int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, fin, workspace, workspace_bytes, st);
   if (rc) return rc;
   if (!use_frame_fea && io->d_frame_fea != nullptr)
     HMMC_CHECK_CUDA(cudaMemsetAsync(io->d_frame_fea, 0, sizeof(float) * size_t(b) * F * D, st));
-  head_losses_kernel<<<1, 1, 0, st>>>(losses_out, kinds, w_fam, w_vtm, w_ftm, use_frame_fea);
-  HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
 
