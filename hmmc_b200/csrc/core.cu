@@ -183,6 +183,10 @@ int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, floa
   EpiStoreF32::Params ep{C, ldc, split_stride, alpha};
   static const char* force = getenv("HMMC_FORCE_BN");   // tuning aid (tools/gemm_bench.py)
   if (force != nullptr && atoi(force) == 128) return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
+  if (force != nullptr && atoi(force) == 512) {     // CTA-pair kernel (tools/gemm_bench.py)
+    GemmProblem<EpiStoreF32> pr{A, lda, B, ldb, M, N, K, planes, splits, ep};
+    return launch_umma_grouped_pair<EpiStoreF32>(&pr, 1, st);
+  }
   if (N % 256 == 0 || N > 1024) return launch_umma_gemm<256, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
   return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
 }

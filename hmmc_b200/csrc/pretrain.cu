@@ -741,10 +741,13 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
       p2[k] = GemmProblem<EpiStoreF32>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
                                        G.rows, D, Kq, planes, L.splits[k], e2};
     }
-    rc = (L.bn1 == 256) ? launch_umma_grouped<256, EpiInfoNCE>(p1, nb, st) : launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st);
+    static const int pair1 = tune_int("HMMC_PAIR_S", 1), pair2 = tune_int("HMMC_PAIR_U", 1);   // CTA-pair kernels
+    if (L.bn1 == 256 && pair1) rc = launch_umma_grouped_pair<EpiInfoNCE>(p1, nb, st);
+    else rc = (L.bn1 == 256) ? launch_umma_grouped<256, EpiInfoNCE>(p1, nb, st) : launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st);
     if (rc) return rc;
     if (need_grad) {
-      rc = (L.bn2 == 256) ? launch_umma_grouped<256, EpiStoreF32>(p2, nb, st) : launch_umma_grouped<128, EpiStoreF32>(p2, nb, st);
+      if (L.bn2 == 256 && pair2) rc = launch_umma_grouped_pair<EpiStoreF32>(p2, nb, st);
+      else rc = (L.bn2 == 256) ? launch_umma_grouped<256, EpiStoreF32>(p2, nb, st) : launch_umma_grouped<128, EpiStoreF32>(p2, nb, st);
       if (rc) return rc;
     }
   }

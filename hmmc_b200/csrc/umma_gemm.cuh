@@ -234,6 +234,179 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Same roles and epilogues, but two CTAs of a cluster share every 256(M) x 256(N) tile: each CTA loads
+// its own 128 rows of A and HALF of the B tile (128 rows), the leader's thread issues
+// tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs, and each CTA's epilogue
+// warps drain their own 128 accumulator rows.  A stage is 32 KB instead of 48 KB, so six stages fit:
+// half the L2 -> SM bytes per FLOP and 1.5x more latency tolerance for the TMA ring.
+constexpr int UMMA_PAIR_BN = 256;
+constexpr int UMMA_PAIR_STAGES = 6;
+constexpr uint32_t UMMA_PAIR_A_BYTES = UMMA_BM * UMMA_BK * 2;               // 16 KB
+constexpr uint32_t UMMA_PAIR_B_BYTES = (UMMA_PAIR_BN / 2) * UMMA_BK * 2;    // 16 KB
+constexpr uint32_t UMMA_PAIR_STAGE_BYTES = UMMA_PAIR_A_BYTES + UMMA_PAIR_B_BYTES;
+constexpr size_t UMMA_PAIR_SMEM_BYTES =
+    size_t(UMMA_PAIR_STAGES) * UMMA_PAIR_STAGE_BYTES + 1024 + 256 + UMMA_EPI_WARPS * 32 * 80;
+
+template <class Epi>
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ GroupedArgs<Epi> g) {
+  constexpr int BN = UMMA_PAIR_BN;
+  constexpr int STAGES = UMMA_PAIR_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * UMMA_PAIR_STAGE_BYTES);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bar_base = ptx::smem_u32(bars);
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (STAGES + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  constexpr uint32_t TMEM_COLS = 512, ACC_STRIDE = 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = ptx::cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < g.num_problems; ++p) {
+      ptx::prefetch_tmap(&tm.a[p]);
+      ptx::prefetch_tmap(&tm.b[p]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(full_bar(i), 1);      // the leader's producer arrives; bytes come from both CTAs
+      ptx::mbar_init(empty_bar(i), 1);     // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull_bar(i), 1);
+      ptx::mbar_init(tempty_bar(i), 2 * UMMA_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile t of a problem = (m2, n_blk, split) with m2 indexing 256-row super tiles; tile_begin[] was
+  // built with num_m_blk = number of super tiles (see launch_umma_grouped_pair)
+  const int num_tiles = g.tile_begin[g.num_problems];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int p = find_problem(g, t);
+        const GemmShape& s = g.shape[p];
+        const int tl = t - g.tile_begin[p];
+        const int tiles_mn = s.num_m_blk * s.num_n_blk;
+        const int split = tl / tiles_mn;
+        const int mn = tl - split * tiles_mn;
+        const int m2 = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, s.num_seg * s.kb_per_seg);
+        for (int i = kb0; i < kb1; ++i) {
+          const int seg = i / s.kb_per_seg, kb = i - seg * s.kb_per_seg;
+          const int ak = (seg == 0 ? s.a_k0[0] : (seg == 1 ? s.a_k0[1] : s.a_k0[2])) + kb * UMMA_BK;
+          const int bk = (seg == 0 ? s.b_k0[0] : (seg == 1 ? s.b_k0[1] : s.b_k0[2])) + kb * UMMA_BK;
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (cta == 0) ptx::mbar_expect_tx(full_bar(stage), 2u * UMMA_PAIR_STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * UMMA_PAIR_STAGE_BYTES;
+          ptx::tma_load_2d_pair(sa, &tm.a[p], full_bar(stage), ak, (m2 * 2 + int(cta)) * UMMA_BM);
+          ptx::tma_load_2d_pair(sa + UMMA_PAIR_A_BYTES, &tm.b[p], full_bar(stage), bk, n_blk * BN + int(cta) * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * UMMA_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int p = find_problem(g, t);
+        const GemmShape& s = g.shape[p];
+        const int split = (t - g.tile_begin[p]) / (s.num_m_blk * s.num_n_blk);
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, s.num_seg * s.kb_per_seg);
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int i = kb0; i < kb1; ++i) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * UMMA_PAIR_STAGE_BYTES;
+          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + UMMA_PAIR_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < UMMA_BK / 16; ++k)
+            ptx::umma_bf16_ss_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (i > kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit_pair(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit_pair(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int HALF_N = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    Epi epi;
+    epi.stage = smem + size_t(STAGES) * UMMA_PAIR_STAGE_BYTES + 256 + size_t(warp - 4) * (32 * 80);
+    epi.lane = lane;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int p = find_problem(g, t);
+      const GemmShape& s = g.shape[p];
+      const typename Epi::Params& ep = g.ep[p];
+      const int tl = t - g.tile_begin[p];
+      const int tiles_mn = s.num_m_blk * s.num_n_blk;
+      const int split = tl / tiles_mn;
+      const int mn = tl - split * tiles_mn;
+      const int m2 = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
+      const int row = (m2 * 2 + int(cta)) * UMMA_BM + quad * 32 + lane;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * HALF_N;
+      epi.begin_tile(ep, s, row, n_blk, split);
+#pragma unroll 1
+      for (int c = 0; c < HALF_N / 32; ++c) {
+        float v[32];
+        ptx::tmem_ld_x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+      epi.end_tile(ep, s, row, n_blk * 2 + half, split);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ epilogues
 
 // C[split][m, n] = alpha * acc
@@ -443,6 +616,73 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, g);
   HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+// CTA-pair launch of a grouped GEMM (BN = 256).  GemmShape::num_m_blk counts 256-row super tiles;
+// everything else (segments, split-K, epilogue parameters) is identical to launch_umma_grouped.
+template <class Epi>
+int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t stream) {
+  constexpr int BN = UMMA_PAIR_BN;
+  HMMC_REQUIRE(n >= 1 && n <= UMMA_MAX_PROBLEMS, "umma gemm: %d problems (max %d)", n, UMMA_MAX_PROBLEMS);
+  TmapSet tm;
+  GroupedArgs<Epi> g;
+  g.num_problems = 0;
+  g.tile_begin[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmProblem<Epi>& pr = probs[i];
+    HMMC_REQUIRE(pr.K % UMMA_BK == 0 && pr.K > 0, "umma gemm: K=%d must be a positive multiple of %d", pr.K, UMMA_BK);
+    HMMC_REQUIRE(pr.planes == 1 || pr.planes == 2, "umma gemm: planes must be 1 or 2");
+    HMMC_REQUIRE(pr.lda % 8 == 0 && pr.ldb % 8 == 0, "umma gemm: leading dimensions must be multiples of 8");
+    HMMC_REQUIRE((reinterpret_cast<uintptr_t>(pr.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.B) & 15) == 0,
+                 "umma gemm: operands must be 16-byte aligned");
+    if (pr.M <= 0 || pr.N <= 0) continue;
+    const int k = g.num_problems;
+    GemmShape& s = g.shape[k];
+    s.M = pr.M;
+    s.N = pr.N;
+    s.num_m_blk = (pr.M + 2 * UMMA_BM - 1) / (2 * UMMA_BM);      // super tiles of 256 rows
+    s.num_n_blk = (pr.N + BN - 1) / BN;
+    fill_segments(s, pr.planes, pr.K);
+    const int total_kb = s.num_seg * s.kb_per_seg;
+    int splits = pr.splits < 1 ? 1 : (pr.splits > total_kb ? total_kb : pr.splits);
+    s.kb_per_split = (total_kb + splits - 1) / splits;
+    s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;
+    int rc = make_tmap_bf16(&tm.a[k], pr.A, uint64_t(pr.M), uint64_t(pr.planes) * pr.K, uint64_t(pr.lda), UMMA_BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tm.b[k], pr.B, uint64_t(pr.N), uint64_t(pr.planes) * pr.K, uint64_t(pr.ldb), BN / 2);
+    if (rc) return rc;
+    g.ep[k] = pr.ep;
+    g.tile_begin[k + 1] = g.tile_begin[k] + s.num_m_blk * s.num_n_blk * s.num_splits;
+    g.num_problems = k + 1;
+  }
+  if (g.num_problems == 0) return HMMC_OK;
+  for (int k = g.num_problems; k < UMMA_MAX_PROBLEMS; ++k) {
+    g.tile_begin[k + 1] = g.tile_begin[g.num_problems];
+    tm.a[k] = tm.a[0];
+    tm.b[k] = tm.b[0];
+    g.shape[k] = g.shape[0];
+    g.ep[k] = g.ep[0];
+  }
+  auto kern = umma_gemm_pair_kernel<Epi>;
+  HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(UMMA_PAIR_SMEM_BYTES)));
+  const int tiles = g.tile_begin[g.num_problems];
+  int pairs = sm_count() / 2;
+  if (pairs > tiles) pairs = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(UMMA_THREADS);
+  cfg.dynamicSmemBytes = UMMA_PAIR_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  HMMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, g));
   return HMMC_OK;
 }
 
