@@ -211,12 +211,16 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * HALF_N;
       epi.begin_tile(ep, s, row, n_blk, split);
-#pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
-        float v[32];
-        ptx::tmem_ld_x32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-        epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v);
+      {
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        float v[2][32];
+        ptx::tmem_ld_x32(taddr, v[0]);
+#pragma unroll
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < HALF_N / 32) ptx::tmem_ld_x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v[c & 1]);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -384,12 +388,16 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * HALF_N;
       epi.begin_tile(ep, s, row, n_blk, split);
-#pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
-        float v[32];
-        ptx::tmem_ld_x32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-        epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v);
+      {
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        float v[2][32];
+        ptx::tmem_ld_x32(taddr, v[0]);
+#pragma unroll
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < HALF_N / 32) ptx::tmem_ld_x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v[c & 1]);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();

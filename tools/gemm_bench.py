@@ -6,7 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hmmc_b200 import ops
 
-shapes = [(1536, 12288, 512), (1536, 512, 12288), (4096, 4096, 4096), (8192, 8192, 2048), (3072, 12288, 512)]
+import os
+if os.environ.get("SHAPES"):
+    shapes = [tuple(int(x) for x in t.split("x")) for t in os.environ["SHAPES"].split(",")]
+else:
+    shapes = None
+_default = [(1536, 12288, 512), (1536, 512, 12288), (4096, 4096, 4096), (8192, 8192, 2048), (3072, 12288, 512)]
+shapes = shapes or _default
 for M, N, K in shapes:
     A = (torch.randn(M, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
     B = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
