@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include <stdlib.h>
 
 namespace hmmc {
 
@@ -62,6 +63,7 @@ struct TmapSet {
 template <class Epi>
 struct GroupedArgs {
   int num_problems;
+  int probe;                 // tuning aid: 2 = epilogue skips the TMEM reads
   int tile_begin[UMMA_MAX_PROBLEMS + 1];
   GemmShape shape[UMMA_MAX_PROBLEMS];
   typename Epi::Params ep[UMMA_MAX_PROBLEMS];
@@ -388,7 +390,7 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * HALF_N;
       epi.begin_tile(ep, s, row, n_blk, split);
-      {
+      if (g.probe != 2) {
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
         ptx::tmem_ld_x32(taddr, v[0]);
@@ -487,6 +489,7 @@ struct EpiInfoNCE {
     __nv_bfloat16* E;         // [M, e_planes * N] or nullptr
     int64_t ldE;
     int e_planes;
+    int probe;                // tuning aid: 1 = skip the exponential (epilogue cost probe)
   };
   uint8_t* stage;
   int lane;
@@ -516,7 +519,7 @@ struct EpiInfoNCE {
     float e[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      e[j] = ptx::ex2_approx(fmaf(v[j], p.a2, -p.c2));
+      e[j] = p.probe ? fmaf(v[j], p.a2, -p.c2) : ptx::ex2_approx(fmaf(v[j], p.a2, -p.c2));
       if (col0 + j >= s.N) e[j] = 0.f;
       acc_sum += e[j];
     }
@@ -582,6 +585,7 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
   TmapSet tm;
   GroupedArgs<Epi> g;
   g.num_problems = 0;
+  g.probe = getenv("HMMC_PROBE_EPI") ? atoi(getenv("HMMC_PROBE_EPI")) : 0;
   g.tile_begin[0] = 0;
   for (int i = 0; i < n; ++i) {
     const GemmProblem<Epi>& pr = probs[i];
@@ -636,6 +640,7 @@ int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t 
   TmapSet tm;
   GroupedArgs<Epi> g;
   g.num_problems = 0;
+  g.probe = getenv("HMMC_PROBE_EPI") ? atoi(getenv("HMMC_PROBE_EPI")) : 0;
   g.tile_begin[0] = 0;
   for (int i = 0; i < n; ++i) {
     const GemmProblem<Epi>& pr = probs[i];
