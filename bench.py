@@ -555,6 +555,14 @@ def main():
                              "note": "ema / head: eager run with CUDA events right after the timed region"},
             "issue_mode": graph_note}
 
+    # ---- fine-tune head leg (config 3), all ranks
+    if not args.no_retrieval:
+        try:
+            ft = finetune_leg(args, W, rank, local, dev)
+            if rank == 0:
+                line["finetune_head"] = ft
+        except Exception as e:   # noqa: BLE001
+            line["finetune_head"] = {"error": repr(e)[:300]}
     # ---- retrieval legs: config 2 on rank 0; config 5 (gallery sharded over all ranks)
     if rank == 0 and not args.no_retrieval:
         line["retrieval"] = retrieval_leg(args, dev)
@@ -583,6 +591,57 @@ def main():
             sys.stderr.flush()
             os._exit(0)
         dist.destroy_process_group()
+
+
+def finetune_leg(args, W, rank, local, dev):
+    """BASELINE config 3: fine-tune head, 32 samples per GPU (global batch 32*W), 12 frames: packed
+    all-gather + VTM/FTM symmetric CrossEn forward and backward.  All ranks take part."""
+    import torch.distributed as dist
+    from hmmc_b200 import modeling
+    from hmmc_b200 import synthetic as syn
+    from hmmc_b200.graphs import GraphedStep
+    out = {}
+    for b in ([32] if W > 1 else [32, 256]):
+        t, v, fr = syn.finetune_inputs(b, seed=300 + rank)
+        task = types.SimpleNamespace(local_rank=local, top_frames=2, use_frame_fea=True, head_precision="bf16x3")
+        m = modeling.BirdModel(modeling.default_cross_config(), task)
+        ins = [torch.from_numpy(x).to(dev).requires_grad_(True) for x in (t, v, fr)]
+
+        def step():
+            for x in ins:
+                x.grad = None
+            loss = m.head_loss(*ins)
+            loss.backward()
+            return loss
+        try:
+            g = GraphedStep(step)
+            run, mode = g.replay, "cuda graph replay"
+        except Exception as e:   # noqa: BLE001
+            run, mode = step, "eager (%s)" % repr(e)[:80]
+            torch.cuda.synchronize()
+        for _ in range(5):
+            run()
+        if W > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 100
+        e0.record()
+        for _ in range(reps):
+            loss = run()
+        e1.record()
+        if W > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if W > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        out["b%d_per_gpu" % b] = {"global_batch": b * W, "ms_per_step": ms, "samples_per_s": b * W / (ms / 1e3),
+                                  "loss": float(loss), "issue_mode": mode}
+    out["workload"] = "BASELINE config 3: fine-tune head fwd+bwd (packed all-gather + 13 symmetric CrossEn matrices), bf16x3"
+    return out
 
 
 def retrieval_leg(args, dev):
