@@ -563,6 +563,12 @@ def main():
                 line["finetune_head"] = ft
         except Exception as e:   # noqa: BLE001
             line["finetune_head"] = {"error": repr(e)[:300]}
+    # ---- optimizer step that follows the head's backward, rank 0
+    if rank == 0 and not args.no_retrieval:
+        try:
+            line["optimizer_step"] = optimizer_leg(args, dev, sizes, hbm_peak, peak_src)
+        except Exception as e:   # noqa: BLE001
+            line["optimizer_step"] = {"error": repr(e)[:300]}
     # ---- retrieval legs: config 2 on rank 0; config 5 (gallery sharded over all ranks)
     if rank == 0 and not args.no_retrieval:
         line["retrieval"] = retrieval_leg(args, dev)
@@ -591,6 +597,76 @@ def main():
             sys.stderr.flush()
             os._exit(0)
         dist.destroy_process_group()
+
+
+def optimizer_leg(args, dev, sizes, hbm_peak, peak_src):
+    """clip_grad_norm_(all, 1.0) + BertAdam.step over the 362 tensors / 172 M parameters the EMA walks
+    (main_pretrain.py:277-286), as prep_optimizer configures it (warmup_cosine, b2 0.98, two lr groups,
+    decay / no decay).  GPU: three launches per step.  CPU: the reference's per-parameter op sequence
+    (oracle/torch_port.py) on the host cores."""
+    from hmmc_b200 import _lib
+    from hmmc_b200.optimization import BertAdam
+    n = sum(sizes)
+    flat = torch.randn(n, device=dev) * 0.02
+    gflat = torch.randn(n, device=dev) * 1e-4
+    params = [torch.nn.Parameter(x) for x in torch.split(flat, sizes)]
+    grads = list(torch.split(gflat, sizes))
+    common = dict(schedule='warmup_cosine', warmup=0.1, t_total=10000, b1=0.9, b2=0.98, e=1e-6, max_grad_norm=1.0)
+    decay = [p for p in params if p.numel() >= 4096]
+    nodecay = [p for p in params if p.numel() < 4096]
+    opt = BertAdam([dict(common, params=decay, lr=1e-7, weight_decay=0.2),
+                    dict(common, params=nodecay, lr=1e-7, weight_decay=0.0)], lr=1e-7)
+
+    def one():
+        for p, g in zip(params, grads):
+            p.grad = g
+        opt.step(global_max_norm=1.0)
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    reps = 20
+    l0 = lib.hmmc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        one()
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / reps
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    launches = (lib.hmmc_launch_count() - l0) // reps
+    algo = 32.0 * n          # norm pass reads g (4 B); update pass reads p, g, m, v and writes p, m, v (28 B)
+    out = {"workload": "clip_grad_norm_(1.0) + BertAdam.step, %d tensors, %d fp32 parameters" % (len(sizes), n),
+           "ms_per_step": ms, "host_issue_ms_per_step": host_ms, "launches_per_step": int(launches),
+           "params_per_s": n / (ms / 1e3), "grad_norm": float(opt.last_grad_norm),
+           "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo, "traffic": None,
+                        "peak_source": peak_src}}
+    assert bool(torch.isfinite(flat).all())
+    del opt, params, grads, flat, gflat
+    torch.cuda.empty_cache()
+    if not args.no_cpu_baseline:
+        from oracle import torch_port as P
+        frac = 8                                   # every 8th tensor: ~1/8 of the parameters, same size mix
+        csz = sizes[::frac]
+        cp = [torch.randn(k) * 0.02 for k in csz]
+        cg = [torch.randn(k) * 1e-4 for k in csz]
+        st = P.bert_adam_state(cp)
+        groups = [dict(common, lr=1e-7, weight_decay=0.2), dict(common, lr=1e-7, weight_decay=0.0)]
+        gof = [0 if k >= 4096 else 1 for k in csz]
+        P.clip_and_bert_adam_step(cp, cg, st, groups, gof, 1.0)
+        t0 = time.perf_counter()
+        k = 0
+        while k < 3 or (time.perf_counter() - t0 < 5.0 and k < 20):
+            P.clip_and_bert_adam_step(cp, cg, st, groups, gof, 1.0)
+            k += 1
+        cms = (time.perf_counter() - t0) * 1e3 / k
+        out["cpu_baseline"] = {"value": sum(csz) / (cms / 1e3), "unit": "params/s", "cores": torch.get_num_threads(),
+                               "kind": "port", "ms_per_sample_step": cms,
+                               "sample": "every %dth of the %d tensors (%d parameters), %d steps" % (frac, len(sizes), sum(csz), k)}
+    return out
 
 
 def finetune_leg(args, W, rank, local, dev):

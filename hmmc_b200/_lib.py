@@ -58,6 +58,11 @@ SIGNATURES = {
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
+    "hmmc_bert_adam_workspace_bytes": (c_size_t, [c_int, c_int64]),
+    "hmmc_bert_adam_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int64, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hmmc_clip_grad_norm_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p,
+                                          c_size_t, c_void_p]),
     "hmmc_enqueue_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_queue), c_void_p, c_int64,
                                   c_int, c_void_p, c_void_p]),
     "hmmc_scale_tensors": (c_int, [POINTER(c_uint64), POINTER(c_int64), c_int, c_void_p, c_void_p]),

@@ -138,3 +138,37 @@ def ema_param_numels(total=172325632, count=362):
     assert rest > 0, rest
     sizes.append(rest)
     return sizes
+
+
+OPTIM_SIZES = ((37, 5), (1000,), (3,), (90, 100), (8192,), (8193,), (1,), (64, 129))
+OPTIM_GROUP_OF = (0, 1, 1, 0, 0, 1, 1, 0)
+
+
+def optim_groups(case="pretrain"):
+    """Parameter-group hyper-parameters.  'pretrain': the shape prep_optimizer builds
+    (main_pretrain.py:168-202: decay / no-decay groups with their own lr, warmup_cosine, b2=0.98,
+    per-parameter max_grad_norm 1.0).  'plain': constant lr (t_total=-1), no per-parameter clip.
+    'linear': warmup_linear with the constructor's default betas."""
+    if case == "pretrain":
+        common = dict(schedule='warmup_cosine', warmup=0.1, t_total=40, b1=0.9, b2=0.98, e=1e-6, max_grad_norm=1.0)
+        return [dict(common, lr=1e-4, weight_decay=0.2), dict(common, lr=5e-5, weight_decay=0.0)]
+    if case == "plain":
+        common = dict(schedule='warmup_linear', warmup=-1, t_total=-1, b1=0.9, b2=0.999, e=1e-6, max_grad_norm=-1)
+        return [dict(common, lr=3e-4, weight_decay=0.01), dict(common, lr=3e-4, weight_decay=0.0)]
+    if case == "linear":
+        common = dict(schedule='warmup_linear', warmup=0.25, t_total=8, b1=0.9, b2=0.999, e=1e-6, max_grad_norm=1.0)
+        return [dict(common, lr=2e-4, weight_decay=0.01), dict(common, lr=1e-4, weight_decay=0.0)]
+    raise ValueError(case)
+
+
+def optim_tensors(seed=11, sizes=OPTIM_SIZES):
+    """Initial fp32 parameters of the optimizer parity cases."""
+    rs = np.random.RandomState(seed)
+    return [(_randn(rs, *shp) * 0.05).astype(np.float32) for shp in sizes]
+
+
+def optim_grads(step, seed=12, sizes=OPTIM_SIZES, scales=(0.02, 0.002, 0.05, 0.0005, 0.004, 0.03)):
+    """Gradients of step `step`; the scales alternate between clipped (norm > 1) and unclipped steps."""
+    rs = np.random.RandomState(seed + 977 * step)
+    s = scales[step % len(scales)]
+    return [(_randn(rs, *shp) * s).astype(np.float32) for shp in sizes]

@@ -149,6 +149,33 @@ int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_
 /* elements handled by one thread block of hmmc_ema_multi (for building block_offsets) */
 int hmmc_ema_block_elems(void);
 
+/* SURVEY.md §8(f) N3 — the optimizer step that follows the head's backward:
+ *   torch.nn.utils.clip_grad_norm_(model.parameters(), G)   (main_pretrain.py:277,
+ *                                                            main_task_retrieval.py:291)
+ *   BertAdam.step()                                          (modules/optimization.py:103-168)
+ * for a table of n fp32 tensors in three launches.  Tables are device arrays as for
+ * hmmc_ema_multi (block_offsets has n+1 entries, built with hmmc_ema_block_elems()).
+ * hyper is a device table [n][8] fp32: lr_scheduled, weight_decay, b1, 1-b1, b2, 1-b2, e,
+ * max_grad_norm (the per-parameter clip inside step(); <= 0: none).  global_max_norm <= 0: no
+ * global clip.  Per element, in the reference's order and rounding:
+ *   g <- g*cg*ct;  m <- m*b1 + (1-b1)*g;  v <- v*b2 + (1-b2)*g*g;
+ *   u <- m/(sqrt(v)+e) [+ wd*p];  p <- p - lr*u
+ * with cg = min(1, G/(||g_all|| + 1e-6)), ct = min(1, max_grad_norm/(||g_t||*cg + 1e-6)).
+ * write_back_grads != 0 also stores the clipped gradients (the reference clips p.grad in
+ * place and zeroes it right after).  norms_out: NULL or device fp32 [n+1] receiving the
+ * per-tensor gradient norms and, last, the total norm clip_grad_norm_ returns. */
+size_t hmmc_bert_adam_workspace_bytes(int n, int64_t total_blocks);
+int hmmc_bert_adam_multi(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs,
+                         const uint64_t* v_ptrs, const int64_t* numels, const int32_t* dtypes,
+                         const int64_t* block_offsets, int n, int64_t total_blocks, const float* hyper,
+                         float global_max_norm, int write_back_grads, float* norms_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* clip_grad_norm_ on its own: gradients scaled in place by min(1, max_norm/(total + 1e-6));
+ * workspace sized by hmmc_bert_adam_workspace_bytes. */
+int hmmc_clip_grad_norm_multi(const uint64_t* g_ptrs, const int64_t* numels, const int64_t* block_offsets, int n,
+                              int64_t total_blocks, float max_norm, float* norms_out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* _dequeue_and_enqueue (modules/modeling.py:244-284) after the all-gather:
  * L2-normalise (eps 1e-12) the gathered keys and write them as queue columns
  * [ptr, ptr+B) (frame queues: columns [(ptr)*F, (ptr+B)*F), frame index fastest), in

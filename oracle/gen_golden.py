@@ -240,11 +240,47 @@ def gen_eval(M, metrics, R):
     print("eval multi tv", tvm, "vt", vtm)
 
 
+OPTIM_CASES = (("pretrain", 6, 1.0, (0, 5)), ("plain", 3, None, (0, 1, 2)), ("linear", 4, None, (3,)))
+
+
+def gen_optim(M, metrics, R):
+    """clip_grad_norm_ + the reference's BertAdam (modules/optimization.py), a few steps on CPU."""
+    from modules.optimization import BertAdam
+    out = {}
+    for case, nsteps, gmax, keep in OPTIM_CASES:
+        groups = syn.optim_groups(case)
+        params = [torch.nn.Parameter(_t(x)) for x in syn.optim_tensors()]
+        pg = [dict(g, params=[p for p, gi in zip(params, syn.OPTIM_GROUP_OF) if gi == k]) for k, g in enumerate(groups)]
+        opt = BertAdam(pg, lr=groups[0]['lr'])
+        totals, lrs = [], []
+        for st in range(nsteps):
+            for p, g in zip(params, syn.optim_grads(st)):
+                p.grad = _t(g)
+            if gmax is not None:
+                totals.append(float(torch.nn.utils.clip_grad_norm_(params, gmax)))
+            opt.step()
+            lrs.append(sorted(set(opt.get_lr())))
+            if st in keep:
+                for i, p in enumerate(params):
+                    out["%s_p%d_s%d" % (case, i, st)] = p.data.numpy().copy()
+            opt.zero_grad()
+        for i, p in enumerate(params):
+            out["%s_m%d" % (case, i)] = opt.state[p]['next_m'].numpy().copy()
+            out["%s_v%d" % (case, i)] = opt.state[p]['next_v'].numpy().copy()
+        out["%s_totals" % case] = np.array(totals, dtype=np.float64)
+        out["%s_lrs" % case] = np.array(lrs, dtype=np.float64)
+        print("optim", case, "steps", nsteps, "total norms", totals, "lr", lrs[-1])
+    np.savez_compressed(os.path.join(OUT, "optim.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     M, metrics, R = ref_shim.load()
-    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval):
+    only = sys.argv[1:]
+    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim):
+        if only and fn.__name__[4:] not in only:
+            continue
         fn(M, metrics, R)
     print("golden fixtures written to", OUT)
 

@@ -140,3 +140,45 @@ def eval_sim_and_rank(T, V, Fr, top_k, tile=256):
         out.append({"R1": float(np.sum(ind == 0)) * 100 / len(ind), "MR": np.median(ind) + 1,
                     "MeanR": np.mean(ind) + 1})
     return sim, out
+
+
+# ----------------------------------------------------------------------------- optimizer (N3)
+def bert_adam_state(params):
+    # modules/optimization.py:124-130
+    return [{'step': 0, 'next_m': torch.zeros_like(p), 'next_v': torch.zeros_like(p)} for p in params]
+
+
+def _clip_(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ on a list of gradient tensors (2-norm), in place."""
+    norms = [torch.linalg.vector_norm(g, 2.0) for g in grads]
+    total = torch.linalg.vector_norm(torch.stack(norms), 2.0)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(coef)
+    return total
+
+
+def clip_and_bert_adam_step(params, grads, state, groups, group_of, global_max_norm=None):
+    """main_pretrain.py:277 + modules/optimization.py:103-168 as the reference runs them: one
+    parameter at a time, every elementwise op a separate pass over the tensor."""
+    from oracle.optim_oracle import lr_scheduled
+    grads = [g.clone() for g in grads]
+    total = None
+    if global_max_norm is not None:
+        total = _clip_(grads, global_max_norm)
+    for i, (p, grad) in enumerate(zip(params, grads)):
+        group = groups[group_of[i]]
+        st = state[i]
+        next_m, next_v = st['next_m'], st['next_v']
+        beta1, beta2 = group['b1'], group['b2']
+        if group['max_grad_norm'] > 0:
+            _clip_([grad], group['max_grad_norm'])
+        next_m.mul_(beta1).add_(grad, alpha=1 - beta1)
+        next_v.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+        update = next_m / (next_v.sqrt() + group['e'])
+        if group['weight_decay'] > 0.0:
+            update += group['weight_decay'] * p
+        update_with_lr = lr_scheduled(group, st['step']) * update
+        p.add_(-update_with_lr)
+        st['step'] += 1
+    return total

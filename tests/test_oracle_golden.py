@@ -216,3 +216,69 @@ def test_torch_port(golden):
     Tn, Vn, Fn, _, _ = syn.eval_inputs(1000, 1000, seed=4)
     sim, (tv, vt) = P.eval_sim_and_rank(torch.from_numpy(Tn), torch.from_numpy(Vn), torch.from_numpy(Fn), 2)
     assert tv["R1"] == g["tv"][0] and vt["R1"] == g["vt"][0] and tv["MeanR"] == g["tv"][4]
+
+
+def run_optim_oracle(case, nsteps, gmax, keep):
+    from oracle import optim_oracle as OO
+    groups = syn.optim_groups(case)
+    p = syn.optim_tensors()
+    m = [np.zeros_like(x) for x in p]
+    v = [np.zeros_like(x) for x in p]
+    steps = [0] * len(p)
+    kept, totals = {}, []
+    for st in range(nsteps):
+        p, m, v, _, tot = OO.clip_and_step(p, syn.optim_grads(st), m, v, steps, groups, syn.OPTIM_GROUP_OF, gmax)
+        totals.append(tot)
+        if st in keep:
+            kept[st] = p
+    lrs = sorted({OO.lr_scheduled(groups[gi], steps[i]) for i, gi in enumerate(syn.OPTIM_GROUP_OF)})
+    return kept, m, v, totals, lrs
+
+
+def test_optim_oracle_unclipped_is_bit_exact(golden):
+    """No clipping anywhere ('plain'): next_m / next_v bit for bit, p within 1 ulp (torch's CPU sqrt
+    is not correctly rounded, see oracle/optim_oracle.py)."""
+    g = golden("optim")
+    kept, m, v, _, lrs = run_optim_oracle("plain", 3, None, (0, 1, 2))
+    n = len(m)
+    for i in range(n):
+        assert np.array_equal(m[i], g["plain_m%d" % i]), i
+        assert np.array_equal(v[i], g["plain_v%d" % i]), i
+    for st in (0, 1, 2):
+        for i in range(n):
+            ref = g["plain_p%d_s%d" % (i, st)]
+            d = np.abs(kept[st][i].astype(np.float64) - ref)
+            one_ulp = 2.0 ** -23 * np.maximum(np.abs(ref), 2.0 ** -6)     # of p before the (tiny) update
+            assert (d <= one_ulp).all() and (d > 0).mean() < 0.02, (st, i, d.max(), (d > 0).mean())
+    assert np.allclose(lrs, g["plain_lrs"][-1], rtol=1e-15)
+
+
+@pytest.mark.parametrize("case,nsteps,gmax,keep", [("pretrain", 6, 1.0, (0, 5)), ("linear", 4, None, (3,))])
+def test_optim_oracle_clipped(golden, case, nsteps, gmax, keep):
+    """Global (clip_grad_norm_) and per-parameter (inside BertAdam.step) clipping active."""
+    g = golden("optim")
+    kept, m, v, totals, lrs = run_optim_oracle(case, nsteps, gmax, keep)
+    if gmax is not None:
+        np.testing.assert_allclose(np.array(totals, np.float64), g[case + "_totals"], rtol=1e-6)
+    for i in range(len(m)):
+        # ~1e-7 relative from the norm (see oracle/optim_oracle.py); atol covers cancelled elements
+        for got, ref in [(m[i], g["%s_m%d" % (case, i)]), (v[i], g["%s_v%d" % (case, i)])] + \
+                [(kept[st][i], g["%s_p%d_s%d" % (case, i, st)]) for st in keep]:
+            np.testing.assert_allclose(got, ref, rtol=3e-6, atol=1e-6 * float(np.abs(ref).max()))
+    np.testing.assert_allclose(lrs, g[case + "_lrs"][-1], rtol=1e-15)
+
+
+def test_optim_torch_port(golden):
+    """The CPU-baseline port of the optimizer step is the reference's op sequence."""
+    import torch
+    from oracle import torch_port as P
+    g = golden("optim")
+    groups = syn.optim_groups("pretrain")
+    params = [torch.from_numpy(x.copy()) for x in syn.optim_tensors()]
+    state = P.bert_adam_state(params)
+    for st in range(6):
+        grads = [torch.from_numpy(x) for x in syn.optim_grads(st)]
+        P.clip_and_bert_adam_step(params, grads, state, groups, syn.OPTIM_GROUP_OF, 1.0)
+    for i, p in enumerate(params):
+        assert np.array_equal(p.numpy(), g["pretrain_p%d_s5" % i]), i
+        assert np.array_equal(state[i]['next_m'].numpy(), g["pretrain_m%d" % i]), i
