@@ -24,7 +24,8 @@ def _make(case):
 def _order(params, opt):
     """Index of each parameter in the optimizer's walk order (group by group)."""
     flat = [p for g in opt.param_groups for p in g['params']]
-    return [flat.index(p) for p in params]
+    ids = [id(p) for p in flat]
+    return [ids.index(id(p)) for p in params]
 
 
 @pytest.mark.parametrize("case,nsteps,gmax", CASES)
