@@ -499,6 +499,93 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __re
   }
 }
 
+// Vectorised variant for even D and 8-byte aligned sources (the normal case): 64 columns x 64 dims per
+// block, float2 loads, bf16x2 / float2 stores, so every global access moves 128-256 B per warp.
+// Needs the norms pre-pass.  Falls back to scalar stores when the first destination column is odd.
+__global__ void __launch_bounds__(256)
+enqueue_vec_kernel(int nsamples, int D, EnqueueArgs a, const float* __restrict__ norms,
+                   int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
+  constexpr int CB = 64, DB = 64;
+  __shared__ float inv[CB];
+  __shared__ int64_t soff[CB];
+  __shared__ float tile[CB][DB + 1];     // [column][d]
+  const int qi = blockIdx.z;
+  const int mult = a.mult[qi];
+  const int ncols = nsamples * mult;
+  const int c0 = blockIdx.x * CB;
+  if (ptr >= 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) queue_ptr[0] = new_ptr;
+  } else {
+    ptr = int(queue_ptr[0]);
+  }
+  if (c0 >= ncols) return;
+  const int Kq = a.Kq[qi];
+  const int col_base = ptr * mult;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* src = a.src[qi];
+  if (threadIdx.x < CB) {
+    const int c = min(c0 + threadIdx.x, ncols - 1);
+    const int smp = c / mult, f = c - smp * mult;
+    soff[threadIdx.x] = int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
+    inv[threadIdx.x] = (c0 + threadIdx.x < ncols) ? 1.0f / norms[a.norm_off[qi] + c0 + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int planes = a.planes;
+  float* dk = a.dk[qi];
+  __nv_bfloat16* pkd = a.pack_kd[qi];
+  __nv_bfloat16* pdk = a.pack_dk[qi];
+  const int d0 = blockIdx.y * DB;
+  const int d = d0 + 2 * lane;           // this lane's two dims in the read phase
+  // read: warp w takes columns w, w+8, ...; x * (1/n) is within 1 ulp of F.normalize's x / n
+#pragma unroll
+  for (int i = 0; i < CB / 8; ++i) {
+    const int cc = warp + 8 * i, c = c0 + cc;
+    float2 v = make_float2(0.f, 0.f);
+    if (c < ncols && d < D) {
+      v = __ldg(reinterpret_cast<const float2*>(src + soff[cc] + d));
+      const float s = inv[cc];
+      v.x *= s; v.y *= s;
+      if (pkd != nullptr) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v.x, h0, l0);
+        split_bf16(v.y, h1, l1);
+        const int64_t o = int64_t(col_base + c) * planes * D + d;
+        *reinterpret_cast<__nv_bfloat162*>(pkd + o) = __nv_bfloat162(h0, h1);
+        if (planes == 2) *reinterpret_cast<__nv_bfloat162*>(pkd + o + D) = __nv_bfloat162(l0, l1);
+      }
+    }
+    tile[cc][2 * lane] = v.x;
+    tile[cc][2 * lane + 1] = v.y;
+  }
+  __syncthreads();
+  // write transposed: warp w takes dims w, w+8, ...; lane l the columns 2l, 2l+1
+  const int cpair = c0 + 2 * lane;
+  const bool even = ((col_base + c0) & 1) == 0;
+#pragma unroll
+  for (int i = 0; i < DB / 8; ++i) {
+    const int dd = warp + 8 * i, dg = d0 + dd;
+    if (dg >= D || cpair >= ncols) continue;
+    const float v0 = tile[2 * lane][dd], v1 = tile[2 * lane + 1][dd];
+    const bool two = cpair + 1 < ncols;
+    float* o = dk + int64_t(dg) * Kq + col_base + cpair;
+    if (even && two) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+    else { o[0] = v0; if (two) o[1] = v1; }
+    if (pdk != nullptr) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      __nv_bfloat16* q = pdk + int64_t(dg) * planes * Kq + col_base + cpair;
+      if (even && two) {
+        *reinterpret_cast<__nv_bfloat162*>(q) = __nv_bfloat162(h0, h1);
+        if (planes == 2) *reinterpret_cast<__nv_bfloat162*>(q + Kq) = __nv_bfloat162(l0, l1);
+      } else {
+        q[0] = h0; if (two) q[1] = h1;
+        if (planes == 2) { q[Kq] = l0; if (two) q[Kq + 1] = l1; }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pack / unpack rows
 struct RowPackArgs {
   uint64_t ptrs[8];
@@ -935,7 +1022,17 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   const int dchunk = dchunk_env > 0 ? dchunk_env : (scratch != nullptr ? 64 : ENQ_DCHUNK);
   const int dchunks = (D + dchunk - 1) / dchunk;
   const int p_arg = device_ptr ? -1 : int(ptr_host), np_arg = device_ptr ? 0 : int((ptr_host + B) % K);
-  if (cb_env == 128) {
+  static const int vec_env = tune_int("HMMC_ENQ_VEC", 1);
+  bool vec_ok = vec_env != 0 && scratch != nullptr && (D % 2) == 0;
+  for (int i = 0; i < 5 && vec_ok; ++i) {
+    vec_ok = (reinterpret_cast<uintptr_t>(a.src[i]) % 8 == 0) && (a.src_stride[i] % 2 == 0) && (a.Kq[i] % 2 == 0) &&
+             (reinterpret_cast<uintptr_t>(a.dk[i]) % 8 == 0) && (reinterpret_cast<uintptr_t>(a.pack_kd[i]) % 4 == 0) &&
+             (reinterpret_cast<uintptr_t>(a.pack_dk[i]) % 4 == 0);
+  }
+  if (vec_ok) {
+    dim3 grid((B * F + 63) / 64, (D + 63) / 64, 5);
+    enqueue_vec_kernel<<<grid, 256, 0, st>>>(B, D, a, scratch, queue_ptr, p_arg, np_arg);
+  } else if (cb_env == 128) {
     dim3 grid((B * F + 127) / 128, dchunks, 5);
     enqueue_kernel<128><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg);
   } else {

@@ -105,6 +105,40 @@ def test_enqueue_wrap_and_packed_copies(golden, prec):
                                cu(k["frame_proj_k"]))
 
 
+@pytest.mark.parametrize("ptr,b", [(3, 5), (4, 5), (0, 7), (6, 16)])
+def test_enqueue_ragged_and_odd_pointer(ptr, b):
+    """Shapes the vectorised scatter must guard: odd first column (scalar stores), odd batch (last
+    column pair half empty), D not a multiple of the 64-wide tile.  Checked against numpy."""
+    K, F, D = 22, 3, 70
+    m = _model(K, F, D, "bf16x3")
+    q0 = syn.queues(K, F=F, D=D, seed=3)
+    _load_queues(m, q0)
+    m.queue_ptr.fill_(ptr)
+    k = syn.pretrain_inputs(b, F=F, D=D, seed=31)
+    m._dequeue_and_enqueue(cu(k["v_fea_k"]), cu(k["tag_fea_k"]), cu(k["title_fea_k"]), cu(k["frame_fea_k"]),
+                           cu(k["frame_proj_k"]))
+    assert int(m.queue_ptr) == (ptr + b) % K
+    src = {"queue_v_cross_ng": (k["v_fea_k"], 1), "queue_tag_cross_ng": (k["tag_fea_k"], 1),
+           "queue_title_cross_ng": (k["title_fea_k"], 1), "queue_frame_cross_ng": (k["frame_fea_k"], F),
+           "queue_frame_proj_ng": (k["frame_proj_k"], F)}
+    for n, (x, mult) in src.items():
+        x = x.reshape(-1, D).astype(np.float64)
+        xn = (x / np.maximum(np.sqrt((x * x).sum(1, keepdims=True)), 1e-12)).T
+        want = q0[n].copy()
+        want[:, ptr * mult:(ptr + b) * mult] = xn
+        got = getattr(m, n).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-7, err_msg=n)
+        # untouched columns are bit-identical
+        keep = np.ones(want.shape[1], bool)
+        keep[ptr * mult:(ptr + b) * mult] = False
+        assert np.array_equal(got[:, keep], q0[n][:, keep]), n
+    for buf in m._queue_buffers():
+        st = ops.queue_state(buf, ops.resolve_precision("bf16x3"))
+        kd, dk = st.pack_kd.clone(), st.pack_dk.clone()
+        st.repack()
+        assert torch.equal(kd, st.pack_kd) and torch.equal(dk, st.pack_dk)
+
+
 def test_ema_bit_exact(golden):
     g = golden("ema")
     ps, pks = syn.ema_tensors()
