@@ -278,3 +278,43 @@ def test_graphed_step_matches_eager():
     assert torch.equal(m1.model_pairs[0][1].w, m2.model_pairs[0][1].w)
     for n in names:
         assert torch.equal(t1[n].grad, t2[n].grad), n
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+def test_checkpoint_round_trip_rebuilds_operand_copies(prec, tmp_path):
+    """N4: a state_dict written after some enqueues, loaded into a fresh model through init_preweight,
+    gives the same loss / gradients / next enqueue bit for bit (the bf16 operand copies are re-derived)."""
+    import io
+    from hmmc_b200 import checkpoint as C
+    K, F, D, b = 128, 4, 128, 16
+    a = _model(K, F, D, prec)
+    _load_queues(a, syn.queues(K, F=F, D=D, seed=3))
+    for step in range(3):
+        k = syn.pretrain_inputs(b, F=F, D=D, seed=40 + step)
+        a._dequeue_and_enqueue(cu(k["v_fea_k"]), cu(k["tag_fea_k"]), cu(k["title_fea_k"]), cu(k["frame_fea_k"]),
+                               cu(k["frame_proj_k"]))
+    buf = io.BytesIO()
+    torch.save(a.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf, map_location="cpu")
+    assert set(C.QUEUE_KEYS) <= set(sd) and sd["queue_frame_cross_ng"].shape == (D, K * F)
+    bm = _model(K, F, D, prec)
+    # touch the fresh model's operand copies first so that a stale pack would be noticed
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=50)
+    order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k",
+             "frame_proj_k"]
+
+    def run(m):
+        t = {n: cu(inp[n], grad=n in ("v_fea", "frame_fea", "title_fea", "frame_pred")) for n in order}
+        loss = m.head_loss(*[t[n] for n in order])
+        loss.backward()
+        return loss.detach(), t["frame_fea"].grad
+    run(bm)
+    C.init_preweight(bm, sd)
+    assert bm._hmmc_load_report == ([], [], [])
+    assert int(bm.queue_ptr) == int(a.queue_ptr) == 48
+    la, ga = run(a)
+    lb, gb = run(bm)
+    assert torch.equal(la, lb) and torch.equal(ga, gb)
+    for n in syn.QUEUE_NAMES:
+        assert torch.equal(getattr(a, n), getattr(bm, n)), n

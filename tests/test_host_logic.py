@@ -50,3 +50,70 @@ def test_bert_adam_mirror_validation_and_schedules():
             for x in (0.0, 0.001, 0.05, 0.1, 0.37, 0.99, 1.0, 1.2):
                 for w in (0.002, 0.1, 0.25):
                     assert getattr(opt, name)(x, w) == getattr(ref, name)(x, w)
+
+
+def _tiny_pretrain_model():
+    import types
+    from hmmc_b200 import modeling
+    task = types.SimpleNamespace(local_rank=0, top_frames=3, contrast_momentum=0.99, contrast_temperature=0.07,
+                                 contrast_num_negative=8, max_frames=2, use_frame_fea=True, head_precision="fp32")
+    return modeling.BirdPreTrainedModel(modeling.default_cross_config(temporal_hidden_size=16), task)
+
+
+def test_checkpoint_keys_and_load_semantics(tmp_path):
+    """state_dict carries the reference's queue buffers ([D,Kq] fp32 + queue_ptr) and nothing derived;
+    init_preweight renames gamma/beta, applies the prefix, reports missing / unexpected keys and bumps
+    the buffers' version counters (which is what triggers the re-pack of the bf16 operand copies)."""
+    import types
+    import torch
+    from hmmc_b200 import checkpoint as C
+    m = _tiny_pretrain_model()
+    sd = m.state_dict()
+    assert set(C.QUEUE_KEYS) <= set(sd.keys())
+    assert all("pack" not in k for k in sd)
+    assert sd["queue_frame_proj_ng"].shape == (16, 16) and sd["queue_ptr"].dtype == torch.long
+    m.add_module("ln", torch.nn.LayerNorm(16))
+    src = {k: torch.randn_like(v) if v.is_floating_point() else torch.full_like(v, 4) for k, v in sd.items()}
+    src["ln.gamma"] = torch.full((16,), 2.0)
+    src["ln.beta"] = torch.full((16,), -1.0)
+    src["stray.weight"] = torch.zeros(1)
+    before = m.queue_v_cross_ng._version
+    C.init_preweight(m, dict(src))
+    missing, unexpected, errors = m._hmmc_load_report
+    assert torch.equal(m.ln.weight.data, src["ln.gamma"]) and torch.equal(m.ln.bias.data, src["ln.beta"])
+    assert torch.equal(m.queue_v_cross_ng, src["queue_v_cross_ng"]) and int(m.queue_ptr) == 4
+    assert m.queue_v_cross_ng._version > before
+    assert missing == [] and errors == []
+    # with a prefix every key moves under it: nothing matches a module without that prefix
+    m2 = _tiny_pretrain_model()
+    C.init_preweight(m2, dict(sd), prefix="module.")
+    assert set(m2._hmmc_load_report[0]) >= set(C.QUEUE_KEYS)
+    # save_model writes the reference's file name and torch.load reads it back
+    args = types.SimpleNamespace(output_dir=str(tmp_path))
+    f = C.save_model(3, args, m, type_name="pretrain")
+    assert f.endswith("pytorch_model.bin.pretrain.3")
+    m3 = C.load_head_state(_tiny_pretrain_model(), f)
+    assert torch.equal(m3.queue_tag_cross_ng, m.queue_tag_cross_ng)
+
+
+def test_init_preweight_matches_reference():
+    import pytest
+    import torch
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.load()
+    from modules.until_module import PreTrainedModel
+    from hmmc_b200 import checkpoint as C
+    a, b = _tiny_pretrain_model(), _tiny_pretrain_model()
+    for m in (a, b):
+        m.add_module("ln", torch.nn.LayerNorm(16))
+    sd = {k: torch.randn_like(v) if v.is_floating_point() else torch.full_like(v, 2) for k, v in a.state_dict().items()}
+    sd["ln.gamma"] = sd.pop("ln.weight")
+    sd["extra.thing"] = torch.zeros(2)
+    del sd["queue_tag_cross_ng"]
+    PreTrainedModel.init_preweight(a, dict(sd), task_config=None)
+    C.init_preweight(b, dict(sd))
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and (ka == "queue_tag_cross_ng" or torch.equal(va, vb)), ka
+    assert b._hmmc_load_report[0] == ["queue_tag_cross_ng"]
