@@ -197,3 +197,84 @@ def _eval_plan(per, lo, hi, dev):
         _eval_plans.clear()
     _eval_plans[key] = plan
     return plan
+
+
+# ---------------------------------------------------------------------------------------------
+# eval_epoch (main_task_retrieval.py:358-524)
+# ---------------------------------------------------------------------------------------------
+class _NullLogger:
+    def info(self, *a, **k):
+        pass
+
+
+def cache_eval_features(args, model, test_dataloader, device, multi_sentence_=False, cut_off_points_=()):
+    """Step 1 of eval_epoch (main_task_retrieval.py:391-440): run the encoders batch by batch and keep
+    the features.  Returns ONE tensor per stream on `device` (texts [Nt,D], videos [Nv,D], frames
+    [Nv,F,D], titles [Nv,D] or None) instead of the reference's four Python lists of batch tensors.
+    In the multi-sentence layout a video is encoded only at its cut-off caption, like the reference."""
+    texts, videos, frames, titles = [], [], [], []
+    total_video_num = 0
+    cut = set(cut_off_points_)
+    task = getattr(args, "task", "retrieval")
+    for batch in test_dataloader:
+        batch = tuple(t.to(device) for t in batch)
+        if task == "retrieval_VT":
+            query_ids, query_mask, video, video_frame, title_ids, title_mask = batch
+        elif task == "retrieval":
+            query_ids, query_mask, video, video_frame = batch
+        else:
+            raise ValueError("wrong task type:{}".format(task))
+        texts.append(model.text_encoder(query_ids, query_mask))
+        if multi_sentence_:
+            b = video.shape[0]
+            s_, e_ = total_video_num, total_video_num + b
+            filter_inds = [i - s_ for i in range(s_, e_) if i in cut]
+            if len(filter_inds) > 0:
+                visual_output, frame_output = model.visual_encoder(video[filter_inds, ...], video_frame)
+                videos.append(visual_output)
+                frames.append(frame_output)
+            total_video_num += b
+        else:
+            visual_output, frame_output = model.visual_encoder(video, video_frame)
+            videos.append(visual_output)
+            frames.append(frame_output)
+            if task == "retrieval_VT":
+                titles.append(model.text_encoder(title_ids, title_mask))
+    flat = lambda xs: torch.cat([x.reshape(-1, x.shape[-1]) for x in xs], dim=0).float()
+    fr = torch.cat([f.reshape(-1, f.shape[-2], f.shape[-1]) for f in frames], dim=0).float()
+    return flat(texts), flat(videos), fr, (flat(titles) if titles else None)
+
+
+def eval_epoch(args, model, test_dataloader, device, n_gpu, logger=None):
+    """Drop-in for main_task_retrieval.py:358-524: cache the features, build the similarity matrix
+    (sim + sim_frame when --use_frame_fea, + weight_title * sim_title for retrieval_VT), log and return
+    the text-to-video metrics of `logging_rank`.
+
+    The reference fans text tiles out over `n_gpu` devices of one process with threads and peer copies
+    (:447-488); here a process owns one GPU and everything stays in one gallery tensor on it — `n_gpu`
+    is accepted for signature compatibility.  Galleries too large for an [Nt, Nv] matrix go through
+    `fused_eval_ranks` (sharded over the ranks of the process group) instead."""
+    logger = logger or _NullLogger()
+    if hasattr(model, 'module'):
+        model = model.module
+    model = model.to(device)
+    model.eval()
+    logger.info("args.task:{}".format(getattr(args, "task", "retrieval")))
+    multi_sentence_ = False
+    cut_off_points_ = []
+    ds = getattr(test_dataloader, "dataset", None)
+    if ds is not None and getattr(ds, 'multi_sentence_per_video', False):
+        multi_sentence_ = True
+        cut_off_points_ = [itm - 1 for itm in ds.cut_off_points]
+    logger.info("multi_sentence_:{}".format(multi_sentence_))
+    with torch.no_grad():
+        text, video, frames, title = cache_eval_features(args, model, test_dataloader, device, multi_sentence_,
+                                                         cut_off_points_)
+        use_frame = bool(getattr(args, "use_frame_fea", True))
+        sim = similarity_matrix(model, text, video, frames, use_frame_fea=use_frame)
+        if getattr(args, "task", "retrieval") == "retrieval_VT":
+            tsim = ops.loose_similarity_raw(ops._f32c(text, "text"), ops._f32c(title, "title"), _scale_of(model),
+                                            ops.PREC_FP32)
+            sim = sim + model.weight_title * tsim
+    logger.info("sim matrix size:  {}".format(tuple(sim.shape)))
+    return M.logging_rank(sim, multi_sentence_, cut_off_points_, logger)

@@ -172,3 +172,22 @@ def optim_grads(step, seed=12, sizes=OPTIM_SIZES, scales=(0.02, 0.002, 0.05, 0.0
     rs = np.random.RandomState(seed + 977 * step)
     s = scales[step % len(scales)]
     return [(_randn(rs, *shp) * s).astype(np.float32) for shp in sizes]
+
+
+def eval_epoch_case(multi, batch):
+    """Features and a fake dataloader layout for the eval_epoch parity cases: batches of index tensors
+    (query_ids = caption index, video = video index of that caption); the stub encoders of the test
+    and of oracle/gen_golden.py look the features up by these indices."""
+    if multi:
+        rs = np.random.RandomState(21)
+        per = rs.randint(1, 8, size=40)
+        T, V, Fr, gt, cut = eval_inputs(int(per.sum()), 40, seed=22, per_video=per)
+        vid_of_caption = np.repeat(np.arange(40), per)
+        cut_1based = [c + 1 for c in cut]            # the dataset stores them 1-based (eval_epoch subtracts 1)
+    else:
+        T, V, Fr, gt, _ = eval_inputs(200, 200, seed=23, corr=0.07)
+        vid_of_caption = np.arange(200)
+        cut_1based = None
+    n = T.shape[0]
+    batches = [(np.arange(i, min(i + batch, n)), vid_of_caption[i:i + batch]) for i in range(0, n, batch)]
+    return T, V, Fr, batches, cut_1based

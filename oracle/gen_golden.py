@@ -240,6 +240,43 @@ def gen_eval(M, metrics, R):
     print("eval multi tv", tvm, "vt", vtm)
 
 
+def gen_eval_epoch(M, metrics, R):
+    """The reference's eval_epoch (main_task_retrieval.py:358-524) on CPU with index-lookup stub encoders."""
+    import logging
+    R.logger = logging.getLogger("gen_golden")
+    out = {}
+    for tag, multi, batch in (("square", False, 64), ("multi", True, 32)):
+        T, V, Fr, batches, cut = syn.eval_epoch_case(multi, batch)
+        s = ref_shim.finetune_self(top_frames=2)
+
+        class _Txt:
+            logit_scale = s.text_encoder.logit_scale
+
+            def __call__(self, ids, mask):
+                return _t(T)[ids[:, 0]]
+        s.text_encoder = _Txt()
+        s.visual_encoder = lambda video, video_frame: (_t(V)[video[:, 0]], _t(Fr)[video[:, 0]])
+        s.to = lambda device: s
+        s.eval = lambda: None
+
+        class _DS:
+            multi_sentence_per_video = multi
+            cut_off_points = cut
+            sentence_num = T.shape[0]
+            video_num = V.shape[0]
+
+        class _DL(list):
+            dataset = _DS()
+        dl = _DL([(torch.from_numpy(ci)[:, None], torch.ones(len(ci), 1, dtype=torch.long),
+                   torch.from_numpy(vi)[:, None], torch.full((len(ci),), 12)) for ci, vi in batches])
+        args = types.SimpleNamespace(task="retrieval", use_frame_fea=True)
+        tv = R.eval_epoch(args, s, dl, torch.device("cpu"), 1)
+        out[tag + "_keys"] = np.array(sorted(tv.keys()))
+        out[tag + "_vals"] = np.array([tv[k] for k in sorted(tv.keys())], dtype=np.float64)
+        print("eval_epoch", tag, tv)
+    np.savez(os.path.join(OUT, "eval_epoch.npz"), **out)
+
+
 OPTIM_CASES = (("pretrain", 6, 1.0, (0, 5)), ("plain", 3, None, (0, 1, 2)), ("linear", 4, None, (3,)))
 
 
@@ -278,7 +315,7 @@ def main():
     torch.manual_seed(0)
     M, metrics, R = ref_shim.load()
     only = sys.argv[1:]
-    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim):
+    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim, gen_eval_epoch):
         if only and fn.__name__[4:] not in only:
             continue
         fn(M, metrics, R)

@@ -146,3 +146,44 @@ def test_fused_eval_matches_materialised(prec, layout):
         # two fp32-grade evaluations of the same scores: only exact near-ties may flip
         assert int((t2v.cpu().numpy() != ot).sum()) <= max(2, Nt // 300)
         assert int((v2t.cpu().numpy() != ov).sum()) <= max(2, Nv // 100)
+
+
+@pytest.mark.parametrize("tag,multi,batch", [("square", False, 64), ("multi", True, 32)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_eval_epoch_matches_reference(golden, tag, multi, batch, prec):
+    """N2: eval_epoch (feature cache with the multi-sentence cut-off filter, one gallery tensor,
+    similarity, logging_rank) returns the metrics the reference's eval_epoch returned on the same
+    fake dataloader (tests/golden/eval_epoch.npz)."""
+    g = golden("eval_epoch")
+    T, V, Fr, batches, cut = syn.eval_epoch_case(multi, batch)
+    Tc, Vc, Fc = cu(T), cu(V), cu(Fr)
+    calls = {"visual": 0}
+
+    class Txt:
+        logit_scale = torch.tensor(4.6052)
+
+        def __call__(self, ids, mask):
+            return Tc[ids[:, 0]]
+
+    def visual(video, video_frame):
+        calls["visual"] += video.shape[0]
+        return Vc[video[:, 0]], Fc[video[:, 0]]
+    task = types.SimpleNamespace(local_rank=0, top_frames=2, use_frame_fea=True, head_precision=prec)
+    m = modeling.BirdModel(modeling.default_cross_config(), task, text_encoder=Txt(), visual_encoder=visual)
+
+    class DS:
+        multi_sentence_per_video = multi
+        cut_off_points = cut
+        sentence_num = T.shape[0]
+        video_num = V.shape[0]
+
+    class DL(list):
+        dataset = DS()
+    dl = DL([(torch.from_numpy(ci)[:, None], torch.ones(len(ci), 1, dtype=torch.long),
+              torch.from_numpy(vi)[:, None], torch.full((len(ci),), 12)) for ci, vi in batches])
+    args = types.SimpleNamespace(task="retrieval", use_frame_fea=True)
+    tv = retrieval.eval_epoch(args, m, dl, torch.device("cuda"), 1)
+    assert calls["visual"] == V.shape[0]            # every video encoded exactly once
+    assert sorted(tv.keys()) == list(g[tag + "_keys"])
+    got = np.array([tv[k] for k in sorted(tv.keys())], dtype=np.float64)
+    np.testing.assert_allclose(got, g[tag + "_vals"], rtol=1e-6)

@@ -117,3 +117,29 @@ def test_init_preweight_matches_reference():
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and (ka == "queue_tag_cross_ng" or torch.equal(va, vb)), ka
     assert b._hmmc_load_report[0] == ["queue_tag_cross_ng"]
+
+
+def test_cache_eval_features_filters_videos_at_cut_off_points():
+    """eval_epoch step 1 (main_task_retrieval.py:391-440): in the multi-sentence layout a video is
+    encoded once, at its last caption; features come back as one tensor per stream."""
+    import types
+    import torch
+    from hmmc_b200 import synthetic as syn
+    T, V, Fr, batches, cut = syn.eval_epoch_case(True, 32)
+    Tt, Vt, Ft = torch.from_numpy(T), torch.from_numpy(V), torch.from_numpy(Fr)
+    seen = []
+
+    def visual(video, video_frame):
+        seen.extend(int(i) for i in video[:, 0])
+        return Vt[video[:, 0]], Ft[video[:, 0]]
+    model = types.SimpleNamespace(text_encoder=lambda ids, mask: Tt[ids[:, 0]], visual_encoder=visual)
+    dl = [(torch.from_numpy(ci)[:, None], torch.ones(len(ci), 1, dtype=torch.long), torch.from_numpy(vi)[:, None],
+           torch.full((len(ci),), 12)) for ci, vi in batches]
+    args = types.SimpleNamespace(task="retrieval")
+    text, video, frames, title = retrieval.cache_eval_features(args, model, dl, torch.device("cpu"), True,
+                                                               [c - 1 for c in cut])
+    assert seen == list(range(V.shape[0])) and title is None
+    assert torch.equal(text, Tt) and torch.equal(video, Vt) and torch.equal(frames, Ft)
+    import pytest
+    with pytest.raises(ValueError):
+        retrieval.cache_eval_features(types.SimpleNamespace(task="caption"), model, dl, torch.device("cpu"))

@@ -48,3 +48,9 @@ def test_reference_metric_signatures():
             list(inspect.signature(getattr(GM, n)).parameters), n
     assert list(inspect.signature(R._run_on_single_gpu).parameters) == \
         list(inspect.signature(GR._run_on_single_gpu).parameters)
+    ref_ev = list(inspect.signature(R.eval_epoch).parameters)
+    assert list(inspect.signature(GR.eval_epoch).parameters)[:len(ref_ev)] == ref_ev
+    import modules.optimization as RO
+    import hmmc_b200.optimization as GO
+    assert list(inspect.signature(RO.BertAdam.__init__).parameters) == list(inspect.signature(GO.BertAdam.__init__).parameters)
+    assert set(RO.SCHEDULES) == set(GO.SCHEDULES)
