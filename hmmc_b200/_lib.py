@@ -77,6 +77,9 @@ SIGNATURES = {
     "hmmc_sym_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "hmmc_sym_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float,
                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hmmc_sym_ce_packed_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "hmmc_sym_ce_packed_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_void_p,
+                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "hmmc_sim_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "hmmc_sim_topk_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_int,
                                   c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

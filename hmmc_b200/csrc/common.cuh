@@ -123,6 +123,14 @@ int rownorm_pack(const float* x, int64_t R, int D, int64_t ldx, float eps, int p
 int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                     int64_t split_stride, int M, int N, int K, int planes, int splits, float alpha,
                     cudaStream_t st);
+// several store-GEMMs (each with its own split count) in one grouped launch
+struct StoreGemm {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  float* C; int64_t ldc; int64_t split_stride;
+  int M, N, K, splits;
+};
+int umma_gemm_store_grouped(const StoreGemm* g, int n, int planes, float alpha, cudaStream_t st);
 // number of split-K partials umma_gemm_store(splits) really writes
 int umma_effective_splits(int K, int planes, int splits);
 // src [rows, cols] fp32 -> straight [rows, planes*cols] and transposed [cols, planes*rows] bf16 plane

@@ -191,6 +191,25 @@ int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, floa
   return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
 }
 
+int umma_gemm_store_grouped(const StoreGemm* g, int n, int planes, float alpha, cudaStream_t st) {
+  if (n <= 0) return HMMC_OK;
+  bool wide = n <= UMMA_MAX_PROBLEMS;
+  for (int i = 0; i < n; ++i) wide = wide && (g[i].N % 256 == 0);
+  if (!wide) {           // shapes the 256-wide tile does not divide: one launch each
+    for (int i = 0; i < n; ++i) {
+      const int rc = umma_gemm_store(g[i].A, g[i].lda, g[i].B, g[i].ldb, g[i].C, g[i].ldc, g[i].split_stride, g[i].M,
+                                     g[i].N, g[i].K, planes, g[i].splits, alpha, st);
+      if (rc) return rc;
+    }
+    return HMMC_OK;
+  }
+  GemmProblem<EpiStoreF32> pr[UMMA_MAX_PROBLEMS];
+  for (int i = 0; i < n; ++i)
+    pr[i] = GemmProblem<EpiStoreF32>{g[i].A, g[i].lda, g[i].B, g[i].ldb, g[i].M, g[i].N, g[i].K, planes, g[i].splits,
+                                     EpiStoreF32::Params{g[i].C, g[i].ldc, g[i].split_stride, alpha}};
+  return launch_umma_grouped<256, EpiStoreF32>(pr, n, st);
+}
+
 int umma_effective_splits(int K, int planes, int splits) { return effective_splits(K, planes, splits); }
 
 }  // namespace hmmc

@@ -166,6 +166,226 @@ __global__ void gallery_scatter_kernel(const float* __restrict__ dG, int B, int 
   for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] = dG[g * D + d];
 }
 
+// ------------------------------------------------------------------ fused kernels of the tensor-core path
+// Row r of the stacked operand matrix: r < B -> text row r; else gallery row g = r - B = fp*B + j.
+// The three operands with their row strides (elements): contiguous tensors have ldt = ldv = D,
+// ldf = F*D; the packed layout [text | video | frames] of the all-gather has all three = (2+F)*D.
+struct SymOperands {
+  const float* text; int64_t ldt;
+  const float* video; int64_t ldv;
+  const float* frames; int64_t ldf;
+};
+struct SymGrads {
+  float* text; int64_t ldt;
+  float* video; int64_t ldv;
+  float* frames; int64_t ldf;
+};
+__device__ __forceinline__ const float* symce_src_row(const SymOperands& o, int B, int voff, int D, int r) {
+  if (r < B) return o.text + int64_t(r) * o.ldt;
+  const int g = r - B, fp = g / B, j = g - fp * B;
+  return (fp < voff) ? o.video + int64_t(j) * o.ldv : o.frames + int64_t(j) * o.ldf + int64_t(fp - voff) * D;
+}
+
+// Normalise (x / ||x||, no eps: loose_similarity) the B text rows and the NG gallery rows and write the
+// bf16 plane packs the three GEMMs read: straight [rows, planes*D] and transposed [D, planes*rows].
+// Block = 32 consecutive rows (B % 32 == 0, so a block never mixes text and gallery rows), staged whole
+// in shared memory (32 x (D+1) floats): every input element is read once, one block-wide sync.
+__global__ void __launch_bounds__(1024)
+symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, __nv_bfloat16* __restrict__ Tp,
+                  __nv_bfloat16* __restrict__ TTp, __nv_bfloat16* __restrict__ Gp, __nv_bfloat16* __restrict__ GTp) {
+  extern __shared__ float tile[];                 // [32][D + 1]
+  const int ld = D + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 32;
+  const int NG = (voff + F) * B;
+  const bool is_text = r0 < B;
+  const int R = is_text ? B : NG;                 // rows of this operand
+  const int q0 = is_text ? r0 : r0 - B;           // first row inside its operand
+  __nv_bfloat16* straight = is_text ? Tp : Gp;
+  __nv_bfloat16* transposed = is_text ? TTp : GTp;
+  {
+    const int rr = warp;                          // 32 warps: one row each
+    const float* x = symce_src_row(src, B, voff, D, r0 + rr);
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = x[d]; tile[rr * ld + d] = v; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float n = sqrtf(ss);
+    for (int d = lane; d < D; d += 32) {
+      const float v = tile[rr * ld + d] / n;
+      tile[rr * ld + d] = v;
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      const int64_t o = int64_t(q0 + rr) * planes * D + d;
+      straight[o] = hi;
+      if (planes == 2) straight[o + D] = lo;
+    }
+  }
+  if (transposed == nullptr) return;
+  __syncthreads();
+  for (int d = warp; d < D; d += 32) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(tile[lane * ld + d], hi, lo);
+    const int64_t o = int64_t(d) * planes * R + q0 + lane;
+    transposed[o] = hi;
+    if (planes == 2) transposed[o + R] = lo;
+  }
+}
+
+// Row and column log-sum-exp of S_all in one launch.  Blocks [0, row_blocks): one warp per (text row,
+// similarity block) pair, 8 pairs per block; the remaining blocks take 32 columns each.
+__global__ void __launch_bounds__(256)
+symce_lse_kernel(const float* __restrict__ S, int B, int NB, int row_blocks, float* __restrict__ lse_row,
+                 float* __restrict__ lse_col) {
+  __shared__ float sm[8][32], ss[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ncol = int64_t(NB) * B;
+  if (int(blockIdx.x) < row_blocks) {
+    const int pair = blockIdx.x * 8 + warp;          // = i * NB + fp: consecutive warps read consecutive memory
+    if (pair >= B * NB) return;
+    const int i = pair / NB, fp = pair - i * NB;
+    const float* row = S + int64_t(i) * ncol + int64_t(fp) * B;
+    float m = -INFINITY;
+    for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < B; j += 32) s += expf(row[j] - m);
+    s = warp_sum(s);
+    if (lane == 0) lse_row[fp * B + i] = m + logf(s);
+    return;
+  }
+  const int64_t col = int64_t(blockIdx.x - row_blocks) * 32 + lane;
+  float m = -INFINITY, s = 0.f;
+  if (col < ncol) {
+    for (int i = warp; i < B; i += 8) {
+      const float v = S[int64_t(i) * ncol + col];
+      if (v > m) { s = s * expf(m - v) + 1.f; m = v; } else { s += expf(v - m); }
+    }
+  }
+  sm[warp][lane] = m;
+  ss[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && col < ncol) {
+    float Mx = sm[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) Mx = fmaxf(Mx, sm[w][lane]);
+    float Ssum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) Ssum += (sm[w][lane] == -INFINITY) ? 0.f : ss[w][lane] * expf(sm[w][lane] - Mx);
+    lse_col[col] = Mx + logf(Ssum);
+  }
+}
+
+// loss = sum_fp w_fp/B sum_i (lse_row + lse_col - 2 S_ii)   (one block, fixed order)
+__global__ void symce_loss_kernel(const float* __restrict__ S, int B, int NB, const float* __restrict__ lse_row,
+                                  const float* __restrict__ lse_col, int voff, float w0, float wf,
+                                  float* __restrict__ loss_out) {
+  __shared__ float red[32];
+  const int64_t ncol = int64_t(NB) * B;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < NB * B; k += blockDim.x) {
+    const int fp = k / B, i = k - fp * B;
+    const float w = ((fp < voff) ? w0 : wf) / float(B);
+    acc += w * (lse_row[k] + lse_col[k] - 2.f * S[int64_t(i) * ncol + k]);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) loss_out[0] = acc;
+}
+
+// G = dL/dS computed on the fly from S and the two LSE vectors and written straight as the bf16
+// plane packs of the backward GEMMs: Sp [B, planes*NG] and STp [NG, planes*B].  32x32 tiles.
+__global__ void __launch_bounds__(256)
+symce_gradpack_kernel(const float* __restrict__ S, int B, int NB, const float* __restrict__ lse_row,
+                      const float* __restrict__ lse_col, int voff, float w0, float wf, int planes,
+                      __nv_bfloat16* __restrict__ Sp, __nv_bfloat16* __restrict__ STp) {
+  __shared__ float tile[32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NG = NB * B;
+  const int c0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int c = c0 + lane;
+  const int fp = c0 / B;                       // B % 32 == 0: a tile lies inside one similarity block
+  const int j = c - fp * B;
+  const float w = ((fp < voff) ? w0 : wf) / float(B);
+  const float lc = lse_col[c];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ii = warp * 4 + k, i = i0 + ii;
+    const float v = S[int64_t(i) * NG + c];
+    const float g = w * (expf(v - lse_row[fp * B + i]) + expf(v - lc) - (j == i ? 2.f : 0.f));
+    __nv_bfloat16 hi, lo;
+    split_bf16(g, hi, lo);
+    const int64_t o = int64_t(i) * planes * NG + c;
+    Sp[o] = hi;
+    if (planes == 2) Sp[o + NG] = lo;
+    tile[ii][lane] = g;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int cc = warp * 4 + k;
+    __nv_bfloat16 hi, lo;
+    split_bf16(tile[lane][cc], hi, lo);
+    const int64_t o = int64_t(c0 + cc) * planes * B + i0 + lane;
+    STp[o] = hi;
+    if (planes == 2) STp[o + B] = lo;
+  }
+}
+
+// Chain the gradients w.r.t. the normalised rows back to the raw inputs, all operands in one launch.
+// Text row i: g = fixed-order sum of the split-K partials; gallery row g: read in gallery order, written
+// to dvideo / dframes in their own layouts.  One warp per row, the row kept in registers (D <= 32*NV).
+template <int NV>
+__global__ void symce_unnorm_kernel(SymOperands src, int B, int F, int voff, int D,
+                                    const float* __restrict__ gt_parts, int n_splits, int64_t split_stride,
+                                    const float* __restrict__ gg, SymGrads out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int NG = (voff + F) * B;
+  if (r >= B + NG) return;
+  const float* x = symce_src_row(src, B, voff, D, r);
+  float* dst;
+  const float* grow;
+  int ns = 1;
+  if (r < B) {
+    dst = out.text ? out.text + int64_t(r) * out.ldt : nullptr;
+    grow = gt_parts + int64_t(r) * D;
+    ns = n_splits;
+  } else {
+    const int g = r - B, fp = g / B, j = g - fp * B;
+    dst = (fp < voff) ? (out.video ? out.video + int64_t(j) * out.ldv : nullptr)
+                      : (out.frames ? out.frames + int64_t(j) * out.ldf + int64_t(fp - voff) * D : nullptr);
+    grow = gg + int64_t(g) * D;
+  }
+  if (dst == nullptr) return;
+  float gv[NV], xv[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int d = lane + 32 * k;
+    gv[k] = 0.f;
+    xv[k] = (d < D) ? x[d] : 0.f;
+  }
+#pragma unroll 4
+  for (int s0 = 0; s0 < ns; ++s0) {
+    const float* gs = grow + int64_t(s0) * split_stride;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int d = lane + 32 * k;
+      if (d < D) gv[k] += gs[d];
+    }
+  }
+  float ss = 0.f, xg = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { ss = fmaf(xv[k], xv[k], ss); xg = fmaf(xv[k], gv[k], xg); }
+  ss = warp_sum(ss);
+  xg = warp_sum(xg);
+  const float n = sqrtf(ss);
+  const float proj = xg / (n * n);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int d = lane + 32 * k;
+    if (d < D) dst[d] = (gv[k] - xv[k] * proj) / n;
+  }
+}
+
 }  // namespace hmmc
 
 using namespace hmmc;
@@ -270,7 +490,7 @@ struct SymCeWs {
 };
 constexpr int SYMCE_MAX_SPLITS = 32;
 static bool symce_tensor_ok(int B, int D, int prec) {
-  return prec != HMMC_PREC_FP32 && B % 64 == 0 && D % 64 == 0;
+  return prec != HMMC_PREC_FP32 && B % 64 == 0 && D % 64 == 0 && D <= 1024;
 }
 static void symce_carve(Workspace& ws, SymCeWs& w, int B, int F, int D, int prec) {
   const size_t NB = size_t(1 + F);
@@ -304,10 +524,11 @@ size_t hmmc_sym_ce_workspace_bytes(int B, int F, int D, int prec) {
   return ws.used + 256;
 }
 
-int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* frames, int B, int F, int D, float scale,
-                        float w_vtm, float w_ftm, int prec, float* loss_out, float* dtext, float* dvideo,
-                        float* dframes, void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale, float w_vtm, float w_ftm, int prec,
+                       float* loss_out, const SymGrads& grads, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+  const float *text = src.text, *video = src.video, *frames = src.frames;
+  float *dtext = grads.text, *dvideo = grads.video, *dframes = grads.frames;
   HMMC_REQUIRE(text && loss_out && B > 0 && D > 0 && F >= 0, "sym_ce: bad arguments");
   const int voff = (video != nullptr) ? 1 : 0;   // video == NULL: frame_loss alone (modules/modeling.py:665-673)
   HMMC_REQUIRE(voff + F > 0, "sym_ce: neither video nor frames given");
@@ -321,6 +542,61 @@ int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* fram
   if (!ws.ok()) { set_error("sym_ce: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
   const bool need_grad = dtext || dvideo || dframes;
   int rc;
+  if (symce_tensor_ok(B, D, prec)) {
+    // tensor-core path: 7 launches (4 without gradients)
+    const int NG = NB * B, P = planes_of(prec);
+    const float wf = (F > 0) ? w_ftm / float(F) : 0.f;
+    const size_t prep_smem = size_t(32) * (D + 1) * sizeof(float);
+    static int prep_smem_set = 0;
+    if (prep_smem > 48 * 1024 && prep_smem_set < int(prep_smem)) {
+      HMMC_CHECK_CUDA(cudaFuncSetAttribute(symce_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prep_smem)));
+      prep_smem_set = int(prep_smem);
+    }
+    symce_prep_kernel<<<unsigned((B + NG) / 32), 1024, prep_smem, st>>>(src, B, F, voff, D, P, w.Tp,
+                                                                need_grad ? w.TTp : nullptr, w.Gp,
+                                                                need_grad ? w.GTp : nullptr);
+    HMMC_CHECK_LAUNCH();
+    if ((rc = umma_gemm_store(w.Tp, int64_t(P) * D, w.Gp, int64_t(P) * D, w.S, NG, 0, B, NG, D, P, 1, scale, st))) return rc;
+    const int row_blocks = (B * NB + 7) / 8;
+    symce_lse_kernel<<<unsigned(row_blocks + (NG + 31) / 32), 256, 0, st>>>(w.S, B, NB, row_blocks, w.lse_row, w.lse_col);
+    HMMC_CHECK_LAUNCH();
+    symce_loss_kernel<<<1, 1024, 0, st>>>(w.S, B, NB, w.lse_row, w.lse_col, voff, w_vtm, wf, loss_out);
+    HMMC_CHECK_LAUNCH();
+    if (!need_grad) return HMMC_OK;
+    symce_gradpack_kernel<<<dim3(NG / 32, B / 32), 256, 0, st>>>(w.S, B, NB, w.lse_row, w.lse_col, voff, w_vtm, wf, P,
+                                                                  w.Sp, w.STp);
+    HMMC_CHECK_LAUNCH();
+    // backward contractions in one grouped launch:
+    //   g_that[i,d] = scale * sum_g G[i,g] ghat[g,d]   long K (= NG), few output tiles: split-K partials
+    //   g_ghat[g,d] = scale * sum_i G[i,g] that[i,d]
+    // the split count fills the SMs the g_ghat tiles leave idle
+    const int tiles = ((B + 127) / 128) * ((D + 255) / 256);
+    const int other = (dvideo != nullptr || dframes != nullptr) ? ((NG + 127) / 128) * ((D + 255) / 256) : 0;
+    int sp = (sm_count() - other) / (tiles > 0 ? tiles : 1);
+    if (sp < 1) sp = 1;
+    if (sp > 16) sp = 16;
+    const int eff = umma_effective_splits(NG, P, sp);
+    StoreGemm gm[2];
+    int ng = 0;
+    if (dtext != nullptr)
+      gm[ng++] = StoreGemm{w.Sp, int64_t(P) * NG, w.GTp, int64_t(P) * NG, w.parts, D, int64_t(B) * D, B, D, NG, sp};
+    if (dvideo != nullptr || dframes != nullptr)
+      gm[ng++] = StoreGemm{w.STp, int64_t(P) * B, w.TTp, int64_t(P) * B, w.gg, D, 0, NG, D, B, 1};
+    if ((rc = umma_gemm_store_grouped(gm, ng, P, scale, st))) return rc;
+    HMMC_REQUIRE(D <= 1024, "sym_ce: D=%d above the tensor-core path's limit of 1024", D);
+    if (D <= 512)
+      symce_unnorm_kernel<16><<<unsigned((B + NG + 7) / 8), 256, 0, st>>>(src, B, F, voff, D, w.parts, eff,
+                                                                          int64_t(B) * D, w.gg, grads);
+    else
+      symce_unnorm_kernel<32><<<unsigned((B + NG + 7) / 8), 256, 0, st>>>(src, B, F, voff, D, w.parts, eff,
+                                                                          int64_t(B) * D, w.gg, grads);
+    HMMC_CHECK_LAUNCH();
+    return HMMC_OK;
+  }
+  HMMC_REQUIRE(src.ldt == D && (video == nullptr || src.ldv == D) && (F == 0 || src.ldf == int64_t(F) * D) &&
+                   (dtext == nullptr || grads.ldt == D) && (dvideo == nullptr || grads.ldv == D) &&
+                   (dframes == nullptr || grads.ldf == int64_t(F) * D),
+               "sym_ce: the CUDA-core path needs contiguous operands");
   if ((rc = rownorm_pack(text, B, D, D, 0.f, 1, w.that, nullptr, nullptr, 0, st))) return rc;
   gallery_norm_kernel<<<unsigned((int64_t(NB) * B + 7) / 8), 256, 0, st>>>(video, frames, B, F, voff, D, w.ghat);
   HMMC_CHECK_LAUNCH();
@@ -382,6 +658,60 @@ int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* fram
       unnormalize_grad_kernel<<<unsigned((int64_t(B) * F + 7) / 8), 256, 0, st>>>(frames, w.ghat + int64_t(B) * D, dframes, int64_t(B) * F, D);
       HMMC_CHECK_LAUNCH();
     }
+  }
+  return HMMC_OK;
+}
+
+
+int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* frames, int B, int F, int D, float scale,
+                        float w_vtm, float w_ftm, int prec, float* loss_out, float* dtext, float* dvideo,
+                        float* dframes, void* workspace, size_t workspace_bytes, void* stream) {
+  const SymOperands src{text, D, video, D, frames, int64_t(F) * D};
+  const SymGrads grads{dtext, D, dvideo, D, dframes, int64_t(F) * D};
+  return sym_ce_impl(src, B, F, D, scale, w_vtm, w_ftm, prec, loss_out, grads, workspace, workspace_bytes,
+                     static_cast<cudaStream_t>(stream));
+}
+
+size_t hmmc_sym_ce_packed_workspace_bytes(int B, int F, int D, int prec) {
+  // + contiguous copies of the operands and of their gradients for the CUDA-core path
+  return hmmc_sym_ce_workspace_bytes(B, F, D, prec) + 2 * (size_t(B) * (2 + F) * D * sizeof(float) + 512);
+}
+
+int hmmc_sym_ce_packed_fwd_bwd(const float* packed, int B, int F, int D, float scale, float w_vtm, float w_ftm,
+                               int prec, float* loss_out, float* dpacked, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  HMMC_REQUIRE(packed && loss_out && B > 0 && D > 0 && F >= 0, "sym_ce_packed: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t ld = int64_t(2 + F) * D;
+  if (symce_tensor_ok(B, D, prec)) {
+    const SymOperands src{packed, ld, packed + D, ld, packed + 2 * D, ld};
+    const SymGrads grads{dpacked, ld, dpacked ? dpacked + D : nullptr, ld, dpacked ? dpacked + 2 * D : nullptr, ld};
+    return sym_ce_impl(src, B, F, D, scale, w_vtm, w_ftm, prec, loss_out, grads, workspace, workspace_bytes, st);
+  }
+  // CUDA-core path: un-pack into contiguous operands, run, re-pack the gradients
+  Workspace ws(workspace, workspace_bytes);
+  float* ops3 = ws.take<float>(size_t(B) * ld);
+  float* grd3 = ws.take<float>(size_t(B) * ld);
+  HMMC_REQUIRE(ws.ok(), "sym_ce_packed: workspace too small (%zu needed, %zu given)", ws.used, workspace_bytes);
+  float* t = ops3;
+  float* v = t + int64_t(B) * D;
+  float* f = v + int64_t(B) * D;
+  const int32_t widths[3] = {D, D, F * D};
+  const int n = (F > 0) ? 3 : 2;
+  const uint64_t src_ptrs[3] = {reinterpret_cast<uint64_t>(t), reinterpret_cast<uint64_t>(v), reinterpret_cast<uint64_t>(f)};
+  int rc;
+  if ((rc = hmmc_unpack_rows(packed, src_ptrs, widths, n, B, stream))) return rc;
+  float* dt = dpacked ? grd3 : nullptr;
+  float* dv = dpacked ? dt + int64_t(B) * D : nullptr;
+  float* df = (dpacked && F > 0) ? dv + int64_t(B) * D : nullptr;
+  char* rest = static_cast<char*>(workspace) + align_up(ws.used, 256);
+  const SymOperands src{t, D, v, D, F > 0 ? f : nullptr, int64_t(F) * D};
+  const SymGrads grads{dt, D, dv, D, df, int64_t(F) * D};
+  if ((rc = sym_ce_impl(src, B, F, D, scale, w_vtm, w_ftm, prec, loss_out, grads, rest,
+                        workspace_bytes - align_up(ws.used, 256), st))) return rc;
+  if (dpacked != nullptr) {
+    const uint64_t g_ptrs[3] = {reinterpret_cast<uint64_t>(dt), reinterpret_cast<uint64_t>(dv), reinterpret_cast<uint64_t>(df)};
+    if ((rc = hmmc_pack_rows(g_ptrs, widths, n, B, dpacked, stream))) return rc;
   }
   return HMMC_OK;
 }

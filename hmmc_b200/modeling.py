@@ -342,11 +342,11 @@ class BirdModel(ContrastiveHeadMixin, nn.Module):
         packed = torch.cat([query_output.reshape(b, D), visual_output.reshape(b, D),
                             frame_output.reshape(b, F * D)], dim=1)
         full = dist_collect(packed)
-        B = full.shape[0]
-        q = full[:, :D]
-        v = full[:, D:2 * D]
-        fr = full[:, 2 * D:].reshape(B, F, D)
-        return self.finetune_head_loss(q, v, fr)
+        if not bool(getattr(self.task_config, "use_frame_fea", True)):
+            return self.finetune_head_loss(full[:, :D], full[:, D:2 * D], None)
+        # the fused head reads the gathered rows in place and returns the gradient in the same layout
+        return ops.sym_ce_packed(full, F, D, self._logit_scale(), self.weight_VTM_finetune,
+                                 self.weight_FTM_finetune, self.head_precision)
 
     def forward(self, query_ids, query_mask, video_data, video_frame, idx, global_step):
         query_ids = query_ids.view(-1, query_ids.shape[-1])

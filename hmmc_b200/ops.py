@@ -492,6 +492,46 @@ def sym_ce(text, video, frames, scale, w_vtm, w_ftm, precision=None):
                           resolve_precision(precision))
 
 
+def sym_ce_packed_raw(packed, F, D, scale, w_vtm, w_ftm, prec, need_grad):
+    """Fused fine-tune head on the all-gather's own layout: rows [text | video | frames(F*D)].
+    Returns (loss, dpacked) with dpacked in the same layout (what the gather's backward consumes)."""
+    lib = _lib.load()
+    B = packed.shape[0]
+    if packed.shape[1] != (2 + F) * D:
+        raise HmmcError("sym_ce_packed: row width %d is not (2+F)*D = %d" % (packed.shape[1], (2 + F) * D))
+    nbytes = lib.hmmc_sym_ce_packed_workspace_bytes(B, F, D, prec)
+    ws = workspace(packed.device, nbytes)
+    loss = torch.empty((), dtype=torch.float32, device=packed.device)
+    dp = torch.empty_like(packed) if need_grad else None
+    _lib.check(lib.hmmc_sym_ce_packed_fwd_bwd(_p(packed), B, F, D, float(scale), float(w_vtm), float(w_ftm), prec,
+                                              _p(loss), _p(dp), _p(ws), ws.numel(), _stream()),
+               "hmmc_sym_ce_packed_fwd_bwd")
+    return loss, dp
+
+
+class _SymCePackedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, F, D, scale, w_vtm, w_ftm, prec):
+        loss, dp = sym_ce_packed_raw(_f32c(packed, "packed"), F, D, scale, w_vtm, w_ftm, prec, packed.requires_grad)
+        if dp is not None:
+            ctx.save_for_backward(dp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        if getattr(ctx, "consumed", False):
+            raise HmmcError("the fused head's gradients were already consumed (retain_graph is not supported)")
+        ctx.consumed = True
+        scale_inplace([dp], g)                    # in place: the buffer is ours
+        return dp, None, None, None, None, None, None
+
+
+def sym_ce_packed(packed, F, D, scale, w_vtm, w_ftm, precision=None):
+    return _SymCePackedFn.apply(packed, int(F), int(D), float(scale), float(w_vtm), float(w_ftm),
+                                resolve_precision(precision))
+
+
 # ----------------------------------------------------------------------------- eval
 
 def sim_topk(text, video, frames, scale, top_k, precision=None, want_sim=True, want_fsim=True):

@@ -236,6 +236,15 @@ size_t hmmc_sym_ce_workspace_bytes(int B, int F, int D, int prec);
 int hmmc_sym_ce_fwd_bwd(const float* text, const float* video, const float* frames, int B, int F, int D,
                         float scale, float w_vtm, float w_ftm, int prec, float* loss_out, float* dtext,
                         float* dvideo, float* dframes, void* workspace, size_t workspace_bytes, void* stream);
+/* Same head on the layout the differentiable all-gather moves (modules/modeling.py:698-700 gathers the
+ * three tensors; here they travel as one row [text(D) | video(D) | frames(F*D)] per sample):
+ * packed [B, (2+F)*D]; dpacked (NULL: forward only) receives the gradient in the same layout, which is
+ * what the gather's backward (reduce-scatter) consumes.  No un-pack / re-pack copies on the
+ * tensor-core path. */
+size_t hmmc_sym_ce_packed_workspace_bytes(int B, int F, int D, int prec);
+int hmmc_sym_ce_packed_fwd_bwd(const float* packed, int B, int F, int D, float scale, float w_vtm, float w_ftm,
+                               int prec, float* loss_out, float* dpacked, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* ------------------------------------------------------------------------ eval */
 

@@ -88,3 +88,21 @@ def test_single_row_and_no_grad():
     with torch.no_grad():
         l = m.head_loss(cu(t), cu(v), cu(fr))
     assert abs(float(l) - float(O.finetune_loss(t, v, fr))) < 1e-4
+
+
+@pytest.mark.parametrize("B,prec", [(256, "bf16x3"), (64, "bf16"), (32, "bf16x3"), (32, "fp32")])
+def test_packed_layout_equals_separate_tensors(B, prec):
+    """hmmc_sym_ce_packed_fwd_bwd (rows [text | video | frames], the all-gather's layout) gives the
+    loss and gradients of hmmc_sym_ce_fwd_bwd on the three separate tensors, bit for bit."""
+    F, D = 12, 512
+    t, v, fr = [cu(x) for x in syn.finetune_inputs(B, seed=7)]
+    p = ops.resolve_precision(prec)
+    loss, dt, dv, df = ops.sym_ce_raw(t, v, fr, 100.0, 0.85, 0.15, p, True)
+    packed = torch.cat([t, v, fr.reshape(B, F * D)], dim=1).contiguous()
+    loss_p, dp = ops.sym_ce_packed_raw(packed, F, D, 100.0, 0.85, 0.15, p, True)
+    assert torch.equal(loss, loss_p)
+    assert torch.equal(dp[:, :D], dt) and torch.equal(dp[:, D:2 * D], dv)
+    assert torch.equal(dp[:, 2 * D:].reshape(B, F, D), df)
+    # forward only
+    loss_f, none = ops.sym_ce_packed_raw(packed, F, D, 100.0, 0.85, 0.15, p, False)
+    assert none is None and torch.equal(loss_f, loss)
