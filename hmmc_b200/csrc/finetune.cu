@@ -191,15 +191,15 @@ __device__ __forceinline__ const float* symce_src_row(const SymOperands& o, int 
 // Block = 32 consecutive rows (B % 32 == 0, so a block never mixes text and gallery rows), staged whole
 // in shared memory (32 x (D+1) floats): every input element is read once, one block-wide sync.
 __global__ void __launch_bounds__(1024)
-symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, __nv_bfloat16* __restrict__ Tp,
+symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, int Bk, int NGk,
+                  __nv_bfloat16* __restrict__ Tp,
                   __nv_bfloat16* __restrict__ TTp, __nv_bfloat16* __restrict__ Gp, __nv_bfloat16* __restrict__ GTp) {
   extern __shared__ float tile[];                 // [32][D + 1]
   const int ld = D + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 32;
-  const int NG = (voff + F) * B;
   const bool is_text = r0 < B;
-  const int R = is_text ? B : NG;                 // rows of this operand
+  const int R = is_text ? Bk : NGk;               // K extent (padded to 64) of the transposed pack
   const int q0 = is_text ? r0 : r0 - B;           // first row inside its operand
   __nv_bfloat16* straight = is_text ? Tp : Gp;
   __nv_bfloat16* transposed = is_text ? TTp : GTp;
@@ -295,7 +295,7 @@ __global__ void symce_loss_kernel(const float* __restrict__ S, int B, int NB, co
 // plane packs of the backward GEMMs: Sp [B, planes*NG] and STp [NG, planes*B].  32x32 tiles.
 __global__ void __launch_bounds__(256)
 symce_gradpack_kernel(const float* __restrict__ S, int B, int NB, const float* __restrict__ lse_row,
-                      const float* __restrict__ lse_col, int voff, float w0, float wf, int planes,
+                      const float* __restrict__ lse_col, int voff, float w0, float wf, int planes, int Bk, int NGk,
                       __nv_bfloat16* __restrict__ Sp, __nv_bfloat16* __restrict__ STp) {
   __shared__ float tile[32][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,9 +313,9 @@ symce_gradpack_kernel(const float* __restrict__ S, int B, int NB, const float* _
     const float g = w * (expf(v - lse_row[fp * B + i]) + expf(v - lc) - (j == i ? 2.f : 0.f));
     __nv_bfloat16 hi, lo;
     split_bf16(g, hi, lo);
-    const int64_t o = int64_t(i) * planes * NG + c;
+    const int64_t o = int64_t(i) * planes * NGk + c;
     Sp[o] = hi;
-    if (planes == 2) Sp[o + NG] = lo;
+    if (planes == 2) Sp[o + NGk] = lo;
     tile[ii][lane] = g;
   }
   __syncthreads();
@@ -324,9 +324,9 @@ symce_gradpack_kernel(const float* __restrict__ S, int B, int NB, const float* _
     const int cc = warp * 4 + k;
     __nv_bfloat16 hi, lo;
     split_bf16(tile[lane][cc], hi, lo);
-    const int64_t o = int64_t(c0 + cc) * planes * B + i0 + lane;
+    const int64_t o = int64_t(c0 + cc) * planes * Bk + i0 + lane;
     STp[o] = hi;
-    if (planes == 2) STp[o + B] = lo;
+    if (planes == 2) STp[o + Bk] = lo;
   }
 }
 
@@ -490,7 +490,10 @@ struct SymCeWs {
 };
 constexpr int SYMCE_MAX_SPLITS = 32;
 static bool symce_tensor_ok(int B, int D, int prec) {
-  return prec != HMMC_PREC_FP32 && B % 64 == 0 && D % 64 == 0 && D <= 1024;
+  // bf16x3 (fp32-parity) takes any multiple of 32 rows; the single-plane bf16 mode keeps its former
+  // 64-row granularity and leaves smaller batches on the exact CUDA-core path
+  if (prec == HMMC_PREC_FP32 || D % 64 != 0 || D > 1024) return false;
+  return prec == HMMC_PREC_BF16X3 ? (B % 32 == 0) : (B % 64 == 0);
 }
 static void symce_carve(Workspace& ws, SymCeWs& w, int B, int F, int D, int prec) {
   const size_t NB = size_t(1 + F);
@@ -506,13 +509,15 @@ static void symce_carve(Workspace& ws, SymCeWs& w, int B, int F, int D, int prec
   w.parts = nullptr;
   w.splits = 1;
   if (symce_tensor_ok(B, D, prec)) {
+    // contraction extents of the backward GEMMs, padded with zero columns to the 64-wide k-block
     const size_t P = size_t(planes_of(prec));
+    const size_t Bk = align_up(size_t(B), 64), NGk = align_up(NB * B, 64);
     w.Tp = ws.take<__nv_bfloat16>(size_t(B) * P * D);
-    w.TTp = ws.take<__nv_bfloat16>(size_t(D) * P * B);
+    w.TTp = ws.take<__nv_bfloat16>(size_t(D) * P * Bk);
     w.Gp = ws.take<__nv_bfloat16>(NB * B * P * D);
-    w.GTp = ws.take<__nv_bfloat16>(size_t(D) * P * NB * B);
-    w.Sp = ws.take<__nv_bfloat16>(size_t(B) * P * NB * B);
-    w.STp = ws.take<__nv_bfloat16>(NB * B * P * B);
+    w.GTp = ws.take<__nv_bfloat16>(size_t(D) * P * NGk);
+    w.Sp = ws.take<__nv_bfloat16>(size_t(B) * P * NGk);
+    w.STp = ws.take<__nv_bfloat16>(NB * B * P * Bk);
     w.parts = ws.take<float>(size_t(SYMCE_MAX_SPLITS) * B * D);
   }
 }
@@ -545,14 +550,23 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
   if (symce_tensor_ok(B, D, prec)) {
     // tensor-core path: 7 launches (4 without gradients)
     const int NG = NB * B, P = planes_of(prec);
+    const int Bk = int(align_up(size_t(B), 64)), NGk = int(align_up(size_t(NG), 64));
     const float wf = (F > 0) ? w_ftm / float(F) : 0.f;
+    if (need_grad && Bk != B) {
+      HMMC_CHECK_CUDA(cudaMemsetAsync(w.TTp, 0, size_t(D) * P * Bk * sizeof(__nv_bfloat16), st));
+      HMMC_CHECK_CUDA(cudaMemsetAsync(w.STp, 0, size_t(NG) * P * Bk * sizeof(__nv_bfloat16), st));
+    }
+    if (need_grad && NGk != NG) {
+      HMMC_CHECK_CUDA(cudaMemsetAsync(w.GTp, 0, size_t(D) * P * NGk * sizeof(__nv_bfloat16), st));
+      HMMC_CHECK_CUDA(cudaMemsetAsync(w.Sp, 0, size_t(B) * P * NGk * sizeof(__nv_bfloat16), st));
+    }
     const size_t prep_smem = size_t(32) * (D + 1) * sizeof(float);
     static int prep_smem_set = 0;
     if (prep_smem > 48 * 1024 && prep_smem_set < int(prep_smem)) {
       HMMC_CHECK_CUDA(cudaFuncSetAttribute(symce_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prep_smem)));
       prep_smem_set = int(prep_smem);
     }
-    symce_prep_kernel<<<unsigned((B + NG) / 32), 1024, prep_smem, st>>>(src, B, F, voff, D, P, w.Tp,
+    symce_prep_kernel<<<unsigned((B + NG) / 32), 1024, prep_smem, st>>>(src, B, F, voff, D, P, Bk, NGk, w.Tp,
                                                                 need_grad ? w.TTp : nullptr, w.Gp,
                                                                 need_grad ? w.GTp : nullptr);
     HMMC_CHECK_LAUNCH();
@@ -564,7 +578,7 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
     HMMC_CHECK_LAUNCH();
     if (!need_grad) return HMMC_OK;
     symce_gradpack_kernel<<<dim3(NG / 32, B / 32), 256, 0, st>>>(w.S, B, NB, w.lse_row, w.lse_col, voff, w_vtm, wf, P,
-                                                                  w.Sp, w.STp);
+                                                                  Bk, NGk, w.Sp, w.STp);
     HMMC_CHECK_LAUNCH();
     // backward contractions in one grouped launch:
     //   g_that[i,d] = scale * sum_g G[i,g] ghat[g,d]   long K (= NG), few output tiles: split-K partials
@@ -575,13 +589,13 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
     int sp = (sm_count() - other) / (tiles > 0 ? tiles : 1);
     if (sp < 1) sp = 1;
     if (sp > 16) sp = 16;
-    const int eff = umma_effective_splits(NG, P, sp);
+    const int eff = umma_effective_splits(NGk, P, sp);
     StoreGemm gm[2];
     int ng = 0;
     if (dtext != nullptr)
-      gm[ng++] = StoreGemm{w.Sp, int64_t(P) * NG, w.GTp, int64_t(P) * NG, w.parts, D, int64_t(B) * D, B, D, NG, sp};
+      gm[ng++] = StoreGemm{w.Sp, int64_t(P) * NGk, w.GTp, int64_t(P) * NGk, w.parts, D, int64_t(B) * D, B, D, NGk, sp};
     if (dvideo != nullptr || dframes != nullptr)
-      gm[ng++] = StoreGemm{w.STp, int64_t(P) * B, w.TTp, int64_t(P) * B, w.gg, D, 0, NG, D, B, 1};
+      gm[ng++] = StoreGemm{w.STp, int64_t(P) * Bk, w.TTp, int64_t(P) * Bk, w.gg, D, 0, NG, D, Bk, 1};
     if ((rc = umma_gemm_store_grouped(gm, ng, P, scale, st))) return rc;
     HMMC_REQUIRE(D <= 1024, "sym_ce: D=%d above the tensor-core path's limit of 1024", D);
     if (D <= 512)

@@ -90,7 +90,7 @@ def test_single_row_and_no_grad():
     assert abs(float(l) - float(O.finetune_loss(t, v, fr))) < 1e-4
 
 
-@pytest.mark.parametrize("B,prec", [(256, "bf16x3"), (64, "bf16"), (32, "bf16x3"), (32, "fp32")])
+@pytest.mark.parametrize("B,prec", [(256, "bf16x3"), (64, "bf16"), (32, "bf16x3"), (96, "bf16x3"), (32, "bf16"), (32, "fp32")])
 def test_packed_layout_equals_separate_tensors(B, prec):
     """hmmc_sym_ce_packed_fwd_bwd (rows [text | video | frames], the all-gather's layout) gives the
     loss and gradients of hmmc_sym_ce_fwd_bwd on the three separate tensors, bit for bit."""
