@@ -563,6 +563,12 @@ def main():
                 line["finetune_head"] = ft
         except Exception as e:   # noqa: BLE001
             line["finetune_head"] = {"error": repr(e)[:300]}
+    # ---- north_star target shape: loss forward+backward alone at batch 256, rank 0
+    if rank == 0 and not args.no_retrieval:
+        try:
+            line["loss_b256"] = loss_target_leg(args, dev, tf_peak, peak_src)
+        except Exception as e:   # noqa: BLE001
+            line["loss_b256"] = {"error": repr(e)[:300]}
     # ---- optimizer step that follows the head's backward, rank 0
     if rank == 0 and not args.no_retrieval:
         try:
@@ -597,6 +603,59 @@ def main():
             sys.stderr.flush()
             os._exit(0)
         dist.destroy_process_group()
+
+
+def loss_target_leg(args, dev, tf_peak, peak_src):
+    """BASELINE north_star target: the fused HM + MoCo loss forward/backward at batch 256, 12 frames,
+    dim 512, queue 1024 (no EMA, no enqueue), CUDA-graph replay, in the bf16 mode and in the
+    fp32-parity bf16x3 mode (which executes 3x the algorithmic FLOPs on the tensor cores)."""
+    from hmmc_b200 import ops
+    from hmmc_b200 import synthetic as syn
+    from hmmc_b200.graphs import GraphedStep
+    b, F, D, K = 256, 12, 512, 1024
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    qs = {n: torch.from_numpy(x).to(dev) for n, x in syn.queues(K, F=F, D=D, seed=3).items()}
+    t = {n: torch.from_numpy(x).to(dev) for n, x in inp.items()}
+    qn = ("v_fea", "title_fea", "frame_fea", "frame_pred")
+    for n in qn:
+        t[n].requires_grad_(True)
+    algo = FLOPS_ALGO(b, F, D, K)
+    out = {"workload": "pre-train head loss fwd+bwd only, b=256 F=12 D=512 K=1024", "algorithmic_flops": algo,
+           "peak": tf_peak, "peak_source": peak_src, "unit": "TFLOP/s"}
+    for prec in ("bf16", "bf16x3"):
+        def run(prec=prec):
+            for n in qn:
+                t[n].grad = None
+            total, _ = ops.pretrain_head(t["v_fea"], t["title_fea"], t["frame_fea"], t["frame_pred"], t["v_fea_k"],
+                                         t["title_fea_k"], t["frame_fea_k"], t["frame_proj_k"], qs["queue_v_cross_ng"],
+                                         qs["queue_title_cross_ng"], qs["queue_frame_proj_ng"],
+                                         qs["queue_frame_cross_ng"], 0.07, 0.05, 0.45, 0.45, True, prec)
+            total.backward()
+            return total
+        for _ in range(3):
+            run()
+        try:
+            g = GraphedStep(run)
+            fn, mode = g.replay, "cuda graph replay"
+        except Exception as e:   # noqa: BLE001
+            fn, mode = run, "eager (%s)" % repr(e)[:80]
+            torch.cuda.synchronize()
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 200
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        executed = algo * (3 if prec == "bf16x3" else 1)
+        out[prec] = {"ms": ms, "samples_per_s": b / (ms / 1e3), "achieved": algo / (ms * 1e-3) / 1e12,
+                     "frac": algo / (ms * 1e-3) / 1e12 / tf_peak, "executed_tflops": executed / (ms * 1e-3) / 1e12,
+                     "executed_frac": executed / (ms * 1e-3) / 1e12 / tf_peak, "issue_mode": mode}
+    return out
 
 
 def optimizer_leg(args, dev, sizes, hbm_peak, peak_src):

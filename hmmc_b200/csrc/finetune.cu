@@ -142,21 +142,6 @@ __global__ void symce_grad_kernel(float* __restrict__ S, int B, int NB, const fl
   if (threadIdx.x == 0) row_loss[i] = loss;
 }
 
-// out[i] = sum_s parts[s*stride + i]  (split-K partials of the tensor-core backward GEMM)
-__global__ void sum_partials_kernel(const float* __restrict__ parts, int n_splits, int64_t stride, int64_t count,
-                                    float* __restrict__ out) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float acc = 0.f;
-  for (int s0 = 0; s0 < n_splits; s0 += 4) {
-    float a[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = (s0 + j < n_splits) ? parts[int64_t(s0 + j) * stride + i] : 0.f;
-    acc += (a[0] + a[1]) + (a[2] + a[3]);
-  }
-  out[i] = acc;
-}
-
 // scatter gallery-ordered gradient rows back: dvideo[j] = dG[0*B + j], dframes[j,f] = dG[(f+1)*B + j]
 __global__ void gallery_scatter_kernel(const float* __restrict__ dG, int B, int F, int voff, int D,
                                        float* __restrict__ dvideo, float* __restrict__ dframes) {
@@ -614,17 +599,10 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
   if ((rc = rownorm_pack(text, B, D, D, 0.f, 1, w.that, nullptr, nullptr, 0, st))) return rc;
   gallery_norm_kernel<<<unsigned((int64_t(NB) * B + 7) / 8), 256, 0, st>>>(video, frames, B, F, voff, D, w.ghat);
   HMMC_CHECK_LAUNCH();
+  // CUDA-core path (fp32 mode, or shapes the tensor-core tiling does not take)
   const int NG = NB * B;
-  const bool tc = symce_tensor_ok(B, D, prec);     // tcgen05 for the three contractions
-  const int P = planes_of(prec);
   // S_all = scale * that . ghat^T   [B, NG]
-  if (tc) {
-    if ((rc = pack_dual(w.that, B, D, P, w.Tp, need_grad ? w.TTp : nullptr, st))) return rc;
-    if ((rc = pack_dual(w.ghat, NG, D, P, w.Gp, need_grad ? w.GTp : nullptr, st))) return rc;
-    if ((rc = umma_gemm_store(w.Tp, int64_t(P) * D, w.Gp, int64_t(P) * D, w.S, NG, 0, B, NG, D, P, 1, scale, st))) return rc;
-  } else {
-    if ((rc = gemm_f32(w.that, D, 1, w.ghat, D, 1, w.S, NG, B, NG, D, scale, st))) return rc;
-  }
+  if ((rc = gemm_f32(w.that, D, 1, w.ghat, D, 1, w.S, NG, B, NG, D, scale, st))) return rc;
   symce_row_lse_kernel<<<B, 256, 0, st>>>(w.S, B, NB, w.lse_row);
   HMMC_CHECK_LAUNCH();
   symce_col_lse_kernel<<<unsigned((NG + 31) / 32), 256, 0, st>>>(w.S, B, NB, w.lse_col);
@@ -635,32 +613,15 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
   sum_to_scalar_kernel<<<1, 256, 0, st>>>(w.row_loss, B, loss_out, 0);
   HMMC_CHECK_LAUNCH();
   if (!need_grad) return HMMC_OK;
-  if (tc && (rc = pack_dual(w.S, B, NG, P, w.Sp, w.STp, st))) return rc;     // G and G^T as bf16 planes
   if (dtext != nullptr) {
     // g_that[i,d] = scale * sum_g G[i,g] ghat[g,d]
-    if (tc) {
-      // long K (= NG), few output tiles: split-K partials, then a fixed-order sum
-      const int tiles = ((B + 127) / 128) * ((D + 255) / 256);
-      int sp = sm_count() / (tiles > 0 ? tiles : 1);
-      if (sp < 1) sp = 1;
-      if (sp > SYMCE_MAX_SPLITS) sp = SYMCE_MAX_SPLITS;
-      const int eff = umma_effective_splits(NG, P, sp);
-      if ((rc = umma_gemm_store(w.Sp, int64_t(P) * NG, w.GTp, int64_t(P) * NG, w.parts, D, int64_t(B) * D, B, D, NG, P,
-                                sp, scale, st))) return rc;
-      const int64_t cnt = int64_t(B) * D;
-      sum_partials_kernel<<<unsigned((cnt + 255) / 256), 256, 0, st>>>(w.parts, eff, cnt, cnt, w.gt);
-      HMMC_CHECK_LAUNCH();
-    } else if ((rc = gemm_f32(w.S, NG, 1, w.ghat, 1, D, w.gt, D, B, D, NG, scale, st))) return rc;
+    if ((rc = gemm_f32(w.S, NG, 1, w.ghat, 1, D, w.gt, D, B, D, NG, scale, st))) return rc;
     unnormalize_grad_kernel<<<unsigned((B + 7) / 8), 256, 0, st>>>(text, w.gt, dtext, B, D);
     HMMC_CHECK_LAUNCH();
   }
   if (dvideo != nullptr || dframes != nullptr) {
     // g_ghat[g,d] = scale * sum_i G[i,g] that[i,d]
-    if (tc) {
-      if ((rc = umma_gemm_store(w.STp, int64_t(P) * B, w.TTp, int64_t(P) * B, w.gg, D, 0, NG, D, B, P, 1, scale, st))) return rc;
-    } else if ((rc = gemm_f32(w.S, 1, NG, w.that, 1, D, w.gg, D, NG, D, B, scale, st))) return rc;
-    // chain through the normalisation in gallery order (reuse ghat buffer for the raw rows is not
-    // possible, so un-normalise against the raw inputs row by row after scattering)
+    if ((rc = gemm_f32(w.S, 1, NG, w.that, 1, D, w.gg, D, NG, D, B, scale, st))) return rc;
     if (dvideo != nullptr) {
       unnormalize_grad_kernel<<<unsigned((B + 7) / 8), 256, 0, st>>>(video, w.gg, dvideo, B, D);
       HMMC_CHECK_LAUNCH();
