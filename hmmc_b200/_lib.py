@@ -37,6 +37,7 @@ SIGNATURES = {
     "hmmc_version": (c_int, []),
     "hmmc_launch_count": (ctypes.c_ulonglong, []),
     "hmmc_device_check": (c_int, []),
+    "hmmc_set_reserved_sms": (c_int, [c_int]),
     "hmmc_rownorm_pack": (c_int, [c_void_p, c_int64, c_int, c_int64, c_float, c_int, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),
     "hmmc_gemm_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,

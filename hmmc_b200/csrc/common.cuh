@@ -40,6 +40,7 @@ void count_launch();
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
+int gemm_sm_budget();     // sm_count() minus the SMs reserved through hmmc_set_reserved_sms
 
 // Bump allocator over the caller's workspace.
 struct Workspace {

@@ -33,6 +33,20 @@ int sm_count() {
   return cached[dev];
 }
 
+// SMs the persistent GEMM grids leave free (a collective running beside them needs somewhere to live:
+// a persistent CTA that cannot become resident stalls its share of the tiles until the collective ends)
+static int g_reserved_sms = -1;
+int gemm_sm_budget() {
+  if (g_reserved_sms < 0) {
+    const char* e = getenv("HMMC_RESERVED_SMS");
+    g_reserved_sms = e ? atoi(e) : 0;
+    if (g_reserved_sms < 0) g_reserved_sms = 0;
+  }
+  int n = sm_count() - g_reserved_sms;
+  return n < 2 ? 2 : n;
+}
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -221,6 +235,11 @@ extern "C" {
 const char* hmmc_last_error(void) { return g_err; }
 int hmmc_version(void) { return 100; }
 unsigned long long hmmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hmmc_set_reserved_sms(int n) {
+  hmmc::set_reserved_sms(n);
+  return HMMC_OK;
+}
 
 int hmmc_device_check(void) {
   int dev = 0;

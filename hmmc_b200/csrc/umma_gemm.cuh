@@ -625,7 +625,8 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
   auto kern = umma_gemm_kernel<BN, Epi>;
   HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
   const int tiles = g.tile_begin[g.num_problems];
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int budget = gemm_sm_budget();
+  const int grid = tiles < budget ? tiles : budget;
   kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, g);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
@@ -680,7 +681,7 @@ int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t 
   auto kern = umma_gemm_pair_kernel<Epi>;
   HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(UMMA_PAIR_SMEM_BYTES)));
   const int tiles = g.tile_begin[g.num_problems];
-  int pairs = sm_count() / 2;
+  int pairs = gemm_sm_budget() / 2;
   if (pairs > tiles) pairs = tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);

@@ -18,6 +18,7 @@ the methods here can be mixed into (or swapped for) the reference's classes:
 All arithmetic runs in libhmmc_head.so (see ops.py); there is no PyTorch fallback.
 """
 import logging
+import os
 from types import SimpleNamespace
 
 import torch
@@ -31,6 +32,10 @@ logger = logging.getLogger(__name__)
 # modules/cross-base/cross_config.json (head-relevant keys)
 DEFAULT_CROSS_CONFIG = dict(temporal_hidden_size=512, weight_FAM=0.05, weight_VTM=0.45, weight_FTM=0.45,
                             weight_MLM=0.05, weight_VTM_finetune=0.85, weight_FTM_finetune=0.15)
+
+
+# SMs left to the key all-gather while it overlaps the loss (tuned on 2 and 8 B200)
+GATHER_RESERVED_SMS = int(os.environ.get("HMMC_GATHER_RESERVED_SMS", "0"))
 
 
 def default_cross_config(**over):
@@ -166,6 +171,9 @@ class ContrastiveHeadMixin:
             return (W, b, F, D, [ops._f32c(t, "key") for t in keys], None, lambda: None)
         send = ops.pack_rows(keys)
         gathered, wait = parallel.all_gather_rows_async(send)
+        # the collective's CTAs share the SMs with the loss kernels issued until _enqueue_gathered:
+        # keep some SMs out of the persistent GEMM grids meanwhile
+        ops.set_reserved_sms(GATHER_RESERVED_SMS)
         return (W, b, F, D, None, gathered, wait)
 
     @torch.no_grad()
@@ -173,6 +181,8 @@ class ContrastiveHeadMixin:
         W, b, F, D, direct, gathered, wait = handle
         K = self.contrast_num_negative
         wait()
+        if W > 1:
+            ops.set_reserved_sms(0)
         if torch.cuda.is_current_stream_capturing():
             # CUDA-graph capture: the pointer is read and advanced on the device at every replay
             if K % (W * b) != 0:

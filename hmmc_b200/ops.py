@@ -54,6 +54,11 @@ def workspace(device, nbytes):
     return buf
 
 
+def set_reserved_sms(n):
+    """SMs the persistent GEMM grids leave free from now on (see include/hmmc_head.h)."""
+    _lib.check(_lib.load().hmmc_set_reserved_sms(int(n)), "hmmc_set_reserved_sms")
+
+
 def device_check():
     _lib.check(_lib.load().hmmc_device_check(), "hmmc_device_check")
 

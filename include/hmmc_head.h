@@ -55,6 +55,10 @@ int hmmc_version(void);
 unsigned long long hmmc_launch_count(void);
 /* 0 when the current device is sm_100 (B200); HMMC_ERR_UNSUPPORTED otherwise. */
 int hmmc_device_check(void);
+/* Leave n SMs out of the persistent GEMM grids launched from now on (0 = use them all).  The host
+ * sets this while a collective (the key all-gather of _dequeue_and_enqueue) runs beside the loss:
+ * a persistent CTA that cannot become resident would hold its tiles back until the collective ends. */
+int hmmc_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------ operands */
 
