@@ -31,6 +31,10 @@ class hmmc_pretrain_io(Structure):
                                         "d_frame_pred")]
 
 
+class hmmc_mlp_params(Structure):
+    _fields_ = [(n, c_void_p) for n in ("W1", "b1", "gamma", "beta", "W2", "b2", "running_mean", "running_var")]
+
+
 # name -> (restype, argtypes); must list every symbol of include/hmmc_head.h
 SIGNATURES = {
     "hmmc_last_error": (c_char_p, []),
@@ -59,6 +63,15 @@ SIGNATURES = {
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
+    "hmmc_mlp_ctx_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "hmmc_mlp_fwd_a": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_mlp_params), c_int, c_int, c_void_p,
+                               c_size_t, POINTER(c_void_p), c_void_p]),
+    "hmmc_mlp_fwd_b": (c_int, [c_int, c_int, c_int, c_int, POINTER(hmmc_mlp_params), c_float, c_float, ctypes.c_double,
+                               c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hmmc_mlp_bwd_a": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_mlp_params), c_int, c_void_p, c_size_t,
+                               c_void_p, c_void_p, POINTER(c_void_p), c_void_p]),
+    "hmmc_mlp_bwd_b": (c_int, [c_int, c_int, c_int, c_int, POINTER(hmmc_mlp_params), ctypes.c_double, c_int, c_void_p,
+                               c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hmmc_bert_adam_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "hmmc_bert_adam_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int64, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libhmmc_head.so")
-SOURCES = ["core.cu", "pretrain.cu", "finetune.cu", "eval.cu", "eval_fused.cu", "optim.cu"]
+SOURCES = ["core.cu", "pretrain.cu", "finetune.cu", "eval.cu", "eval_fused.cu", "optim.cu", "mlp.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

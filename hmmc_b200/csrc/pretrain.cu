@@ -822,8 +822,12 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
       e1.E = static_cast<__nv_bfloat16*>(L.E[k]);
       e1.ldE = int64_t(planes) * Kq;
       e1.e_planes = planes;
-      static const int probe = tune_int("HMMC_PROBE_NOEXP", 0);
+#ifdef HMMC_ENABLE_PROBES
+      static const int probe = tune_int("HMMC_PROBE_NOEXP", 0);     // skips the exponentials: changes results
       e1.probe = probe;
+#else
+      e1.probe = 0;
+#endif
       p1[k] = GemmProblem<EpiInfoNCE>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
                                       int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1};
       EpiStoreF32::Params e2{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};

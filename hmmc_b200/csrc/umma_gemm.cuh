@@ -551,6 +551,17 @@ struct EpiInfoNCE {
 
 // ------------------------------------------------------------------ host side
 
+// Epilogue probes (profiles/r1_gemm_analysis.md) skip parts of the epilogue to attribute time; they
+// change results, so they exist only in builds with -DHMMC_ENABLE_PROBES.
+static inline int probe_mode() {
+#ifdef HMMC_ENABLE_PROBES
+  const char* e = getenv("HMMC_PROBE_EPI");
+  return e ? atoi(e) : 0;
+#else
+  return 0;
+#endif
+}
+
 // bf16 row-major [rows, cols] (leading dimension ld elements) -> 2-D tensor map with a
 // [box_rows x 64] box and the 128-byte swizzle.
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
@@ -585,7 +596,7 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
   TmapSet tm;
   GroupedArgs<Epi> g;
   g.num_problems = 0;
-  g.probe = getenv("HMMC_PROBE_EPI") ? atoi(getenv("HMMC_PROBE_EPI")) : 0;
+  g.probe = probe_mode();
   g.tile_begin[0] = 0;
   for (int i = 0; i < n; ++i) {
     const GemmProblem<Epi>& pr = probs[i];
@@ -641,7 +652,7 @@ int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t 
   TmapSet tm;
   GroupedArgs<Epi> g;
   g.num_problems = 0;
-  g.probe = getenv("HMMC_PROBE_EPI") ? atoi(getenv("HMMC_PROBE_EPI")) : 0;
+  g.probe = probe_mode();
   g.tile_begin[0] = 0;
   for (int i = 0; i < n; ++i) {
     const GemmProblem<Epi>& pr = probs[i];

@@ -191,3 +191,13 @@ def eval_epoch_case(multi, batch):
     n = T.shape[0]
     batches = [(np.arange(i, min(i + batch, n)), vid_of_caption[i:i + batch]) for i in range(0, n, batch)]
     return T, V, Fr, batches, cut_1based
+
+
+def mlp_case(M=64, Din=64, Dh=128, Dout=64, seed=31):
+    """Inputs, parameters (non-trivial BatchNorm affine and running statistics) and the upstream
+    gradient of the MLP parity cases."""
+    rs = np.random.RandomState(seed)
+    f = lambda *shp, s=1.0: (_randn(rs, *shp) * s).astype(np.float32)
+    return dict(x=f(M, Din), W1=f(Dh, Din, s=Din ** -0.5), b1=f(Dh, s=0.1), gamma=(1.0 + f(Dh, s=0.2)).astype(np.float32),
+                beta=f(Dh, s=0.3), W2=f(Dout, Dh, s=Dh ** -0.5), b2=f(Dout, s=0.1),
+                rm=f(Dh, s=0.1), rv=(1.0 + np.abs(f(Dh, s=0.2))).astype(np.float32), dy=f(M, Dout, s=0.05))

@@ -215,6 +215,40 @@ int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, in
 int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int32_t* widths_host, int n,
                      int64_t rows, void* stream);
 
+/* SURVEY.md §8(f) N1 — the projector / predictor MLP applied to the frame features right before the
+ * head (modules/modeling.py:788-807 with num_layers = 2, used at :355-377):
+ *   y = Linear2(ReLU(BatchNorm1d(Linear1(x))))      x [M, Din], W1 [Dh, Din], W2 [Dout, Dh]
+ * forward and backward on the tensor cores (prec bf16 or bf16x3).  The reference converts these
+ * MLPs to SyncBatchNorm (:127-129): the batch statistics span all ranks' rows, so each direction
+ * is two calls around one exchange the host performs on a device buffer of 2*Dh doubles:
+ *   hmmc_mlp_fwd_a  -> *stats_out = (sum h, sum h^2) of this rank   [host: all-reduce SUM]
+ *   hmmc_mlp_fwd_b  (count = rows of all ranks; training = 0 uses the running statistics instead;
+ *                    training = 1 also updates running_mean / running_var with `momentum`)
+ *   hmmc_mlp_bwd_a  -> dW2, db2, *sums_out = (sum dZ, sum dZ*xhat)  [host: all-reduce SUM]
+ *   hmmc_mlp_bwd_b  -> dx, dW1, db1, dgamma, dbeta (parameter gradients are this rank's, as with
+ *                    SyncBatchNorm + DDP)
+ * `ctx` (hmmc_mlp_ctx_bytes) carries everything between the four calls and must stay untouched from
+ * fwd_a to bwd_b.  Any gradient pointer may be NULL. */
+typedef struct {
+  const float* W1;      /* [Dh, Din]  linear_hidden.1.weight */
+  const float* b1;      /* [Dh]       linear_hidden.1.bias   */
+  const float* gamma;   /* [Dh]       linear_hidden.2.weight */
+  const float* beta;    /* [Dh]       linear_hidden.2.bias   */
+  const float* W2;      /* [Dout, Dh] linear_out.weight      */
+  const float* b2;      /* [Dout]     linear_out.bias        */
+  float* running_mean;  /* [Dh] or NULL */
+  float* running_var;   /* [Dh] or NULL */
+} hmmc_mlp_params;
+size_t hmmc_mlp_ctx_bytes(int M, int Din, int Dh, int Dout, int prec, int need_grad);
+int hmmc_mlp_fwd_a(const float* x, int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, int prec, int need_grad,
+                   void* ctx, size_t ctx_bytes, double** stats_out, void* stream);
+int hmmc_mlp_fwd_b(int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, float eps, float momentum, double count,
+                   int training, int prec, int need_grad, void* ctx, size_t ctx_bytes, float* y, void* stream);
+int hmmc_mlp_bwd_a(const float* dy, int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, int prec, void* ctx,
+                   size_t ctx_bytes, float* dW2, float* db2, double** sums_out, void* stream);
+int hmmc_mlp_bwd_b(int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, double count, int prec, void* ctx,
+                   size_t ctx_bytes, float* dx, float* dW1, float* db1, float* dgamma, float* dbeta, void* stream);
+
 /* ---------------------------------------------------------- fine-tune head (HM) */
 
 /* loose_similarity (modules/modeling.py:207-229), forward.  vis is [Bv*Fv, D]

@@ -277,6 +277,32 @@ def gen_eval_epoch(M, metrics, R):
     np.savez(os.path.join(OUT, "eval_epoch.npz"), **out)
 
 
+def gen_mlp(M, metrics, R):
+    """The reference's MLP class (modules/modeling.py:788-807) on CPU: training-mode forward + backward,
+    running statistics afterwards, and an eval-mode forward."""
+    c = syn.mlp_case()
+    m = M.MLP(in_dim=64, inner_dim=128, out_dim=64, num_layers=2)
+    lin1, bn = m.linear_hidden[1], m.linear_hidden[2]
+    with torch.no_grad():
+        lin1.weight.copy_(_t(c["W1"])); lin1.bias.copy_(_t(c["b1"]))
+        bn.weight.copy_(_t(c["gamma"])); bn.bias.copy_(_t(c["beta"]))
+        bn.running_mean.copy_(_t(c["rm"])); bn.running_var.copy_(_t(c["rv"]))
+        m.linear_out.weight.copy_(_t(c["W2"])); m.linear_out.bias.copy_(_t(c["b2"]))
+    m.train()
+    x = _t(c["x"], grad=True)
+    y = m(x)
+    y.backward(_t(c["dy"]))
+    out = dict(y=y.detach().numpy(), dx=x.grad.numpy(), dW1=lin1.weight.grad.numpy(), db1=lin1.bias.grad.numpy(),
+               dgamma=bn.weight.grad.numpy(), dbeta=bn.bias.grad.numpy(), dW2=m.linear_out.weight.grad.numpy(),
+               db2=m.linear_out.bias.grad.numpy(), rm=bn.running_mean.numpy().copy(), rv=bn.running_var.numpy().copy(),
+               nbt=int(bn.num_batches_tracked), keys=np.array(sorted(m.state_dict().keys())))
+    m.eval()
+    with torch.no_grad():
+        out["y_eval"] = m(_t(c["x"])).numpy()
+    np.savez_compressed(os.path.join(OUT, "mlp.npz"), **out)
+    print("mlp golden: |y|", float(np.abs(out["y"]).mean()), "keys", list(out["keys"]))
+
+
 OPTIM_CASES = (("pretrain", 6, 1.0, (0, 5)), ("plain", 3, None, (0, 1, 2)), ("linear", 4, None, (3,)))
 
 
@@ -315,7 +341,7 @@ def main():
     torch.manual_seed(0)
     M, metrics, R = ref_shim.load()
     only = sys.argv[1:]
-    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim, gen_eval_epoch):
+    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim, gen_eval_epoch, gen_mlp):
         if only and fn.__name__[4:] not in only:
             continue
         fn(M, metrics, R)

@@ -1,0 +1,46 @@
+"""TEST INFRASTRUCTURE ONLY — numpy float64 restatement of the reference's two-layer MLP
+(modules/modeling.py:788-807: Linear -> BatchNorm1d (training mode) -> ReLU -> Linear) with its
+analytic backward, pinned against the reference class itself (tests/golden/mlp.npz written by
+oracle/gen_golden.py).  Imported by tests/ and tools/multi_gpu_check.py only."""
+import numpy as np
+
+
+def forward(x, W1, b1, gamma, beta, W2, b2, eps=1e-5, running=None):
+    """running = (mean, var): eval mode.  Returns (y, cache)."""
+    x = np.asarray(x, np.float64)
+    h = x @ np.asarray(W1, np.float64).T + np.asarray(b1, np.float64)
+    if running is None:
+        mean, var = h.mean(0), h.var(0)
+    else:
+        mean, var = np.asarray(running[0], np.float64), np.asarray(running[1], np.float64)
+    invstd = 1.0 / np.sqrt(var + eps)
+    xhat = (h - mean) * invstd
+    z = xhat * np.asarray(gamma, np.float64) + np.asarray(beta, np.float64)
+    a = np.maximum(z, 0.0)
+    y = a @ np.asarray(W2, np.float64).T + np.asarray(b2, np.float64)
+    return y, dict(x=x, h=h, mean=mean, var=var, invstd=invstd, xhat=xhat, z=z, a=a)
+
+
+def running_stats(cache, rm, rv, momentum=0.1):
+    """nn.BatchNorm1d's update: biased batch variance normalises, the unbiased one is tracked."""
+    n = cache["h"].shape[0]
+    new_rm = (1 - momentum) * np.asarray(rm, np.float64) + momentum * cache["mean"]
+    new_rv = (1 - momentum) * np.asarray(rv, np.float64) + momentum * cache["var"] * n / max(n - 1, 1)
+    return new_rm, new_rv
+
+
+def backward(dy, cache, W1, gamma, W2):
+    dy = np.asarray(dy, np.float64)
+    W1, W2, gamma = (np.asarray(t, np.float64) for t in (W1, W2, gamma))
+    n = dy.shape[0]
+    dW2 = dy.T @ cache["a"]
+    db2 = dy.sum(0)
+    da = dy @ W2
+    dz = da * (cache["z"] > 0)
+    dbeta = dz.sum(0)
+    dgamma = (dz * cache["xhat"]).sum(0)
+    dh = gamma * cache["invstd"] * (dz - dbeta / n - cache["xhat"] * dgamma / n)
+    dW1 = dh.T @ cache["x"]
+    db1 = dh.sum(0)
+    dx = dh @ W1
+    return dict(dx=dx, dW1=dW1, db1=db1, dgamma=dgamma, dbeta=dbeta, dW2=dW2, db2=db2)

@@ -282,3 +282,32 @@ def test_optim_torch_port(golden):
     for i, p in enumerate(params):
         assert np.array_equal(p.numpy(), g["pretrain_p%d_s5" % i]), i
         assert np.array_equal(state[i]['next_m'].numpy(), g["pretrain_m%d" % i]), i
+
+
+def test_mlp_oracle_vs_reference_class(golden):
+    """oracle/mlp_oracle.py against the reference's own MLP (Linear -> BatchNorm1d -> ReLU -> Linear) run on
+    CPU in fp32: outputs, every gradient, the running statistics and the eval-mode forward."""
+    from oracle import mlp_oracle as MO
+    g = golden("mlp")
+    c = syn.mlp_case()
+    y, cache = MO.forward(c["x"], c["W1"], c["b1"], c["gamma"], c["beta"], c["W2"], c["b2"])
+    assert _rel(y, g["y"]) < 2e-6
+    grads = MO.backward(c["dy"], cache, c["W1"], c["gamma"], c["W2"])
+    for k in ("dx", "dW1", "dgamma", "dbeta", "dW2", "db2"):
+        assert _rel(grads[k], g[k]) < 5e-6, k
+    # db1 is zero in exact arithmetic (the bias cancels inside the BatchNorm): only rounding noise on both sides
+    assert np.abs(grads["db1"]).max() < 1e-12 and np.abs(g["db1"]).max() < 1e-6
+    rm, rv = MO.running_stats(cache, c["rm"], c["rv"])
+    assert _rel(rm, g["rm"]) < 1e-6 and _rel(rv, g["rv"]) < 1e-6
+    y_eval, _ = MO.forward(c["x"], c["W1"], c["b1"], c["gamma"], c["beta"], c["W2"], c["b2"], running=(rm, rv))
+    assert _rel(y_eval, g["y_eval"]) < 2e-6
+
+
+def test_mlp_mirror_state_dict_keys(golden):
+    from hmmc_b200.mlp import MLP
+    g = golden("mlp")
+    m = MLP(in_dim=64, inner_dim=128, out_dim=64, num_layers=2)
+    assert sorted(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    import torch
+    with pytest.raises(Exception):
+        m(torch.zeros(4, 64))            # CPU tensors: there is no CPU path
