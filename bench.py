@@ -569,6 +569,12 @@ def main():
             line["loss_b256"] = loss_target_leg(args, dev, tf_peak, peak_src)
         except Exception as e:   # noqa: BLE001
             line["loss_b256"] = {"error": repr(e)[:300]}
+    # ---- projector / predictor MLP right before the head, rank 0
+    if rank == 0 and not args.no_retrieval:
+        try:
+            line["mlp"] = mlp_leg(args, dev, tf_peak, peak_src)
+        except Exception as e:   # noqa: BLE001
+            line["mlp"] = {"error": repr(e)[:300]}
     # ---- optimizer step that follows the head's backward, rank 0
     if rank == 0 and not args.no_retrieval:
         try:
@@ -655,6 +661,68 @@ def loss_target_leg(args, dev, tf_peak, peak_src):
         out[prec] = {"ms": ms, "samples_per_s": b / (ms / 1e3), "achieved": algo / (ms * 1e-3) / 1e12,
                      "frac": algo / (ms * 1e-3) / 1e12 / tf_peak, "executed_tflops": executed / (ms * 1e-3) / 1e12,
                      "executed_frac": executed / (ms * 1e-3) / 1e12 / tf_peak, "issue_mode": mode}
+    return out
+
+
+def mlp_leg(args, dev, tf_peak, peak_src):
+    """One projector MLP (modules/modeling.py:788-807: 512 -> 4096 -> BatchNorm -> ReLU -> 512) forward +
+    backward on the b*F = 1536 frame rows of the pre-train step, fp32-parity (bf16x3) and bf16 modes."""
+    from hmmc_b200.graphs import GraphedStep
+    from hmmc_b200.mlp import MLP
+    M, Din, Dh, Dout = args.batch * args.frames, args.dim, 4096, args.dim
+    algo = 6 * 2.0 * M * Din * Dh        # two forward and four backward GEMMs of equal size
+    out = {"workload": "MLP fwd+bwd, %d rows, %d -> %d -> %d, training-mode BatchNorm" % (M, Din, Dh, Dout),
+           "algorithmic_flops": algo, "peak": tf_peak, "unit": "TFLOP/s", "peak_source": peak_src}
+    x = torch.randn(M, Din, device=dev, requires_grad=True)
+    dy = torch.randn(M, Dout, device=dev) * 0.05
+    for prec in ("bf16", "bf16x3"):
+        m = MLP(Din, Dh, Dout, 2, precision=prec).to(dev).train()
+
+        def step():
+            x.grad = None
+            for p in m.parameters():
+                p.grad = None
+            y = m(x)
+            y.backward(dy)
+            return y
+        for _ in range(3):
+            step()
+        try:
+            g = GraphedStep(step)
+            fn, mode = g.replay, "cuda graph replay"
+        except Exception as e:   # noqa: BLE001
+            fn, mode = step, "eager (%s)" % repr(e)[:80]
+            torch.cuda.synchronize()
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 100
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ex = algo * (3 if prec == "bf16x3" else 1)
+        out[prec] = {"ms": ms, "rows_per_s": M / (ms / 1e3), "achieved": algo / (ms * 1e-3) / 1e12,
+                     "frac": algo / (ms * 1e-3) / 1e12 / tf_peak, "executed_frac": ex / (ms * 1e-3) / 1e12 / tf_peak,
+                     "issue_mode": mode}
+    if not args.no_cpu_baseline:
+        # the reference class restated with torch modules, on the host cores
+        ref = torch.nn.Sequential(torch.nn.Linear(Din, Dh), torch.nn.BatchNorm1d(Dh), torch.nn.ReLU(inplace=True),
+                                  torch.nn.Linear(Dh, Dout)).train()
+        xc = torch.randn(M, Din, requires_grad=True)
+        dyc = torch.randn(M, Dout) * 0.05
+        ref(xc).backward(dyc)
+        t0 = time.perf_counter()
+        k = 0
+        while k < 3 or (time.perf_counter() - t0 < 3.0 and k < 50):
+            ref(xc).backward(dyc)
+            k += 1
+        cms = (time.perf_counter() - t0) * 1e3 / k
+        out["cpu_baseline"] = {"value": M / (cms / 1e3), "unit": "rows/s", "ms": cms, "cores": torch.get_num_threads(),
+                               "kind": "port", "sample": "%d full fwd+bwd passes of the same shape" % k}
     return out
 
 

@@ -119,9 +119,17 @@ bn_relu_pack_kernel(const float* __restrict__ H, int M, int N, const float* __re
   }
 }
 
-__global__ void add_bias_kernel(float* __restrict__ Y, int64_t total, int N, const float* __restrict__ b) {
+// out = fixed-order sum of the split-K partials (+ bias).  The long contractions (K = Dh) run as
+// several shorter accumulation chains: tcgen05 truncates when it accumulates, so the error grows with
+// the chain length (2e-5 at K = 4096 in the bf16x3 mode, 5e-6 at 512), and the few output tiles of
+// these GEMMs need the extra parallelism anyway.
+__global__ void sum_partials_bias_kernel(const float* __restrict__ parts, int n_splits, int64_t stride, int64_t total,
+                                         int N, const float* __restrict__ bias, float* __restrict__ out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < total) Y[i] += b[i % N];
+  if (i >= total) return;
+  float acc = 0.f;
+  for (int s0 = 0; s0 < n_splits; ++s0) acc += parts[int64_t(s0) * stride + i];
+  out[i] = acc + (bias ? bias[i % N] : 0.f);
 }
 
 // dZ = dA * [z > 0] in place, z = (h - mean) * invstd * gamma + beta; column sums of dZ and dZ * xhat
@@ -227,9 +235,15 @@ __global__ void double_to_float_kernel(const double* __restrict__ src, int n, fl
 }
 
 // ------------------------------------------------------------------ context layout
+constexpr int MLP_MAX_SPLITS = 8;
+static int mlp_splits(int K) {
+  int sp = K / 512;
+  return sp < 1 ? 1 : (sp > MLP_MAX_SPLITS ? MLP_MAX_SPLITS : sp);
+}
+
 struct MlpCtx {
   __nv_bfloat16 *Xp, *XTp, *W1p, *W1Tp, *W2p, *W2Tp, *Ap, *ATp, *dYp, *dYTp, *dHp, *dHTp;
-  float *H, *dA, *mean, *invstd;
+  float *H, *dA, *mean, *invstd, *parts;
   double *stats_local, *stats, *sums_local, *sums, *colsum;
 };
 static void mlp_carve(Workspace& ws, MlpCtx& c, int M, int Din, int Dh, int Dout, int P, bool need_grad) {
@@ -243,6 +257,7 @@ static void mlp_carve(Workspace& ws, MlpCtx& c, int M, int Din, int Dh, int Dout
   c.W2p = ws.take<__nv_bfloat16>(size_t(Dout) * p * Dh);
   c.H = ws.take<float>(size_t(M) * Dh);
   c.Ap = ws.take<__nv_bfloat16>(size_t(M) * p * Dh);
+  c.parts = ws.take<float>(size_t(MLP_MAX_SPLITS) * M * (Dout > Din ? Dout : Din));
   c.XTp = c.W1Tp = c.W2Tp = c.ATp = c.dYp = c.dYTp = c.dHp = c.dHTp = nullptr;
   c.dA = nullptr;
   c.sums_local = c.sums = c.colsum = nullptr;
@@ -329,12 +344,12 @@ int hmmc_mlp_fwd_b(int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, f
   bn_relu_pack_kernel<<<dim3((Dh + 31) / 32, (M + 31) / 32), 256, 0, st>>>(c.H, M, Dh, c.mean, c.invstd, p->gamma, p->beta,
                                                                            P, c.Ap, c.ATp);
   HMMC_CHECK_LAUNCH();
-  if ((rc = umma_gemm_store(c.Ap, int64_t(P) * Dh, c.W2p, int64_t(P) * Dh, y, Dout, 0, M, Dout, Dh, P, 1, 1.0f, st))) return rc;
-  if (p->b2 != nullptr) {
-    const int64_t total = int64_t(M) * Dout;
-    add_bias_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(y, total, Dout, p->b2);
-    HMMC_CHECK_LAUNCH();
-  }
+  const int sp = mlp_splits(Dh);
+  const int64_t total = int64_t(M) * Dout;
+  if ((rc = umma_gemm_store(c.Ap, int64_t(P) * Dh, c.W2p, int64_t(P) * Dh, c.parts, Dout, total, M, Dout, Dh, P, sp, 1.0f, st))) return rc;
+  sum_partials_bias_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(c.parts, umma_effective_splits(Dh, P, sp), total,
+                                                                         total, Dout, p->b2, y);
+  HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
 
@@ -391,8 +406,15 @@ int hmmc_mlp_bwd_b(int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, d
   StoreGemm g[2];
   int n = 0;
   if (dW1 != nullptr) g[n++] = StoreGemm{c.dHTp, int64_t(P) * M, c.XTp, int64_t(P) * M, dW1, Din, 0, Dh, Din, M, 1};
-  if (dx != nullptr) g[n++] = StoreGemm{c.dHp, int64_t(P) * Dh, c.W1Tp, int64_t(P) * Dh, dx, Din, 0, M, Din, Dh, 1};
+  const int sp = mlp_splits(Dh);
+  const int64_t total = int64_t(M) * Din;
+  if (dx != nullptr) g[n++] = StoreGemm{c.dHp, int64_t(P) * Dh, c.W1Tp, int64_t(P) * Dh, c.parts, Din, total, M, Din, Dh, sp};
   if ((rc = umma_gemm_store_grouped(g, n, P, 1.0f, st))) return rc;
+  if (dx != nullptr) {
+    sum_partials_bias_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(c.parts, umma_effective_splits(Dh, P, sp), total,
+                                                                           total, Din, nullptr, dx);
+    HMMC_CHECK_LAUNCH();
+  }
   return HMMC_OK;
 }
 

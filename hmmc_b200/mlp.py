@@ -33,17 +33,17 @@ def _exchange_view(buf, ptr, n):
 
 class _MlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W1, b1, gamma, beta, W2, b2, running_mean, running_var, eps, momentum, training, prec, group):
+    def forward(ctx, x, W1, b1, gamma, beta, W2, b2, running_mean, running_var, eps, momentum, training, prec, group,
+                need):
         lib = _lib.load()
         x = _f32c(x, "x")
         ts = [_f32c(t, "parameter") for t in (W1, b1, gamma, beta, W2, b2)]
         M, Din = x.shape
         Dh, Dout = W1.shape[0], W2.shape[0]
-        need = torch.is_grad_enabled() and any(t.requires_grad for t in (x, W1, b1, gamma, beta, W2, b2))
         world = dist.get_world_size(group) if (training and group is not None) else 1
         nbytes = lib.hmmc_mlp_ctx_bytes(M, Din, Dh, Dout, prec, int(need))
         buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device)       # lives until the backward
-        ps = _params_struct(*ts, running_mean if training else running_mean, running_var)
+        ps = _params_struct(*ts, running_mean, running_var)
         sptr = ctypes.c_void_p()
         _lib.check(lib.hmmc_mlp_fwd_a(_p(x), M, Din, Dh, Dout, ctypes.byref(ps), prec, int(need), _p(buf), buf.numel(),
                                       ctypes.byref(sptr), _stream()), "hmmc_mlp_fwd_a")
@@ -81,7 +81,7 @@ class _MlpFn(torch.autograd.Function):
             dist.all_reduce(_exchange_view(buf, sptr, 2 * Dh), group=ctx.group)
         _lib.check(lib.hmmc_mlp_bwd_b(M, Din, Dh, Dout, ctypes.byref(ps), float(world * M), prec, _p(buf), buf.numel(),
                                       _p(dx), _p(dW1), _p(db1), _p(dgamma), _p(dbeta), _stream()), "hmmc_mlp_bwd_b")
-        return dx, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None, None
+        return dx, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None, None, None
 
 
 def mlp_forward(x, W1, b1, gamma, beta, W2, b2, running_mean=None, running_var=None, eps=1e-5, momentum=0.1,
@@ -90,7 +90,10 @@ def mlp_forward(x, W1, b1, gamma, beta, W2, b2, running_mean=None, running_var=N
     prec = resolve_precision(precision)
     if prec == PREC_FP32:
         prec = PREC_BF16X3          # the fp32-parity mode of the tensor cores; there is no CUDA-core MLP path
-    return _MlpFn.apply(x, W1, b1, gamma, beta, W2, b2, running_mean, running_var, eps, momentum, training, prec, group)
+    # autograd.Function.forward runs with gradients disabled: decide here whether a backward can follow
+    need = torch.is_grad_enabled() and any(t.requires_grad for t in (x, W1, b1, gamma, beta, W2, b2))
+    return _MlpFn.apply(x, W1, b1, gamma, beta, W2, b2, running_mean, running_var, eps, momentum, training, prec, group,
+                        need)
 
 
 class MLP(nn.Module):

@@ -43,4 +43,20 @@ def backward(dy, cache, W1, gamma, W2):
     dW1 = dh.T @ cache["x"]
     db1 = dh.sum(0)
     dx = dh @ W1
-    return dict(dx=dx, dW1=dW1, db1=db1, dgamma=dgamma, dbeta=dbeta, dW2=dW2, db2=db2)
+    return dict(dx=dx, dW1=dW1, db1=db1, dgamma=dgamma, dbeta=dbeta, dW2=dW2, db2=db2, da=da)
+
+
+def relu_flip_slack(cache, grads, W1, gamma, width):
+    """ReLU is not smooth: an implementation whose pre-activations differ from this one by up to `width`
+    may take the other branch for elements with |z| < width, and each such element moves dZ by the full
+    upstream value.  Upper bounds (L2) of what those elements can contribute to dx, dW1, dgamma, dbeta —
+    the slack a comparison against another precision has to grant on top of its relative tolerance."""
+    amb = np.abs(cache["z"]) < width
+    r, c = np.nonzero(amb)
+    w = np.abs(grads["da"][r, c]) * np.abs(np.asarray(gamma, np.float64)[c] * cache["invstd"][c])
+    W1 = np.asarray(W1, np.float64)
+    return dict(count=int(amb.sum()),
+                dx=float(np.sum(w * np.linalg.norm(W1[c], axis=1))),
+                dW1=float(np.sum(w * np.linalg.norm(cache["x"][r], axis=1))),
+                dgamma=float(np.sum(np.abs(grads["da"][r, c] * cache["xhat"][r, c]))),
+                dbeta=float(np.sum(np.abs(grads["da"][r, c]))))

@@ -69,8 +69,14 @@ def test_mlp_reference_size_vs_oracle():
     ref = MO.backward(c["dy"], cache, c["W1"], c["gamma"], c["W2"])
     assert rel(y.detach().cpu().numpy(), y64) < 1e-5
     got = _grads(m, lin1, bn, x)
+    # 6.3 M pre-activations: a few dozen lie within the fp32-level error of the GEMM around zero and may
+    # take the other ReLU branch (as they would between any two fp32 implementations); the bound of what
+    # those elements can move is granted on top of the 5e-5 relative tolerance
+    slack = MO.relu_flip_slack(cache, ref, c["W1"], c["gamma"], width=2e-5)
+    assert slack["count"] < 400
     for k in ("dx", "dW1", "dgamma", "dbeta", "dW2", "db2"):
-        assert rel(got[k].cpu().numpy(), ref[k]) < 5e-5, k
+        err = np.linalg.norm(got[k].cpu().numpy().astype(np.float64) - ref[k])
+        assert err < 5e-5 * np.linalg.norm(ref[k]) + slack.get(k, 0.0), (k, err, slack)
     rm, rv = MO.running_stats(cache, c["rm"], c["rv"])
     assert rel(bn.running_mean.cpu().numpy(), rm) < 1e-5 and rel(bn.running_var.cpu().numpy(), rv) < 1e-5
 
