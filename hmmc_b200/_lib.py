@@ -63,6 +63,8 @@ SIGNATURES = {
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
+    "hmmc_visual_tail_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hmmc_visual_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_mlp_ctx_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "hmmc_mlp_fwd_a": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_mlp_params), c_int, c_int, c_void_p,
                                c_size_t, POINTER(c_void_p), c_void_p]),

@@ -234,6 +234,62 @@ __global__ void double_to_float_kernel(const double* __restrict__ src, int n, fl
   if (i < n) dst[i] = float(src[i]);
 }
 
+// ------------------------------------------------------------------ visual encoder tail
+// VisualEncoder.forward, modules/module_cross.py:207-213:
+//   h = temporal_out + original   (residual; original alone without the temporal transformer)
+//   visual_output[b] = mean_f ( h[b,f] / ||h[b,f]|| )
+// One block per sample, one warp per frame row; the F normalised rows meet in shared memory and are
+// averaged in frame order.
+__global__ void visual_tail_fwd_kernel(const float* __restrict__ temporal, const float* __restrict__ original, int F,
+                                       int D, float* __restrict__ out) {
+  extern __shared__ float rows[];      // [F][D]
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int f = warp; f < F; f += nw) {
+    const int64_t o = (int64_t(b) * F + f) * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float v = original[o + d] + (temporal ? temporal[o + d] : 0.f);
+      rows[f * D + d] = v;
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float n = sqrtf(ss);
+    for (int d = lane; d < D; d += 32) rows[f * D + d] /= n;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) acc += rows[f * D + d];
+    out[int64_t(b) * D + d] = acc / float(F);
+  }
+}
+
+// dh[b,f] = (g[b] - hhat (hhat . g[b])) / (F ||h||): one warp per frame row; the same gradient reaches
+// the temporal branch and the residual branch.
+__global__ void visual_tail_bwd_kernel(const float* __restrict__ temporal, const float* __restrict__ original,
+                                       const float* __restrict__ dout, int64_t rows, int F, int D,
+                                       float* __restrict__ dh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t o = r * D;
+  const float* g = dout + (r / F) * D;
+  float ss = 0.f, hg = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = original[o + d] + (temporal ? temporal[o + d] : 0.f);
+    ss = fmaf(v, v, ss);
+    hg = fmaf(v, g[d], hg);
+  }
+  ss = warp_sum(ss);
+  hg = warp_sum(hg);
+  const float n = sqrtf(ss);
+  const float proj = hg / (n * n), scale = 1.0f / (n * float(F));
+  for (int d = lane; d < D; d += 32) {
+    const float v = original[o + d] + (temporal ? temporal[o + d] : 0.f);
+    dh[o + d] = (g[d] - v * proj) * scale;
+  }
+}
+
 // ------------------------------------------------------------------ context layout
 constexpr int MLP_MAX_SPLITS = 8;
 static int mlp_splits(int K) {
@@ -415,6 +471,31 @@ int hmmc_mlp_bwd_b(int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, d
                                                                            total, Din, nullptr, dx);
     HMMC_CHECK_LAUNCH();
   }
+  return HMMC_OK;
+}
+
+int hmmc_visual_tail_fwd(const float* temporal, const float* original, int B, int F, int D, float* out, void* stream) {
+  HMMC_REQUIRE(original && out && B > 0 && F > 0 && D > 0, "visual_tail_fwd: bad arguments");
+  const size_t smem = size_t(F) * D * sizeof(float);
+  HMMC_REQUIRE(smem <= 200 * 1024, "visual_tail_fwd: F*D = %d floats exceed the shared-memory staging", F * D);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    HMMC_CHECK_CUDA(cudaFuncSetAttribute(visual_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    smem_set = smem;
+  }
+  const int warps = F < 16 ? F : 16;
+  visual_tail_fwd_kernel<<<B, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(temporal, original, F, D, out);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_visual_tail_bwd(const float* temporal, const float* original, const float* dout, int B, int F, int D,
+                         float* dhidden, void* stream) {
+  HMMC_REQUIRE(original && dout && dhidden && B > 0 && F > 0 && D > 0, "visual_tail_bwd: bad arguments");
+  const int64_t rows = int64_t(B) * F;
+  visual_tail_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(temporal, original, dout,
+                                                                                                  rows, F, D, dhidden);
+  HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
 

@@ -133,3 +133,33 @@ class MLP(nn.Module):
         if training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         return y
+
+
+class _VisualTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, temporal, original):
+        o = _f32c(original, "visual_hidden_original")
+        t = _f32c(temporal, "visual_hidden") if temporal is not None else None
+        B, F, D = o.shape
+        out = torch.empty(B, D, dtype=torch.float32, device=o.device)
+        _lib.check(_lib.load().hmmc_visual_tail_fwd(_p(t), _p(o), B, F, D, _p(out), _stream()), "hmmc_visual_tail_fwd")
+        ctx.save_for_backward(o, *([t] if t is not None else []))
+        ctx.has_t = t is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        o = ctx.saved_tensors[0]
+        t = ctx.saved_tensors[1] if ctx.has_t else None
+        B, F, D = o.shape
+        dh = torch.empty_like(o)
+        _lib.check(_lib.load().hmmc_visual_tail_bwd(_p(t), _p(o), _p(_f32c(g, "grad_output")), B, F, D, _p(dh), _stream()),
+                   "hmmc_visual_tail_bwd")
+        return (dh if ctx.has_t else None), dh
+
+
+def visual_tail(visual_hidden, visual_hidden_original):
+    """modules/module_cross.py:207-213: ``visual_hidden`` = output of the temporal transformer (None when
+    use_temp is off), ``visual_hidden_original`` = the per-frame CLIP features [bs, frames, D].
+    Returns (visual_output [bs, D], frame_output) exactly as VisualEncoder.forward does."""
+    return _VisualTailFn.apply(visual_hidden, visual_hidden_original), visual_hidden_original

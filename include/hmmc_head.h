@@ -249,6 +249,14 @@ int hmmc_mlp_bwd_a(const float* dy, int M, int Din, int Dh, int Dout, const hmmc
 int hmmc_mlp_bwd_b(int M, int Din, int Dh, int Dout, const hmmc_mlp_params* p, double count, int prec, void* ctx,
                    size_t ctx_bytes, float* dx, float* dW1, float* db1, float* dgamma, float* dbeta, void* stream);
 
+/* Tail of VisualEncoder.forward (modules/module_cross.py:207-213), the op that produces the video
+ * embedding the head consumes:  out[b] = mean_f normalize(temporal[b,f] + original[b,f])  with
+ * temporal NULL when the temporal transformer is off.  temporal / original [B,F,D], out [B,D].
+ * Backward: dhidden [B,F,D] is the gradient w.r.t. the sum, i.e. w.r.t. BOTH branches. */
+int hmmc_visual_tail_fwd(const float* temporal, const float* original, int B, int F, int D, float* out, void* stream);
+int hmmc_visual_tail_bwd(const float* temporal, const float* original, const float* dout, int B, int F, int D,
+                         float* dhidden, void* stream);
+
 /* ---------------------------------------------------------- fine-tune head (HM) */
 
 /* loose_similarity (modules/modeling.py:207-229), forward.  vis is [Bv*Fv, D]

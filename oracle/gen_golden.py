@@ -303,6 +303,34 @@ def gen_mlp(M, metrics, R):
     print("mlp golden: |y|", float(np.abs(out["y"]).mean()), "keys", list(out["keys"]))
 
 
+def gen_visual_tail(M, metrics, R):
+    """VisualEncoder.forward (modules/module_cross.py:178-216) with stub CLIP / temporal transformer that
+    return fixed tensors: the residual + normalise + mean tail is the reference's own code."""
+    import modules.module_cross as MC
+    rs = np.random.RandomState(41)
+    bs, F, D = 6, 12, 64
+    orig = _t(rs.randn(bs * F, D).astype(np.float32), grad=True)
+    temp = _t(rs.randn(F, bs, D).astype(np.float32), grad=True)        # LND, as the temporal transformer returns
+    g = rs.randn(bs, D).astype(np.float32)
+    out = {}
+    for use_temp in (True, False):
+        for t in (orig, temp):
+            t.grad = None
+        s = types.SimpleNamespace(use_temp=use_temp, encode_image=lambda video, video_frame: orig,
+                                  frame_position_embeddings=torch.nn.Embedding(48, D),
+                                  temporal_transformer=lambda x, mask: temp)
+        vo, fo = MC.VisualEncoder.forward(s, torch.zeros(bs, F, 3, 2, 2), F)
+        vo.backward(_t(g))
+        tag = "temp" if use_temp else "notemp"
+        out["out_" + tag] = vo.detach().numpy()
+        out["dorig_" + tag] = orig.grad.numpy().copy()
+        if use_temp:
+            out["dtemp"] = temp.grad.numpy().copy()
+        assert fo.shape == (bs, F, D)
+    np.savez(os.path.join(OUT, "visual_tail.npz"), orig=orig.detach().numpy(), temp=temp.detach().numpy(), g=g, **out)
+    print("visual tail golden", out["out_temp"].shape)
+
+
 OPTIM_CASES = (("pretrain", 6, 1.0, (0, 5)), ("plain", 3, None, (0, 1, 2)), ("linear", 4, None, (3,)))
 
 
@@ -341,7 +369,7 @@ def main():
     torch.manual_seed(0)
     M, metrics, R = ref_shim.load()
     only = sys.argv[1:]
-    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim, gen_eval_epoch, gen_mlp):
+    for fn in (gen_metrics, gen_similarity, gen_finetune, gen_contrastive, gen_pretrain, gen_ema, gen_eval, gen_optim, gen_eval_epoch, gen_mlp, gen_visual_tail):
         if only and fn.__name__[4:] not in only:
             continue
         fn(M, metrics, R)

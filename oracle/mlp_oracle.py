@@ -60,3 +60,16 @@ def relu_flip_slack(cache, grads, W1, gamma, width):
                 dW1=float(np.sum(w * np.linalg.norm(cache["x"][r], axis=1))),
                 dgamma=float(np.sum(np.abs(grads["da"][r, c] * cache["xhat"][r, c]))),
                 dbeta=float(np.sum(np.abs(grads["da"][r, c]))))
+
+
+def visual_tail(temporal, original):
+    """modules/module_cross.py:207-213 in float64: (visual_output, per-row norms)."""
+    h = np.asarray(original, np.float64) + (np.asarray(temporal, np.float64) if temporal is not None else 0.0)
+    n = np.linalg.norm(h, axis=-1, keepdims=True)
+    return (h / n).mean(1), h, n
+
+
+def visual_tail_backward(g, h, n):
+    g = np.asarray(g, np.float64)[:, None, :]
+    hh = h / n
+    return (g - hh * (hh * g).sum(-1, keepdims=True)) / (n * h.shape[1])

@@ -105,3 +105,31 @@ def test_mlp_rows_not_multiple_of_64_forward_only_and_loud_backward():
     assert rel(y.cpu().numpy(), y64) < 1e-5
     with pytest.raises(HmmcError):
         m(cu(c["x"], True))
+
+
+@pytest.mark.parametrize("use_temp", [True, False])
+def test_visual_tail_vs_reference(golden, use_temp):
+    """Residual + per-frame L2-normalise + mean over frames (modules/module_cross.py:207-213) against the
+    reference's own VisualEncoder.forward (stub encoders) and the float64 oracle."""
+    from hmmc_b200.mlp import visual_tail
+    g = golden("visual_tail")
+    orig = cu(g["orig"].reshape(6, 12, 64), True)
+    temp = cu(np.ascontiguousarray(g["temp"].transpose(1, 0, 2)), True) if use_temp else None
+    out, frame_output = visual_tail(temp, orig)
+    out.backward(cu(g["g"]))
+    tag = "temp" if use_temp else "notemp"
+    assert frame_output is orig
+    assert rel(out.detach().cpu().numpy(), g["out_" + tag]) < 1e-6
+    assert rel(orig.grad.cpu().numpy().reshape(72, 64), g["dorig_" + tag]) < 2e-6
+    if use_temp:
+        assert rel(temp.grad.cpu().numpy().transpose(1, 0, 2), g["dtemp"]) < 2e-6
+    # the pre-train size: 128 x 12 x 512
+    rs = np.random.RandomState(5)
+    o, t = rs.randn(128, 12, 512).astype(np.float32), rs.randn(128, 12, 512).astype(np.float32)
+    gg = rs.randn(128, 512).astype(np.float32)
+    oo, tt = cu(o, True), (cu(t, True) if use_temp else None)
+    out, _ = visual_tail(tt, oo)
+    out.backward(cu(gg))
+    ref, h, n = MO.visual_tail(t if use_temp else None, o)
+    assert rel(out.detach().cpu().numpy(), ref) < 1e-6
+    assert rel(oo.grad.cpu().numpy(), MO.visual_tail_backward(gg, h, n)) < 2e-6

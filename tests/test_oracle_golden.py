@@ -311,3 +311,17 @@ def test_mlp_mirror_state_dict_keys(golden):
     import torch
     with pytest.raises(Exception):
         m(torch.zeros(4, 64))            # CPU tensors: there is no CPU path
+
+
+def test_visual_tail_oracle_vs_reference(golden):
+    from oracle import mlp_oracle as MO
+    g = golden("visual_tail")
+    orig = g["orig"].reshape(6, 12, 64)
+    temp = g["temp"].transpose(1, 0, 2)                 # LND -> NLD as VisualEncoder.forward permutes it
+    for tag, t in (("temp", temp), ("notemp", None)):
+        out, h, n = MO.visual_tail(t, orig)
+        assert _rel(out, g["out_" + tag]) < 2e-6
+        dh = MO.visual_tail_backward(g["g"], h, n)
+        assert _rel(dh.reshape(72, 64), g["dorig_" + tag]) < 5e-6
+        if t is not None:
+            assert _rel(dh.transpose(1, 0, 2), g["dtemp"]) < 5e-6
