@@ -17,21 +17,41 @@
 namespace hmmc {
 
 // ------------------------------------------------------------------ column reductions
-// sum over rows of v (and of w, when given) for 32 columns per block; 8 warps stride the rows.
-// MODE 0: v = A, w = A*A        (forward statistics of H)
-// MODE 1: v = A                 (db2 = column sums of dY)
+// Column sums over the rows of an [M, N] matrix, two levels so that the grid fills the machine:
+// block (x, y) = 32 columns x one slab of COL_SLAB rows -> partial sums part[y][c]; a second, tiny
+// kernel adds the slabs in order (double).  Deterministic, no atomics.
+//   MODE 0: (sum h, sum h^2)              forward statistics of H
+//   MODE 1: (sum v)                       db2 = column sums of dY
+//   MODE 2: dZ = dA * [z > 0] in place, (sum dZ, sum dZ * xhat)       backward sums
+constexpr int COL_SLAB = 128;
 template <int MODE>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ A, int M, int N, double* __restrict__ s0, double* __restrict__ s1) {
+colsum_partial_kernel(float* __restrict__ A, const float* __restrict__ H, int M, int N, const float* __restrict__ mean,
+                      const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      double* __restrict__ part0, double* __restrict__ part1) {
   __shared__ double r0[8][32], r1[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
+  const int row_begin = blockIdx.y * COL_SLAB, row_end = min(row_begin + COL_SLAB, M);
+  // fp64 accumulators: the variance is a difference of two sums (sum h^2 / n - mean^2)
   double a0 = 0.0, a1 = 0.0;
   if (c < N) {
-    for (int r = warp; r < M; r += 8) {
-      const double v = double(A[int64_t(r) * N + c]);
-      a0 += v;
-      if (MODE == 0) a1 += v * v;
+    float mu = 0.f, is = 0.f, g = 0.f, b = 0.f;
+    if (MODE == 2) { mu = mean[c]; is = invstd[c]; g = gamma[c]; b = beta[c]; }
+#pragma unroll 4
+    for (int r = row_begin + warp; r < row_end; r += 8) {
+      const int64_t o = int64_t(r) * N + c;
+      if (MODE == 2) {
+        const float xh = (H[o] - mu) * is;
+        const float dz = (fmaf(xh, g, b) > 0.f) ? A[o] : 0.f;
+        A[o] = dz;
+        a0 += double(dz);
+        a1 += double(dz) * double(xh);
+      } else {
+        const double v = double(A[o]);
+        a0 += v;
+        if (MODE == 0) a1 += v * v;
+      }
     }
   }
   r0[warp][lane] = a0;
@@ -41,8 +61,26 @@ colsum_kernel(const float* __restrict__ A, int M, int N, double* __restrict__ s0
     double t0 = 0.0, t1 = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { t0 += r0[w][lane]; t1 += r1[w][lane]; }
-    s0[c] = t0;
-    if (MODE == 0) s1[c] = t1;
+    part0[int64_t(blockIdx.y) * N + c] = t0;
+    if (MODE != 1) part1[int64_t(blockIdx.y) * N + c] = t1;
+  }
+}
+
+// slabs added in order; results as doubles into up to two destinations (local copy + exchange buffer)
+__global__ void colsum_finish_kernel(const double* __restrict__ part0, const double* __restrict__ part1, int n_slabs, int N,
+                                     double* __restrict__ dst_a, double* __restrict__ dst_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int y = 0; y < n_slabs; ++y) {
+    s0 += part0[int64_t(y) * N + c];
+    if (part1 != nullptr) s1 += part1[int64_t(y) * N + c];
+  }
+  dst_a[c] = s0;
+  if (dst_b != nullptr) dst_b[c] = s0;
+  if (part1 != nullptr) {
+    dst_a[N + c] = s1;
+    if (dst_b != nullptr) dst_b[N + c] = s1;
   }
 }
 
@@ -130,38 +168,6 @@ __global__ void sum_partials_bias_kernel(const float* __restrict__ parts, int n_
   float acc = 0.f;
   for (int s0 = 0; s0 < n_splits; ++s0) acc += parts[int64_t(s0) * stride + i];
   out[i] = acc + (bias ? bias[i % N] : 0.f);
-}
-
-// dZ = dA * [z > 0] in place, z = (h - mean) * invstd * gamma + beta; column sums of dZ and dZ * xhat
-__global__ void __launch_bounds__(256)
-dz_sums_kernel(float* __restrict__ dA, const float* __restrict__ H, int M, int N, const float* __restrict__ mean,
-               const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-               double* __restrict__ s0, double* __restrict__ s1) {
-  __shared__ double r0[8][32], r1[8][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  double a0 = 0.0, a1 = 0.0;
-  if (c < N) {
-    const float mu = mean[c], is = invstd[c], g = gamma[c], b = beta[c];
-    for (int r = warp; r < M; r += 8) {
-      const int64_t o = int64_t(r) * N + c;
-      const float xh = (H[o] - mu) * is;
-      const float dz = (fmaf(xh, g, b) > 0.f) ? dA[o] : 0.f;
-      dA[o] = dz;
-      a0 += double(dz);
-      a1 += double(dz) * double(xh);
-    }
-  }
-  r0[warp][lane] = a0;
-  r1[warp][lane] = a1;
-  __syncthreads();
-  if (warp == 0 && c < N) {
-    double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { t0 += r0[w][lane]; t1 += r1[w][lane]; }
-    s0[c] = t0;
-    s1[c] = t1;
-  }
 }
 
 // Parameter gradients of the normalisation from the LOCAL sums (DDP reduces parameter gradients
@@ -300,6 +306,7 @@ static int mlp_splits(int K) {
 struct MlpCtx {
   __nv_bfloat16 *Xp, *XTp, *W1p, *W1Tp, *W2p, *W2Tp, *Ap, *ATp, *dYp, *dYTp, *dHp, *dHTp;
   float *H, *dA, *mean, *invstd, *parts;
+  double *cpart0, *cpart1;
   double *stats_local, *stats, *sums_local, *sums, *colsum;
 };
 static void mlp_carve(Workspace& ws, MlpCtx& c, int M, int Din, int Dh, int Dout, int P, bool need_grad) {
@@ -314,6 +321,9 @@ static void mlp_carve(Workspace& ws, MlpCtx& c, int M, int Din, int Dh, int Dout
   c.H = ws.take<float>(size_t(M) * Dh);
   c.Ap = ws.take<__nv_bfloat16>(size_t(M) * p * Dh);
   c.parts = ws.take<float>(size_t(MLP_MAX_SPLITS) * M * (Dout > Din ? Dout : Din));
+  const size_t slabs = size_t((M + COL_SLAB - 1) / COL_SLAB);
+  c.cpart0 = ws.take<double>(slabs * (Dh > Dout ? Dh : Dout));
+  c.cpart1 = ws.take<double>(slabs * (Dh > Dout ? Dh : Dout));
   c.XTp = c.W1Tp = c.W2Tp = c.ATp = c.dYp = c.dYTp = c.dHp = c.dHTp = nullptr;
   c.dA = nullptr;
   c.sums_local = c.sums = c.colsum = nullptr;
@@ -371,9 +381,12 @@ int hmmc_mlp_fwd_a(const float* x, int M, int Din, int Dh, int Dout, const hmmc_
   if ((rc = pack_dual(p->W1, Dh, Din, P, c.W1p, c.W1Tp, st))) return rc;
   if ((rc = pack_dual(p->W2, Dout, Dh, P, c.W2p, c.W2Tp, st))) return rc;
   if ((rc = umma_gemm_store(c.Xp, int64_t(P) * Din, c.W1p, int64_t(P) * Din, c.H, Dh, 0, M, Dh, Din, P, 1, 1.0f, st))) return rc;
-  colsum_kernel<0><<<(Dh + 31) / 32, 256, 0, st>>>(c.H, M, Dh, c.stats_local, c.stats_local + Dh);
+  const int slabs = (M + COL_SLAB - 1) / COL_SLAB;
+  colsum_partial_kernel<0><<<dim3((Dh + 31) / 32, slabs), 256, 0, st>>>(c.H, nullptr, M, Dh, nullptr, nullptr, nullptr,
+                                                                        nullptr, c.cpart0, c.cpart1);
   HMMC_CHECK_LAUNCH();
-  HMMC_CHECK_CUDA(cudaMemcpyAsync(c.stats, c.stats_local, size_t(2) * Dh * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  colsum_finish_kernel<<<(Dh + 255) / 256, 256, 0, st>>>(c.cpart0, c.cpart1, slabs, Dh, c.stats_local, c.stats);
+  HMMC_CHECK_LAUNCH();
   if (stats_out != nullptr) *stats_out = c.stats;
   return HMMC_OK;
 }
@@ -420,6 +433,7 @@ int hmmc_mlp_bwd_a(const float* dy, int M, int Din, int Dh, int Dout, const hmmc
   mlp_carve(ws, c, M, Din, Dh, Dout, P, true);
   HMMC_REQUIRE(ws.ok(), "mlp: context too small (%zu needed, %zu given)", ws.used, ctx_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int slabs = (M + COL_SLAB - 1) / COL_SLAB;
   if ((rc = pack_dual(dy, M, Dout, P, c.dYp, c.dYTp, st))) return rc;
   // dA = dY W2 [M, Dh]  and  dW2 = dY^T A [Dout, Dh]  in one grouped launch
   StoreGemm g[2];
@@ -428,15 +442,19 @@ int hmmc_mlp_bwd_a(const float* dy, int M, int Din, int Dh, int Dout, const hmmc
   if (dW2 != nullptr) g[n++] = StoreGemm{c.dYTp, int64_t(P) * M, c.ATp, int64_t(P) * M, dW2, Dh, 0, Dout, Dh, M, 1};
   if ((rc = umma_gemm_store_grouped(g, n, P, 1.0f, st))) return rc;
   if (db2 != nullptr) {
-    colsum_kernel<1><<<(Dout + 31) / 32, 256, 0, st>>>(dy, M, Dout, c.colsum, nullptr);
+    colsum_partial_kernel<1><<<dim3((Dout + 31) / 32, slabs), 256, 0, st>>>(const_cast<float*>(dy), nullptr, M, Dout, nullptr,
+                                                                            nullptr, nullptr, nullptr, c.cpart0, nullptr);
+    HMMC_CHECK_LAUNCH();
+    colsum_finish_kernel<<<(Dout + 255) / 256, 256, 0, st>>>(c.cpart0, nullptr, slabs, Dout, c.colsum, nullptr);
     HMMC_CHECK_LAUNCH();
     double_to_float_kernel<<<(Dout + 255) / 256, 256, 0, st>>>(c.colsum, Dout, db2);
     HMMC_CHECK_LAUNCH();
   }
-  dz_sums_kernel<<<(Dh + 31) / 32, 256, 0, st>>>(c.dA, c.H, M, Dh, c.mean, c.invstd, p->gamma, p->beta, c.sums_local,
-                                                 c.sums_local + Dh);
+  colsum_partial_kernel<2><<<dim3((Dh + 31) / 32, slabs), 256, 0, st>>>(c.dA, c.H, M, Dh, c.mean, c.invstd, p->gamma, p->beta,
+                                                                        c.cpart0, c.cpart1);
   HMMC_CHECK_LAUNCH();
-  HMMC_CHECK_CUDA(cudaMemcpyAsync(c.sums, c.sums_local, size_t(2) * Dh * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  colsum_finish_kernel<<<(Dh + 255) / 256, 256, 0, st>>>(c.cpart0, c.cpart1, slabs, Dh, c.sums_local, c.sums);
+  HMMC_CHECK_LAUNCH();
   if (sums_out != nullptr) *sums_out = c.sums;
   return HMMC_OK;
 }

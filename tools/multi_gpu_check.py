@@ -99,6 +99,40 @@ def main():
     if rank == 0:
         print("sharded fused eval W=%d ok: %d captions x %d videos, mean t2v rank %.3f" %
               (W, int(per.sum()), Nv, float(t2v.float().mean()) + 1))
+
+    # 4. MLP with SyncBatchNorm: the batch statistics span all ranks' rows (modules/modeling.py:127-129)
+    from hmmc_b200.mlp import MLP
+    from oracle import mlp_oracle as MO
+    Mr = 64
+    c = syn.mlp_case(M=Mr * W, Din=64, Dh=128, Dout=64, seed=61)
+    m = MLP(64, 128, 64, 2, precision="bf16x3")
+    torch.nn.SyncBatchNorm.convert_sync_batchnorm(m)          # in place on the children, as the reference relies on
+    m = m.to(dev).train()
+    lin1, bn = m.linear_hidden[1], m.linear_hidden[2]
+    assert isinstance(bn, torch.nn.SyncBatchNorm)
+    with torch.no_grad():
+        lin1.weight.copy_(cu(c["W1"])); lin1.bias.copy_(cu(c["b1"]))
+        bn.weight.copy_(cu(c["gamma"])); bn.bias.copy_(cu(c["beta"]))
+        bn.running_mean.copy_(cu(c["rm"])); bn.running_var.copy_(cu(c["rv"]))
+        m.linear_out.weight.copy_(cu(c["W2"])); m.linear_out.bias.copy_(cu(c["b2"]))
+    sl = slice(rank * Mr, (rank + 1) * Mr)
+    x = cu(c["x"][sl], True)
+    y = m(x)
+    y.backward(cu(c["dy"][sl]))
+    y64, cache = MO.forward(c["x"], c["W1"], c["b1"], c["gamma"], c["beta"], c["W2"], c["b2"])
+    ref = MO.backward(c["dy"], cache, c["W1"], c["gamma"], c["W2"])
+    assert rel(y.detach().cpu().numpy(), y64[sl]) < 1e-5
+    assert rel(x.grad.cpu().numpy(), ref["dx"][sl]) < 5e-5
+    rm, rv = MO.running_stats(cache, c["rm"], c["rv"])
+    assert rel(bn.running_mean.cpu().numpy(), rm) < 1e-5 and rel(bn.running_var.cpu().numpy(), rv) < 1e-5
+    # parameter gradients are per rank (DDP sums them): their sum over ranks is the global gradient
+    for name, t in (("dW1", lin1.weight.grad), ("dgamma", bn.weight.grad), ("dbeta", bn.bias.grad),
+                    ("dW2", m.linear_out.weight.grad), ("db2", m.linear_out.bias.grad)):
+        tot = t.clone()
+        dist.all_reduce(tot)
+        assert rel(tot.cpu().numpy(), ref[name]) < 5e-5, name
+    if rank == 0:
+        print("MLP + SyncBatchNorm W=%d ok: %d rows per rank" % (W, Mr))
     dist.barrier()
     dist.destroy_process_group()
 
