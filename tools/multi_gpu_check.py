@@ -121,8 +121,14 @@ def main():
     y.backward(cu(c["dy"][sl]))
     y64, cache = MO.forward(c["x"], c["W1"], c["b1"], c["gamma"], c["beta"], c["W2"], c["b2"])
     ref = MO.backward(c["dy"], cache, c["W1"], c["gamma"], c["W2"])
+    if os.environ.get("HMMC_CHECK_DEBUG"):
+        print("rank", rank, "y", rel(y.detach().cpu().numpy(), y64[sl]), "dx", rel(x.grad.cpu().numpy(), ref["dx"][sl]),
+              "dgamma_local_sum?", float(bn.weight.grad.abs().sum()), flush=True)
     assert rel(y.detach().cpu().numpy(), y64[sl]) < 1e-5
-    assert rel(x.grad.cpu().numpy(), ref["dx"][sl]) < 5e-5
+    # elements whose pre-activation lies within the GEMM's rounding of zero may take the other ReLU branch
+    slack = MO.relu_flip_slack(cache, ref, c["W1"], c["gamma"], width=2e-5)
+    err = np.linalg.norm(x.grad.cpu().numpy().astype(np.float64) - ref["dx"][sl])
+    assert err < 5e-5 * np.linalg.norm(ref["dx"][sl]) + slack["dx"], (err, slack)
     rm, rv = MO.running_stats(cache, c["rm"], c["rv"])
     assert rel(bn.running_mean.cpu().numpy(), rm) < 1e-5 and rel(bn.running_var.cpu().numpy(), rv) < 1e-5
     # parameter gradients are per rank (DDP sums them): their sum over ranks is the global gradient
@@ -130,7 +136,8 @@ def main():
                     ("dW2", m.linear_out.weight.grad), ("db2", m.linear_out.bias.grad)):
         tot = t.clone()
         dist.all_reduce(tot)
-        assert rel(tot.cpu().numpy(), ref[name]) < 5e-5, name
+        err = np.linalg.norm(tot.cpu().numpy().astype(np.float64) - ref[name])
+        assert err < 5e-5 * np.linalg.norm(ref[name]) + slack.get(name, 0.0), (name, err, slack)
     if rank == 0:
         print("MLP + SyncBatchNorm W=%d ok: %d rows per rank" % (W, Mr))
     dist.barrier()
