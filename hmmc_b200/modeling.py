@@ -351,7 +351,9 @@ class BirdModel(ContrastiveHeadMixin, nn.Module):
         # one packed exchange instead of the reference's three dist_collect calls
         packed = torch.cat([query_output.reshape(b, D), visual_output.reshape(b, D),
                             frame_output.reshape(b, F * D)], dim=1)
-        full = dist_collect(packed)
+        # every rank evaluates the same global loss on the same gathered rows: the gather's backward needs no
+        # exchange (parallel.all_gather_cat_replicated); dist_collect keeps the general reduce-scatter
+        full = parallel.all_gather_cat_replicated(packed)
         if not bool(getattr(self.task_config, "use_frame_fea", True)):
             return self.finetune_head_loss(full[:, :D], full[:, D:2 * D], None)
         # the fused head reads the gathered rows in place and returns the gradient in the same layout

@@ -57,6 +57,37 @@ class _AllGatherCat(torch.autograd.Function):
         return out
 
 
+class _AllGatherCatReplicated(torch.autograd.Function):
+    """All-gather whose consumer is evaluated IDENTICALLY on every rank (the fine-tune head: every rank
+    computes the same global loss from the same gathered rows with deterministic kernels).
+    The SUM reduce-scatter of the generic backward then adds W bit-identical copies of the same
+    gradient, so rank r's result is W x its own rows of its own gradient: no communication."""
+
+    @staticmethod
+    def forward(ctx, x):
+        W, rank = world()
+        x = x.contiguous()
+        out = x.new_empty((W * x.shape[0],) + tuple(x.shape[1:]))
+        _all_gather_into(out, x)
+        ctx.b, ctx.W, ctx.rank = x.shape[0], W, rank
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank * ctx.b:(ctx.rank + 1) * ctx.b] * float(ctx.W)
+
+
+def all_gather_cat_replicated(x):
+    """all_gather_cat for a consumer that is replicated on all ranks (see _AllGatherCatReplicated);
+    HMMC_REPLICATED_GATHER_BWD=0 restores the reduce-scatter."""
+    W, _ = world()
+    if W == 1:
+        return x.contiguous()
+    if os.environ.get("HMMC_REPLICATED_GATHER_BWD", "1") == "0":
+        return _AllGatherCat.apply(x)
+    return _AllGatherCatReplicated.apply(x)
+
+
 def all_gather_cat(x):
     """Differentiable concat-all-gather on dim 0."""
     W, _ = world()

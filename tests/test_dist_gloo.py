@@ -36,6 +36,14 @@ def _worker(rank, W, port, ret):
         f2 = dist_collect(x2)
         (f2 * float(rank + 1)).sum().backward()
         assert torch.allclose(x2.grad, torch.full((b, 5), float(sum(range(1, W + 1)))))
+        # a consumer replicated on all ranks (the fine-tune head): the communication-free backward gives
+        # the reduce-scatter's result bit for bit
+        coef2 = torch.randn(W * b, 5, generator=torch.Generator().manual_seed(7))
+        xa = torch.randn(b, 5, generator=torch.Generator().manual_seed(10 + rank), requires_grad=True)
+        xb = xa.detach().clone().requires_grad_(True)
+        (parallel.all_gather_cat(xa) * coef2).pow(2).sum().backward()
+        (parallel.all_gather_cat_replicated(xb) * coef2).pow(2).sum().backward()
+        assert torch.equal(xa.grad, xb.grad)
         # key gather, sharding and count merge
         rows = parallel.all_gather_rows(torch.full((2, 4), float(rank)))
         assert rows.shape == (2 * W, 4) and rows[2 * (W - 1), 0] == W - 1
