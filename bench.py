@@ -769,7 +769,10 @@ def optimizer_leg(args, dev, sizes, hbm_peak, peak_src):
            "ms_per_step": ms, "host_issue_ms_per_step": host_ms, "launches_per_step": int(launches),
            "params_per_s": n / (ms / 1e3), "grad_norm": float(opt.last_grad_norm),
            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo, "traffic": None,
+                        "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of grad_sqnorm_kernel and bert_adam_kernel,
+                        # profiles/r1_ncu_optimizer.md
+                        "traffic": 689346000 + 5794000 + 2757263000 + 2014940000,
                         "peak_source": peak_src}}
     assert bool(torch.isfinite(flat).all())
     del opt, params, grads, flat, gflat
