@@ -385,10 +385,10 @@ struct EnqueueArgs {
 
 constexpr int ENQ_DCHUNK = 128;
 
-// Block = CB consecutive queue columns x ENQ_DCHUNK embedding dims of one queue.  Phase 1: the
-// warps compute max(||x||,1e-12) of the block's CB key vectors.  Phase 2: 32(d) x CB(col) tiles go
-// through shared memory so the [D,Kq] layouts are written CB columns (CB*4 contiguous bytes) at a
-// time.  CB = 32 for small batches (more blocks), 128 for large ones (longer DRAM bursts).
+// Scalar scatter (odd D, unaligned sources, no norm scratch): block = CB = 32 consecutive queue columns x
+// dchunk embedding dims of one queue.  Phase 1: the block's key norms (read from the pre-pass, or computed
+// here).  Phase 2: 32(d) x 32(col) tiles go through shared memory so the [D,Kq] layouts are written 32
+// columns (128 contiguous bytes) at a time.  The normal case runs enqueue_vec_kernel below.
 // ptr >= 0: the host-tracked pointer (block 0 stores new_ptr);  ptr < 0: read the pointer from
 // queue_ptr[0] on the device (CUDA-graph replay: no host value can be baked in) and leave the
 // advance to advance_ptr_kernel.
@@ -1021,12 +1021,10 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
     key_norms_kernel<<<dim3((B * F + 7) / 8, 5), 256, 0, st>>>(B, D, a, scratch);
     HMMC_CHECK_LAUNCH();
   }
-  static const int dchunk_env = tune_int("HMMC_ENQ_DCHUNK", 0);
-  static const int cb_env = tune_int("HMMC_ENQ_CB", 32);
-  const int dchunk = dchunk_env > 0 ? dchunk_env : (scratch != nullptr ? 64 : ENQ_DCHUNK);
+  const int dchunk = scratch != nullptr ? 64 : ENQ_DCHUNK;
   const int dchunks = (D + dchunk - 1) / dchunk;
   const int p_arg = device_ptr ? -1 : int(ptr_host), np_arg = device_ptr ? 0 : int((ptr_host + B) % K);
-  static const int vec_env = tune_int("HMMC_ENQ_VEC", 1);
+  static const int vec_env = tune_int("HMMC_ENQ_VEC", 1);     // 0: force the scalar kernel (tools/enqueue_bench.py)
   bool vec_ok = vec_env != 0 && scratch != nullptr && (D % 2) == 0;
   for (int i = 0; i < 5 && vec_ok; ++i) {
     vec_ok = (reinterpret_cast<uintptr_t>(a.src[i]) % 8 == 0) && (a.src_stride[i] % 2 == 0) && (a.Kq[i] % 2 == 0) &&
@@ -1036,9 +1034,6 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   if (vec_ok) {
     dim3 grid((B * F + 63) / 64, (D + 63) / 64, 5);
     enqueue_vec_kernel<<<grid, 256, 0, st>>>(B, D, a, scratch, queue_ptr, p_arg, np_arg);
-  } else if (cb_env == 128) {
-    dim3 grid((B * F + 127) / 128, dchunks, 5);
-    enqueue_kernel<128><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg);
   } else {
     dim3 grid((B * F + 31) / 32, dchunks, 5);
     enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg);

@@ -163,3 +163,24 @@ def test_finetune_single_sample_and_frames_only():
     ref = O.frame_loss(t, fr, dtype=np.float64)
     assert abs(float(fl.detach()) - float(ref)) / abs(float(ref)) < 1e-5
     assert tt.grad is not None and tf.grad is not None and bool(torch.isfinite(tf.grad).all())
+
+
+def test_reserved_sms_do_not_change_results():
+    """hmmc_set_reserved_sms only shrinks the persistent GEMM grids: same tiles, same bits."""
+    b, F, D, K = 32, 12, 512, 1024
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    qs = syn.queues(K, F=F, D=D, seed=3)
+    outs = []
+    try:
+        for reserved in (0, 40, 140):
+            ops.set_reserved_sms(reserved)
+            m = _pre(K, F, D, "bf16")
+            _load(m, qs)
+            t = {n: cu(inp[n], grad=n in QN) for n in ORDER}
+            loss = m.head_loss(*[t[n] for n in ORDER])
+            loss.backward()
+            outs.append((loss.detach().clone(), t["frame_pred"].grad.clone()))
+    finally:
+        ops.set_reserved_sms(0)
+    for l, g in outs[1:]:
+        assert torch.equal(l, outs[0][0]) and torch.equal(g, outs[0][1])
