@@ -63,6 +63,7 @@ SIGNATURES = {
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
+    "hmmc_pretrain_head_release_event": (c_int, [c_void_p]),
     "hmmc_visual_tail_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_visual_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_mlp_ctx_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),

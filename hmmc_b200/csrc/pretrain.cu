@@ -11,6 +11,10 @@ static int tune_int(const char* name, int dflt) {     // tuning aids (tools/*_be
   return v ? atoi(v) : dflt;
 }
 
+// one-shot event recorded by the next InfoNCE driver call right after its last queue-reading launch
+// (hmmc_pretrain_head_release_event)
+static thread_local cudaEvent_t g_release_event = nullptr;
+
 // ------------------------------------------------------------------ queue packing
 // dk [D,Kq] fp32  ->  pack_kd [Kq, planes*D] and pack_dk [D, planes*Kq] (bf16 hi / lo planes).
 // 32x32 tile transpose through shared memory so both global sides stay coalesced.
@@ -753,6 +757,8 @@ static void launch_finish(const FinishArgs& fa, int total_rows, int D, float inv
 
 static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
                        int prec, const LossFinal& fin, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  cudaEvent_t release = g_release_event;     // one-shot: consumed by this call whatever its outcome
+  g_release_event = nullptr;
   HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
   HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
   HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
@@ -844,6 +850,8 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
       if (rc) return rc;
     }
   }
+  // every kernel that reads the queues has been issued: let the enqueue start on another stream
+  if (release != nullptr) HMMC_CHECK_CUDA(cudaEventRecord(release, st));
   // 4. positives, loss, gradient
   FinishArgs fa;
   fa.n = ng;
@@ -898,6 +906,11 @@ static int check_pos_mode(int pos_mode, int Fq, int Fk) {
 }  // namespace hmmc
 
 extern "C" {
+
+int hmmc_pretrain_head_release_event(void* cuda_event) {
+  g_release_event = static_cast<cudaEvent_t>(cuda_event);
+  return HMMC_OK;
+}
 
 size_t hmmc_infonce_workspace_bytes(int64_t R, int D, int Kq, int prec) {
   Workspace ws(nullptr, 0);

@@ -38,6 +38,18 @@ DEFAULT_CROSS_CONFIG = dict(temporal_hidden_size=512, weight_FAM=0.05, weight_VT
 GATHER_RESERVED_SMS = int(os.environ.get("HMMC_GATHER_RESERVED_SMS", "0"))
 
 
+# run the enqueue next to the tail of the loss on a side stream (0: strictly after it)
+ENQUEUE_OVERLAP = os.environ.get("HMMC_ENQUEUE_OVERLAP", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def default_cross_config(**over):
     cfg = dict(DEFAULT_CROSS_CONFIG)
     cfg.update(over)
@@ -279,15 +291,28 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
         mark()
         pending = self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         mark()
+        # the queues are free once the two GEMMs have read them: the enqueue then runs on a side stream next to
+        # the rest of the loss (positives, gradient projection, reductions) and is joined before returning
+        released = torch.cuda.Event() if ENQUEUE_OVERLAP and marks is None else None
         total, parts = ops.pretrain_head(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
                                          v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k,
                                          self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
                                          self.queue_frame_cross_ng, self.contrast_temperature, self.weight_FAM,
                                          self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
-                                         self.head_precision)
+                                         self.head_precision, release_event=released)
         self.last_loss_parts = parts            # [FAM, VTM, FTM], device tensor (the reference logs them)
         mark()
-        self._enqueue_gathered(pending)
+        if released is None:
+            self._enqueue_gathered(pending)
+        else:
+            main = torch.cuda.current_stream()
+            side = _side_stream(main.device)
+            side.wait_event(released)
+            with torch.cuda.stream(side):
+                self._enqueue_gathered(pending)
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
         mark()
         if loss_MLM is None:
             return total

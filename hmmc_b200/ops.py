@@ -221,7 +221,8 @@ class _PretrainHeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k,
-                q_v, q_title, q_frame_proj, q_frame_cross, temperature, w_fam, w_vtm, w_ftm, use_frame_fea, prec):
+                q_v, q_title, q_frame_proj, q_frame_cross, temperature, w_fam, w_vtm, w_ftm, use_frame_fea, prec,
+                release_event=None):
         lib = _lib.load()
         b, F, D = frame_fea.shape
         qin = [v_fea, title_fea, frame_fea, frame_pred]
@@ -235,6 +236,10 @@ class _PretrainHeadFn(torch.autograd.Function):
         nbytes = lib.hmmc_pretrain_head_workspace_bytes(b, F, D, K, prec)
         ws = workspace(t[0].device, nbytes)
         losses = torch.empty(4, dtype=torch.float32, device=t[0].device)
+        if release_event is not None:
+            release_event.record()               # materialises the handle; the library records it again later
+            _lib.check(lib.hmmc_pretrain_head_release_event(ctypes.c_void_p(release_event.cuda_event)),
+                       "hmmc_pretrain_head_release_event")
         _lib.check(lib.hmmc_pretrain_head_fwd_bwd(ctypes.byref(io), b, F, D, *[ctypes.byref(s[0]) for s in structs],
                                                   float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
                                                   int(bool(use_frame_fea)), prec, _p(losses), _p(ws), ws.numel(),
@@ -255,16 +260,18 @@ class _PretrainHeadFn(torch.autograd.Function):
         ctx.consumed = True
         scale_inplace([grads[i] for i in range(4) if ctx.need[i]], g)      # in place: the buffers are ours
         out = [grads[i].reshape(ctx.meta[i][0]).to(ctx.meta[i][1]) if ctx.need[i] else None for i in range(4)]
-        return tuple(out) + (None,) * 14
+        return tuple(out) + (None,) * 15
 
 
 def pretrain_head(v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k,
                   q_v, q_title, q_frame_proj, q_frame_cross, temperature, w_fam, w_vtm, w_ftm, use_frame_fea=True,
-                  precision=None):
+                  precision=None, release_event=None):
+    """release_event: a torch.cuda.Event the library records on the current stream right after the last kernel
+    that reads the queues (the enqueue may then overlap the rest of the loss on another stream)."""
     return _PretrainHeadFn.apply(v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k,
                                  frame_proj_k, q_v, q_title, q_frame_proj, q_frame_cross, float(temperature),
                                  float(w_fam), float(w_vtm), float(w_ftm), bool(use_frame_fea),
-                                 resolve_precision(precision))
+                                 resolve_precision(precision), release_event)
 
 
 # ----------------------------------------------------------------------------- EMA / enqueue

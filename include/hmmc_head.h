@@ -137,6 +137,11 @@ typedef struct {
   float* d_frame_fea;
   float* d_frame_pred;
 } hmmc_pretrain_io;
+/* One-shot: the next hmmc_pretrain_head_fwd_bwd / hmmc_infonce_queue_fwd_bwd call on this host thread
+ * records `cuda_event` (a cudaEvent_t) on its stream right after the last kernel that reads the queues.
+ * The enqueue of the step (which overwrites queue columns) can then run on another stream that waits for
+ * the event, overlapping the rest of the loss (positives, gradient projection, reductions). */
+int hmmc_pretrain_head_release_event(void* cuda_event);
 size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec);
 int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
                                const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
