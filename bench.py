@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--queue", type=int, default=1024)
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="issue EMA and loss strictly one after the other (default: the query-side GEMMs of the loss "
+                         "run beside the EMA, as the reference's forward order allows)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -375,13 +378,23 @@ def main():
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     ema_events, head_events = [], []
+    split = modeling.LOSS_OVERLAP and not args.no_overlap
 
-    def step(inputs, timed):
+    def step(inputs, timed, sequential=False):
         for n in q_names:
             inputs[n].grad = None
         if timed:
             e0, e1, e2 = ev(), ev(), ev()
             e0.record()
+        if split and not timed and not sequential:
+            # the reference's own order (modules/modeling.py:340-377): queries first, then the momentum update and
+            # the key encoders, then the losses -> the query-side GEMMs of the loss run beside the EMA
+            begun = model.head_loss_begin(*[inputs[n] for n in order[:4]])
+            with torch.no_grad():
+                model._momentum_update()
+            loss = model.head_loss_end(begun, *[inputs[n] for n in order[4:]])
+            loss.backward()
+            return loss
         with torch.no_grad():
             model._momentum_update()
         if timed:
@@ -455,7 +468,7 @@ def main():
         # separate short run with CUDA events inside head_loss: pack+gather launch | loss kernels | wait+enqueue
         model._hmmc_marks = []
         for _ in range(20):
-            step(devt, False)
+            step(devt, False, True)
         torch.cuda.synchronize()
         mk = model._hmmc_marks
         model._hmmc_marks = None
@@ -464,6 +477,25 @@ def main():
                           [float(x) for x in seg[5:].mean(0)]))
     ms_ema = float(np.mean([a.elapsed_time(c) for a, c in ema_events]))
     ms_head = float(np.mean([a.elapsed_time(c) for a, c in head_events]))
+    # the step with EMA and loss strictly one after the other (replayed as a graph too): what the head costs when
+    # nothing hides it, and how much the concurrent schedule saves
+    ms_seq = None
+    if graphed is not None and split:
+        try:
+            gseq = GraphedStep(lambda: step(devt, False, True))
+            for _ in range(3):
+                gseq.replay()
+            barrier()
+            q0, q1 = ev(), ev()
+            q0.record()
+            for _ in range(50):
+                gseq.replay()
+            q1.record()
+            barrier()
+            ms_seq = q0.elapsed_time(q1) / 50
+        except Exception:   # noqa: BLE001
+            ms_seq = None
+            torch.cuda.synchronize()
 
     # ---- timed region 2: end to end through the public API with host buffers.
     # Every step: ONE host->device copy of the step's packed inputs from pinned memory (on a copy
@@ -527,7 +559,8 @@ def main():
     ema_gbs = ema_bytes / (ms_ema * 1e-3) / 1e9
     head_flops = FLOPS_ALGO(b, F, D, K)
     if graphed is not None:
-        ms_head = max(ms_step - ms_ema, 1e-6)      # replayed step minus the EMA kernel (events cannot sit inside a replay)
+        # replayed (sequential) step minus the EMA kernel (events cannot sit inside a replay)
+        ms_head = max((ms_seq if ms_seq is not None else ms_step) - ms_ema, 1e-6)
     head_tf = head_flops / (ms_head * 1e-3) / 1e12
 
     line = {"metric": "hm_moco_head_fwd_bwd_throughput", "value": value, "unit": "samples/s", "n_gpus": W,
@@ -551,6 +584,9 @@ def main():
                               "frac": head_tf / tf_peak, "algorithmic_flops": head_flops, "ms": ms_head,
                               "peak_source": peak_src},
             "breakdown_ms": {"ema": ms_ema, "head_fwd_bwd_enqueue": ms_head, "head_detail": detail,
+                             "sequential_step": ms_seq,
+                             "schedule": ("query-side GEMMs of the loss beside the EMA (head_loss_begin / head_loss_end)"
+                                          if split else "EMA, then loss, then enqueue"),
                              "host_issue_per_step": cpu_issue_ms,
                              "note": "ema / head: eager run with CUDA events right after the timed region"},
             "issue_mode": graph_note}

@@ -64,6 +64,7 @@ SIGNATURES = {
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
     "hmmc_pretrain_head_release_event": (c_int, [c_void_p]),
+    "hmmc_pretrain_head_phase": (c_int, [c_int]),
     "hmmc_visual_tail_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_visual_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_mlp_ctx_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -14,6 +14,9 @@ static int tune_int(const char* name, int dflt) {     // tuning aids (tools/*_be
 // one-shot event recorded by the next InfoNCE driver call right after its last queue-reading launch
 // (hmmc_pretrain_head_release_event)
 static thread_local cudaEvent_t g_release_event = nullptr;
+// one-shot phase selector of the next driver call (hmmc_pretrain_head_phase): 0 = everything,
+// 1 = normalise + the two GEMM passes (needs the queries only), 2 = the rest (needs the keys)
+static thread_local int g_phase = 0;
 
 // ------------------------------------------------------------------ queue packing
 // dk [D,Kq] fp32  ->  pack_kd [Kq, planes*D] and pack_dk [D, planes*Kq] (bf16 hi / lo planes).
@@ -757,8 +760,10 @@ static void launch_finish(const FinishArgs& fa, int total_rows, int D, float inv
 
 static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
                        int prec, const LossFinal& fin, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  cudaEvent_t release = g_release_event;     // one-shot: consumed by this call whatever its outcome
+  cudaEvent_t release = g_release_event;     // one-shots: consumed by this call whatever its outcome
   g_release_event = nullptr;
+  const int phase = g_phase;
+  g_phase = 0;
   HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
   HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
   HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
@@ -801,9 +806,10 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
     pa.row_begin[i + 1] = pa.row_begin[i] + (i < ng ? groups[i].rows : 0);
   }
   const int total_rows = pa.row_begin[ng];
+  int rc;
+  if (phase != 2) {
   prep_rows_kernel<<<(total_rows + 7) / 8, 256, 0, st>>>(pa, D, planes);
   HMMC_CHECK_LAUNCH();
-  int rc;
   if (prec == HMMC_PREC_FP32) {
     for (int k = 0; k < nb; ++k) {
       const GroupDesc& G = groups[blocks[k].group];
@@ -851,7 +857,9 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
     }
   }
   // every kernel that reads the queues has been issued: let the enqueue start on another stream
+  }   // phase != 2
   if (release != nullptr) HMMC_CHECK_CUDA(cudaEventRecord(release, st));
+  if (phase == 1) return HMMC_OK;
   // 4. positives, loss, gradient
   FinishArgs fa;
   fa.n = ng;
@@ -907,6 +915,12 @@ static int check_pos_mode(int pos_mode, int Fq, int Fk) {
 
 extern "C" {
 
+int hmmc_pretrain_head_phase(int phase) {
+  HMMC_REQUIRE(phase >= 0 && phase <= 2, "pretrain_head_phase: phase must be 0, 1 or 2");
+  g_phase = phase;
+  return HMMC_OK;
+}
+
 int hmmc_pretrain_head_release_event(void* cuda_event) {
   g_release_event = static_cast<cudaEvent_t>(cuda_event);
   return HMMC_OK;
@@ -952,8 +966,10 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
                                float w_ftm, int use_frame_fea, int prec, float* losses_out, void* workspace,
                                size_t workspace_bytes, void* stream) {
   HMMC_REQUIRE(io && q_v && q_title && q_frame_proj && q_frame_cross && losses_out, "pretrain_head: null argument");
-  HMMC_REQUIRE(io->v_fea && io->title_fea && io->frame_fea && io->frame_pred && io->v_fea_k && io->title_fea_k &&
-               io->frame_fea_k && io->frame_proj_k, "pretrain_head: null embedding pointer");
+  const int phase = g_phase;      // peeked here, consumed by the driver below
+  HMMC_REQUIRE(io->v_fea && io->title_fea && io->frame_fea && io->frame_pred, "pretrain_head: null embedding pointer");
+  HMMC_REQUIRE(phase == 1 || (io->v_fea_k && io->title_fea_k && io->frame_fea_k && io->frame_proj_k),
+               "pretrain_head: null key pointer");
   HMMC_REQUIRE(b > 0 && F >= 2 && D > 0, "pretrain_head: bad sizes b=%d F=%d D=%d", b, F, D);
   HMMC_REQUIRE(workspace != nullptr, "pretrain_head: null workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -981,7 +997,7 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
   LossFinal fin{losses_out, 1, w_fam, w_vtm, w_ftm, use_frame_fea};
   int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, fin, workspace, workspace_bytes, st);
   if (rc) return rc;
-  if (!use_frame_fea && io->d_frame_fea != nullptr)
+  if (phase != 1 && !use_frame_fea && io->d_frame_fea != nullptr)
     HMMC_CHECK_CUDA(cudaMemsetAsync(io->d_frame_fea, 0, sizeof(float) * size_t(b) * F * D, st));
   return HMMC_OK;
 }

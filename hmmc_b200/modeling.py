@@ -43,10 +43,16 @@ ENQUEUE_OVERLAP = os.environ.get("HMMC_ENQUEUE_OVERLAP", "1") != "0"
 _side_streams = {}
 
 
-def _side_stream(device):
-    key = device.index if device.index is not None else torch.cuda.current_device()
+# split the head around the momentum update / key encoders (head_loss_begin / head_loss_end); 0: one fused call
+LOSS_OVERLAP = os.environ.get("HMMC_LOSS_OVERLAP", "1") != "0"
+# SMs kept out of the loss GEMM grids while they run beside the EMA (tools/overlap_probe.py)
+LOSS_GEMM_RESERVED = int(os.environ.get("HMMC_LOSS_GEMM_RESERVED", "120"))
+
+
+def _side_stream(device, name="enqueue", priority=0):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), name)
     if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
+        _side_streams[key] = torch.cuda.Stream(device=device, priority=priority)
     return _side_streams[key]
 
 
@@ -318,6 +324,51 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
             return total
         return total + self.weight_MLM * loss_MLM
 
+    def head_loss_begin(self, v_fea, frame_fea, title_fea, frame_pred):
+        """Query-side half of head_loss: normalisation and both GEMM passes against the queues, issued on a
+        high-priority side stream so that they run beside `_momentum_update()` and the key encoders that the
+        reference's forward executes next (modules/modeling.py:364-377).  The GEMM grids are kept on a few SMs
+        (LOSS_GEMM_RESERVED): the EMA is HBM-bound and needs the others to saturate the memory system.
+        Returns the state for head_loss_end."""
+        b, D = v_fea.shape[0], v_fea.shape[-1]
+        side = _side_stream(torch.cuda.current_stream().device, "loss", priority=-1)
+        ops.set_reserved_sms(LOSS_GEMM_RESERVED)
+        try:
+            state = ops.pretrain_head_begin(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
+                                            self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
+                                            self.queue_frame_cross_ng, self.contrast_temperature, self.weight_FAM,
+                                            self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
+                                            self.head_precision, stream=side)
+        finally:
+            ops.set_reserved_sms(0)
+        state_done = torch.cuda.Event()
+        state_done.record(side)
+        return (state, state_done, (v_fea, frame_fea, title_fea, frame_pred))
+
+    def head_loss_end(self, begun, v_fea_k, frame_fea_k, title_fea_k, tag_fea_k, frame_proj_k, loss_MLM=None):
+        """Key-side half: the enqueue (and the wait for the key all-gather) starts at once on a side stream —
+        the queues are no longer read — while positives, losses and gradients run on the current stream."""
+        state, gemm_done, (v_fea, frame_fea, title_fea, frame_pred) = begun
+        b, D = v_fea.shape[0], v_fea.shape[-1]
+        main = torch.cuda.current_stream()
+        main.wait_event(gemm_done)
+        pending = self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+        keys_ready = torch.cuda.Event()
+        keys_ready.record(main)
+        total, parts = ops.pretrain_head_end(state, v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
+                                             v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k)
+        self.last_loss_parts = parts
+        side = _side_stream(main.device)
+        side.wait_event(keys_ready)
+        with torch.cuda.stream(side):
+            self._enqueue_gathered(pending)
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
+        if loss_MLM is None:
+            return total
+        return total + self.weight_MLM * loss_MLM
+
     def forward(self, video_data, video_frame, tag_ids, tag_mask, title_ids, title_mask, global_step):
         tag_ids = tag_ids.view(-1, tag_ids.shape[-1])
         tag_mask = tag_mask.view(-1, tag_mask.shape[-1])
@@ -334,6 +385,8 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
         frame_pred = self.v_predictor(frame_proj)
         frame_fea = frame_fea.view(bs, frame, hidden)
         frame_pred = frame_pred.view(bs, frame, hidden)
+        # the queries exist: their half of the loss runs beside the momentum update and the key encoders
+        begun = self.head_loss_begin(v_fea, frame_fea, title_fea, frame_pred) if LOSS_OVERLAP else None
         with torch.no_grad():  # no gradient to keys
             self._momentum_update()  # update the key encoder
             tag_fea_k = self.text_encoder_k(tag_ids, tag_mask)
@@ -344,6 +397,8 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
             frame_fea_k = frame_fea_k.view(bs, frame, hidden)
             frame_proj_k = frame_proj_k.view(bs, frame, hidden)
         loss_MLM = self.get_mlm_loss(title_ids, title_mask)
+        if begun is not None:
+            return self.head_loss_end(begun, v_fea_k, frame_fea_k, title_fea_k, tag_fea_k, frame_proj_k, loss_MLM)
         return self.head_loss(v_fea, frame_fea, title_fea, frame_pred, v_fea_k, frame_fea_k, title_fea_k,
                               tag_fea_k, frame_proj_k, loss_MLM)
 

@@ -274,6 +274,91 @@ def pretrain_head(v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k,
                                  resolve_precision(precision), release_event)
 
 
+class PretrainHeadState:
+    """What pretrain_head_begin leaves for pretrain_head_end (buffers, argument structs, the workspace)."""
+    __slots__ = ("t", "grads", "structs", "keep", "ws", "losses", "dims", "args", "need", "meta", "queues")
+
+
+def _head_call(state, keys, phase, stream):
+    lib = _lib.load()
+    b, F, D, K, prec = state.dims
+    kp = [k.data_ptr() for k in keys] if keys is not None else [0, 0, 0, 0]
+    io = hmmc_pretrain_io(*[x.data_ptr() for x in state.t], *kp,
+                          *[(g.data_ptr() if g is not None else 0) for g in state.grads])
+    temperature, w_fam, w_vtm, w_ftm, use_frame_fea = state.args
+    _lib.check(lib.hmmc_pretrain_head_phase(phase), "hmmc_pretrain_head_phase")
+    _lib.check(lib.hmmc_pretrain_head_fwd_bwd(ctypes.byref(io), b, F, D, *[ctypes.byref(s) for s in state.structs],
+                                              float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
+                                              int(bool(use_frame_fea)), prec, _p(state.losses), _p(state.ws),
+                                              state.ws.numel(), stream), "hmmc_pretrain_head_fwd_bwd")
+
+
+def pretrain_head_begin(v_fea, title_fea, frame_fea, frame_pred, q_v, q_title, q_frame_proj, q_frame_cross,
+                        temperature, w_fam, w_vtm, w_ftm, use_frame_fea=True, precision=None, stream=None):
+    """First half of the fused pre-train head: normalise the queries and run both GEMM passes against the
+    queues (everything that does not need the keys), issued on `stream` (a torch.cuda.Stream; default: the
+    current one).  All buffers are allocated on the CURRENT stream; the caller orders `stream` after the
+    queries and joins it before pretrain_head_end.  In the reference the queries exist before
+    _momentum_update() and the key encoders run (modules/modeling.py:340-377)."""
+    prec = resolve_precision(precision)
+    st = PretrainHeadState()
+    b, F, D = frame_fea.shape
+    qin = [v_fea, title_fea, frame_fea, frame_pred]
+    st.t = [_f32c(x, "embedding") for x in qin]
+    st.need = [x.requires_grad for x in qin] if torch.is_grad_enabled() else [False] * 4
+    any_grad = any(st.need)
+    st.grads = [torch.empty_like(x) if any_grad else None for x in st.t]
+    pairs = [_queue_struct(qb, prec) for qb in (q_v, q_title, q_frame_proj, q_frame_cross)]
+    st.structs = [p_[0] for p_ in pairs]
+    st.keep = pairs
+    K = q_v.shape[1]
+    lib = _lib.load()
+    nbytes = lib.hmmc_pretrain_head_workspace_bytes(b, F, D, K, prec)
+    st.ws = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=st.t[0].device)    # private: must survive until end
+    st.losses = torch.empty(4, dtype=torch.float32, device=st.t[0].device)
+    st.dims = (b, F, D, K, prec)
+    st.args = (temperature, w_fam, w_vtm, w_ftm, use_frame_fea)
+    st.meta = [(x.shape, x.dtype) for x in qin]
+    st.queues = (q_v, q_title, q_frame_proj, q_frame_cross)
+    if stream is not None:
+        ready = torch.cuda.Event()          # queries, fresh buffers and (re)packed queues are ready here
+        ready.record()
+        stream.wait_event(ready)
+    _head_call(st, None, 1, stream.cuda_stream if stream is not None else _stream())
+    return st
+
+
+class _PretrainHeadEndFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v_fea, title_fea, frame_fea, frame_pred, state, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+        keys = [_f32c(x, "key embedding") for x in (v_fea_k, title_fea_k, frame_fea_k, frame_proj_k)]
+        _head_call(state, keys, 2, _stream())
+        ctx.need = state.need
+        ctx.meta = state.meta
+        if any(state.need):
+            ctx.save_for_backward(*state.grads)
+        total, parts = state.losses[0], state.losses[1:]
+        ctx.mark_non_differentiable(parts)
+        return total, parts
+
+    @staticmethod
+    def backward(ctx, g, _gparts):
+        grads = list(ctx.saved_tensors)
+        if getattr(ctx, "consumed", False):
+            raise HmmcError("the fused head's gradients were already consumed (retain_graph is not supported)")
+        ctx.consumed = True
+        scale_inplace([grads[i] for i in range(4) if ctx.need[i]], g)
+        out = [grads[i].reshape(ctx.meta[i][0]).to(ctx.meta[i][1]) if ctx.need[i] else None for i in range(4)]
+        return tuple(out) + (None,) * 5
+
+
+def pretrain_head_end(state, v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+    """Second half: positives, losses and gradients, on the current stream.  The four query tensors are passed
+    again only so that autograd routes the gradients to them.  Returns (total, parts[3])."""
+    return _PretrainHeadEndFn.apply(v_fea, title_fea, frame_fea, frame_pred, state, v_fea_k, title_fea_k, frame_fea_k,
+                                    frame_proj_k)
+
+
 # ----------------------------------------------------------------------------- EMA / enqueue
 
 _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}

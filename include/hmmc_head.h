@@ -142,6 +142,14 @@ typedef struct {
  * The enqueue of the step (which overwrites queue columns) can then run on another stream that waits for
  * the event, overlapping the rest of the loss (positives, gradient projection, reductions). */
 int hmmc_pretrain_head_release_event(void* cuda_event);
+/* One-shot phase selector of the next hmmc_pretrain_head_fwd_bwd call on this host thread:
+ *   1 = normalise the queries and run the two GEMM passes against the queues (needs only the query tensors
+ *       and the gradient buffers; the key pointers of `io` may be NULL),
+ *   2 = positives, losses, gradients (needs the keys), on the SAME arguments and an untouched workspace,
+ *   0 = both (default).
+ * In the reference the queries exist before `_momentum_update()` and the key encoders run
+ * (modules/modeling.py:340-377), so phase 1 can execute beside them on another stream. */
+int hmmc_pretrain_head_phase(int phase);
 size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec);
 int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
                                const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,

@@ -318,3 +318,39 @@ def test_checkpoint_round_trip_rebuilds_operand_copies(prec, tmp_path):
     assert torch.equal(la, lb) and torch.equal(ga, gb)
     for n in syn.QUEUE_NAMES:
         assert torch.equal(getattr(a, n), getattr(bm, n)), n
+
+
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3", "fp32"])
+def test_split_head_equals_fused_call(prec):
+    """head_loss_begin (query side, on a side stream with a reduced GEMM grid) + head_loss_end (key side) give
+    the loss, the gradients and the queues of the one-call head_loss bit for bit, also with the momentum
+    update issued in between as the reference's forward does."""
+    K, F, D, b = 128, 4, 128, 16
+    inp = syn.pretrain_inputs(b, F=F, D=D, seed=61)
+    qs = syn.queues(K, F=F, D=D, seed=62)
+    order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k",
+             "frame_proj_k"]
+    res = []
+    for split in (False, True):
+        m = _model(K, F, D, prec)
+        _load_queues(m, qs)
+        t = {n: cu(inp[n], grad=n in ("v_fea", "title_fea", "frame_fea", "frame_pred")) for n in order}
+        for _ in range(2):                       # two steps: the second one sees the enqueued keys
+            for n in order[:4]:
+                t[n].grad = None
+            if split:
+                begun = m.head_loss_begin(*[t[n] for n in order[:4]])
+                junk = torch.randn(1 << 20, device="cuda").sum()       # unrelated work on the main stream
+                loss = m.head_loss_end(begun, *[t[n] for n in order[4:]])
+            else:
+                loss = m.head_loss(*[t[n] for n in order])
+            loss.backward()
+        torch.cuda.synchronize()
+        res.append((loss.detach().clone(), [t[n].grad.clone() for n in order[:4]],
+                    [getattr(m, n).clone() for n in syn.QUEUE_NAMES], int(m.queue_ptr)))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, c in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, c)
+    for a, c in zip(res[0][2], res[1][2]):
+        assert torch.equal(a, c)
+    assert res[0][3] == res[1][3] == 32
