@@ -479,6 +479,26 @@ def main():
     ms_head = float(np.mean([a.elapsed_time(c) for a, c in head_events]))
     # the step with EMA and loss strictly one after the other (replayed as a graph too): what the head costs when
     # nothing hides it, and how much the concurrent schedule saves
+    # the EMA kernel alone, replayed back to back (2 GB per launch: nothing stays in L2): its duration without the
+    # host gaps an eager launch carries
+    if graphed is not None:
+        try:
+            def ema_only():
+                with torch.no_grad():
+                    model._momentum_update()
+            gema = GraphedStep(ema_only)
+            for _ in range(3):
+                gema.replay()
+            barrier()
+            q0, q1 = ev(), ev()
+            q0.record()
+            for _ in range(30):
+                gema.replay()
+            q1.record()
+            barrier()
+            ms_ema = q0.elapsed_time(q1) / 30
+        except Exception:   # noqa: BLE001
+            torch.cuda.synchronize()
     ms_seq = None
     if graphed is not None and split:
         try:
