@@ -608,7 +608,7 @@ def main():
                              "schedule": ("query-side GEMMs of the loss beside the EMA (head_loss_begin / head_loss_end)"
                                           if split else "EMA, then loss, then enqueue"),
                              "host_issue_per_step": cpu_issue_ms,
-                             "note": "ema / head: eager run with CUDA events right after the timed region"},
+                             "note": "ema: the kernel alone, replayed back to back from a graph; head: the sequential step (graph replay) minus ema; eager fallbacks use CUDA events around the calls"},
             "issue_mode": graph_note}
 
     # ---- fine-tune head leg (config 3), all ranks
