@@ -378,7 +378,7 @@ def main():
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     ema_events, head_events = [], []
-    split = modeling.LOSS_OVERLAP and not args.no_overlap
+    split = modeling.use_split_schedule() and not args.no_overlap
 
     def step(inputs, timed, sequential=False):
         for n in q_names:
