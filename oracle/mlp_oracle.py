@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — numpy float64 restatement of the reference's two-layer MLP
 (modules/modeling.py:788-807: Linear -> BatchNorm1d (training mode) -> ReLU -> Linear) with its
 analytic backward, pinned against the reference class itself (tests/golden/mlp.npz written by
-oracle/gen_golden.py).  Imported by tests/ and tools/multi_gpu_check.py only."""
+oracle/gen_golden.py).  Imported by tests/ and tests/multi_gpu_check.py only."""
 import numpy as np
 
 

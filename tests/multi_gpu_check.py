@@ -1,7 +1,7 @@
 """Multi-GPU parity check, run under torchrun on a GPU box:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multi_gpu_check.py
+        tests/multi_gpu_check.py
 
 Checks, against the numpy oracle evaluated on the gathered inputs:
   1. fine-tune head: every rank's loss equals the global loss; each rank's gradient equals
