@@ -31,6 +31,10 @@ class hmmc_pretrain_io(Structure):
                                         "d_frame_pred")]
 
 
+class hmmc_head_schedule(Structure):
+    _fields_ = [("phase", c_int32), ("reserved", c_int32), ("queues_released", c_void_p)]
+
+
 class hmmc_mlp_params(Structure):
     _fields_ = [(n, c_void_p) for n in ("W1", "b1", "gamma", "beta", "W2", "b2", "running_mean", "running_var")]
 
@@ -58,13 +62,15 @@ SIGNATURES = {
                                            POINTER(hmmc_queue), POINTER(hmmc_queue), POINTER(hmmc_queue), c_float,
                                            c_float, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
+    "hmmc_pretrain_head_fwd_bwd_sched": (c_int, [POINTER(hmmc_pretrain_io), c_int, c_int, c_int, POINTER(hmmc_queue),
+                                                 POINTER(hmmc_queue), POINTER(hmmc_queue), POINTER(hmmc_queue), c_float,
+                                                 c_float, c_float, c_float, c_int, c_int, c_void_p,
+                                                 POINTER(hmmc_head_schedule), c_void_p, c_size_t, c_void_p]),
     "hmmc_enqueue_norm_direct": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                          POINTER(hmmc_queue), c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "hmmc_ema_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float,
                                c_float, c_void_p]),
     "hmmc_ema_block_elems": (c_int, []),
-    "hmmc_pretrain_head_release_event": (c_int, [c_void_p]),
-    "hmmc_pretrain_head_phase": (c_int, [c_int]),
     "hmmc_visual_tail_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_visual_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hmmc_mlp_ctx_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),

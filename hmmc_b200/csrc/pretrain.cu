@@ -11,12 +11,6 @@ static int tune_int(const char* name, int dflt) {     // tuning aids (tools/*_be
   return v ? atoi(v) : dflt;
 }
 
-// one-shot event recorded by the next InfoNCE driver call right after its last queue-reading launch
-// (hmmc_pretrain_head_release_event)
-static thread_local cudaEvent_t g_release_event = nullptr;
-// one-shot phase selector of the next driver call (hmmc_pretrain_head_phase): 0 = everything,
-// 1 = normalise + the two GEMM passes (needs the queries only), 2 = the rest (needs the keys)
-static thread_local int g_phase = 0;
 
 // ------------------------------------------------------------------ queue packing
 // dk [D,Kq] fp32  ->  pack_kd [Kq, planes*D] and pack_dk [D, planes*Kq] (bf16 hi / lo planes).
@@ -758,12 +752,14 @@ static void launch_finish(const FinishArgs& fa, int total_rows, int D, float inv
     infonce_finish_kernel<NE, (NE <= 16 ? 2 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
 }
 
+// sched (may be null = everything, no event): which half of the work to issue and the event to record once the
+// queues are no longer read (hmmc_head_schedule in include/hmmc_head.h)
 static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
-                       int prec, const LossFinal& fin, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  cudaEvent_t release = g_release_event;     // one-shots: consumed by this call whatever its outcome
-  g_release_event = nullptr;
-  const int phase = g_phase;
-  g_phase = 0;
+                       int prec, const LossFinal& fin, const hmmc_head_schedule* sched, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  const int phase = sched ? sched->phase : 0;
+  cudaEvent_t release = sched ? static_cast<cudaEvent_t>(sched->queues_released) : nullptr;
+  HMMC_REQUIRE(phase >= 0 && phase <= 2, "infonce: schedule phase must be 0, 1 or 2 (got %d)", phase);
   HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
   HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
   HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
@@ -915,17 +911,6 @@ static int check_pos_mode(int pos_mode, int Fq, int Fk) {
 
 extern "C" {
 
-int hmmc_pretrain_head_phase(int phase) {
-  HMMC_REQUIRE(phase >= 0 && phase <= 2, "pretrain_head_phase: phase must be 0, 1 or 2");
-  g_phase = phase;
-  return HMMC_OK;
-}
-
-int hmmc_pretrain_head_release_event(void* cuda_event) {
-  g_release_event = static_cast<cudaEvent_t>(cuda_event);
-  return HMMC_OK;
-}
-
 size_t hmmc_infonce_workspace_bytes(int64_t R, int D, int Kq, int prec) {
   Workspace ws(nullptr, 0);
   InfoNCELayout L;
@@ -946,7 +931,7 @@ int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, 
   GroupDesc g{q, dq, b * Fq, Fq};
   BlockDesc blk{0, keys, pos_mode, Fk, queue, weight / float(b), 0};
   LossFinal fin{loss_out, 0, 0.f, 0.f, 0.f, 1};
-  return run_infonce(&g, 1, &blk, 1, b, D, temperature, prec, fin, workspace, workspace_bytes,
+  return run_infonce(&g, 1, &blk, 1, b, D, temperature, prec, fin, nullptr, workspace, workspace_bytes,
                      static_cast<cudaStream_t>(stream));
 }
 
@@ -965,8 +950,19 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
                                const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
                                float w_ftm, int use_frame_fea, int prec, float* losses_out, void* workspace,
                                size_t workspace_bytes, void* stream) {
+  return hmmc_pretrain_head_fwd_bwd_sched(io, b, F, D, q_v, q_title, q_frame_proj, q_frame_cross, temperature, w_fam,
+                                          w_vtm, w_ftm, use_frame_fea, prec, losses_out, nullptr, workspace,
+                                          workspace_bytes, stream);
+}
+
+int hmmc_pretrain_head_fwd_bwd_sched(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
+                                     const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
+                                     const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
+                                     float w_ftm, int use_frame_fea, int prec, float* losses_out,
+                                     const hmmc_head_schedule* sched, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   HMMC_REQUIRE(io && q_v && q_title && q_frame_proj && q_frame_cross && losses_out, "pretrain_head: null argument");
-  const int phase = g_phase;      // peeked here, consumed by the driver below
+  const int phase = sched ? sched->phase : 0;
   HMMC_REQUIRE(io->v_fea && io->title_fea && io->frame_fea && io->frame_pred, "pretrain_head: null embedding pointer");
   HMMC_REQUIRE(phase == 1 || (io->v_fea_k && io->title_fea_k && io->frame_fea_k && io->frame_proj_k),
                "pretrain_head: null key pointer");
@@ -995,7 +991,7 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
   int ng = use_frame_fea ? 4 : 3;
   for (int k = 0; k < nb; ++k) blocks[k].coef *= wk[blocks[k].kind];
   LossFinal fin{losses_out, 1, w_fam, w_vtm, w_ftm, use_frame_fea};
-  int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, fin, workspace, workspace_bytes, st);
+  int rc = run_infonce(groups, ng, blocks, nb, b, D, temperature, prec, fin, sched, workspace, workspace_bytes, st);
   if (rc) return rc;
   if (phase != 1 && !use_frame_fea && io->d_frame_fea != nullptr)
     HMMC_CHECK_CUDA(cudaMemsetAsync(io->d_frame_fea, 0, sizeof(float) * size_t(b) * F * D, st));

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import (PREC_BF16, PREC_BF16X3, PREC_FP32, PRECISIONS, POS_FRAME_NEIGHBOUR, POS_FRAMES_TO_ONE,
-                   POS_ONE_TO_FRAMES, POS_PAIR, HmmcError, hmmc_pretrain_io, hmmc_queue)
+                   POS_ONE_TO_FRAMES, POS_PAIR, HmmcError, hmmc_head_schedule, hmmc_pretrain_io, hmmc_queue)
 
 DEFAULT_PRECISION = os.environ.get("HMMC_PRECISION", "bf16x3")
 
@@ -236,14 +236,16 @@ class _PretrainHeadFn(torch.autograd.Function):
         nbytes = lib.hmmc_pretrain_head_workspace_bytes(b, F, D, K, prec)
         ws = workspace(t[0].device, nbytes)
         losses = torch.empty(4, dtype=torch.float32, device=t[0].device)
+        sched = hmmc_head_schedule(0, 0, None)
         if release_event is not None:
             release_event.record()               # materialises the handle; the library records it again later
-            _lib.check(lib.hmmc_pretrain_head_release_event(ctypes.c_void_p(release_event.cuda_event)),
-                       "hmmc_pretrain_head_release_event")
-        _lib.check(lib.hmmc_pretrain_head_fwd_bwd(ctypes.byref(io), b, F, D, *[ctypes.byref(s[0]) for s in structs],
-                                                  float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
-                                                  int(bool(use_frame_fea)), prec, _p(losses), _p(ws), ws.numel(),
-                                                  _stream()), "hmmc_pretrain_head_fwd_bwd")
+            sched.queues_released = release_event.cuda_event
+        _lib.check(lib.hmmc_pretrain_head_fwd_bwd_sched(ctypes.byref(io), b, F, D,
+                                                        *[ctypes.byref(s[0]) for s in structs], float(temperature),
+                                                        float(w_fam), float(w_vtm), float(w_ftm),
+                                                        int(bool(use_frame_fea)), prec, _p(losses), ctypes.byref(sched),
+                                                        _p(ws), ws.numel(), _stream()),
+                   "hmmc_pretrain_head_fwd_bwd_sched")
         ctx.need = need
         ctx.meta = [(x.shape, x.dtype) for x in qin]
         if any_grad:
@@ -286,11 +288,12 @@ def _head_call(state, keys, phase, stream):
     io = hmmc_pretrain_io(*[x.data_ptr() for x in state.t], *kp,
                           *[(g.data_ptr() if g is not None else 0) for g in state.grads])
     temperature, w_fam, w_vtm, w_ftm, use_frame_fea = state.args
-    _lib.check(lib.hmmc_pretrain_head_phase(phase), "hmmc_pretrain_head_phase")
-    _lib.check(lib.hmmc_pretrain_head_fwd_bwd(ctypes.byref(io), b, F, D, *[ctypes.byref(s) for s in state.structs],
-                                              float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
-                                              int(bool(use_frame_fea)), prec, _p(state.losses), _p(state.ws),
-                                              state.ws.numel(), stream), "hmmc_pretrain_head_fwd_bwd")
+    sched = hmmc_head_schedule(phase, 0, None)
+    _lib.check(lib.hmmc_pretrain_head_fwd_bwd_sched(ctypes.byref(io), b, F, D, *[ctypes.byref(s) for s in state.structs],
+                                                    float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
+                                                    int(bool(use_frame_fea)), prec, _p(state.losses),
+                                                    ctypes.byref(sched), _p(state.ws), state.ws.numel(), stream),
+               "hmmc_pretrain_head_fwd_bwd_sched")
 
 
 def pretrain_head_begin(v_fea, title_fea, frame_fea, frame_pred, q_v, q_title, q_frame_proj, q_frame_cross,

@@ -137,25 +137,33 @@ typedef struct {
   float* d_frame_fea;
   float* d_frame_pred;
 } hmmc_pretrain_io;
-/* One-shot: the next hmmc_pretrain_head_fwd_bwd / hmmc_infonce_queue_fwd_bwd call on this host thread
- * records `cuda_event` (a cudaEvent_t) on its stream right after the last kernel that reads the queues.
- * The enqueue of the step (which overwrites queue columns) can then run on another stream that waits for
- * the event, overlapping the rest of the loss (positives, gradient projection, reductions). */
-int hmmc_pretrain_head_release_event(void* cuda_event);
-/* One-shot phase selector of the next hmmc_pretrain_head_fwd_bwd call on this host thread:
- *   1 = normalise the queries and run the two GEMM passes against the queues (needs only the query tensors
- *       and the gradient buffers; the key pointers of `io` may be NULL),
- *   2 = positives, losses, gradients (needs the keys), on the SAME arguments and an untouched workspace,
- *   0 = both (default).
- * In the reference the queries exist before `_momentum_update()` and the key encoders run
- * (modules/modeling.py:340-377), so phase 1 can execute beside them on another stream. */
-int hmmc_pretrain_head_phase(int phase);
 size_t hmmc_pretrain_head_workspace_bytes(int b, int F, int D, int K, int prec);
 int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
                                const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
                                const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
                                float w_ftm, int use_frame_fea, int prec, float* losses_out, void* workspace,
                                size_t workspace_bytes, void* stream);
+/* The same call with an explicit schedule (NULL = the call above):
+ *   phase 1 = normalise the queries and run the two GEMM passes against the queues (needs only the query
+ *             tensors and the gradient buffers; the key pointers of `io` may be NULL),
+ *   phase 2 = positives, losses, gradients (needs the keys), on the SAME arguments and an untouched workspace,
+ *   phase 0 = both.
+ * In the reference the queries exist before `_momentum_update()` and the key encoders run
+ * (modules/modeling.py:340-377), so phase 1 can execute beside them on another stream.
+ * queues_released: NULL or a cudaEvent_t recorded on `stream` right after the last kernel that reads the
+ * queues; the enqueue of the step (which overwrites queue columns) can then run on another stream that
+ * waits for it, beside the rest of the loss. */
+typedef struct {
+  int phase;
+  int reserved;
+  void* queues_released;
+} hmmc_head_schedule;
+int hmmc_pretrain_head_fwd_bwd_sched(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,
+                                     const hmmc_queue* q_title, const hmmc_queue* q_frame_proj,
+                                     const hmmc_queue* q_frame_cross, float temperature, float w_fam, float w_vtm,
+                                     float w_ftm, int use_frame_fea, int prec, float* losses_out,
+                                     const hmmc_head_schedule* sched, void* workspace, size_t workspace_bytes,
+                                     void* stream);
 
 /* _momentum_update (modules/modeling.py:238-242): p_k <- p_k*m + p*(1-m) for a table of
  * tensors, each in its own dtype (0 = fp32, 1 = fp16, 2 = bf16), three separately
