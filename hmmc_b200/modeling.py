@@ -239,6 +239,8 @@ def patch_reference_classes(*classes):
                 setattr(cls, name, fn)
         if hasattr(cls, "_dequeue_and_enqueue") and cls.__name__ == "BirdPreTrainedModel":
             cls.head_loss = BirdPreTrainedModel.head_loss
+            cls.head_loss_begin = BirdPreTrainedModel.head_loss_begin
+            cls.head_loss_end = BirdPreTrainedModel.head_loss_end
     return classes
 
 

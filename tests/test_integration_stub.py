@@ -24,6 +24,8 @@ def test_patch_reference_classes():
         for n in names:
             assert getattr(M.BirdModel, n) is getattr(B.ContrastiveHeadMixin, n)
         assert M.BirdPreTrainedModel.head_loss is B.BirdPreTrainedModel.head_loss
+        assert M.BirdPreTrainedModel.head_loss_begin is B.BirdPreTrainedModel.head_loss_begin
+        assert M.BirdPreTrainedModel.head_loss_end is B.BirdPreTrainedModel.head_loss_end
     finally:
         for c, d in saved.items():
             for k in list(vars(c)):
