@@ -1,6 +1,7 @@
 // Fine-tune (hierarchical matching) head: loose_similarity, CrossEn and the fused
 // symmetric-CE loss over the text x video and the F text x frame similarity matrices.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace hmmc {
 
@@ -474,6 +475,13 @@ struct SymCeWs {
   int splits;
 };
 constexpr int SYMCE_MAX_SPLITS = 32;
+// split-K cap of the text-gradient GEMM: more slices shorten the GEMM but lengthen the un-normalise pass that adds
+// them (B=256 raw call: 83.4 us at 16, 78.6 at 8, 80.7 at 4)
+static int symce_split_cap() {
+  static const int v = [] { const char* e = getenv("HMMC_SYMCE_SPLITS"); int x = e ? atoi(e) : 8; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
+  return v;
+}
+#define SYMCE_SPLIT_CAP symce_split_cap()
 static bool symce_tensor_ok(int B, int D, int prec) {
   // bf16x3 (fp32-parity) takes any multiple of 32 rows; the single-plane bf16 mode keeps its former
   // 64-row granularity and leaves smaller batches on the exact CUDA-core path
@@ -573,7 +581,7 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
     const int other = (dvideo != nullptr || dframes != nullptr) ? ((NG + 127) / 128) * ((D + 255) / 256) : 0;
     int sp = (sm_count() - other) / (tiles > 0 ? tiles : 1);
     if (sp < 1) sp = 1;
-    if (sp > 16) sp = 16;
+    if (sp > SYMCE_SPLIT_CAP) sp = SYMCE_SPLIT_CAP;
     const int eff = umma_effective_splits(NGk, P, sp);
     StoreGemm gm[2];
     int ng = 0;
