@@ -22,7 +22,6 @@ import os
 from types import SimpleNamespace
 
 import torch
-import torch.distributed as dist
 from torch import nn
 
 from . import ops, parallel

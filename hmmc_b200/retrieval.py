@@ -111,7 +111,6 @@ def fused_eval_ranks(text, video_local, frames_local, per_video, scale=100.0, to
     parallel.shard_range(Nv)), per_video [Nv] caption counts of ALL videos.
     Returns (t2v ranks [Nt] int32 tensor, v2t ranks [Nv] int32 tensor), identical on every rank.
     """
-    import ctypes
     from . import _lib
     lib = _lib.load()
     prec = ops.resolve_precision(precision)
