@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU)
     python bench.py --impl reference ...                      # the reference's CPU path (oracle port)
+    python bench.py --impl reference-gpu ...                  # the same op sequence on the GPU (torch eager)
 
 One "step" of the default workload is the pre-train head of BASELINE.json config 4 on one
 rank: momentum EMA over the 172,325,632 key-encoder parameters, the FAM + VTM + FTM InfoNCE
@@ -32,7 +33,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "gallery"])
     ap.add_argument("--texts", type=int, default=1000000, help="gallery workload: captions (10 per video)")
     ap.add_argument("--videos", type=int, default=100000, help="gallery workload: videos")
@@ -52,11 +53,21 @@ def parse():
     return ap.parse_args()
 
 
-# kernels of this library in one step: ema, prep, S-GEMM, U-GEMM, finish, loss reduce, head losses,
-# enqueue (+ pointer advance under graph capture), scale; + pack_rows when the keys are gathered
-LAUNCHES_PER_STEP = lambda W: 10 + (1 if W > 1 else 0)
 FLOPS_ALGO = lambda b, F, D, K: 2 * 2.0 * D * b * (F * K * F + K * F + F * K + 2 * K)   # SURVEY.md §8d, fwd + bwd
 EMA_ELEMS = 172325632
+
+
+# DRAM bytes per launch of the dominant kernels, extracted from the committed `ncu --set full` captures by
+# tools/ncu_traffic.py (dram__bytes_read.sum + dram__bytes_write.sum); None when a kernel is not in the file
+NCU_TRAFFIC_FILE = "profiles/r2_ncu_traffic.json"
+
+
+def ncu_traffic(*kernels):
+    try:
+        tab = json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))["kernels"]
+        return int(sum(tab[k]["dram_bytes_read"] + tab[k]["dram_bytes_write"] for k in kernels))
+    except Exception:   # noqa: BLE001
+        return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -172,6 +183,95 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def gpu_eager_pretrain_ms(args, dev, steps, warmup, with_ema=True):
+    """The reference's op sequence (oracle/torch_port.pretrain_step) on CUDA tensors: what a user of the
+    reference gets on this GPU today (torch eager: cuBLAS / ATen kernels).  Returns ms per step (CUDA events)."""
+    from hmmc_b200 import synthetic as syn
+    from oracle import torch_port as P
+    b, F, D, K = args.batch, args.frames, args.dim, args.queue
+    inp_np = syn.pretrain_inputs(b, F=F, D=D, seed=2)
+    qs = {n: torch.from_numpy(x).to(dev) for n, x in syn.queues(K, F=F, D=D, seed=3).items()}
+    ema = None
+    if with_ema:
+        sizes = syn.ema_param_numels()
+        ps = list(torch.split(torch.randn(sum(sizes), device=dev), sizes))
+        pks = [torch.nn.Parameter(x.clone(), requires_grad=False) for x in torch.split(torch.randn(sum(sizes), device=dev), sizes)]
+        ema = (ps, pks)
+    base = {k: torch.from_numpy(v).to(dev) for k, v in inp_np.items()}
+    ptr = 0
+
+    def one():
+        nonlocal ptr
+        inp = {k: v.detach().requires_grad_(k in ("v_fea", "title_fea", "frame_fea", "frame_pred")) for k, v in base.items()}
+        _, ptr = P.pretrain_step(inp, qs, ptr, K, 0.07, ema=ema)
+        if ptr + b > K:
+            ptr = 0
+    for _ in range(max(warmup, 2)):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    del ema
+    torch.cuda.empty_cache()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_reference_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    steps = max(1, min(args.steps, 50))
+    ms = gpu_eager_pretrain_ms(args, dev, steps, args.warmup)
+    value = args.batch / (ms / 1e3)
+    print(json.dumps({"impl": "reference-gpu", "metric": "hm_moco_head_fwd_bwd_throughput", "value": value,
+                      "unit": "samples/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 2), "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": workload_config(args, 1),
+                      "note": "the reference's own op sequence (oracle/torch_port.py, pinned to reference-generated "
+                              "goldens) on CUDA tensors: torch eager, fp32, ~1100 launches for the EMA and 48 "
+                              "contrastive_loss calls; the reference itself is absent on the GPU box"}))
+
+
+def gpu_eager_legs(args, dev):
+    """The other configs through the same port on the GPU (rank 0, N = 1): loss only at b=256, fine-tune head at
+    B=256, config-2 eval.  ms each, CUDA events."""
+    from hmmc_b200 import synthetic as syn
+    from oracle import torch_port as P
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    a2 = argparse.Namespace(**vars(args))
+    a2.batch = 256
+    out["loss_b256_ms"] = gpu_eager_pretrain_ms(a2, dev, 10, 2, with_ema=False)
+    t, v, fr = [torch.from_numpy(x).to(dev) for x in syn.finetune_inputs(256, seed=300)]
+
+    def ft():
+        P.finetune_step(t.detach().requires_grad_(True), v.detach().requires_grad_(True), fr.detach().requires_grad_(True))
+    out["finetune_B256_ms"] = timed(ft, 20)
+    T, V, Fr, gt, _ = syn.eval_inputs(1000, 1000, seed=4)
+    T, V, Fr = [torch.from_numpy(x).to(dev) for x in (T, V, Fr)]
+    out["eval_1k_ms"] = timed(lambda: P.eval_sim_and_rank(T, V, Fr, 2), 5)
+    out["note"] = ("oracle/torch_port.py (the reference's op sequence) on CUDA tensors, torch eager fp32; eval includes the "
+                   "reference's per-tile D2H copies and its numpy ranking on the host")
+    return out
+
+
 def workload_config(args, W):
     return {"workload": "pretrain head step (BASELINE config 4): EMA(172.3M params) + FAM/VTM/FTM InfoNCE fwd+bwd + "
                         "key all-gather + enqueue",
@@ -183,6 +283,9 @@ def workload_config(args, W):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+GRAPHS = []        # every GraphedStep of this process (released before the process group is destroyed)
+
+
 def gallery_data(Nv, cap, D, F, lo, hi, dev):
     """Synthetic config-5 set: captions [Nv*cap, D] (replicated), videos/frames for [lo, hi).
     Generated in fixed blocks of 4096 videos so every world size sees the same bytes."""
@@ -317,6 +420,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args)
     if args.workload == "gallery":
         return run_gallery(args)
 
@@ -386,6 +491,8 @@ def main():
         if timed:
             e0, e1, e2 = ev(), ev(), ev()
             e0.record()
+        # deferred schedule (several ranks): the previous step's key all-gather + enqueue run beside the EMA
+        model.start_pending_exchange()
         if split and not timed and not sequential:
             # the reference's own order (modules/modeling.py:340-377): queries first, then the momentum update and
             # the key encoders, then the losses -> the query-side GEMMs of the loss run beside the EMA
@@ -415,6 +522,10 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(devt, False)
     barrier()
+    l0 = lib.hmmc_launch_count()
+    step(devt, False)
+    launches_per_step = int(lib.hmmc_launch_count() - l0)      # kernels of this library in one step (counted, eager)
+    barrier()
 
     # One step = a fixed sequence of launches: capture it once, replay it (hmmc_b200/graphs.py).
     graphed = None
@@ -426,6 +537,7 @@ def main():
             from hmmc_b200.graphs import GraphedStep
             dbg("capturing")
             graphed = GraphedStep(lambda: step(devt, False))
+            GRAPHS.append(graphed)
             dbg("captured")
             graph_note = "cuda graph replay"
         except Exception as e:   # noqa: BLE001
@@ -451,11 +563,23 @@ def main():
         run_step()
     cpu_issue_ms = 1e3 * (time.perf_counter() - cpu_t0) / args.steps     # host time to ISSUE one step (no sync)
     t1.record()
+    # the timed region is exactly args.steps steps; the same step keeps running (untimed) until the clock
+    # sampler has covered at least one second of it, so that the record has enough samples
+    t_clock = time.perf_counter()
     barrier()
+    extra = 0
+    while time.perf_counter() - cpu_t0 < 1.0:
+        for _ in range(50):
+            run_step()
+        extra += 50
+        torch.cuda.synchronize()
     clk = clocks.stop()
+    clk["window"] = "timed region + %d more untimed steps of the same workload (%.2f s in all)" % (
+        extra, time.perf_counter() - cpu_t0)
+    barrier()
     launches = lib.hmmc_launch_count() - launches0
     if graphed is not None:
-        launches = LAUNCHES_PER_STEP(W) * args.steps      # a replay re-runs the captured launches
+        launches = launches_per_step * args.steps         # a replay re-runs the captured launches
     dbg("timed region 1 done")
     # per-kernel timing for the roofline: a short eager run right after, events around the EMA launch
     for _ in range(20):
@@ -464,17 +588,6 @@ def main():
     dbg("eager breakdown done")
     ms_total = t0.elapsed_time(t1)
     detail = None
-    if os.environ.get("HMMC_BENCH_DETAIL"):
-        # separate short run with CUDA events inside head_loss: pack+gather launch | loss kernels | wait+enqueue
-        model._hmmc_marks = []
-        for _ in range(20):
-            step(devt, False, True)
-        torch.cuda.synchronize()
-        mk = model._hmmc_marks
-        model._hmmc_marks = None
-        seg = np.array([[mk[4 * i + j].elapsed_time(mk[4 * i + j + 1]) for j in range(3)] for i in range(20)])
-        detail = dict(zip(["pack_and_gather_launch_ms", "loss_fwd_bwd_ms", "gather_wait_and_enqueue_ms"],
-                          [float(x) for x in seg[5:].mean(0)]))
     ms_ema = float(np.mean([a.elapsed_time(c) for a, c in ema_events]))
     ms_head = float(np.mean([a.elapsed_time(c) for a, c in head_events]))
     # the step with EMA and loss strictly one after the other (replayed as a graph too): what the head costs when
@@ -487,6 +600,7 @@ def main():
                 with torch.no_grad():
                     model._momentum_update()
             gema = GraphedStep(ema_only)
+            GRAPHS.append(gema)
             for _ in range(3):
                 gema.replay()
             barrier()
@@ -503,6 +617,7 @@ def main():
     if graphed is not None and split:
         try:
             gseq = GraphedStep(lambda: step(devt, False, True))
+            GRAPHS.append(gseq)
             for _ in range(3):
                 gseq.replay()
             barrier()
@@ -595,8 +710,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"kernel": "ema_multi_kernel", "bound": "hbm", "achieved": ema_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ema_gbs / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_head_kernels.md
-                         "traffic": 1378661000 + 646582528,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+                         "traffic": ncu_traffic("ema_multi_kernel"), "traffic_source": NCU_TRAFFIC_FILE,
                          "algorithmic_bytes": ema_bytes, "ms": ms_ema, "peak_source": peak_src},
             "roofline_head": {"kernels": "infonce fwd+bwd (5 query blocks: rownorm_pack, umma S-GEMM+exp epilogue, "
                                          "umma U-GEMM, finish, reduce) + pack + enqueue",
@@ -649,21 +764,51 @@ def main():
                                                            "checks", "metrics", "clocks")}
         except Exception as e:   # noqa: BLE001
             line["retrieval_large"] = {"error": repr(e)[:300]}
-    if rank == 0 and not args.no_cpu_baseline:
+    if W > 1:
+        # multi-rank parity (tests/multi_gpu_check.py; the numpy oracle is the checker): gathered enqueue ==
+        # oracle concat (eager / deferred / graph replay), fine-tune loss and gradients == W = 1 on the
+        # concatenated batch, replicated backward == reduce-scatter, sharded eval == one GPU
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import multi_gpu_check as MG
+            chk = MG.run_checks(W, rank, local, dev, which=MG.CHECKS[:3])
+        except Exception as e:   # noqa: BLE001
+            chk = {"pass": False, "failures": [repr(e)[:300]]}
+        line["checks"] = chk
+    if rank == 0 and W == 1 and not args.no_cpu_baseline:
+        # rank 0 at N = 1 only: under torchrun the other ranks would spin in a barrier on the same cores
         ms, n, cores, sample = cpu_pretrain_steps(args, max_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": b / (ms / 1e3), "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": sample, "ms_per_step": ms}
+    if rank == 0 and W == 1 and not args.no_retrieval:
+        # what a user of the reference gets on this GPU today: its op sequence in torch eager
+        try:
+            gms = gpu_eager_pretrain_ms(args, dev, 10, 2)
+            eager = {"pretrain_step_ms": gms, "value": b / (gms / 1e3), "unit": "samples/s", "kind": "port on cuda"}
+            eager.update(gpu_eager_legs(args, dev))
+            eager["ours_over_eager"] = {
+                "pretrain_step": gms / ms_step,
+                "loss_b256": eager["loss_b256_ms"] / line["loss_b256"]["bf16"]["ms"] if "bf16" in line.get("loss_b256", {}) else None,
+                "finetune_B256": eager["finetune_B256_ms"] / line["finetune_head"]["b256_per_gpu"]["ms_per_step"]
+                if "b256_per_gpu" in line.get("finetune_head", {}) else None,
+                "eval_1k": eager["eval_1k_ms"] / line["retrieval"]["ms"] if "ms" in line.get("retrieval", {}) else None}
+            line["gpu_eager_baseline"] = eager
+        except Exception as e:   # noqa: BLE001
+            line["gpu_eager_baseline"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if W > 1:
         dist.barrier()
         torch.cuda.synchronize()
-        if graphed is not None:
-            # a captured graph that contains NCCL work keeps the communicator busy at teardown
-            # (destroy_process_group never returns): drop the graph and leave without the destroy
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
+        # graphs that captured NCCL work must be destroyed before the communicator
+        for gobj in GRAPHS:
+            try:
+                gobj.release()
+            except Exception:   # noqa: BLE001
+                pass
+        del GRAPHS[:]
+        sys.stdout.flush()
+        sys.stderr.flush()
         dist.destroy_process_group()
 
 
@@ -826,9 +971,8 @@ def optimizer_leg(args, dev, sizes, hbm_peak, peak_src):
            "params_per_s": n / (ms / 1e3), "grad_norm": float(opt.last_grad_norm),
            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": algo,
-                        # dram__bytes_read.sum + dram__bytes_write.sum of grad_sqnorm_kernel and bert_adam_kernel,
-                        # profiles/r1_ncu_optimizer.md
-                        "traffic": 689346000 + 5794000 + 2757263000 + 2014940000,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of grad_sqnorm_kernel and bert_adam_kernel
+                        "traffic": ncu_traffic("grad_sqnorm_kernel", "bert_adam_kernel"), "traffic_source": NCU_TRAFFIC_FILE,
                         "peak_source": peak_src}}
     assert bool(torch.isfinite(flat).all())
     del opt, params, grads, flat, gflat
@@ -877,6 +1021,7 @@ def finetune_leg(args, W, rank, local, dev):
             return loss
         try:
             g = GraphedStep(step)
+            GRAPHS.append(g)
             run, mode = g.replay, "cuda graph replay"
         except Exception as e:   # noqa: BLE001
             run, mode = step, "eager (%s)" % repr(e)[:80]

@@ -32,7 +32,7 @@ class hmmc_pretrain_io(Structure):
 
 
 class hmmc_head_schedule(Structure):
-    _fields_ = [("phase", c_int32), ("reserved", c_int32), ("queues_released", c_void_p)]
+    _fields_ = [("phase", c_int32), ("reserved_sms", c_int32), ("queues_released", c_void_p)]
 
 
 class hmmc_mlp_params(Structure):
@@ -45,13 +45,14 @@ SIGNATURES = {
     "hmmc_version": (c_int, []),
     "hmmc_launch_count": (ctypes.c_ulonglong, []),
     "hmmc_device_check": (c_int, []),
-    "hmmc_set_reserved_sms": (c_int, [c_int]),
     "hmmc_rownorm_pack": (c_int, [c_void_p, c_int64, c_int, c_int64, c_float, c_int, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),
     "hmmc_gemm_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                               c_int, c_int, c_int, c_float, c_void_p]),
     "hmmc_umma_gemm_nt": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
                                   c_int, c_int, c_float, c_void_p]),
+    "hmmc_umma_gemm_nt_tiled": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int,
+                                        c_int, c_int, c_float, c_int, c_void_p]),
     "hmmc_queue_pack": (c_int, [POINTER(hmmc_queue), c_void_p]),
     "hmmc_infonce_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "hmmc_infonce_queue_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -39,8 +39,25 @@ void count_launch();
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Launch with programmatic stream serialisation: the kernel may start while the previous kernel of the stream
+// drains, and must execute griddepcontrol.wait (ptx::grid_dependency_wait) before it touches global memory.
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int sm_count();
-int gemm_sm_budget();     // sm_count() minus the SMs reserved through hmmc_set_reserved_sms
 
 // Bump allocator over the caller's workspace.
 struct Workspace {
@@ -120,10 +137,12 @@ int gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t s
              int64_t ldc, int M, int N, int K, float alpha, cudaStream_t st);
 int rownorm_pack(const float* x, int64_t R, int D, int64_t ldx, float eps, int planes, float* xhat, float* inv_norm,
                  void* packed, int64_t ldp, cudaStream_t st);
-// tcgen05 GEMM, C[split] = alpha * A.B^T (fp32 out); splits > 1 writes partial sums split_stride apart
+// tcgen05 GEMM, C[split] = alpha * A.B^T (fp32 out); splits > 1 writes partial sums split_stride apart.
+// tiling: 0 = chosen from the shape; 128 / 256 = single-CTA kernel with that tile width; 512 = CTA-pair
+// kernel (256 x 256 tiles) -- explicit values are for hmmc_umma_gemm_nt_tiled (tools/gemm_bench.py)
 int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                     int64_t split_stride, int M, int N, int K, int planes, int splits, float alpha,
-                    cudaStream_t st);
+                    cudaStream_t st, int tiling = 0);
 // several store-GEMMs (each with its own split count) in one grouped launch
 struct StoreGemm {
   const void* A; int64_t lda;

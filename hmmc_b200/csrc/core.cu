@@ -33,20 +33,6 @@ int sm_count() {
   return cached[dev];
 }
 
-// SMs the persistent GEMM grids leave free (a collective running beside them needs somewhere to live:
-// a persistent CTA that cannot become resident stalls its share of the tiles until the collective ends)
-static int g_reserved_sms = -1;
-int gemm_sm_budget() {
-  if (g_reserved_sms < 0) {
-    const char* e = getenv("HMMC_RESERVED_SMS");
-    g_reserved_sms = e ? atoi(e) : 0;
-    if (g_reserved_sms < 0) g_reserved_sms = 0;
-  }
-  int n = sm_count() - g_reserved_sms;
-  return n < 2 ? 2 : n;
-}
-void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -64,7 +50,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                   uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -72,10 +59,16 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
   }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};   // bytes, dimension 1
-  cuuint32_t box[2] = {UMMA_BK, box_rows};
+  if (box_cols != 64 && box_cols != 32) {
+    set_error("make_tmap_bf16: box of %u columns (64 = operand loads, 32 = epilogue store tiles)", box_cols);
+    return HMMC_ERR_ARG;
+  }
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  // the swizzle span equals the box's inner extent: 128 B for the operand tiles, 64 B for the store tiles
+  const CUtensorMapSwizzle sw = (box_cols == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", int(r),
@@ -193,14 +186,14 @@ int rownorm_pack(const float* x, int64_t R, int D, int64_t ldx, float eps, int p
 
 int umma_gemm_store(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                     int64_t split_stride, int M, int N, int K, int planes, int splits, float alpha,
-                    cudaStream_t st) {
+                    cudaStream_t st, int tiling) {
   EpiStoreF32::Params ep{C, ldc, split_stride, alpha};
-  static const char* force = getenv("HMMC_FORCE_BN");   // tuning aid (tools/gemm_bench.py)
-  if (force != nullptr && atoi(force) == 128) return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
-  if (force != nullptr && atoi(force) == 512) {     // CTA-pair kernel (tools/gemm_bench.py)
+  if (tiling == 128) return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
+  if (tiling == 512) {     // CTA-pair kernel, 256 x 256 tiles
     GemmProblem<EpiStoreF32> pr{A, lda, B, ldb, M, N, K, planes, splits, ep};
     return launch_umma_grouped_pair<EpiStoreF32>(&pr, 1, st);
   }
+  if (tiling == 256) return launch_umma_gemm<256, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
   if (N % 256 == 0 || N > 1024) return launch_umma_gemm<256, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
   return launch_umma_gemm<128, EpiStoreF32>(A, lda, B, ldb, M, N, K, planes, splits, ep, st);
 }
@@ -236,11 +229,6 @@ const char* hmmc_last_error(void) { return g_err; }
 int hmmc_version(void) { return 100; }
 unsigned long long hmmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int hmmc_set_reserved_sms(int n) {
-  hmmc::set_reserved_sms(n);
-  return HMMC_OK;
-}
-
 int hmmc_device_check(void) {
   int dev = 0;
   HMMC_CHECK_CUDA(cudaGetDevice(&dev));
@@ -272,6 +260,15 @@ int hmmc_umma_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, fl
                       int K, int planes, float alpha, void* stream) {
   HMMC_REQUIRE(A && B && C, "umma_gemm_nt: null operand");
   return umma_gemm_store(A, lda, B, ldb, C, ldc, 0, M, N, K, planes, 1, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int hmmc_umma_gemm_nt_tiled(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M,
+                            int N, int K, int planes, float alpha, int tiling, void* stream) {
+  HMMC_REQUIRE(A && B && C, "umma_gemm_nt_tiled: null operand");
+  HMMC_REQUIRE(tiling == 0 || tiling == 128 || tiling == 256 || tiling == 512,
+               "umma_gemm_nt_tiled: tiling must be 0, 128, 256 or 512 (got %d)", tiling);
+  return umma_gemm_store(A, lda, B, ldb, C, ldc, 0, M, N, K, planes, 1, alpha, static_cast<cudaStream_t>(stream),
+                         tiling);
 }
 
 }  // extern "C"

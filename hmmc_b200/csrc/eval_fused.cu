@@ -172,7 +172,7 @@ template <int K>
 __global__ void __launch_bounds__(EV_THREADS, 1)
 eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ EvalArgs a) {
-  using Cfg = UmmaCfg<EV_BN>;
+  using Cfg = UmmaCfg<EV_BN, EpiStoreF32>;   // ring geometry only; this kernel has its own epilogue
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -651,12 +651,11 @@ static int eval_launch(const void* text_packed, const void* gallery_packed, int6
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, gallery_packed, uint64_t(a.num_n_blk) * EV_BN, uint64_t(planes) * D, uint64_t(planes) * D, EV_BN);
   if (rc) return rc;
-  using Cfg = UmmaCfg<EV_BN>;
+  using Cfg = UmmaCfg<EV_BN, EpiStoreF32>;   // ring geometry only; this kernel has its own epilogue
   const int work = (a.mode == 1) ? a.num_m_blk : a.n_diag_tiles;
   if (work <= 0) return HMMC_OK;
   // counting sweep in one bf16 plane: CTA pairs with the caption tile resident in shared memory
-  static const char* no_pair = getenv("HMMC_EVAL_NO_PAIR");
-  if (a.mode == 1 && planes == 1 && D / UMMA_BK <= EVP_MAX_KB && no_pair == nullptr) {
+  if (a.mode == 1 && planes == 1 && D / UMMA_BK <= EVP_MAX_KB) {
     CUtensorMap tmBh;
     rc = make_tmap_bf16(&tmBh, gallery_packed, uint64_t(a.num_n_blk) * EV_BN, uint64_t(D), uint64_t(D), EV_BN / 2);
     if (rc) return rc;

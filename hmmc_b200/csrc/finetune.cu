@@ -477,11 +477,7 @@ struct SymCeWs {
 constexpr int SYMCE_MAX_SPLITS = 32;
 // split-K cap of the text-gradient GEMM: more slices shorten the GEMM but lengthen the un-normalise pass that adds
 // them (B=256 raw call: 83.4 us at 16, 78.6 at 8, 80.7 at 4)
-static int symce_split_cap() {
-  static const int v = [] { const char* e = getenv("HMMC_SYMCE_SPLITS"); int x = e ? atoi(e) : 8; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
-  return v;
-}
-#define SYMCE_SPLIT_CAP symce_split_cap()
+constexpr int SYMCE_SPLIT_CAP = 8;
 static bool symce_tensor_ok(int B, int D, int prec) {
   // bf16x3 (fp32-parity) takes any multiple of 32 rows; the single-plane bf16 mode keeps its former
   // 64-row granularity and leaves smaller batches on the exact CUDA-core path

@@ -2,15 +2,11 @@
 // momentum EMA and the pack/unpack helpers of the key all-gather.
 #include "common.cuh"
 #include "umma_gemm.cuh"
-#include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace hmmc {
-
-static int tune_int(const char* name, int dflt) {     // tuning aids (tools/*_bench.py)
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 
 // ------------------------------------------------------------------ queue packing
 // dk [D,Kq] fp32  ->  pack_kd [Kq, planes*D] and pack_dk [D, planes*Kq] (bf16 hi / lo planes).
@@ -83,8 +79,16 @@ struct PrepArgs {
   int n;
 };
 
-// one warp per row, all query tensors of the call in one launch (F.normalize, eps 1e-12)
-__global__ void prep_rows_kernel(PrepArgs a, int D, int planes) {
+// One warp per row, all query tensors of the call in one launch (F.normalize, eps 1e-12).
+// The bf16 operand copy carries the factor pack_scale = log2(e)/T, so that the S-GEMM's accumulators are
+// logits in base-2 units (see EpiInfoNCE); the fp32 copy stays the plain unit vector.
+// Block 0 also clears the finish kernel's arrival counter.
+template <int V>   // float4 per lane (D == 128 * V), 0 = any D (scalar accesses)
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const __grid_constant__ PrepArgs a, int D, int planes, float pack_scale, unsigned* finish_counter) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && finish_counter != nullptr) *finish_counter = 0u;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= a.row_begin[a.n]) return;
@@ -94,20 +98,48 @@ __global__ void prep_rows_kernel(PrepArgs a, int D, int planes) {
     if (i < a.n && row >= a.row_begin[i]) gi = i;
   const int r = row - a.row_begin[gi];
   const float* xr = a.x[gi] + int64_t(r) * D;
-  float ss = 0.f;
-  for (int d = lane; d < D; d += 32) { const float v = xr[d]; ss = fmaf(v, v, ss); }
-  ss = warp_sum(ss);
-  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);     // x * (1/n): within 1 ulp of F.normalize's x / n
   float* xh = a.xhat[gi];
   __nv_bfloat16* pk = a.packed[gi];
-  for (int d = lane; d < D; d += 32) {
-    const float v = xr[d] * inv;
-    if (xh != nullptr) xh[int64_t(r) * D + d] = v;
-    if (pk != nullptr) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(v, hi, lo);
-      pk[int64_t(r) * planes * D + d] = hi;
-      if (planes == 2) pk[int64_t(r) * planes * D + D + d] = lo;
+  if (V > 0) {
+    float4 v[V > 0 ? V : 1];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(xr) + lane + 32 * i);
+      ss = fmaf(v[i].x, v[i].x, ss); ss = fmaf(v[i].y, v[i].y, ss);
+      ss = fmaf(v[i].z, v[i].z, ss); ss = fmaf(v[i].w, v[i].w, ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);     // x * (1/n): within 1 ulp of F.normalize's x / n
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 h = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+      const int d = 4 * (lane + 32 * i);
+      if (xh != nullptr) *reinterpret_cast<float4*>(xh + int64_t(r) * D + d) = h;
+      if (pk != nullptr) {
+        const float s[4] = {h.x * pack_scale, h.y * pack_scale, h.z * pack_scale, h.w * pack_scale};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16(s[j], hi[j], lo[j]);
+        __nv_bfloat16* o = pk + int64_t(r) * planes * D + d;
+        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+        if (planes == 2) *reinterpret_cast<uint2*>(o + D) = *reinterpret_cast<const uint2*>(lo);
+      }
+    }
+  } else {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = xr[d]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int d = lane; d < D; d += 32) {
+      const float v = xr[d] * inv;
+      if (xh != nullptr) xh[int64_t(r) * D + d] = v;
+      if (pk != nullptr) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v * pack_scale, hi, lo);
+        pk[int64_t(r) * planes * D + d] = hi;
+        if (planes == 2) pk[int64_t(r) * planes * D + D + d] = lo;
+      }
     }
   }
 }
@@ -118,6 +150,8 @@ __global__ void prep_rows_kernel(PrepArgs a, int D, int planes) {
 // positive terms selected by pos_mode, and writes the row's loss shares and dL/dq_r
 // (SURVEY.md 8a').  A tensor that is the query of two losses (title_fea: VTM and FTM) gets
 // both contributions here, so its gradient is written once.
+// The last block to finish adds the per-row loss shares in a fixed order and writes the scalars
+// (no separate reduction launch; the order does not depend on which block is last).
 constexpr int FIN_MAXD = 2048;            // D <= 32 lanes * FIN_MAXE
 constexpr int FIN_MAXE = FIN_MAXD / 32;
 
@@ -142,128 +176,7 @@ struct FinishArgs {
   int n;
 };
 
-template <int NE, int OCC>   // NE = elements per lane = D / 32 rounded up; OCC = blocks per SM to compile for
-__global__ void __launch_bounds__(256, OCC)
-infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax,
-                      float* __restrict__ row_loss /* [3][total_rows] */) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int total_rows = a.row_begin[a.n];
-  if (row >= total_rows) return;
-  int gi = 0;
-#pragma unroll
-  for (int i = 1; i < MAX_GROUPS; ++i)
-    if (i < a.n && row >= a.row_begin[i]) gi = i;
-  const RowGroup& G = a.g[gi];
-  const int r = row - a.row_begin[gi];
-  const int n = r / G.Fq, f = r - n * G.Fq;
-
-  float qv[NE], g[NE];
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NE; ++i) {
-    const int d = lane + i * 32;
-    qv[i] = (d < D) ? G.q[int64_t(r) * D + d] : 0.f;
-    g[i] = 0.f;
-    ss = fmaf(qv[i], qv[i], ss);
-  }
-  ss = warp_sum(ss);
-  const float nq_raw = sqrtf(ss);
-  const float nq = fmaxf(nq_raw, 1e-12f);
-#pragma unroll
-  for (int i = 0; i < NE; ++i) qv[i] = qv[i] / nq;   // q_hat
-
-  float loss_kind[3] = {0.f, 0.f, 0.f};
-  for (int ci = 0; ci < G.ncontrib; ++ci) {
-    const Contribution& C = G.c[ci];
-    // S_r: negatives' sum of exp(l - cmax)
-    float S = 0.f, S1 = 0.f;
-    for (int p = lane; p < C.n_parts; p += 64) {
-      const float a0 = C.rowsum_part[int64_t(p) * G.rows + r];
-      const float a1 = (p + 32 < C.n_parts) ? C.rowsum_part[int64_t(p + 32) * G.rows + r] : 0.f;
-      S += a0;
-      S1 += a1;
-    }
-    S = warp_sum(S + S1);
-    int nterm, kbase, kstep;
-    if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
-    else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
-    else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kbase = n * C.Fk; kstep = 1; }
-    else { nterm = 1; kbase = n; kstep = 0; }
-    float loss = 0.f, sum_invZ = 0.f;
-    const float scale = C.coef * invT;
-    for (int t = 0; t < nterm; ++t) {
-      int kr = kbase + t * kstep;
-      if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
-        const int fk = (t == 0) ? f + 1 : f - 1;      // pairs (i, i+1) and (i+1, i) of frame_self_loss
-        if (fk < 0 || fk >= C.Fk) continue;           // warp-uniform
-        kr = n * C.Fk + fk;
-      }
-      float kv[NE];
-      float kk = 0.f, qk = 0.f;
-#pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        const int d = lane + i * 32;
-        kv[i] = (d < D) ? __ldg(C.keys + int64_t(kr) * D + d) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < NE; ++i) {
-        kk = fmaf(kv[i], kv[i], kk);
-        qk = fmaf(kv[i], qv[i], qk);
-      }
-      kk = warp_sum(kk);
-      qk = warp_sum(qk);
-      const float nk = fmaxf(sqrtf(kk), 1e-12f);
-      const float lpos = (qk / nk) * invT;
-      const float epos = expf(lpos - cmax);
-      const float Z = epos + S;
-      loss += logf(Z) + cmax - lpos;
-      sum_invZ += 1.0f / Z;
-      // g_hat += coef/T * (p+ - 1) k_hat_t
-      const float w = scale * (epos / Z - 1.0f) / nk;
-#pragma unroll
-      for (int i = 0; i < NE; ++i) g[i] = fmaf(w, kv[i], g[i]);
-    }
-    loss_kind[C.kind] += C.coef * loss;
-    if (G.dq != nullptr) {
-      // g_hat += coef/T * (sum_t 1/Z_t) U_r ;  U_r = sum over the split-K partials (loads batched per split)
-      const float wu = scale * sum_invZ;
-      // two splits per iteration: 2*NE independent loads in flight per lane
-      for (int sidx = 0; sidx < C.n_splits; sidx += 2) {
-        const float* up0 = C.U_part + int64_t(sidx) * C.split_stride + int64_t(r) * D;
-        const bool two = sidx + 1 < C.n_splits;
-        const float* up1 = two ? up0 + C.split_stride : up0;
-        float u0[NE], u1[NE];
-#pragma unroll
-        for (int i = 0; i < NE; ++i) {
-          const int d = lane + i * 32;
-          u0[i] = (d < D) ? __ldg(up0 + d) : 0.f;
-          u1[i] = (d < D && two) ? __ldg(up1 + d) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < NE; ++i) g[i] = fmaf(wu, u0[i] + u1[i], g[i]);
-      }
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) row_loss[int64_t(k) * total_rows + row] = loss_kind[k];
-  }
-  if (G.dq == nullptr) return;
-  // dq = (g_hat - q_hat (q_hat . g_hat)) / ||q||
-  float qg = 0.f;
-#pragma unroll
-  for (int i = 0; i < NE; ++i) qg = fmaf(qv[i], g[i], qg);
-  qg = warp_sum(qg);
-  const bool clamped = nq_raw < 1e-12f;   // F.normalize clamps: q_hat = q/eps is then linear in q
-#pragma unroll
-  for (int i = 0; i < NE; ++i) {
-    const int d = lane + i * 32;
-    if (d < D) G.dq[int64_t(r) * D + d] = clamped ? g[i] / nq : (g[i] - qv[i] * qg) / nq;
-  }
-}
-
-// Per-kind sums in a fixed order (deterministic) and the final scalars, one launch:
+// Per-kind sums in a fixed order (deterministic) and the final scalars:
 //   mode 0: out[0] += fam + vtm + ftm                     (hmmc_infonce_queue_fwd_bwd)
 //   mode 1: out[0..3] = total, FAM, VTM, FTM; the slots arrive weighted (w * loss) and are
 //           reported unweighted as well               (hmmc_pretrain_head_fwd_bwd)
@@ -273,11 +186,22 @@ struct LossFinal {
   float w_fam, w_vtm, w_ftm;
   int use_frame_fea;
 };
-__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total_rows, LossFinal f) {
+
+// Called by every thread of a block at the end of the finish kernel.  The block that arrives last sums
+// row_loss[3][total_rows] (each thread a fixed strided subset, then a fixed tree) and writes the result.
+__device__ __forceinline__ void finish_losses(const float* __restrict__ row_loss, int total_rows, const LossFinal& f,
+                                              unsigned* counter) {
   __shared__ float red[32];
   __shared__ float kinds[3];
+  __shared__ bool last;
+  __threadfence();                          // this block's row_loss stores before its arrival
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   for (int k = 0; k < 3; ++k) {
-    const float* v = row_loss + int64_t(k) * total_rows;
+    const volatile float* v = row_loss + int64_t(k) * total_rows;
     float acc = 0.f;
     for (int i = threadIdx.x; i < total_rows; i += 4 * blockDim.x) {
       const int i1 = i + blockDim.x, i2 = i + 2 * blockDim.x, i3 = i + 3 * blockDim.x;
@@ -292,6 +216,7 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total
     __syncthreads();
   }
   if (threadIdx.x != 0) return;
+  *counter = 0u;                            // ready for the next call on this workspace
   if (f.mode == 0) {
     f.out[0] += kinds[0] + kinds[1] + kinds[2];
   } else {
@@ -301,6 +226,302 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int total
     f.out[2] = (f.w_vtm != 0.f) ? vtm / f.w_vtm : 0.f;
     f.out[3] = (f.w_ftm != 0.f) ? ftm / f.w_ftm : 0.f;
   }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+__device__ __forceinline__ void axpy4(float w, const float4& x, float4& y) {
+  y.x = fmaf(w, x.x, y.x); y.y = fmaf(w, x.y, y.y); y.z = fmaf(w, x.z, y.z); y.w = fmaf(w, x.w, y.w);
+}
+
+// kexp: factor that brings the negatives' sums (row sums and U) to the e^{l - cmax} scale the positives use
+// (tensor-core path: the GEMM epilogue stores 2^{l log2 e} without the constant max, kexp = e^{-cmax}; fp32 path: 1).
+// Vector version: D == 128 * V, every row is V float4 per lane; all of a row's independent loads (query, two
+// key rows, two split-K partials of U) are issued together, 16 warps per SM.
+template <int V>
+__global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1))
+infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, float cmax, float kexp,
+                          float* __restrict__ row_loss /* [3][total_rows] */, const LossFinal fin, unsigned* counter) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
+  constexpr int D = 128 * V;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int total_rows = a.row_begin[a.n];
+  if (row < total_rows) {
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_GROUPS; ++i)
+      if (i < a.n && row >= a.row_begin[i]) gi = i;
+    const RowGroup& G = a.g[gi];
+    const int r = row - a.row_begin[gi];
+    const int n = r / G.Fq, f = r - n * G.Fq;
+
+    float4 qv[V], g[V];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(G.q + int64_t(r) * D) + lane;
+#pragma unroll
+      for (int i = 0; i < V; ++i) qv[i] = __ldg(qp + 32 * i);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      ss = dot4(qv[i], qv[i], ss);
+      g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ss = warp_sum(ss);
+    const float nq_raw = sqrtf(ss);
+    const float nq = fmaxf(nq_raw, 1e-12f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { qv[i].x /= nq; qv[i].y /= nq; qv[i].z /= nq; qv[i].w /= nq; }   // q_hat
+
+    float loss_kind[3] = {0.f, 0.f, 0.f};
+    for (int ci = 0; ci < G.ncontrib; ++ci) {
+      const Contribution& C = G.c[ci];
+      // ---- issue the independent loads of this contribution: row-sum partials, U partials
+      float S = 0.f, S1 = 0.f;
+      for (int p = lane; p < C.n_parts; p += 64) {
+        const float a0 = __ldg(C.rowsum_part + int64_t(p) * G.rows + r);
+        const float a1 = (p + 32 < C.n_parts) ? __ldg(C.rowsum_part + int64_t(p + 32) * G.rows + r) : 0.f;
+        S += a0;
+        S1 += a1;
+      }
+      float4 us[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) us[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (G.dq != nullptr) {
+        // U_r = sum over the split-K partials, two partials in flight, added in split order
+        for (int s0 = 0; s0 < C.n_splits; s0 += 2) {
+          float4 t[2][V];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const bool on = s0 + k < C.n_splits;
+            const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(on ? s0 + k : s0) * C.split_stride +
+                                                               int64_t(r) * D) + lane;
+#pragma unroll
+            for (int i = 0; i < V; ++i) t[k][i] = on ? __ldg(up + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              us[i].x += t[k][i].x; us[i].y += t[k][i].y; us[i].z += t[k][i].z; us[i].w += t[k][i].w;
+            }
+        }
+      }
+      S = warp_sum(S + S1) * kexp;
+      int nterm, kbase, kstep;
+      if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
+      else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
+      else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kbase = n * C.Fk; kstep = 1; }
+      else { nterm = 1; kbase = n; kstep = 0; }
+      float loss = 0.f, sum_invZ = 0.f;
+      const float scale = C.coef * invT;
+      // positive terms, two key rows in flight per iteration
+      for (int t0 = 0; t0 < nterm; t0 += 2) {
+        int kr[2];
+        bool on[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int t = t0 + k;
+          on[k] = t < nterm;
+          kr[k] = kbase + t * kstep;
+          if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
+            const int fk = (t == 0) ? f + 1 : f - 1;      // pairs (i, i+1) and (i+1, i) of frame_self_loss
+            on[k] = on[k] && fk >= 0 && fk < C.Fk;        // warp-uniform
+            kr[k] = n * C.Fk + fk;
+          }
+        }
+        float4 kv[2][V];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float4* kp = reinterpret_cast<const float4*>(C.keys + int64_t(on[k] ? kr[k] : 0) * D) + lane;
+#pragma unroll
+          for (int i = 0; i < V; ++i) kv[k][i] = on[k] ? __ldg(kp + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (!on[k]) continue;
+          float kk = 0.f, qk = 0.f;
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            kk = dot4(kv[k][i], kv[k][i], kk);
+            qk = dot4(kv[k][i], qv[i], qk);
+          }
+          kk = warp_sum(kk);
+          qk = warp_sum(qk);
+          const float nk = fmaxf(sqrtf(kk), 1e-12f);
+          const float lpos = (qk / nk) * invT;
+          const float epos = expf(lpos - cmax);
+          const float Z = epos + S;
+          loss += logf(Z) + cmax - lpos;
+          sum_invZ += 1.0f / Z;
+          // g_hat += coef/T * (p+ - 1) k_hat_t
+          const float w = scale * (epos / Z - 1.0f) / nk;
+#pragma unroll
+          for (int i = 0; i < V; ++i) axpy4(w, kv[k][i], g[i]);
+        }
+      }
+      loss_kind[C.kind] += C.coef * loss;
+      // g_hat += coef/T * (sum_t 1/Z_t) U_r
+      const float wu = scale * sum_invZ * kexp;
+#pragma unroll
+      for (int i = 0; i < V; ++i) axpy4(wu, us[i], g[i]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) row_loss[int64_t(k) * total_rows + row] = loss_kind[k];
+    }
+    if (G.dq != nullptr) {
+      // dq = (g_hat - q_hat (q_hat . g_hat)) / ||q||
+      float qg = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) qg = dot4(qv[i], g[i], qg);
+      qg = warp_sum(qg);
+      const bool clamped = nq_raw < 1e-12f;   // F.normalize clamps: q_hat = q/eps is then linear in q
+      float4* op = reinterpret_cast<float4*>(G.dq + int64_t(r) * D) + lane;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float4 o;
+        if (clamped) {
+          o = make_float4(g[i].x / nq, g[i].y / nq, g[i].z / nq, g[i].w / nq);
+        } else {
+          o = make_float4((g[i].x - qv[i].x * qg) / nq, (g[i].y - qv[i].y * qg) / nq, (g[i].z - qv[i].z * qg) / nq,
+                          (g[i].w - qv[i].w * qg) / nq);
+        }
+        op[32 * i] = o;
+      }
+    }
+  }
+  finish_losses(row_loss, total_rows, fin, counter);
+}
+
+// Generic version (any D <= FIN_MAXD, scalar accesses).
+template <int NE>   // NE = elements per lane = D / 32 rounded up
+__global__ void __launch_bounds__(256, (NE <= 16 ? 2 : 1))
+infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax, float kexp,
+                      float* __restrict__ row_loss /* [3][total_rows] */, const LossFinal fin, unsigned* counter) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int total_rows = a.row_begin[a.n];
+  if (row < total_rows) {
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_GROUPS; ++i)
+      if (i < a.n && row >= a.row_begin[i]) gi = i;
+    const RowGroup& G = a.g[gi];
+    const int r = row - a.row_begin[gi];
+    const int n = r / G.Fq, f = r - n * G.Fq;
+
+    float qv[NE], g[NE];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int d = lane + i * 32;
+      qv[i] = (d < D) ? G.q[int64_t(r) * D + d] : 0.f;
+      g[i] = 0.f;
+      ss = fmaf(qv[i], qv[i], ss);
+    }
+    ss = warp_sum(ss);
+    const float nq_raw = sqrtf(ss);
+    const float nq = fmaxf(nq_raw, 1e-12f);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) qv[i] = qv[i] / nq;   // q_hat
+
+    float loss_kind[3] = {0.f, 0.f, 0.f};
+    for (int ci = 0; ci < G.ncontrib; ++ci) {
+      const Contribution& C = G.c[ci];
+      // S_r: negatives' sum of exp(l - cmax)
+      float S = 0.f, S1 = 0.f;
+      for (int p = lane; p < C.n_parts; p += 64) {
+        const float a0 = C.rowsum_part[int64_t(p) * G.rows + r];
+        const float a1 = (p + 32 < C.n_parts) ? C.rowsum_part[int64_t(p + 32) * G.rows + r] : 0.f;
+        S += a0;
+        S1 += a1;
+      }
+      S = warp_sum(S + S1) * kexp;
+      int nterm, kbase, kstep;
+      if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
+      else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
+      else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kbase = n * C.Fk; kstep = 1; }
+      else { nterm = 1; kbase = n; kstep = 0; }
+      float loss = 0.f, sum_invZ = 0.f;
+      const float scale = C.coef * invT;
+      for (int t = 0; t < nterm; ++t) {
+        int kr = kbase + t * kstep;
+        if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
+          const int fk = (t == 0) ? f + 1 : f - 1;      // pairs (i, i+1) and (i+1, i) of frame_self_loss
+          if (fk < 0 || fk >= C.Fk) continue;           // warp-uniform
+          kr = n * C.Fk + fk;
+        }
+        float kv[NE];
+        float kk = 0.f, qk = 0.f;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const int d = lane + i * 32;
+          kv[i] = (d < D) ? __ldg(C.keys + int64_t(kr) * D + d) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          kk = fmaf(kv[i], kv[i], kk);
+          qk = fmaf(kv[i], qv[i], qk);
+        }
+        kk = warp_sum(kk);
+        qk = warp_sum(qk);
+        const float nk = fmaxf(sqrtf(kk), 1e-12f);
+        const float lpos = (qk / nk) * invT;
+        const float epos = expf(lpos - cmax);
+        const float Z = epos + S;
+        loss += logf(Z) + cmax - lpos;
+        sum_invZ += 1.0f / Z;
+        // g_hat += coef/T * (p+ - 1) k_hat_t
+        const float w = scale * (epos / Z - 1.0f) / nk;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) g[i] = fmaf(w, kv[i], g[i]);
+      }
+      loss_kind[C.kind] += C.coef * loss;
+      if (G.dq != nullptr) {
+        // g_hat += coef/T * (sum_t 1/Z_t) U_r ;  U_r = sum over the split-K partials, in split order
+        const float wu = scale * sum_invZ * kexp;
+        float us[NE];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) us[i] = 0.f;
+        for (int sidx = 0; sidx < C.n_splits; ++sidx) {
+          const float* up = C.U_part + int64_t(sidx) * C.split_stride + int64_t(r) * D;
+#pragma unroll
+          for (int i = 0; i < NE; ++i) {
+            const int d = lane + i * 32;
+            us[i] += (d < D) ? __ldg(up + d) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NE; ++i) g[i] = fmaf(wu, us[i], g[i]);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) row_loss[int64_t(k) * total_rows + row] = loss_kind[k];
+    }
+    if (G.dq != nullptr) {
+      // dq = (g_hat - q_hat (q_hat . g_hat)) / ||q||
+      float qg = 0.f;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) qg = fmaf(qv[i], g[i], qg);
+      qg = warp_sum(qg);
+      const bool clamped = nq_raw < 1e-12f;   // F.normalize clamps: q_hat = q/eps is then linear in q
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int d = lane + i * 32;
+        if (d < D) G.dq[int64_t(r) * D + d] = clamped ? g[i] / nq : (g[i] - qv[i] * qg) / nq;
+      }
+    }
+  }
+  finish_losses(row_loss, total_rows, fin, counter);
 }
 
 // ------------------------------------------------------------------ EMA
@@ -666,9 +887,9 @@ int hmmc_queue_pack(const hmmc_queue* q, void* stream) {
 namespace hmmc {
 // ---------------------------------------------------------------------------------------
 // Generic fused InfoNCE driver: several query tensors ("groups"), each contracted against one
-// or two queues ("blocks" = GEMM problems), in a fixed number of launches:
-//   prep_rows (1) -> S-GEMM + exp/rowsum/E epilogue (1, grouped) -> U-GEMM (1, grouped, split-K)
-//   -> finish (1) -> loss reduce (1)
+// or two queues ("blocks" = GEMM problems), in four launches:
+//   prep_rows (normalise + pack) -> S-GEMM with the exp / row-sum / E epilogue (grouped)
+//   -> U-GEMM (grouped, split-K, units placed longest-first) -> finish (positives, loss, gradients, loss sums)
 struct BlockDesc {
   int group;                 // which query tensor
   const float* keys;
@@ -685,6 +906,7 @@ struct GroupDesc {
 
 struct InfoNCELayout {       // workspace carving shared by the size query and the run
   float* row_loss;
+  unsigned* counter;
   float* xhat[MAX_GROUPS];
   __nv_bfloat16* packed[MAX_GROUPS];
   float* rowsum_part[MAX_BLOCKS];
@@ -694,12 +916,70 @@ struct InfoNCELayout {       // workspace carving shared by the size query and t
   int bn1, bn2;
 };
 
+// Split-K of the U-GEMMs (U = E.Q^T: a small output, a long contraction).  The launch is a single wave of
+// units (output tile x K slice) placed longest-first on the CTA pairs; the slice length is chosen so that the
+// wave ends everywhere at about the same time, with a charge for every extra partial tile the finish kernel
+// has to read back.  Costs are in k-block steps of one CTA pair (64 contraction elements of a 256 x 256 tile).
+struct SplitChoice { int splits[MAX_BLOCKS]; };
+
+static SplitChoice choose_u_splits(const int* rows, const int* Kq, int nb, int D, int planes, int bn2) {
+  typedef std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int> Key;
+  static std::mutex mu;
+  static std::map<Key, SplitChoice> cache;
+  int kr[MAX_BLOCKS] = {0}, kk[MAX_BLOCKS] = {0};
+  for (int k = 0; k < nb; ++k) { kr[k] = rows[k]; kk[k] = Kq[k]; }
+  const int workers = (bn2 == 256) ? sm_count() / 2 : sm_count();
+  const Key key(nb, D, planes, bn2, kr[0], kr[1], kr[2], kr[3], kr[4], kr[5], kk[0], kk[1], kk[2], kk[3], kk[4], kk[5]);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  const int nseg = (planes == 2) ? 3 : 1;
+  const int m_tile = (bn2 == 256) ? 2 * UMMA_BM : UMMA_BM;
+  int tiles[MAX_BLOCKS], total_kb[MAX_BLOCKS], max_kb = 1;
+  for (int k = 0; k < nb; ++k) {
+    tiles[k] = ((rows[k] + m_tile - 1) / m_tile) * ((D + bn2 - 1) / bn2);
+    total_kb[k] = nseg * (Kq[k] / UMMA_BK);
+    max_kb = std::max(max_kb, total_kb[k]);
+  }
+  SplitChoice best;
+  double best_cost = 1e30;
+  for (int unit = 4; unit <= max_kb; unit += (unit < 48 ? 1 : 4)) {
+    SplitChoice c;
+    std::vector<int> cost;
+    int units = 0;
+    for (int k = 0; k < nb; ++k) {
+      int sp = std::min(32, std::max(1, (total_kb[k] + unit - 1) / unit));
+      const int per = (total_kb[k] + sp - 1) / sp;
+      sp = (total_kb[k] + per - 1) / per;
+      c.splits[k] = sp;
+      for (int s = 0; s < sp; ++s) {
+        const int len = std::min(per, total_kb[k] - s * per);
+        for (int t = 0; t < tiles[k]; ++t) cost.push_back(len + UMMA_UNIT_FIXED_COST);
+      }
+      units += sp * tiles[k];
+    }
+    if (units > UMMA_MAX_UNITS) continue;
+    // every partial tile is written once and read once more by the finish kernel: ~0.25 steps of chip time each
+    const double total = double(lpt_makespan(cost, workers)) + 0.25 * units;
+    if (total < best_cost) { best_cost = total; best = c; }
+  }
+  if (best_cost > 1e29)
+    for (int k = 0; k < nb; ++k) best.splits[k] = 1;
+  for (int k = nb; k < MAX_BLOCKS; ++k) best.splits[k] = 1;
+  std::lock_guard<std::mutex> lk(mu);
+  cache[key] = best;
+  return best;
+}
+
 static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* groups, int ng, const int* blk_group,
                            const int* blk_Kq, int nb, int D, int prec, bool need_grad) {
   const int planes = planes_of(prec);
   int total_rows = 0;
   for (int i = 0; i < ng; ++i) total_rows += groups[i].rows;
   L.row_loss = ws.take<float>(size_t(3) * total_rows);
+  L.counter = ws.take<unsigned>(4);
   for (int i = 0; i < ng; ++i) {
     L.xhat[i] = (prec == HMMC_PREC_FP32) ? ws.take<float>(size_t(groups[i].rows) * D) : nullptr;
     L.packed[i] = (prec != HMMC_PREC_FP32) ? ws.take<__nv_bfloat16>(size_t(groups[i].rows) * planes * D) : nullptr;
@@ -708,18 +988,13 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   for (int k = 0; k < nb; ++k)
     if (blk_Kq[k] % 256 != 0) L.bn1 = 128;
   L.bn2 = (D % 256 == 0) ? 256 : 128;
-  static const int force_bn2 = tune_int("HMMC_U_BN", 0);
-  if (force_bn2 == 128) L.bn2 = 128;
-  // split-K of the U-GEMMs: aim at ~1 wave of equally sized units over the whole group
-  const int nseg = (planes == 2) ? 3 : 1;
-  double work = 0;
-  for (int k = 0; k < nb; ++k) {
-    const int R = groups[blk_group[k]].rows;
-    work += double((R + UMMA_BM - 1) / UMMA_BM) * ((D + L.bn2 - 1) / L.bn2) * nseg * (blk_Kq[k] / UMMA_BK);
+  SplitChoice sc;
+  for (int k = 0; k < MAX_BLOCKS; ++k) sc.splits[k] = 1;
+  if (prec != HMMC_PREC_FP32 && need_grad) {
+    int rows[MAX_BLOCKS];
+    for (int k = 0; k < nb; ++k) rows[k] = groups[blk_group[k]].rows;
+    sc = choose_u_splits(rows, blk_Kq, nb, D, planes, L.bn2);
   }
-  static const int waves10 = tune_int("HMMC_U_WAVES10", 10);      // target waves x 10 (step: 0.3985 ms at 20, 0.3939 at 10)
-  int unit_kb = int(work / (0.1 * waves10 * sm_count())) + 1;
-  if (unit_kb < 8) unit_kb = 8;
   for (int k = 0; k < nb; ++k) {
     const int R = groups[blk_group[k]].rows;
     const int Kq = blk_Kq[k];
@@ -730,11 +1005,8 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
       L.E[k] = ws.take<float>(size_t(R) * Kq);
     } else {
       L.nparts[k] = 2 * ((Kq + L.bn1 - 1) / L.bn1);     // two epilogue halves per tile
-      const int total_kb = nseg * (Kq / UMMA_BK);
-      int sp = (total_kb + unit_kb - 1) / unit_kb;
-      if (sp > 32) sp = 32;
-      L.splits[k] = sp;
-      L.nsplits_eff[k] = effective_splits(Kq, planes, sp);
+      L.splits[k] = sc.splits[k];
+      L.nsplits_eff[k] = effective_splits(Kq, planes, sc.splits[k]);
       L.rowsum_part[k] = ws.take<float>(size_t(L.nparts[k]) * R);
       L.E[k] = need_grad ? ws.take<__nv_bfloat16>(size_t(R) * planes * Kq) : nullptr;
     }
@@ -742,24 +1014,16 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   }
 }
 
-template <int NE>
-static void launch_finish(const FinishArgs& fa, int total_rows, int D, float invT, float cmax, float* row_loss,
-                          cudaStream_t st) {
-  static const int occ = tune_int("HMMC_FIN_OCC", 2);
-  if (NE <= 16 && occ >= 3)
-    infonce_finish_kernel<NE, (NE <= 16 ? 3 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
-  else
-    infonce_finish_kernel<NE, (NE <= 16 ? 2 : 1)><<<(total_rows + 7) / 8, 256, 0, st>>>(fa, D, invT, cmax, row_loss);
-}
-
-// sched (may be null = everything, no event): which half of the work to issue and the event to record once the
-// queues are no longer read (hmmc_head_schedule in include/hmmc_head.h)
+// sched (may be null = everything, no event): which half of the work to issue, the SMs the GEMM grids leave free
+// and the event to record once the queues are no longer read (hmmc_head_schedule in include/hmmc_head.h)
 static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks, int nb, int b, int D, float temperature,
                        int prec, const LossFinal& fin, const hmmc_head_schedule* sched, void* workspace,
                        size_t workspace_bytes, cudaStream_t st) {
   const int phase = sched ? sched->phase : 0;
+  const int reserved_sms = sched ? sched->reserved_sms : 0;
   cudaEvent_t release = sched ? static_cast<cudaEvent_t>(sched->queues_released) : nullptr;
   HMMC_REQUIRE(phase >= 0 && phase <= 2, "infonce: schedule phase must be 0, 1 or 2 (got %d)", phase);
+  HMMC_REQUIRE(reserved_sms >= 0, "infonce: reserved_sms must be >= 0 (got %d)", reserved_sms);
   HMMC_REQUIRE(ng >= 1 && ng <= MAX_GROUPS && nb >= 1 && nb <= MAX_BLOCKS, "infonce: too many groups/blocks");
   HMMC_REQUIRE(D > 0 && D <= FIN_MAXD, "infonce: D=%d exceeds the supported %d", D, FIN_MAXD);
   HMMC_REQUIRE(prec >= 0 && prec <= 2, "infonce: unknown precision %d", prec);
@@ -789,7 +1053,12 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
     set_error("infonce: workspace too small: need %zu bytes, got %zu", ws.used, workspace_bytes);
     return HMMC_ERR_WORKSPACE;
   }
+  const float LOG2E = 1.4426950408889634f;
   const float invT = 1.0f / temperature, cmax = invT;
+  // tensor-core path: the packed queries carry log2(e)/T and the epilogue stores 2^acc; the constant max comes
+  // back as one factor in the finish kernel
+  const float pack_scale = (prec == HMMC_PREC_FP32) ? 1.0f : invT * LOG2E;
+  const float kexp = (prec == HMMC_PREC_FP32) ? 1.0f : expf(-cmax);
   // 1. normalise (+ pack) every query tensor
   PrepArgs pa;
   pa.n = ng;
@@ -802,61 +1071,63 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
     pa.row_begin[i + 1] = pa.row_begin[i] + (i < ng ? groups[i].rows : 0);
   }
   const int total_rows = pa.row_begin[ng];
+  bool vec_q = (D % 128 == 0) && D <= 1024;
+  for (int i = 0; i < ng && vec_q; ++i)
+    vec_q = (reinterpret_cast<uintptr_t>(groups[i].q) % 16 == 0) &&
+            (groups[i].dq == nullptr || reinterpret_cast<uintptr_t>(groups[i].dq) % 16 == 0);
   int rc;
   if (phase != 2) {
-  prep_rows_kernel<<<(total_rows + 7) / 8, 256, 0, st>>>(pa, D, planes);
-  HMMC_CHECK_LAUNCH();
-  if (prec == HMMC_PREC_FP32) {
-    for (int k = 0; k < nb; ++k) {
-      const GroupDesc& G = groups[blocks[k].group];
-      const int Kq = blk_Kq[k];
-      float* S = static_cast<float*>(L.E[k]);
-      if ((rc = gemm_f32(L.xhat[blocks[k].group], D, 1, blocks[k].queue->dk, 1, Kq, S, Kq, G.rows, Kq, D, 1.0f, st))) return rc;
-      exp_rowsum_kernel<<<G.rows, 256, 0, st>>>(S, Kq, Kq, invT, cmax, L.rowsum_part[k]);
-      HMMC_CHECK_LAUNCH();
-      if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
-    }
-  } else {
-    const float LOG2E = 1.4426950408889634f;
-    GemmProblem<EpiInfoNCE> p1[MAX_BLOCKS];
-    GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
-    for (int k = 0; k < nb; ++k) {
-      const GroupDesc& G = groups[blocks[k].group];
-      const int Kq = blk_Kq[k];
-      EpiInfoNCE::Params e1;
-      e1.a2 = invT * LOG2E;
-      e1.c2 = cmax * LOG2E;
-      e1.rowsum_part = L.rowsum_part[k];
-      e1.E = static_cast<__nv_bfloat16*>(L.E[k]);
-      e1.ldE = int64_t(planes) * Kq;
-      e1.e_planes = planes;
-#ifdef HMMC_ENABLE_PROBES
-      static const int probe = tune_int("HMMC_PROBE_NOEXP", 0);     // skips the exponentials: changes results
-      e1.probe = probe;
-#else
-      e1.probe = 0;
-#endif
-      p1[k] = GemmProblem<EpiInfoNCE>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
-                                      int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1};
-      EpiStoreF32::Params e2{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
-      p2[k] = GemmProblem<EpiStoreF32>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
-                                       G.rows, D, Kq, planes, L.splits[k], e2};
-    }
-    static const int pair1 = tune_int("HMMC_PAIR_S", 1), pair2 = tune_int("HMMC_PAIR_U", 1);   // CTA-pair kernels
-    if (L.bn1 == 256 && pair1) rc = launch_umma_grouped_pair<EpiInfoNCE>(p1, nb, st);
-    else rc = (L.bn1 == 256) ? launch_umma_grouped<256, EpiInfoNCE>(p1, nb, st) : launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st);
-    if (rc) return rc;
-    if (need_grad) {
-      if (L.bn2 == 256 && pair2) rc = launch_umma_grouped_pair<EpiStoreF32>(p2, nb, st);
-      else rc = (L.bn2 == 256) ? launch_umma_grouped<256, EpiStoreF32>(p2, nb, st) : launch_umma_grouped<128, EpiStoreF32>(p2, nb, st);
+    const dim3 pgrid((total_rows + 7) / 8), pblock(256);
+    cudaError_t e;
+    if (vec_q && D == 512) e = launch_pdl(prep_rows_kernel<4>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
+    else if (vec_q && D == 256) e = launch_pdl(prep_rows_kernel<2>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
+    else if (vec_q && D == 128) e = launch_pdl(prep_rows_kernel<1>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
+    else if (vec_q && D == 1024) e = launch_pdl(prep_rows_kernel<8>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
+    else e = launch_pdl(prep_rows_kernel<0>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
+    count_launch();
+    HMMC_CHECK_CUDA(e);
+    if (prec == HMMC_PREC_FP32) {
+      for (int k = 0; k < nb; ++k) {
+        const GroupDesc& G = groups[blocks[k].group];
+        const int Kq = blk_Kq[k];
+        float* S = static_cast<float*>(L.E[k]);
+        if ((rc = gemm_f32(L.xhat[blocks[k].group], D, 1, blocks[k].queue->dk, 1, Kq, S, Kq, G.rows, Kq, D, 1.0f, st))) return rc;
+        exp_rowsum_kernel<<<G.rows, 256, 0, st>>>(S, Kq, Kq, invT, cmax, L.rowsum_part[k]);
+        HMMC_CHECK_LAUNCH();
+        if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
+      }
+    } else {
+      GemmProblem<EpiInfoNCE> p1[MAX_BLOCKS];
+      GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
+      for (int k = 0; k < nb; ++k) {
+        const GroupDesc& G = groups[blocks[k].group];
+        const int Kq = blk_Kq[k];
+        EpiInfoNCE::Params e1;
+        e1.rowsum_part = L.rowsum_part[k];
+        e1.e_planes = need_grad ? planes : 0;
+        e1.lo_col0 = Kq;
+        p1[k] = GemmProblem<EpiInfoNCE>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
+                                        int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1,
+                                        L.E[k], int64_t(planes) * Kq, int64_t(planes) * Kq};
+        EpiStoreF32::Params e2{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
+        p2[k] = GemmProblem<EpiStoreF32>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
+                                         G.rows, D, Kq, planes, L.splits[k], e2};
+      }
+      // CTA-pair kernels (256 x 256 tiles) whenever the tile width divides the problem
+      if (L.bn1 == 256) rc = launch_umma_grouped_pair<EpiInfoNCE>(p1, nb, st, reserved_sms);
+      else rc = launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st, reserved_sms);
       if (rc) return rc;
+      if (need_grad) {
+        if (L.bn2 == 256) rc = launch_umma_grouped_pair<EpiStoreF32>(p2, nb, st, reserved_sms);
+        else rc = launch_umma_grouped<128, EpiStoreF32>(p2, nb, st, reserved_sms);
+        if (rc) return rc;
+      }
     }
+    // every kernel that reads the queues has been issued: let the enqueue start on another stream
   }
-  // every kernel that reads the queues has been issued: let the enqueue start on another stream
-  }   // phase != 2
   if (release != nullptr) HMMC_CHECK_CUDA(cudaEventRecord(release, st));
   if (phase == 1) return HMMC_OK;
-  // 4. positives, loss, gradient
+  // 4. positives, loss, gradient, loss sums
   FinishArgs fa;
   fa.n = ng;
   fa.row_begin[0] = 0;
@@ -884,17 +1155,23 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
     C.n_splits = L.nsplits_eff[k];
     C.coef = blocks[k].coef;
     C.kind = blocks[k].kind;
+    vec_q = vec_q && (reinterpret_cast<uintptr_t>(C.keys) % 16 == 0);
   }
   for (int i = 0; i < MAX_GROUPS; ++i)
     if (fa.g[i].ncontrib < 2) fa.g[i].c[1] = fa.g[i].c[0];
+  const dim3 fgrid((total_rows + 7) / 8), fblock(256);
   const int ne = (D + 31) / 32;
-  if (ne <= 4) launch_finish<4>(fa, total_rows, D, invT, cmax, L.row_loss, st);
-  else if (ne <= 16) launch_finish<16>(fa, total_rows, D, invT, cmax, L.row_loss, st);
-  else if (ne <= 32) launch_finish<32>(fa, total_rows, D, invT, cmax, L.row_loss, st);
-  else launch_finish<FIN_MAXE>(fa, total_rows, D, invT, cmax, L.row_loss, st);
-  HMMC_CHECK_LAUNCH();
-  loss_reduce_kernel<<<1, 1024, 0, st>>>(L.row_loss, total_rows, fin);
-  HMMC_CHECK_LAUNCH();
+  cudaError_t e;
+  if (vec_q && D == 512) e = launch_pdl(infonce_finish_vec_kernel<4>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else if (vec_q && D == 256) e = launch_pdl(infonce_finish_vec_kernel<2>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else if (vec_q && D == 128) e = launch_pdl(infonce_finish_vec_kernel<1>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else if (vec_q && D == 1024) e = launch_pdl(infonce_finish_vec_kernel<8>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else if (ne <= 4) e = launch_pdl(infonce_finish_kernel<4>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else if (ne <= 16) e = launch_pdl(infonce_finish_kernel<16>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else if (ne <= 32) e = launch_pdl(infonce_finish_kernel<32>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  else e = launch_pdl(infonce_finish_kernel<FIN_MAXE>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  count_launch();
+  HMMC_CHECK_CUDA(e);
   return HMMC_OK;
 }
 
@@ -1049,8 +1326,7 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   const int dchunk = scratch != nullptr ? 64 : ENQ_DCHUNK;
   const int dchunks = (D + dchunk - 1) / dchunk;
   const int p_arg = device_ptr ? -1 : int(ptr_host), np_arg = device_ptr ? 0 : int((ptr_host + B) % K);
-  static const int vec_env = tune_int("HMMC_ENQ_VEC", 1);     // 0: force the scalar kernel (tools/enqueue_bench.py)
-  bool vec_ok = vec_env != 0 && scratch != nullptr && (D % 2) == 0;
+  bool vec_ok = scratch != nullptr && (D % 2) == 0;
   for (int i = 0; i < 5 && vec_ok; ++i) {
     vec_ok = (reinterpret_cast<uintptr_t>(a.src[i]) % 8 == 0) && (a.src_stride[i] % 2 == 0) && (a.Kq[i] % 2 == 0) &&
              (reinterpret_cast<uintptr_t>(a.dk[i]) % 8 == 0) && (reinterpret_cast<uintptr_t>(a.pack_kd[i]) % 4 == 0) &&

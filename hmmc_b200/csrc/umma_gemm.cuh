@@ -12,12 +12,22 @@
 // operands), which is how the BF16X3 mode (hi*hi + hi*lo + lo*hi) is expressed without
 // duplicating data, and over a [k-block) sub-range per tile for split-K.
 //
+// Work distribution: a grouped launch is a list of units (output tile x split-K slice) of different
+// lengths.  The host assigns them to the CTAs (or CTA pairs) longest-first onto the least-loaded one and
+// passes the schedule in kernel-parameter space, so a launch that is a single wave of long split-K units
+// (U = E.Q^T) finishes everywhere at the same time instead of waiting for the CTAs that drew two long units.
+//
 // The epilogue is a functor (Epi) that sees 32 consecutive accumulator columns of one row
 // at a time; see the Epi* structs below.
+//
+// Every kernel here is launched with programmatic stream serialisation: barrier set-up, TMEM allocation and
+// tensor-map prefetch run while the previous kernel of the stream drains; griddepcontrol.wait precedes the
+// first access to global memory.
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
-#include <stdlib.h>
+#include <algorithm>
+#include <vector>
 
 namespace hmmc {
 
@@ -35,7 +45,7 @@ constexpr int UMMA_BK = 64;
 constexpr int UMMA_EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, half the columns each
 constexpr int UMMA_THREADS = (4 + UMMA_EPI_WARPS) * 32;
 
-template <int BN>
+template <int BN, class Epi>
 struct UmmaCfg {
   static constexpr int STAGES = (BN > 128) ? 4 : 6;
   static constexpr uint32_t A_BYTES = UMMA_BM * UMMA_BK * 2;
@@ -43,30 +53,49 @@ struct UmmaCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;
-  static constexpr uint32_t EPI_STAGE_BYTES = 32 * 80;    // per epilogue warp: 32 rows x (64 + 16 pad) bytes
-  static constexpr size_t SMEM_BYTES =
-      size_t(STAGES) * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + UMMA_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;               // 256 B of mbarriers + the TMEM slot
+  static constexpr uint32_t EPI_OFF = BAR_OFF + 1024;                     // epilogue staging, 1024-byte aligned
+  static constexpr size_t SMEM_BYTES = size_t(EPI_OFF) + 1024 /*align slack*/ + UMMA_EPI_WARPS * Epi::STAGE_BYTES;
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
 };
 
 constexpr int UMMA_MAX_PROBLEMS = 6;
+constexpr int UMMA_MAX_UNITS = 2048;      // units a launch can place explicitly; larger launches go round-robin
+constexpr int UMMA_MAX_WORKERS = 160;     // CTAs (single-CTA kernel) or CTA pairs of a launch
 
 // Tensor maps of a grouped launch (kept in kernel-parameter space: TMA reads them from there).
+// c = the epilogue's output map (TMA store), for epilogues that use one.
 struct TmapSet {
   CUtensorMap a[UMMA_MAX_PROBLEMS];
   CUtensorMap b[UMMA_MAX_PROBLEMS];
+  CUtensorMap c[UMMA_MAX_PROBLEMS];
+};
+
+// Which units worker w (a CTA or a CTA pair) processes, in order.
+struct UnitSchedule {
+  int explicit_order;                           // 0: worker w takes units w, w + workers, ...
+  int num_units;
+  uint16_t begin[UMMA_MAX_WORKERS + 1];
+  uint16_t order[UMMA_MAX_UNITS];
+  __device__ __forceinline__ int count(int w, int workers) const {
+    return explicit_order ? int(begin[w + 1]) - int(begin[w]) : (num_units - w + workers - 1) / workers;
+  }
+  __device__ __forceinline__ int unit(int w, int workers, int i) const {
+    return explicit_order ? int(order[int(begin[w]) + i]) : w + i * workers;
+  }
 };
 
 // A grouped launch = up to UMMA_MAX_PROBLEMS independent GEMMs sharing one persistent grid.
-// Tiles are numbered problem after problem; CTA c works on tiles c, c+grid, c+2*grid, ...
+// Units are numbered problem after problem: unit = tile_begin[p] + split * (m tiles * n tiles) + n_blk * m tiles + m_blk.
 template <class Epi>
 struct GroupedArgs {
   int num_problems;
-  int probe;                 // tuning aid: 2 = epilogue skips the TMEM reads
   int tile_begin[UMMA_MAX_PROBLEMS + 1];
   GemmShape shape[UMMA_MAX_PROBLEMS];
   typename Epi::Params ep[UMMA_MAX_PROBLEMS];
+  UnitSchedule sched;
 };
 
 template <class Epi>
@@ -81,11 +110,11 @@ __device__ __forceinline__ int find_problem(const GroupedArgs<Epi>& g, int t) {
 template <int BN, class Epi>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ GroupedArgs<Epi> g) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, Epi>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t bar_base = ptx::smem_u32(bars);
   auto full_bar = [&](int i) { return bar_base + 8u * i; };
@@ -101,6 +130,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
     for (int p = 0; p < g.num_problems; ++p) {
       ptx::prefetch_tmap(&tm.a[p]);
       ptx::prefetch_tmap(&tm.b[p]);
+      if (Epi::USES_CMAP) ptx::prefetch_tmap(&tm.c[p]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -123,14 +153,20 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the previous kernel's tail; its results are needed from here on
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
 
-  const int num_tiles = g.tile_begin[g.num_problems];
+  const int workers = gridDim.x;
+  const int w = blockIdx.x;
+  const int my_units = g.sched.count(w, workers);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int u = 0; u < my_units; ++u) {
+        const int t = g.sched.unit(w, workers, u);
         const int p = find_problem(g, t);
         const GemmShape& s = g.shape[p];
         const int tl = t - g.tile_begin[p];
@@ -160,7 +196,8 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int u = 0; u < my_units; ++u) {
+        const int t = g.sched.unit(w, workers, u);
         const int p = find_problem(g, t);
         const GemmShape& s = g.shape[p];
         const int split = (t - g.tile_begin[p]) / (s.num_m_blk * s.num_n_blk);
@@ -195,11 +232,12 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi;
-    // per-warp staging buffer: accumulator rows go through shared memory so that global stores
-    // are whole 64-byte row segments instead of 16 bytes per thread on 32 different lines
-    epi.stage = smem + size_t(STAGES) * Cfg::STAGE_BYTES + 256 + size_t(warp - 4) * Cfg::EPI_STAGE_BYTES;
+    // per-warp staging buffer in shared memory (how it is used is the epilogue's business)
+    epi.stage = smem + Cfg::EPI_OFF + size_t(warp - 4) * Epi::STAGE_BYTES;
     epi.lane = lane;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    epi.init();
+    for (int u = 0; u < my_units; ++u) {
+      const int t = g.sched.unit(w, workers, u);
       const int p = find_problem(g, t);
       const GemmShape& s = g.shape[p];
       const typename Epi::Params& ep = g.ep[p];
@@ -212,7 +250,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * HALF_N;
-      epi.begin_tile(ep, s, row, n_blk, split);
+      epi.begin_tile(ep, s, row, n_blk, split, &tm.c[p]);
       {
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
@@ -230,6 +268,7 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
       epi.end_tile(ep, s, row, n_blk * 2 + half, split);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    epi.finish();
   }
 
   ptx::tc_fence_before();
@@ -251,17 +290,22 @@ constexpr int UMMA_PAIR_STAGES = 6;
 constexpr uint32_t UMMA_PAIR_A_BYTES = UMMA_BM * UMMA_BK * 2;               // 16 KB
 constexpr uint32_t UMMA_PAIR_B_BYTES = (UMMA_PAIR_BN / 2) * UMMA_BK * 2;    // 16 KB
 constexpr uint32_t UMMA_PAIR_STAGE_BYTES = UMMA_PAIR_A_BYTES + UMMA_PAIR_B_BYTES;
-constexpr size_t UMMA_PAIR_SMEM_BYTES =
-    size_t(UMMA_PAIR_STAGES) * UMMA_PAIR_STAGE_BYTES + 1024 + 256 + UMMA_EPI_WARPS * 32 * 80;
+constexpr uint32_t UMMA_PAIR_BAR_OFF = UMMA_PAIR_STAGES * UMMA_PAIR_STAGE_BYTES;
+constexpr uint32_t UMMA_PAIR_EPI_OFF = UMMA_PAIR_BAR_OFF + 1024;
+template <class Epi>
+constexpr size_t umma_pair_smem_bytes() {
+  return size_t(UMMA_PAIR_EPI_OFF) + 1024 + UMMA_EPI_WARPS * Epi::STAGE_BYTES;
+}
 
 template <class Epi>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ GroupedArgs<Epi> g) {
   constexpr int BN = UMMA_PAIR_BN;
   constexpr int STAGES = UMMA_PAIR_STAGES;
+  static_assert(umma_pair_smem_bytes<Epi>() <= 232448, "shared memory budget of one CTA");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * UMMA_PAIR_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UMMA_PAIR_BAR_OFF);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t bar_base = ptx::smem_u32(bars);
   auto full_bar = [&](int i) { return bar_base + 8u * i; };
@@ -281,6 +325,7 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
     for (int p = 0; p < g.num_problems; ++p) {
       ptx::prefetch_tmap(&tm.a[p]);
       ptx::prefetch_tmap(&tm.b[p]);
+      if (Epi::USES_CMAP) ptx::prefetch_tmap(&tm.c[p]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -303,16 +348,19 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
 
-  // tile t of a problem = (m2, n_blk, split) with m2 indexing 256-row super tiles; tile_begin[] was
+  // unit t of a problem = (m2, n_blk, split) with m2 indexing 256-row super tiles; tile_begin[] was
   // built with num_m_blk = number of super tiles (see launch_umma_grouped_pair)
-  const int num_tiles = g.tile_begin[g.num_problems];
+  const int my_units = g.sched.count(pair, num_pairs);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int u = 0; u < my_units; ++u) {
+        const int t = g.sched.unit(pair, num_pairs, u);
         const int p = find_problem(g, t);
         const GemmShape& s = g.shape[p];
         const int tl = t - g.tile_begin[p];
@@ -342,7 +390,8 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int u = 0; u < my_units; ++u) {
+        const int t = g.sched.unit(pair, num_pairs, u);
         const int p = find_problem(g, t);
         const GemmShape& s = g.shape[p];
         const int split = (t - g.tile_begin[p]) / (s.num_m_blk * s.num_n_blk);
@@ -374,9 +423,11 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi;
-    epi.stage = smem + size_t(STAGES) * UMMA_PAIR_STAGE_BYTES + 256 + size_t(warp - 4) * (32 * 80);
+    epi.stage = smem + UMMA_PAIR_EPI_OFF + size_t(warp - 4) * Epi::STAGE_BYTES;
     epi.lane = lane;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
+    epi.init();
+    for (int u = 0; u < my_units; ++u) {
+      const int t = g.sched.unit(pair, num_pairs, u);
       const int p = find_problem(g, t);
       const GemmShape& s = g.shape[p];
       const typename Epi::Params& ep = g.ep[p];
@@ -389,8 +440,8 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * HALF_N;
-      epi.begin_tile(ep, s, row, n_blk, split);
-      if (g.probe != 2) {
+      epi.begin_tile(ep, s, row, n_blk, split, &tm.c[p]);
+      {
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
         ptx::tmem_ld_x32(taddr, v[0]);
@@ -407,6 +458,7 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       epi.end_tile(ep, s, row, n_blk * 2 + half, split);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    epi.finish();
   }
 
   ptx::tc_fence_before();
@@ -427,12 +479,17 @@ struct EpiStoreF32 {
     int64_t split_stride;
     float alpha;
   };
+  static constexpr uint32_t STAGE_BYTES = 32 * 80;    // per warp: 32 rows x (64 + 16 pad) bytes
+  static constexpr bool USES_CMAP = false;
   uint8_t* stage;
   int lane;
   float* tile_out;   // &C[split][row of lane 0 of this warp, 0]
   int row0;
   bool vec_ok;
-  __device__ __forceinline__ void begin_tile(const Params& p, const GemmShape& s, int row, int n_blk, int split) {
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void finish() {}
+  __device__ __forceinline__ void begin_tile(const Params& p, const GemmShape& s, int row, int n_blk, int split,
+                                             const CUtensorMap*) {
     row0 = row - lane;
     tile_out = p.C + int64_t(split) * p.split_stride + int64_t(row0) * p.ldc;
     vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.split_stride & 3) == 0);
@@ -469,68 +526,83 @@ struct EpiStoreF32 {
       __syncwarp();
     }
   }
-  __device__ __forceinline__ void chunk16(const Params& p, const GemmShape& s, int row, int col0, float (&v)[16]) {
-    if (row >= s.M) return;
-    float* o = tile_out + int64_t(lane) * p.ldc;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (col0 + j < s.N) o[col0 + j] = v[j] * p.alpha;
-  }
   __device__ __forceinline__ void end_tile(const Params&, const GemmShape&, int, int, int) {}
 };
 
-// InfoNCE negatives: e = exp2(acc*a2 - c2)  (= exp(l - c) with a2 = log2(e)/T, c2 = c*log2(e));
-// per-row partial sums -> rowsum_part[2*n_blk + half][row]; optional bf16 hi(/lo) planes of e -> E.
-// No logits are written.
+// InfoNCE negatives.  The A operand (the normalised queries) was scaled by log2(e)/T when it was packed, so
+// the accumulator is the logit in base-2 units and e = 2^acc needs one MUFU per element and nothing else; the
+// constant maximum of the log-sum-exp (all logits <= 1/T) is applied by the finish kernel as one factor
+// 2^(-c2) on the row sums and on U (2^(2/T log2 e) still fits fp32 and bf16 comfortably for T >= 0.025).
+// Per-row partial sums -> rowsum_part[2*n_blk + half][row]; bf16 hi(/lo) planes of e -> E through TMA
+// stores: each warp writes its 32 x 32 chunk into a 64B-swizzled staging tile (conflict-free 16-byte stores,
+// two tiles in flight) and one lane hands it to the copy engine, which also clips rows beyond M.
+// No logits are written.  Requires N % 32 == 0 (checked by the host).
 struct EpiInfoNCE {
   struct Params {
-    float a2, c2;
     float* rowsum_part;       // [2 * num_n_blk, M]: one partial per epilogue half-tile
-    __nv_bfloat16* E;         // [M, e_planes * N] or nullptr
-    int64_t ldE;
-    int e_planes;
-    int probe;                // tuning aid: 1 = skip the exponential (epilogue cost probe)
+    int e_planes;             // 0 = forward only (no E), 1, 2
+    int lo_col0;              // column offset of the lo plane inside the E tensor map (= N)
   };
+  static constexpr uint32_t STAGE_BYTES = 2 * 2048;   // per warp: two 32-row x 64-byte TMA store sources
+  static constexpr bool USES_CMAP = true;
   uint8_t* stage;
   int lane;
-  float acc_sum;
+  float s0, s1, s2, s3;
   int row0;
-  __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int row, int, int) {
-    acc_sum = 0.f;
-    row0 = row - lane;
+  uint32_t nbuf;
+  uint32_t sw_off[4];         // this lane's four 16-byte slots inside a staging tile (64B swizzle)
+  const CUtensorMap* cmap;
+  __device__ __forceinline__ void init() {
+    nbuf = 0;
+    const uint32_t base = ptx::smem_u32(stage) + uint32_t(lane) * 64u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sw_off[c] = base + (uint32_t(c ^ ((lane >> 1) & 3)) << 4);
   }
-  // write one bf16 plane of this warp's 32 x 32 chunk: rows staged at an 80-byte pitch, then each
-  // instruction stores eight 64-byte row segments
-  __device__ __forceinline__ void store_plane(const uint32_t (&w)[16], __nv_bfloat16* base, int64_t ldE, int col0, int M) {
-    uint4* srow = reinterpret_cast<uint4*>(stage + lane * 80);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) srow[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  __device__ __forceinline__ void finish() {
+    if (lane == 0) ptx::bulk_wait_group_read<0>();     // the copy engine still reads this CTA's shared memory
     __syncwarp();
-    const int c = lane & 3;
+  }
+  __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int row, int, int, const CUtensorMap* c) {
+    s0 = s1 = s2 = s3 = 0.f;
+    row0 = row - lane;
+    cmap = c;
+  }
+  __device__ __forceinline__ void store_plane(const uint32_t (&w)[16], int gcol) {
+    const uint32_t boff = (nbuf & 1u) * 2048u;
+    ++nbuf;
+    if (lane == 0) ptx::bulk_wait_group_read<1>();     // the store issued two chunks ago has read this tile
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = i * 8 + (lane >> 2);
-      const uint4 x = *reinterpret_cast<const uint4*>(stage + r * 80 + c * 16);
-      if (row0 + r < M) *reinterpret_cast<uint4*>(base + int64_t(row0 + r) * ldE + col0 + c * 8) = x;
+    for (int c = 0; c < 4; ++c)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw_off[c] + boff), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                   "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                   : "memory");
+    ptx::fence_proxy_async();                          // generic-proxy writes -> visible to the copy engine
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(cmap, ptx::smem_u32(stage) + boff, gcol, row0);
+      ptx::bulk_commit_group();
     }
-    __syncwarp();
   }
   __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
     float e[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      e[j] = p.probe ? fmaf(v[j], p.a2, -p.c2) : ptx::ex2_approx(fmaf(v[j], p.a2, -p.c2));
-      if (col0 + j >= s.N) e[j] = 0.f;
-      acc_sum += e[j];
+    for (int j = 0; j < 32; ++j) e[j] = ptx::ex2_approx(v[j]);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      s0 += e[j];
+      s1 += e[j + 1];
+      s2 += e[j + 2];
+      s3 += e[j + 3];
     }
-    if (p.E != nullptr && col0 + 32 <= s.N) {     // warp-uniform
+    if (p.e_planes != 0) {
       uint32_t hi[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
         hi[j] = *reinterpret_cast<uint32_t*>(&h);
       }
-      store_plane(hi, p.E, p.ldE, col0, s.M);
+      store_plane(hi, col0);
       if (p.e_planes == 2) {
         uint32_t lo[16];
 #pragma unroll
@@ -539,32 +611,22 @@ struct EpiInfoNCE {
           __nv_bfloat162 l = __floats2bfloat162_rn(e[2 * j] - __low2float(h), e[2 * j + 1] - __high2float(h));
           lo[j] = *reinterpret_cast<uint32_t*>(&l);
         }
-        store_plane(lo, p.E + s.N, p.ldE, col0, s.M);
+        store_plane(lo, p.lo_col0 + col0);
       }
     }
   }
-  __device__ __forceinline__ void chunk16(const Params&, const GemmShape&, int, int, float (&)[16]) {}
   __device__ __forceinline__ void end_tile(const Params& p, const GemmShape& s, int row, int n_blk, int) {
-    if (row < s.M) p.rowsum_part[int64_t(n_blk) * s.M + row] = acc_sum;
+    if (row < s.M) p.rowsum_part[int64_t(n_blk) * s.M + row] = (s0 + s1) + (s2 + s3);
   }
 };
 
 // ------------------------------------------------------------------ host side
 
-// Epilogue probes (profiles/r1_gemm_analysis.md) skip parts of the epilogue to attribute time; they
-// change results, so they exist only in builds with -DHMMC_ENABLE_PROBES.
-static inline int probe_mode() {
-#ifdef HMMC_ENABLE_PROBES
-  const char* e = getenv("HMMC_PROBE_EPI");
-  return e ? atoi(e) : 0;
-#else
-  return 0;
-#endif
-}
-
 // bf16 row-major [rows, cols] (leading dimension ld elements) -> 2-D tensor map with a
-// [box_rows x 64] box and the 128-byte swizzle.
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// [box_rows x 64] box and the 128-byte swizzle (operand loads), or a [box_rows x 32] box with the 64-byte
+// swizzle (the epilogue's store tiles).
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                   uint32_t box_cols = UMMA_BK);
 
 static inline void fill_segments(GemmShape& s, int planes, int K) {
   s.kb_per_seg = K / UMMA_BK;
@@ -580,23 +642,90 @@ static inline void fill_segments(GemmShape& s, int planes, int K) {
   }
 }
 
-// One problem of a grouped launch as the host describes it.
+// One problem of a grouped launch as the host describes it.  out = the epilogue's output tensor for
+// epilogues that store through TMA (bf16 [M, out_cols], leading dimension out_ld), else unused.
 template <class Epi>
 struct GemmProblem {
   const void* A; int64_t lda;
   const void* B; int64_t ldb;
   int M, N, K, planes, splits;
   typename Epi::Params ep;
+  void* out = nullptr; int64_t out_cols = 0; int64_t out_ld = 0;
 };
 
-template <int BN, class Epi>
-int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t stream) {
-  using Cfg = UmmaCfg<BN>;
+// reserved_sms: SMs this launch leaves free (a bandwidth-bound kernel or a collective running beside the
+// persistent grid needs somewhere to live); a per-call argument, the library keeps no scheduling state.
+static inline int gemm_sm_budget(int reserved_sms) {
+  const int n = sm_count() - (reserved_sms > 0 ? reserved_sms : 0);
+  return n < 2 ? 2 : n;
+}
+
+// cost of a unit in k-block steps: its MMA steps plus the part of its epilogue / turn-around that the
+// pipeline does not hide (~ 6 steps for a 256-wide tile)
+constexpr int UMMA_UNIT_FIXED_COST = 6;
+
+// Longest-processing-time-first placement of the units of a launch onto `workers` CTAs / CTA pairs.
+template <class Epi>
+static inline void build_schedule(GroupedArgs<Epi>& g, int workers) {
+  UnitSchedule& sc = g.sched;
+  const int n = g.tile_begin[g.num_problems];
+  sc.num_units = n;
+  sc.explicit_order = 0;
+  if (n > UMMA_MAX_UNITS || workers > UMMA_MAX_WORKERS || n <= workers) return;
+  std::vector<int> cost(n);
+  bool uniform = true;
+  for (int p = 0; p < g.num_problems; ++p) {
+    const GemmShape& s = g.shape[p];
+    const int tiles_mn = s.num_m_blk * s.num_n_blk;
+    const int total_kb = s.num_seg * s.kb_per_seg;
+    for (int t = g.tile_begin[p]; t < g.tile_begin[p + 1]; ++t) {
+      const int split = (t - g.tile_begin[p]) / tiles_mn;
+      const int kb0 = split * s.kb_per_split;
+      const int kb1 = std::min(kb0 + s.kb_per_split, total_kb);
+      cost[t] = (kb1 - kb0) + UMMA_UNIT_FIXED_COST;
+      uniform = uniform && cost[t] == cost[0];
+    }
+  }
+  if (uniform) return;                         // equal units: round-robin is already optimal
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<long> load(workers, 0);
+  std::vector<std::vector<uint16_t>> mine(workers);
+  for (int i = 0; i < n; ++i) {
+    int best = 0;
+    for (int w = 1; w < workers; ++w)
+      if (load[w] < load[best]) best = w;
+    load[best] += cost[idx[i]];
+    mine[best].push_back(uint16_t(idx[i]));
+  }
+  int pos = 0;
+  for (int w = 0; w < workers; ++w) {
+    sc.begin[w] = uint16_t(pos);
+    for (uint16_t u : mine[w]) sc.order[pos++] = u;
+  }
+  for (int w = workers; w <= UMMA_MAX_WORKERS; ++w) sc.begin[w] = uint16_t(pos);
+  sc.explicit_order = 1;
+}
+
+// makespan (in k-block steps incl. the fixed cost) of the same placement, for choosing split counts
+static inline long lpt_makespan(std::vector<int> cost, int workers) {
+  std::sort(cost.begin(), cost.end(), [](int a, int b) { return a > b; });
+  std::vector<long> load(workers, 0);
+  for (int c : cost) {
+    int best = 0;
+    for (int w = 1; w < workers; ++w)
+      if (load[w] < load[best]) best = w;
+    load[best] += c;
+  }
+  return *std::max_element(load.begin(), load.end());
+}
+
+template <class Epi>
+static inline int fill_problems(const GemmProblem<Epi>* probs, int n, int m_tile, int BN, uint32_t b_box_rows,
+                                TmapSet& tm, GroupedArgs<Epi>& g) {
   HMMC_REQUIRE(n >= 1 && n <= UMMA_MAX_PROBLEMS, "umma gemm: %d problems (max %d)", n, UMMA_MAX_PROBLEMS);
-  TmapSet tm;
-  GroupedArgs<Epi> g;
   g.num_problems = 0;
-  g.probe = probe_mode();
   g.tile_begin[0] = 0;
   for (int i = 0; i < n; ++i) {
     const GemmProblem<Epi>& pr = probs[i];
@@ -610,7 +739,7 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
     GemmShape& s = g.shape[k];
     s.M = pr.M;
     s.N = pr.N;
-    s.num_m_blk = (pr.M + UMMA_BM - 1) / UMMA_BM;
+    s.num_m_blk = (pr.M + m_tile - 1) / m_tile;
     s.num_n_blk = (pr.N + BN - 1) / BN;
     fill_segments(s, pr.planes, pr.K);
     const int total_kb = s.num_seg * s.kb_per_seg;
@@ -619,96 +748,89 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
     s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;   // every split gets >= 1 k-block
     int rc = make_tmap_bf16(&tm.a[k], pr.A, uint64_t(pr.M), uint64_t(pr.planes) * pr.K, uint64_t(pr.lda), UMMA_BM);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tm.b[k], pr.B, uint64_t(pr.N), uint64_t(pr.planes) * pr.K, uint64_t(pr.ldb), BN);
+    rc = make_tmap_bf16(&tm.b[k], pr.B, uint64_t(pr.N), uint64_t(pr.planes) * pr.K, uint64_t(pr.ldb), b_box_rows);
     if (rc) return rc;
+    if (Epi::USES_CMAP && pr.out != nullptr) {
+      HMMC_REQUIRE(pr.N % 32 == 0 && pr.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(pr.out) & 15) == 0,
+                   "umma gemm: TMA-store epilogue needs N %% 32 == 0 and a 16-byte aligned output");
+      rc = make_tmap_bf16(&tm.c[k], pr.out, uint64_t(pr.M), uint64_t(pr.out_cols), uint64_t(pr.out_ld), 32, 32);
+      if (rc) return rc;
+    } else {
+      tm.c[k] = tm.a[k];
+    }
     g.ep[k] = pr.ep;
     g.tile_begin[k + 1] = g.tile_begin[k] + s.num_m_blk * s.num_n_blk * s.num_splits;
     g.num_problems = k + 1;
   }
-  if (g.num_problems == 0) return HMMC_OK;
-  for (int k = g.num_problems; k < UMMA_MAX_PROBLEMS; ++k) {
+  for (int k = g.num_problems; k < UMMA_MAX_PROBLEMS && g.num_problems > 0; ++k) {
     g.tile_begin[k + 1] = g.tile_begin[g.num_problems];
     tm.a[k] = tm.a[0];
     tm.b[k] = tm.b[0];
+    tm.c[k] = tm.c[0];
     g.shape[k] = g.shape[0];
     g.ep[k] = g.ep[0];
   }
-  auto kern = umma_gemm_kernel<BN, Epi>;
-  HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-  const int tiles = g.tile_begin[g.num_problems];
-  const int budget = gemm_sm_budget();
-  const int grid = tiles < budget ? tiles : budget;
-  kern<<<grid, UMMA_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, g);
-  HMMC_CHECK_LAUNCH();
   return HMMC_OK;
+}
+
+template <class Kern, class Epi>
+static inline int launch_gemm(Kern kern, int grid, int cluster, size_t smem, cudaStream_t stream, const TmapSet& tm,
+                              const GroupedArgs<Epi>& g) {
+  HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(UMMA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  count_launch();
+  HMMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, g));
+  return HMMC_OK;
+}
+
+template <int BN, class Epi>
+int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t stream, int reserved_sms = 0) {
+  using Cfg = UmmaCfg<BN, Epi>;
+  TmapSet tm;
+  GroupedArgs<Epi> g;
+  int rc = fill_problems(probs, n, UMMA_BM, BN, BN, tm, g);
+  if (rc) return rc;
+  if (g.num_problems == 0) return HMMC_OK;
+  const int tiles = g.tile_begin[g.num_problems];
+  const int budget = gemm_sm_budget(reserved_sms);
+  const int grid = tiles < budget ? tiles : budget;
+  build_schedule(g, grid);
+  return launch_gemm(umma_gemm_kernel<BN, Epi>, grid, 1, Cfg::SMEM_BYTES, stream, tm, g);
 }
 
 // CTA-pair launch of a grouped GEMM (BN = 256).  GemmShape::num_m_blk counts 256-row super tiles;
 // everything else (segments, split-K, epilogue parameters) is identical to launch_umma_grouped.
 template <class Epi>
-int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t stream) {
+int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t stream, int reserved_sms = 0) {
   constexpr int BN = UMMA_PAIR_BN;
-  HMMC_REQUIRE(n >= 1 && n <= UMMA_MAX_PROBLEMS, "umma gemm: %d problems (max %d)", n, UMMA_MAX_PROBLEMS);
   TmapSet tm;
   GroupedArgs<Epi> g;
-  g.num_problems = 0;
-  g.probe = probe_mode();
-  g.tile_begin[0] = 0;
-  for (int i = 0; i < n; ++i) {
-    const GemmProblem<Epi>& pr = probs[i];
-    HMMC_REQUIRE(pr.K % UMMA_BK == 0 && pr.K > 0, "umma gemm: K=%d must be a positive multiple of %d", pr.K, UMMA_BK);
-    HMMC_REQUIRE(pr.planes == 1 || pr.planes == 2, "umma gemm: planes must be 1 or 2");
-    HMMC_REQUIRE(pr.lda % 8 == 0 && pr.ldb % 8 == 0, "umma gemm: leading dimensions must be multiples of 8");
-    HMMC_REQUIRE((reinterpret_cast<uintptr_t>(pr.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(pr.B) & 15) == 0,
-                 "umma gemm: operands must be 16-byte aligned");
-    if (pr.M <= 0 || pr.N <= 0) continue;
-    const int k = g.num_problems;
-    GemmShape& s = g.shape[k];
-    s.M = pr.M;
-    s.N = pr.N;
-    s.num_m_blk = (pr.M + 2 * UMMA_BM - 1) / (2 * UMMA_BM);      // super tiles of 256 rows
-    s.num_n_blk = (pr.N + BN - 1) / BN;
-    fill_segments(s, pr.planes, pr.K);
-    const int total_kb = s.num_seg * s.kb_per_seg;
-    int splits = pr.splits < 1 ? 1 : (pr.splits > total_kb ? total_kb : pr.splits);
-    s.kb_per_split = (total_kb + splits - 1) / splits;
-    s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;
-    int rc = make_tmap_bf16(&tm.a[k], pr.A, uint64_t(pr.M), uint64_t(pr.planes) * pr.K, uint64_t(pr.lda), UMMA_BM);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tm.b[k], pr.B, uint64_t(pr.N), uint64_t(pr.planes) * pr.K, uint64_t(pr.ldb), BN / 2);
-    if (rc) return rc;
-    g.ep[k] = pr.ep;
-    g.tile_begin[k + 1] = g.tile_begin[k] + s.num_m_blk * s.num_n_blk * s.num_splits;
-    g.num_problems = k + 1;
-  }
+  int rc = fill_problems(probs, n, 2 * UMMA_BM, BN, BN / 2, tm, g);
+  if (rc) return rc;
   if (g.num_problems == 0) return HMMC_OK;
-  for (int k = g.num_problems; k < UMMA_MAX_PROBLEMS; ++k) {
-    g.tile_begin[k + 1] = g.tile_begin[g.num_problems];
-    tm.a[k] = tm.a[0];
-    tm.b[k] = tm.b[0];
-    g.shape[k] = g.shape[0];
-    g.ep[k] = g.ep[0];
-  }
-  auto kern = umma_gemm_pair_kernel<Epi>;
-  HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(UMMA_PAIR_SMEM_BYTES)));
   const int tiles = g.tile_begin[g.num_problems];
-  int pairs = gemm_sm_budget() / 2;
+  int pairs = gemm_sm_budget(reserved_sms) / 2;
   if (pairs > tiles) pairs = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(UMMA_THREADS);
-  cfg.dynamicSmemBytes = UMMA_PAIR_SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  count_launch();
-  HMMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, g));
-  return HMMC_OK;
+  build_schedule(g, pairs);
+  return launch_gemm(umma_gemm_pair_kernel<Epi>, 2 * pairs, 2, umma_pair_smem_bytes<Epi>(), stream, tm, g);
 }
 
 // number of split-K partials launch_umma_grouped will produce for a request of `splits`

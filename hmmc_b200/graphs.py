@@ -1,6 +1,6 @@
 """CUDA-graph capture of a whole head step (EMA + loss forward/backward + key exchange + enqueue).
 
-The step is a fixed sequence of ~10 launches with static shapes, and issuing it from Python costs
+The step is a fixed sequence of ~8 launches with static shapes, and issuing it from Python costs
 more host time than the GPU needs to run it once ranks and collectives are involved; a captured
 graph replays it with one launch.  All device state the step touches (queues, queue_ptr, momentum
 parameters, workspaces) is updated in place by the kernels, so replaying is equivalent to calling
@@ -9,7 +9,14 @@ the step again.
     g = GraphedStep(lambda: step(static_inputs))      # warm-up calls + capture
     for batch in loader:
         static_inputs.copy_(batch); g.replay(); use(g.outputs)
+
+The warm-up calls are REAL steps: each one updates the momentum parameters, enqueues the step's keys and
+advances queue_ptr, exactly like a call outside the graph (the capture pass itself executes nothing).  A
+training loop that must not take extra steps passes ``warmup=0`` after having run its first steps eagerly
+(those already sized the workspaces and built the operand copies the capture relies on).
 """
+import gc
+
 import torch
 
 
@@ -18,12 +25,13 @@ class GraphedStep:
         """``fn()`` runs one step on static input tensors and returns a tensor (or tuple of
         tensors) to keep, e.g. the loss.  Gradients land in the ``.grad`` of the static inputs."""
         self.fn = fn
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                out = fn()
-        torch.cuda.current_stream().wait_stream(s)
+        if warmup > 0:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    fn()
+            torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -32,3 +40,16 @@ class GraphedStep:
     def replay(self):
         self.graph.replay()
         return self.outputs
+
+    def release(self):
+        """Destroy the executable graph (and the NCCL work it holds) - call before
+        torch.distributed.destroy_process_group(): a live graph that captured a collective keeps the
+        communicator busy and the destroy never returns."""
+        torch.cuda.synchronize()
+        self.outputs = None
+        self.fn = None
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+        gc.collect()
+        torch.cuda.synchronize()

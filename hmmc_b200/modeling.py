@@ -18,7 +18,6 @@ the methods here can be mixed into (or swapped for) the reference's classes:
 All arithmetic runs in libhmmc_head.so (see ops.py); there is no PyTorch fallback.
 """
 import logging
-import os
 from types import SimpleNamespace
 
 import torch
@@ -33,26 +32,21 @@ DEFAULT_CROSS_CONFIG = dict(temporal_hidden_size=512, weight_FAM=0.05, weight_VT
                             weight_MLM=0.05, weight_VTM_finetune=0.85, weight_FTM_finetune=0.15)
 
 
-# SMs left to the key all-gather while it overlaps the loss (tuned on 2 and 8 B200)
-GATHER_RESERVED_SMS = int(os.environ.get("HMMC_GATHER_RESERVED_SMS", "0"))
-
-
-# run the enqueue next to the tail of the loss on a side stream (0: strictly after it)
-ENQUEUE_OVERLAP = os.environ.get("HMMC_ENQUEUE_OVERLAP", "1") != "0"
+# Schedule constants (measured on B200; these were environment knobs while being tuned):
+# * the enqueue of a single-rank step runs on a side stream next to the tail of the loss;
+# * on one rank the query-side GEMMs of the loss run beside the momentum update (head_loss_begin / head_loss_end)
+#   with their persistent grids kept on 148 - LOSS_GEMM_RESERVED SMs, because the EMA is HBM-bound and needs the
+#   other SMs to saturate the memory system (tools/overlap_probe.py);
+# * with several ranks the key exchange and the enqueue of step i are deferred to run beside step i+1's momentum
+#   update (nothing reads the queues before step i+1's loss), see ContrastiveHeadMixin.start_pending_exchange.
+LOSS_GEMM_RESERVED = 120
 _side_streams = {}
 
 
-# split the head around the momentum update / key encoders (head_loss_begin / head_loss_end); 0: one fused call
-LOSS_OVERLAP = os.environ.get("HMMC_LOSS_OVERLAP", "1") != "0"
-
-
 def use_split_schedule():
-    """The two-half schedule pays on a single rank (0.408 -> 0.399 ms per step).  With several ranks the key
-    all-gather has to hide behind the loss GEMMs, which the split moves beside the EMA: measured 0.589 ms
-    against 0.537 ms at 8 ranks, so multi-rank runs keep the one-call head."""
-    return LOSS_OVERLAP and parallel.world()[0] == 1
-# SMs kept out of the loss GEMM grids while they run beside the EMA (tools/overlap_probe.py, DESIGN.md §5)
-LOSS_GEMM_RESERVED = int(os.environ.get("HMMC_LOSS_GEMM_RESERVED", "120"))
+    """The two-half schedule pays on a single rank (0.408 -> 0.399 ms per step); with several ranks the side
+    stream beside the EMA carries the deferred key exchange instead."""
+    return parallel.world()[0] == 1
 
 
 def _side_stream(device, name="enqueue", priority=0):
@@ -166,13 +160,14 @@ class ContrastiveHeadMixin:
     @torch.no_grad()
     def _momentum_update(self):
         # p_k <- p_k*m + p*(1-m) for every parameter pair, one launch (modules/modeling.py:238-242).
-        # The pointer table is built once; a few pointers are probed per call to catch re-allocation
-        # (.to(), .half(), load_state_dict with assign); set self._hmmc_ema = None to force a rebuild.
+        # The device pointer table is built once and rebuilt when any parameter has moved (.to(), .half(),
+        # load_state_dict with assign, `.data =`): all pointers are compared on the host every call.
         tab = getattr(self, "_hmmc_ema", None)
-        if tab is not None and not tab.still_valid():
+        pairs = self._ema_pairs()
+        if tab is not None and not tab.still_valid(pairs):
             tab = None
         if tab is None:
-            tab = ops.EmaTable(self._ema_pairs())
+            tab = ops.EmaTable(pairs)
             self._hmmc_ema = tab
         tab.run(self.contrast_momentum)
 
@@ -180,52 +175,108 @@ class ContrastiveHeadMixin:
         return [self.queue_v_cross_ng, self.queue_tag_cross_ng, self.queue_title_cross_ng,
                 self.queue_frame_cross_ng, self.queue_frame_proj_ng]
 
-    @torch.no_grad()
-    def _gather_keys_async(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
-        """Start the exchange of _dequeue_and_enqueue (modules/modeling.py:249-258): ONE packed
-        all-gather instead of five.  Returns a handle for _enqueue_gathered."""
+    # The exchange of _dequeue_and_enqueue (modules/modeling.py:249-258) is ONE packed all-gather of the five
+    # key tensors instead of five; the enqueue kernel reads the gathered rows in place.
+    @staticmethod
+    def _key_blocks(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
         b = v_fea_k.shape[0]
         D = v_fea_k.shape[-1]
         frame_fea_k = frame_fea_k.reshape(b, -1, D)
         frame_proj_k = frame_proj_k.reshape(b, -1, D)
         F = frame_fea_k.shape[1]
-        W, _ = parallel.world()
-        keys = [v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k]
-        if W == 1:
-            return (W, b, F, D, [ops._f32c(t, "key") for t in keys], None, lambda: None)
-        send = ops.pack_rows(keys)
-        gathered, wait = parallel.all_gather_rows_async(send)
-        # the collective's CTAs share the SMs with the loss kernels issued until _enqueue_gathered:
-        # keep some SMs out of the persistent GEMM grids meanwhile
-        ops.set_reserved_sms(GATHER_RESERVED_SMS)
-        return (W, b, F, D, None, gathered, wait)
+        return b, F, D, [v_fea_k.reshape(b, D), tag_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k,
+                         frame_proj_k]
+
+    def _enqueue_ptr_mode(self, B):
+        """-1 = the kernels read and advance queue_ptr on the device (no host copy that a CUDA-graph replay or a
+        deferred enqueue could leave stale); needs K % B == 0, the reference's own operating condition
+        (modules/modeling.py:273-280 has no wrap-around).  Otherwise the host value, one sync per call."""
+        K = self.contrast_num_negative
+        if K % B == 0:
+            return -1
+        if torch.cuda.is_current_stream_capturing():
+            raise ValueError("graph capture of the enqueue needs K %% (world*batch) == 0 (K=%d, B=%d)" % (K, B))
+        return int(self.queue_ptr)
 
     @torch.no_grad()
-    def _enqueue_gathered(self, handle):
-        W, b, F, D, direct, gathered, wait = handle
-        K = self.contrast_num_negative
-        wait()
-        if W > 1:
-            ops.set_reserved_sms(0)
-        if torch.cuda.is_current_stream_capturing():
-            # CUDA-graph capture: the pointer is read and advanced on the device at every replay
-            if K % (W * b) != 0:
-                raise ValueError("graph capture of the enqueue needs K %% (world*batch) == 0 (K=%d, B=%d)" % (K, W * b))
-            ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, -1, K,
-                        ops.resolve_precision(self.head_precision), direct=direct)
-            self._hmmc_ptr = None          # host copy is stale after replays: re-read on the next eager call
+    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None):
+        ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, self._enqueue_ptr_mode(W * b),
+                    self.contrast_num_negative, ops.resolve_precision(self.head_precision), direct=direct)
+
+    def _defer_enqueue(self):
+        v = getattr(self.task_config, "defer_enqueue", None)
+        return parallel.world()[0] > 1 if v is None else bool(v)
+
+    @torch.no_grad()
+    def _stage_keys(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+        """Deferred schedule, end of step i: copy the step's keys into the persistent send buffer.  Their
+        exchange and enqueue are issued by start_pending_exchange() of step i+1 (or flush_pending_enqueue())."""
+        self._join_pending()
+        b, F, D, keys = self._key_blocks(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+        W, _ = parallel.world()
+        dev = keys[0].device
+        width = (3 + 2 * F) * D
+        bufs = getattr(self, "_hmmc_xchg", None)
+        if bufs is None or bufs[0].shape != (b, width) or bufs[1].shape[0] != W * b or bufs[0].device != dev:
+            send = torch.empty(b, width, dtype=torch.float32, device=dev)
+            bufs = (send, send if W == 1 else torch.empty(W * b, width, dtype=torch.float32, device=dev))
+            self._hmmc_xchg = bufs
+        ops.pack_rows(keys, out=bufs[0])
+        self._hmmc_pending = {"dims": (W, b, F, D), "done": None}
+        if not getattr(self, "_hmmc_hooked", False) and isinstance(self, nn.Module):
+            # checkpoints must see the queues with every staged key in place
+            self.register_state_dict_pre_hook(lambda m, *a, **k: m.flush_pending_enqueue())
+            self._register_load_state_dict_pre_hook(lambda *a, **k: self.flush_pending_enqueue())
+            self._hmmc_hooked = True
+
+    @torch.no_grad()
+    def start_pending_exchange(self):
+        """Deferred schedule, start of step i+1: issue the all-gather and the enqueue of step i's keys on a side
+        stream and return at once.  Call it before `_momentum_update()` (forward() does): the exchange then
+        runs beside the HBM-bound parameter update and is joined right before the loss reads the queues.
+        Safe to call at any time; does nothing when no keys are staged."""
+        p = getattr(self, "_hmmc_pending", None)
+        if p is None or p["done"] is not None:
             return
-        ver = self.queue_ptr._version
-        if getattr(self, "_hmmc_ptr", None) is None or self._hmmc_ptr[1] != ver:
-            self._hmmc_ptr = (int(self.queue_ptr), ver)        # one sync, then tracked on the host
-        ptr = self._hmmc_ptr[0]
-        ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, ptr, K,
-                    ops.resolve_precision(self.head_precision), direct=direct)
-        self._hmmc_ptr = ((ptr + W * b) % K, self.queue_ptr._version)
+        W, b, F, D = p["dims"]
+        send, gathered = self._hmmc_xchg
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        fork = torch.cuda.Event()
+        fork.record(main)                  # after step i's kernels (they read the queues) and the staging copy
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            if W > 1:
+                parallel.all_gather_rows_into(gathered, send)
+            self._enqueue_rows(W, b, F, D, gathered=gathered)
+            done = torch.cuda.Event()
+            done.record(side)
+        p["done"] = done
+
+    def _join_pending(self):
+        p = getattr(self, "_hmmc_pending", None)
+        if p is None:
+            return
+        if p["done"] is None:
+            self.start_pending_exchange()
+        torch.cuda.current_stream().wait_event(p["done"])
+        self._hmmc_pending = None
+
+    def flush_pending_enqueue(self):
+        """Make the queue buffers current (stream-ordered on the current stream): call before reading
+        queue_*_ng / queue_ptr directly.  state_dict() and load_state_dict() do it themselves."""
+        self._join_pending()
 
     @torch.no_grad()
     def _dequeue_and_enqueue(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
-        self._enqueue_gathered(self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k))
+        """modules/modeling.py:244-284, immediately (the reference's call): gather, normalise, write columns."""
+        self._join_pending()
+        b, F, D, keys = self._key_blocks(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+        W, _ = parallel.world()
+        if W == 1:
+            self._enqueue_rows(1, b, F, D, direct=[ops._f32c(t, "key") for t in keys])
+        else:
+            self._enqueue_rows(W, b, F, D, gathered=parallel.all_gather_rows(ops.pack_rows(keys)))
 
 
 def patch_reference_classes(*classes):
@@ -237,16 +288,9 @@ def patch_reference_classes(*classes):
             if callable(fn) and not name.startswith("__"):
                 setattr(cls, name, fn)
         if hasattr(cls, "_dequeue_and_enqueue") and cls.__name__ == "BirdPreTrainedModel":
-            cls.head_loss = BirdPreTrainedModel.head_loss
-            cls.head_loss_begin = BirdPreTrainedModel.head_loss_begin
-            cls.head_loss_end = BirdPreTrainedModel.head_loss_end
+            for name in ("head_loss", "head_loss_begin", "head_loss_end", "_enqueue_beside"):
+                setattr(cls, name, getattr(BirdPreTrainedModel, name))
     return classes
-
-
-def _event():
-    e = torch.cuda.Event(enable_timing=True)
-    e.record()
-    return e
 
 
 def _register_queues(mod, D, K, F):
@@ -296,18 +340,18 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
 
     def head_loss(self, v_fea, frame_fea, title_fea, frame_pred, v_fea_k, frame_fea_k, title_fea_k, tag_fea_k,
                   frame_proj_k, loss_MLM=None):
-        """modules/modeling.py:385-424 for dataset != "bird" (the only reachable branch)."""
+        """modules/modeling.py:385-424 for dataset != "bird" (the only reachable branch): the three
+        losses forward and backward, then `_dequeue_and_enqueue` of the step's keys.
+
+        Single rank: the enqueue runs on a side stream next to the tail of the loss and is joined before
+        returning.  Several ranks (or task_config.defer_enqueue): nothing reads the queues again before the
+        NEXT step's loss, so the keys are only staged here; their all-gather and enqueue run beside the next
+        step's momentum update (start_pending_exchange) and are joined right before that step's loss."""
         b = v_fea.shape[0]
         D = v_fea.shape[-1]
-        # the key exchange does not depend on the loss: start it first, enqueue after the loss kernels
-        marks = getattr(self, "_hmmc_marks", None)          # optional CUDA-event breakdown (bench.py)
-        mark = (lambda: marks.append(_event())) if marks is not None else (lambda: None)
-        mark()
-        pending = self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
-        mark()
-        # the queues are free once the two GEMMs have read them: the enqueue then runs on a side stream next to
-        # the rest of the loss (positives, gradient projection, reductions) and is joined before returning
-        released = torch.cuda.Event() if ENQUEUE_OVERLAP and marks is None else None
+        defer = self._defer_enqueue()
+        self._join_pending()                 # the previous step's keys must be in the queues this loss reads
+        released = None if defer else torch.cuda.Event()
         total, parts = ops.pretrain_head(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
                                          v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k,
                                          self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
@@ -315,22 +359,26 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
                                          self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
                                          self.head_precision, release_event=released)
         self.last_loss_parts = parts            # [FAM, VTM, FTM], device tensor (the reference logs them)
-        mark()
-        if released is None:
-            self._enqueue_gathered(pending)
+        if defer:
+            self._stage_keys(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         else:
-            main = torch.cuda.current_stream()
-            side = _side_stream(main.device)
-            side.wait_event(released)
-            with torch.cuda.stream(side):
-                self._enqueue_gathered(pending)
-                done = torch.cuda.Event()
-                done.record(side)
-            main.wait_event(done)
-        mark()
+            # the queues are free once the two GEMMs have read them
+            self._enqueue_beside(released, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         if loss_MLM is None:
             return total
         return total + self.weight_MLM * loss_MLM
+
+    def _enqueue_beside(self, after, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
+        """Immediate enqueue on the side stream, started once `after` (an event of the current stream) has
+        happened and joined into the current stream."""
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        side.wait_event(after)
+        with torch.cuda.stream(side):
+            self._dequeue_and_enqueue(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
 
     def head_loss_begin(self, v_fea, frame_fea, title_fea, frame_pred):
         """Query-side half of head_loss: normalisation and both GEMM passes against the queues, issued on a
@@ -339,40 +387,33 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
         (LOSS_GEMM_RESERVED): the EMA is HBM-bound and needs the others to saturate the memory system.
         Returns the state for head_loss_end."""
         b, D = v_fea.shape[0], v_fea.shape[-1]
+        self._join_pending()
         side = _side_stream(torch.cuda.current_stream().device, "loss", priority=-1)
-        ops.set_reserved_sms(LOSS_GEMM_RESERVED)
-        try:
-            state = ops.pretrain_head_begin(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
-                                            self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
-                                            self.queue_frame_cross_ng, self.contrast_temperature, self.weight_FAM,
-                                            self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
-                                            self.head_precision, stream=side)
-        finally:
-            ops.set_reserved_sms(0)
+        state = ops.pretrain_head_begin(v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
+                                        self.queue_v_cross_ng, self.queue_title_cross_ng, self.queue_frame_proj_ng,
+                                        self.queue_frame_cross_ng, self.contrast_temperature, self.weight_FAM,
+                                        self.weight_VTM, self.weight_FTM, self.task_config.use_frame_fea,
+                                        self.head_precision, stream=side, reserved_sms=LOSS_GEMM_RESERVED)
         state_done = torch.cuda.Event()
         state_done.record(side)
         return (state, state_done, (v_fea, frame_fea, title_fea, frame_pred))
 
     def head_loss_end(self, begun, v_fea_k, frame_fea_k, title_fea_k, tag_fea_k, frame_proj_k, loss_MLM=None):
-        """Key-side half: the enqueue (and the wait for the key all-gather) starts at once on a side stream —
-        the queues are no longer read — while positives, losses and gradients run on the current stream."""
+        """Key-side half: the enqueue starts at once on a side stream - the queues are no longer read - while
+        positives, losses and gradients run on the current stream."""
         state, gemm_done, (v_fea, frame_fea, title_fea, frame_pred) = begun
         b, D = v_fea.shape[0], v_fea.shape[-1]
         main = torch.cuda.current_stream()
         main.wait_event(gemm_done)
-        pending = self._gather_keys_async(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         keys_ready = torch.cuda.Event()
         keys_ready.record(main)
         total, parts = ops.pretrain_head_end(state, v_fea.reshape(b, D), title_fea.reshape(b, D), frame_fea, frame_pred,
                                              v_fea_k.reshape(b, D), title_fea_k.reshape(b, D), frame_fea_k, frame_proj_k)
         self.last_loss_parts = parts
-        side = _side_stream(main.device)
-        side.wait_event(keys_ready)
-        with torch.cuda.stream(side):
-            self._enqueue_gathered(pending)
-            done = torch.cuda.Event()
-            done.record(side)
-        main.wait_event(done)
+        if self._defer_enqueue():
+            self._stage_keys(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
+        else:
+            self._enqueue_beside(keys_ready, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         if loss_MLM is None:
             return total
         return total + self.weight_MLM * loss_MLM
@@ -393,6 +434,8 @@ class BirdPreTrainedModel(ContrastiveHeadMixin, nn.Module):
         frame_pred = self.v_predictor(frame_proj)
         frame_fea = frame_fea.view(bs, frame, hidden)
         frame_pred = frame_pred.view(bs, frame, hidden)
+        # deferred schedule: the previous step's key exchange and enqueue run beside the momentum update
+        self.start_pending_exchange()
         # the queries exist: their half of the loss runs beside the momentum update and the key encoders
         begun = self.head_loss_begin(v_fea, frame_fea, title_fea, frame_pred) if use_split_schedule() else None
         with torch.no_grad():  # no gradient to keys

@@ -4,6 +4,7 @@ happens in libhmmc_head.so on the caller's current CUDA stream.
 """
 import ctypes
 import os
+import weakref
 
 import torch
 
@@ -41,22 +42,25 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-_workspaces = {}
+_workspaces = {}          # (device index, stream handle) -> [buffer, baked into a CUDA graph?]
+_graph_pinned = []        # buffers a capture has baked into a graph: kept alive for the life of the process
 
 
 def workspace(device, nbytes):
-    """One growing scratch buffer per device (all calls are stream-ordered)."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
-    return buf
-
-
-def set_reserved_sms(n):
-    """SMs the persistent GEMM grids leave free from now on (see include/hmmc_head.h)."""
-    _lib.check(_lib.load().hmmc_set_reserved_sms(int(n)), "hmmc_set_reserved_sms")
+    """Scratch buffer of the CURRENT stream (calls on one stream are ordered, so they may share it; calls on
+    different streams - side streams, eval threads, a capture stream - never do).  A buffer that a CUDA-graph
+    capture has seen is never freed when a later call needs a larger one: replays keep writing to it."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    ent = _workspaces.get(key)
+    if ent is None or ent[0].numel() < nbytes:
+        if ent is not None and ent[1]:
+            _graph_pinned.append(ent[0])
+        ent = [torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device), False]
+        _workspaces[key] = ent
+    if torch.cuda.is_current_stream_capturing():
+        ent[1] = True
+    return ent[0]
 
 
 def device_check():
@@ -88,71 +92,91 @@ def gemm_f32(A, B, alpha=1.0):
     return C
 
 
-def umma_gemm_nt(Ap, Bp, K, planes, alpha=1.0):
-    """C = alpha * A . B^T on tcgen05 from plane-packed bf16 operands [rows, planes*K]."""
+def umma_gemm_nt(Ap, Bp, K, planes, alpha=1.0, tiling=0):
+    """C = alpha * A . B^T on tcgen05 from plane-packed bf16 operands [rows, planes*K].
+    tiling: 0 = chosen from the shape, 128 / 256 = single-CTA tile width, 512 = CTA-pair kernel."""
     lib = _lib.load()
     M, N = Ap.shape[0], Bp.shape[0]
     C = torch.empty(M, N, dtype=torch.float32, device=Ap.device)
-    _lib.check(lib.hmmc_umma_gemm_nt(_p(Ap), Ap.stride(0), _p(Bp), Bp.stride(0), _p(C), N, M, N, K, planes,
-                                     float(alpha), _stream()), "hmmc_umma_gemm_nt")
+    _lib.check(lib.hmmc_umma_gemm_nt_tiled(_p(Ap), Ap.stride(0), _p(Bp), Bp.stride(0), _p(C), N, M, N, K, planes,
+                                           float(alpha), int(tiling), _stream()), "hmmc_umma_gemm_nt_tiled")
     return C
 
 
 # ----------------------------------------------------------------------------- queues
 
 class QueueState:
-    """Packed operand copies of one negative queue buffer ([D, Kq] fp32, the
-    reference's state-dict layout, modules/modeling.py:138-149)."""
+    """Derived bf16 operand copies of one negative queue buffer ([D, Kq] fp32, the reference's state-dict
+    layout, modules/modeling.py:138-149).  One state per buffer (held weakly), with the copies of each plane
+    count (1 = bf16, 2 = bf16x3) built on first use.  Staleness is tracked explicitly: `gen` counts writes to the
+    buffer made by the enqueue kernel (which keeps only the plane count in use in step), `buf._version` catches
+    writes made through torch (load_state_dict, copy_)."""
 
-    def __init__(self, buf, planes):
+    def __init__(self, buf):
         assert buf.dim() == 2 and buf.dtype == torch.float32 and buf.is_cuda and buf.is_contiguous()
-        self.buf = buf
+        self.ref = weakref.ref(buf)
         self.D, self.Kq = buf.shape
-        self.planes = planes
-        self.pack_kd = torch.empty(self.Kq, planes * self.D, dtype=torch.bfloat16, device=buf.device)
-        self.pack_dk = torch.empty(self.D, planes * self.Kq, dtype=torch.bfloat16, device=buf.device)
-        self.version = None
-        self.repack()
+        self.gen = 0
+        self.graph_planes = None      # plane count a captured enqueue keeps in step during replays
+        self.packs = {}               # planes -> [pack_kd, pack_dk, gen, version]
 
-    def struct(self):
-        return hmmc_queue(self.buf.data_ptr(), self.pack_kd.data_ptr(), self.pack_dk.data_ptr(), self.D,
-                          self.Kq, self.planes, 0)
+    def pack(self, buf, planes):
+        ent = self.packs.get(planes)
+        if ent is None:
+            ent = [torch.empty(self.Kq, planes * self.D, dtype=torch.bfloat16, device=buf.device),
+                   torch.empty(self.D, planes * self.Kq, dtype=torch.bfloat16, device=buf.device), -1, -1]
+            self.packs[planes] = ent
+        # replays of a captured enqueue change the buffer without passing through Python: copies of the
+        # other plane count are rebuilt on every use from then on
+        unsure = self.graph_planes is not None and self.graph_planes != planes
+        if ent[2] != self.gen or ent[3] != buf._version or unsure:
+            q = hmmc_queue(buf.data_ptr(), ent[0].data_ptr(), ent[1].data_ptr(), self.D, self.Kq, planes, 0)
+            _lib.check(_lib.load().hmmc_queue_pack(ctypes.byref(q), _stream()), "hmmc_queue_pack")
+            ent[2], ent[3] = self.gen, buf._version
+        return ent
 
-    def repack(self):
-        q = self.struct()
-        _lib.check(_lib.load().hmmc_queue_pack(ctypes.byref(q), _stream()), "hmmc_queue_pack")
-        self.version = self.buf._version
+    def repack(self, buf, planes):
+        """Rebuild the copies of `planes` from the buffer unconditionally; returns (pack_kd, pack_dk)."""
+        if planes in self.packs:
+            self.packs[planes][2] = -1
+        ent = self.pack(buf, planes)
+        return ent[0], ent[1]
 
-    def fresh(self):
-        if self.buf._version != self.version:   # someone wrote the buffer through torch (load_state_dict, ...)
-            self.repack()
-        return self
+    def struct(self, buf, planes):
+        ent = self.pack(buf, planes)
+        return hmmc_queue(buf.data_ptr(), ent[0].data_ptr(), ent[1].data_ptr(), self.D, self.Kq, planes, 0)
+
+    def wrote(self, buf, planes):
+        """The enqueue kernel updated the buffer and the copies of `planes` (None: the buffer only)."""
+        self.gen += 1
+        if planes in self.packs:
+            self.packs[planes][2], self.packs[planes][3] = self.gen, buf._version
+        if torch.cuda.is_current_stream_capturing():
+            self.graph_planes = planes
 
 
-_queue_states = {}
+_queue_states = {}        # id(buffer) -> QueueState, dropped when the buffer dies
 
 
-def queue_state(buf, prec):
-    """Packed copies for ``buf``; FP32 precision needs none."""
-    planes = 2 if prec == PREC_BF16X3 else 1
-    if prec == PREC_FP32:
-        return None
-    key = (buf.data_ptr(), tuple(buf.shape), planes)
-    st = _queue_states.get(key)
-    if st is None or st.buf is not buf:
+def queue_state(buf):
+    st = _queue_states.get(id(buf))
+    if st is None or st.ref() is not buf:
         if not buf.is_contiguous():
             raise HmmcError("queue buffers must be contiguous [D, Kq] tensors")
-        st = QueueState(buf, planes)
+        st = QueueState(buf)
+        key = id(buf)
         _queue_states[key] = st
-    return st.fresh()
+        weakref.finalize(buf, _queue_states.pop, key, None)
+    return st
 
 
 def _queue_struct(buf, prec):
-    st = queue_state(buf, prec)
-    if st is not None:
-        return st.struct(), st
-    D, Kq = buf.shape
-    return hmmc_queue(buf.data_ptr(), 0, 0, D, Kq, 1, 0), None
+    """(hmmc_queue for this precision, state or None); FP32 precision needs no copies."""
+    if prec == PREC_FP32:
+        D, Kq = buf.shape
+        return hmmc_queue(buf.data_ptr(), 0, 0, D, Kq, 1, 0), queue_state(buf)
+    st = queue_state(buf)
+    return st.struct(buf, 2 if prec == PREC_BF16X3 else 1), st
 
 
 # ----------------------------------------------------------------------------- InfoNCE vs queue
@@ -236,7 +260,7 @@ class _PretrainHeadFn(torch.autograd.Function):
         nbytes = lib.hmmc_pretrain_head_workspace_bytes(b, F, D, K, prec)
         ws = workspace(t[0].device, nbytes)
         losses = torch.empty(4, dtype=torch.float32, device=t[0].device)
-        sched = hmmc_head_schedule(0, 0, None)
+        sched = hmmc_head_schedule(0, 0, None)        # both phases, all SMs
         if release_event is not None:
             release_event.record()               # materialises the handle; the library records it again later
             sched.queues_released = release_event.cuda_event
@@ -281,14 +305,14 @@ class PretrainHeadState:
     __slots__ = ("t", "grads", "structs", "keep", "ws", "losses", "dims", "args", "need", "meta", "queues")
 
 
-def _head_call(state, keys, phase, stream):
+def _head_call(state, keys, phase, stream, reserved_sms=0):
     lib = _lib.load()
     b, F, D, K, prec = state.dims
     kp = [k.data_ptr() for k in keys] if keys is not None else [0, 0, 0, 0]
     io = hmmc_pretrain_io(*[x.data_ptr() for x in state.t], *kp,
                           *[(g.data_ptr() if g is not None else 0) for g in state.grads])
     temperature, w_fam, w_vtm, w_ftm, use_frame_fea = state.args
-    sched = hmmc_head_schedule(phase, 0, None)
+    sched = hmmc_head_schedule(phase, int(reserved_sms), None)
     _lib.check(lib.hmmc_pretrain_head_fwd_bwd_sched(ctypes.byref(io), b, F, D, *[ctypes.byref(s) for s in state.structs],
                                                     float(temperature), float(w_fam), float(w_vtm), float(w_ftm),
                                                     int(bool(use_frame_fea)), prec, _p(state.losses),
@@ -297,11 +321,13 @@ def _head_call(state, keys, phase, stream):
 
 
 def pretrain_head_begin(v_fea, title_fea, frame_fea, frame_pred, q_v, q_title, q_frame_proj, q_frame_cross,
-                        temperature, w_fam, w_vtm, w_ftm, use_frame_fea=True, precision=None, stream=None):
+                        temperature, w_fam, w_vtm, w_ftm, use_frame_fea=True, precision=None, stream=None,
+                        reserved_sms=0):
     """First half of the fused pre-train head: normalise the queries and run both GEMM passes against the
     queues (everything that does not need the keys), issued on `stream` (a torch.cuda.Stream; default: the
-    current one).  All buffers are allocated on the CURRENT stream; the caller orders `stream` after the
-    queries and joins it before pretrain_head_end.  In the reference the queries exist before
+    current one), with the persistent GEMM grids leaving `reserved_sms` SMs free for whatever runs beside
+    them.  All buffers are allocated on the CURRENT stream; the caller orders `stream` after the queries and
+    joins it before pretrain_head_end.  In the reference the queries exist before
     _momentum_update() and the key encoders run (modules/modeling.py:340-377)."""
     prec = resolve_precision(precision)
     st = PretrainHeadState()
@@ -327,7 +353,7 @@ def pretrain_head_begin(v_fea, title_fea, frame_fea, frame_pred, q_v, q_title, q
         ready = torch.cuda.Event()          # queries, fresh buffers and (re)packed queues are ready here
         ready.record()
         stream.wait_event(ready)
-    _head_call(st, None, 1, stream.cuda_stream if stream is not None else _stream())
+    _head_call(st, None, 1, stream.cuda_stream if stream is not None else _stream(), reserved_sms)
     return st
 
 
@@ -388,9 +414,6 @@ class EmaTable:
             numels.append(p.numel())
             dts.append(_DT[p.dtype])
             offs.append(offs[-1] + (p.numel() + be - 1) // be)
-        live = [(p, pk) for p, pk in pairs if p.numel()]
-        self.probe = [(live[i][0], live[i][1], live[i][0].data_ptr(), live[i][1].data_ptr())
-                      for i in sorted({0, len(live) // 2, len(live) - 1})] if live else []
         self.n = len(numels)
         self.total_blocks = offs[-1]
         self.total_elems = sum(numels)
@@ -403,8 +426,11 @@ class EmaTable:
             self.dtypes = torch.tensor(dts, dtype=torch.int32).to(dev)
             self.offs = u64(offs)
 
-    def still_valid(self):
-        return all(p.data_ptr() == a and pk.data_ptr() == b for p, pk, a, b in self.probe)
+    def still_valid(self, pairs):
+        """True while every (param, param_k) pair still lives where the device table points (.half(), .to(),
+        load_state_dict(assign=True) or `param_k.data = ...` re-allocate): a host-side compare of all pointers."""
+        live = [(p, pk) for p, pk in pairs if p.numel()]
+        return (tuple(pk.data_ptr() for _, pk in live), tuple(p.data_ptr() for p, _ in live)) == self.signature
 
     def run(self, m):
         if not self.n:
@@ -461,9 +487,9 @@ def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, dir
     else:
         _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _p(scratch),
                                          _stream()), "hmmc_enqueue_norm")
+    planes = None if prec == PREC_FP32 else (2 if prec == PREC_BF16X3 else 1)
     for st, buf in zip(keep, queue_bufs5):
-        if st is not None:
-            st.version = buf._version       # the kernel kept the packed copies in step
+        st.wrote(buf, planes)               # the kernel kept the copies of this plane count in step
 
 
 # ----------------------------------------------------------------------------- fine-tune head

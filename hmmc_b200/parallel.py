@@ -7,8 +7,6 @@ the B200 box, gloo in the CPU tests).  The only exchanges of the path are
   * the key all-gather of the pre-train enqueue (modules/modeling.py:249-258);
   * the [Nt] score / count exchange of the sharded-gallery eval.
 """
-import os
-
 import torch
 import torch.distributed as dist
 
@@ -19,12 +17,18 @@ def world():
     return 1, 0
 
 
-def _all_gather_into(out, x):
-    try:
-        dist.all_gather_into_tensor(out, x)
-    except (RuntimeError, NotImplementedError):      # backends without the flat variant
-        W = dist.get_world_size()
-        dist.all_gather(list(out.chunk(W, dim=0)), x)
+# The all-gather whose consumer is replicated on every rank needs no exchange in its backward
+# (_AllGatherCatReplicated); False restores the generic SUM reduce-scatter (tests compare the two).
+REPLICATED_GATHER_BWD = True
+
+
+def _all_gather_into(out, x, async_op=False):
+    """Flat all-gather where the backend has one (NCCL), the list form elsewhere (gloo).  Chosen by backend,
+    never by catching an error: a rank whose collective failed must not issue a different one."""
+    if dist.get_backend() == "nccl":
+        return dist.all_gather_into_tensor(out, x, async_op=async_op)
+    W = dist.get_world_size()
+    return dist.all_gather(list(out.chunk(W, dim=0)), x, async_op=async_op)
 
 
 def _reduce_scatter_sum(out, g):
@@ -78,12 +82,13 @@ class _AllGatherCatReplicated(torch.autograd.Function):
 
 
 def all_gather_cat_replicated(x):
-    """all_gather_cat for a consumer that is replicated on all ranks (see _AllGatherCatReplicated);
-    HMMC_REPLICATED_GATHER_BWD=0 restores the reduce-scatter."""
+    """all_gather_cat for a consumer that is replicated on all ranks (see _AllGatherCatReplicated).
+    Assumption: every rank evaluates a bit-identical loss from the gathered rows (deterministic kernels, same
+    inputs); parallel.REPLICATED_GATHER_BWD = False restores the reduce-scatter."""
     W, _ = world()
     if W == 1:
         return x.contiguous()
-    if os.environ.get("HMMC_REPLICATED_GATHER_BWD", "1") == "0":
+    if not REPLICATED_GATHER_BWD:
         return _AllGatherCat.apply(x)
     return _AllGatherCatReplicated.apply(x)
 
@@ -108,21 +113,16 @@ def all_gather_rows(x):
 
 
 @torch.no_grad()
-def all_gather_rows_async(x):
-    """Start the all-gather of a [b, w] block and return (out, wait): the collective runs on
-    NCCL's stream while the caller keeps launching kernels; call wait() before reading out."""
+def all_gather_rows_into(out, x):
+    """All-gather of a [b, w] block into a caller-owned [W*b, w] buffer, ordered on the CURRENT stream (the
+    deferred key exchange issues it on a side stream; capturable in a CUDA graph)."""
     W, _ = world()
     if W == 1:
-        return x, (lambda: None)
-    out = x.new_empty((W * x.shape[0],) + tuple(x.shape[1:]))
-    if os.environ.get("HMMC_SYNC_GATHER") == "1":
-        _all_gather_into(out, x.contiguous())
-        return out, (lambda: None)
-    try:
-        work = dist.all_gather_into_tensor(out, x.contiguous(), async_op=True)
-    except (RuntimeError, NotImplementedError):
-        work = dist.all_gather(list(out.chunk(W, dim=0)), x.contiguous(), async_op=True)
-    return out, work.wait
+        if out.data_ptr() != x.data_ptr():
+            out.copy_(x)
+        return out
+    _all_gather_into(out, x.contiguous())
+    return out
 
 
 def shard_range(n, W=None, r=None):

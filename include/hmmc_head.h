@@ -55,10 +55,6 @@ int hmmc_version(void);
 unsigned long long hmmc_launch_count(void);
 /* 0 when the current device is sm_100 (B200); HMMC_ERR_UNSUPPORTED otherwise. */
 int hmmc_device_check(void);
-/* Leave n SMs out of the persistent GEMM grids launched from now on (0 = use them all).  The host
- * sets this while a collective (the key all-gather of _dequeue_and_enqueue) runs beside the loss:
- * a persistent CTA that cannot become resident would hold its tiles back until the collective ends. */
-int hmmc_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------ operands */
 
@@ -79,6 +75,11 @@ int hmmc_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int6
  * products (BF16X3).  K % 64 == 0; M, N arbitrary (edge tiles are masked). */
 int hmmc_umma_gemm_nt(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                       int M, int N, int K, int planes, float alpha, void* stream);
+/* The same contraction with the tile configuration named explicitly (measurement aid, tools/gemm_bench.py):
+ * tiling 0 = as hmmc_umma_gemm_nt chooses, 128 / 256 = single-CTA kernel with 128 x tiling tiles,
+ * 512 = CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles). */
+int hmmc_umma_gemm_nt_tiled(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                            int M, int N, int K, int planes, float alpha, int tiling, void* stream);
 
 /* ------------------------------------------------------- pre-train head (MoCo) */
 
@@ -150,12 +151,17 @@ int hmmc_pretrain_head_fwd_bwd(const hmmc_pretrain_io* io, int b, int F, int D, 
  *   phase 0 = both.
  * In the reference the queries exist before `_momentum_update()` and the key encoders run
  * (modules/modeling.py:340-377), so phase 1 can execute beside them on another stream.
+ * reserved_sms: SMs the persistent GEMM grids of THIS call leave free (0 = use them all) -- for a
+ *             bandwidth-bound kernel (the momentum update) or a collective running beside them; a
+ *             persistent CTA that cannot become resident would hold its tiles back.  Per call: the
+ *             library keeps no scheduling state, so concurrent callers (eval threads, side streams)
+ *             cannot disturb each other.
  * queues_released: NULL or a cudaEvent_t recorded on `stream` right after the last kernel that reads the
  * queues; the enqueue of the step (which overwrites queue columns) can then run on another stream that
  * waits for it, beside the rest of the loss. */
 typedef struct {
   int phase;
-  int reserved;
+  int reserved_sms;
   void* queues_released;
 } hmmc_head_schedule;
 int hmmc_pretrain_head_fwd_bwd_sched(const hmmc_pretrain_io* io, int b, int F, int D, const hmmc_queue* q_v,

@@ -1,6 +1,7 @@
 """CPU baseline: a torch restatement of the reference head, op for op as written.
 
-TEST / BENCH INFRASTRUCTURE ONLY (bench.py's cpu_baseline and --impl reference legs).
+TEST / BENCH INFRASTRUCTURE ONLY (bench.py's cpu_baseline, --impl reference and --impl reference-gpu legs;
+device-agnostic, so the same op sequence on `cuda` tensors is the reference's GPU eager path).
 The reference itself is Python and does not exist on the GPU box, so the CPU arm times
 this port: the same ATen op sequence as modules/modeling.py (normalize, b x b matmul +
 diag, queue.clone(), matmul, cat, /T, cross_entropy, autograd backward), including the
@@ -20,7 +21,7 @@ def contrastive_loss(q, k, queue, T):
     l_neg = torch.matmul(q, queue.clone().detach())
     logits = torch.cat([l_pos, l_neg], dim=1)
     logits /= T
-    labels = torch.zeros(logits.shape[0], dtype=torch.long)
+    labels = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)   # the reference: .cuda()
     return F.cross_entropy(logits, labels)
 
 

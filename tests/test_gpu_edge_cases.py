@@ -30,11 +30,13 @@ def _load(m, qs):
             getattr(m, n).copy_(torch.from_numpy(x))
 
 
+@pytest.mark.parametrize("b", [128, 256])
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
-def test_full_size_config4_against_fp64_oracle(prec):
-    """BASELINE config 4 at its real size (b=128, F=12, D=512, K=1024): loss and all four gradients
-    against the float64 oracle; tolerances 1e-5 / 5e-5 (fp32-parity mode) and 1e-3 (bf16)."""
-    b, F, D, K = 128, 12, 512, 1024
+def test_full_size_config4_against_fp64_oracle(prec, b):
+    """BASELINE config 4 at its real size (b=128, F=12, D=512, K=1024) and the north-star shape (b=256):
+    loss and all four gradients against the float64 oracle; tolerances 1e-5 / 5e-5 (fp32-parity mode)
+    and 1e-3 (bf16)."""
+    F, D, K = 12, 512, 1024
     inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
     qs = syn.queues(K, F=F, D=D, seed=3)
     ref_loss, ref_g = O.pretrain_loss_and_grads(inp, qs, 0.07)
@@ -93,11 +95,12 @@ def test_ema_limits_are_exact():
 
 def test_derived_queue_copies_are_idempotent():
     m = _pre(32, 4, 64, "bf16x3")
-    st = ops.queue_state(m.queue_frame_proj_ng, ops.resolve_precision("bf16x3"))
-    kd, dk = st.pack_kd.clone(), st.pack_dk.clone()
-    st.repack()
-    st.repack()
-    assert torch.equal(kd, st.pack_kd) and torch.equal(dk, st.pack_dk)
+    buf = m.queue_frame_proj_ng
+    st = ops.queue_state(buf)
+    kd, dk = [x.clone() for x in st.pack(buf, 2)[:2]]
+    st.repack(buf, 2)
+    kd2, dk2 = st.repack(buf, 2)
+    assert torch.equal(kd, kd2) and torch.equal(dk, dk2)
 
 
 def test_rank_count_known_answers():
@@ -166,21 +169,23 @@ def test_finetune_single_sample_and_frames_only():
 
 
 def test_reserved_sms_do_not_change_results():
-    """hmmc_set_reserved_sms only shrinks the persistent GEMM grids: same tiles, same bits."""
+    """hmmc_head_schedule.reserved_sms only shrinks the persistent GEMM grids of that call: same units, same
+    bits (and no library state is left behind: the plain call afterwards matches too)."""
     b, F, D, K = 32, 12, 512, 1024
     inp = syn.pretrain_inputs(b, F=F, D=D, seed=2)
-    qs = syn.queues(K, F=F, D=D, seed=3)
+    qs = {n: cu(x) for n, x in syn.queues(K, F=F, D=D, seed=3).items()}
+    qb = [qs[n] for n in ("queue_v_cross_ng", "queue_title_cross_ng", "queue_frame_proj_ng", "queue_frame_cross_ng")]
     outs = []
-    try:
-        for reserved in (0, 40, 140):
-            ops.set_reserved_sms(reserved)
-            m = _pre(K, F, D, "bf16")
-            _load(m, qs)
-            t = {n: cu(inp[n], grad=n in QN) for n in ORDER}
-            loss = m.head_loss(*[t[n] for n in ORDER])
-            loss.backward()
-            outs.append((loss.detach().clone(), t["frame_pred"].grad.clone()))
-    finally:
-        ops.set_reserved_sms(0)
-    for l, g in outs[1:]:
-        assert torch.equal(l, outs[0][0]) and torch.equal(g, outs[0][1])
+    for reserved in (0, 40, 140, None):
+        t = {n: cu(inp[n], grad=n in QN) for n in ORDER}
+        q4 = [t["v_fea"], t["title_fea"], t["frame_fea"], t["frame_pred"]]
+        k4 = [t["v_fea_k"], t["title_fea_k"], t["frame_fea_k"], t["frame_proj_k"]]
+        if reserved is None:
+            loss, _ = ops.pretrain_head(*q4, *k4, *qb, 0.07, 0.05, 0.45, 0.45, True, "bf16")
+        else:
+            st = ops.pretrain_head_begin(*q4, *qb, 0.07, 0.05, 0.45, 0.45, True, "bf16", reserved_sms=reserved)
+            loss, _ = ops.pretrain_head_end(st, *q4, *k4)
+        loss.backward()
+        outs.append((loss.detach().clone(), t["frame_pred"].grad.clone(), t["title_fea"].grad.clone()))
+    for l, g, g2 in outs[1:]:
+        assert torch.equal(l, outs[0][0]) and torch.equal(g, outs[0][1]) and torch.equal(g2, outs[0][2])

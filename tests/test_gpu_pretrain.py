@@ -94,10 +94,10 @@ def test_enqueue_wrap_and_packed_copies(golden, prec):
     if prec != "fp32":
         # the packed operand copies written by the enqueue kernel equal a fresh re-pack
         for buf in m._queue_buffers():
-            st = ops.queue_state(buf, ops.resolve_precision(prec))
-            kd, dk = st.pack_kd.clone(), st.pack_dk.clone()
-            st.repack()
-            assert torch.equal(kd, st.pack_kd) and torch.equal(dk, st.pack_dk)
+            st, planes = ops.queue_state(buf), (2 if prec == "bf16x3" else 1)
+            kd, dk = [x.clone() for x in st.pack(buf, planes)[:2]]      # as the enqueue kernel left them
+            kd2, dk2 = st.repack(buf, planes)
+            assert torch.equal(kd, kd2) and torch.equal(dk, dk2)
     # a batch that does not fit raises like the reference's slice assignment
     k = syn.pretrain_inputs(12, F=F, D=D, seed=1)
     with pytest.raises(Exception):
@@ -133,10 +133,10 @@ def test_enqueue_ragged_and_odd_pointer(ptr, b):
         keep[ptr * mult:(ptr + b) * mult] = False
         assert np.array_equal(got[:, keep], q0[n][:, keep]), n
     for buf in m._queue_buffers():
-        st = ops.queue_state(buf, ops.resolve_precision("bf16x3"))
-        kd, dk = st.pack_kd.clone(), st.pack_dk.clone()
-        st.repack()
-        assert torch.equal(kd, st.pack_kd) and torch.equal(dk, st.pack_dk)
+        st = ops.queue_state(buf)
+        kd, dk = [x.clone() for x in st.pack(buf, 2)[:2]]
+        kd2, dk2 = st.repack(buf, 2)
+        assert torch.equal(kd, kd2) and torch.equal(dk, dk2)
 
 
 def test_ema_bit_exact(golden):

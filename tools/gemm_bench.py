@@ -16,7 +16,8 @@ shapes = shapes or _default
 for M, N, K in shapes:
     A = (torch.randn(M, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
     B = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
-    for name, fn in (("hmmc umma", lambda: ops.umma_gemm_nt(A, B, K, 1, 1.0)), ("torch bf16", lambda: A @ B.t())):
+    TILING = int(os.environ.get("TILING", "0"))      # 0 auto, 128 / 256 single-CTA tile width, 512 CTA-pair kernel
+    for name, fn in (("hmmc umma", lambda: ops.umma_gemm_nt(A, B, K, 1, 1.0, TILING)), ("torch bf16", lambda: A @ B.t())):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -27,4 +28,4 @@ for M, N, K in shapes:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        print("%-10s BN=%s M=%5d N=%5d K=%5d  %8.1f us  %7.1f TFLOP/s" % (name, os.environ.get("HMMC_FORCE_BN", "auto"), M, N, K, ms * 1e3, 2.0 * M * N * K / ms / 1e9))
+        print("%-10s BN=%s M=%5d N=%5d K=%5d  %8.1f us  %7.1f TFLOP/s" % (name, os.environ.get("TILING", "auto"), M, N, K, ms * 1e3, 2.0 * M * N * K / ms / 1e9))
