@@ -85,7 +85,8 @@ SIGNATURES = {
                                c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hmmc_bert_adam_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "hmmc_bert_adam_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                     c_int64, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                     c_int64, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
     "hmmc_clip_grad_norm_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p,
                                           c_size_t, c_void_p]),
     "hmmc_enqueue_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_queue), c_void_p, c_int64,

@@ -26,8 +26,12 @@ __device__ __forceinline__ int owner_of_block(const int64_t* __restrict__ block_
 // ---------------------------------------------------------------- pass 1: sum of squares per block
 __global__ void __launch_bounds__(OPT_THREADS)
 grad_sqnorm_kernel(const uint64_t* __restrict__ g_ptrs, const int64_t* __restrict__ numels,
-                   const int64_t* __restrict__ block_offsets, int n, float* __restrict__ partials) {
+                   const int64_t* __restrict__ block_offsets, int n, const float* __restrict__ inv_scale,
+                   float* __restrict__ partials) {
   __shared__ float red[32];
+  // AMP: the norms are those of the UNSCALED gradients fl(g * 1/scale), the values GradScaler.unscale_ would
+  // have left in place (main_pretrain.py:282-284 -> torch.amp.GradScaler.step)
+  const float inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.0f;
   const int64_t blk = blockIdx.x;
   const int t = owner_of_block(block_offsets, n, blk);
   const int64_t begin = (blk - block_offsets[t]) * OPT_BLOCK_ELEMS;
@@ -38,12 +42,19 @@ grad_sqnorm_kernel(const uint64_t* __restrict__ g_ptrs, const int64_t* __restric
     const int64_t nvec = (end - begin) / 4;
     const float4* g4 = reinterpret_cast<const float4*>(g + begin);
     for (int64_t i = threadIdx.x; i < nvec; i += OPT_THREADS) {
-      const float4 v = __ldg(g4 + i);
+      float4 v = __ldg(g4 + i);
+      v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv); v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
       ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
     }
-    for (int64_t i = begin + nvec * 4 + threadIdx.x; i < end; i += OPT_THREADS) ss = fmaf(g[i], g[i], ss);
+    for (int64_t i = begin + nvec * 4 + threadIdx.x; i < end; i += OPT_THREADS) {
+      const float x = __fmul_rn(g[i], inv);
+      ss = fmaf(x, x, ss);
+    }
   } else {
-    for (int64_t i = begin + threadIdx.x; i < end; i += OPT_THREADS) ss = fmaf(g[i], g[i], ss);
+    for (int64_t i = begin + threadIdx.x; i < end; i += OPT_THREADS) {
+      const float x = __fmul_rn(g[i], inv);
+      ss = fmaf(x, x, ss);
+    }
   }
   ss = block_sum(ss, red);
   if (threadIdx.x == 0) partials[blk] = ss;
@@ -111,11 +122,12 @@ clip_coefs_kernel(const float* __restrict__ partials, const int64_t* __restrict_
 }
 
 // ---------------------------------------------------------------- pass 3: the update
-struct AdamHyper { float lr, wd, b1, omb1, b2, omb2, eps, cg, ct; };
+struct AdamHyper { float lr, wd, b1, omb1, b2, omb2, eps, cg, ct, inv; };
 
 // One element of BertAdam.step, each line one rounded op of the reference (optimization.py:141-166);
 // add_(grad, alpha) and addcmul_ are single fused multiply-adds there, everything else rounds separately.
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamHyper& h) {
+  g = __fmul_rn(g, h.inv);                                       // GradScaler's unscale (1 without AMP: exact)
   g = __fmul_rn(__fmul_rn(g, h.cg), h.ct);                       // clip_grad_norm_ twice (global, per tensor)
   m = __fmaf_rn(h.omb1, g, __fmul_rn(m, h.b1));                  // next_m.mul_(b1).add_(grad, alpha=1-b1)
   v = __fmaf_rn(__fmul_rn(h.omb2, g), g, __fmul_rn(v, h.b2));    // next_v.mul_(b2).addcmul_(grad, grad, value=1-b2)
@@ -129,12 +141,14 @@ __global__ void __launch_bounds__(OPT_THREADS)
 bert_adam_kernel(const uint64_t* __restrict__ p_ptrs, const uint64_t* __restrict__ g_ptrs,
                  const uint64_t* __restrict__ m_ptrs, const uint64_t* __restrict__ v_ptrs,
                  const int64_t* __restrict__ numels, const int64_t* __restrict__ block_offsets, int n,
-                 const float* __restrict__ hyper, const float* __restrict__ coefs) {
+                 const float* __restrict__ hyper, const float* __restrict__ coefs,
+                 const float* __restrict__ inv_scale) {
   const int64_t blk = blockIdx.x;
   const int t = owner_of_block(block_offsets, n, blk);
   const int64_t begin = (blk - block_offsets[t]) * OPT_BLOCK_ELEMS;
   const int64_t end = min(begin + int64_t(OPT_BLOCK_ELEMS), numels[t]);
   AdamHyper h;
+  h.inv = inv_scale != nullptr ? __ldg(inv_scale) : 1.0f;
   h.lr = hyper[t * 8 + 0]; h.wd = hyper[t * 8 + 1]; h.b1 = hyper[t * 8 + 2]; h.omb1 = hyper[t * 8 + 3];
   h.b2 = hyper[t * 8 + 4]; h.omb2 = hyper[t * 8 + 5]; h.eps = hyper[t * 8 + 6];
   h.cg = coefs[2 * t]; h.ct = coefs[2 * t + 1];
@@ -186,10 +200,11 @@ static void adam_carve(Workspace& ws, AdamWs& w, int n, int64_t total_blocks) {
 
 // passes 1 + 2
 static int clip_coefs(const uint64_t* g_ptrs, const int64_t* numels, const int64_t* block_offsets, int n,
-                      int64_t total_blocks, const float* hyper, float global_max_norm, float* norms_out, const AdamWs& w,
-                      cudaStream_t st) {
+                      int64_t total_blocks, const float* hyper, float global_max_norm, const float* inv_scale,
+                      float* norms_out, const AdamWs& w, cudaStream_t st) {
   HMMC_CHECK_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
-  grad_sqnorm_kernel<<<unsigned(total_blocks), OPT_THREADS, 0, st>>>(g_ptrs, numels, block_offsets, n, w.partials);
+  grad_sqnorm_kernel<<<unsigned(total_blocks), OPT_THREADS, 0, st>>>(g_ptrs, numels, block_offsets, n, inv_scale,
+                                                                     w.partials);
   HMMC_CHECK_LAUNCH();
   clip_coefs_kernel<<<unsigned(n), OPT_THREADS, 0, st>>>(w.partials, block_offsets, n, hyper, global_max_norm, w.sq,
                                                         w.coefs, norms_out, w.ticket);
@@ -227,8 +242,8 @@ size_t hmmc_bert_adam_workspace_bytes(int n, int64_t total_blocks) {
 int hmmc_bert_adam_multi(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs,
                          const uint64_t* v_ptrs, const int64_t* numels, const int32_t* dtypes,
                          const int64_t* block_offsets, int n, int64_t total_blocks, const float* hyper,
-                         float global_max_norm, int write_back_grads, float* norms_out, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         float global_max_norm, int write_back_grads, const float* inv_scale, float* norms_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
   (void)dtypes;   // fp32 only; the host checks, the table keeps the EMA layout
   if (n <= 0 || total_blocks <= 0) return HMMC_OK;
   HMMC_REQUIRE(p_ptrs && g_ptrs && m_ptrs && v_ptrs && numels && block_offsets && hyper, "bert_adam: null table");
@@ -238,14 +253,14 @@ int hmmc_bert_adam_multi(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const u
   adam_carve(ws, w, n, total_blocks);
   HMMC_REQUIRE(ws.ok(), "bert_adam: workspace too small (%zu needed, %zu given)", ws.used, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = clip_coefs(g_ptrs, numels, block_offsets, n, total_blocks, hyper, global_max_norm, norms_out, w, st);
+  int rc = clip_coefs(g_ptrs, numels, block_offsets, n, total_blocks, hyper, global_max_norm, inv_scale, norms_out, w, st);
   if (rc) return rc;
   if (write_back_grads)
     bert_adam_kernel<true><<<unsigned(total_blocks), OPT_THREADS, 0, st>>>(p_ptrs, g_ptrs, m_ptrs, v_ptrs, numels,
-                                                                            block_offsets, n, hyper, w.coefs);
+                                                                            block_offsets, n, hyper, w.coefs, inv_scale);
   else
     bert_adam_kernel<false><<<unsigned(total_blocks), OPT_THREADS, 0, st>>>(p_ptrs, g_ptrs, m_ptrs, v_ptrs, numels,
-                                                                             block_offsets, n, hyper, w.coefs);
+                                                                             block_offsets, n, hyper, w.coefs, inv_scale);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -264,7 +279,7 @@ int hmmc_clip_grad_norm_multi(const uint64_t* g_ptrs, const int64_t* numels, con
   HMMC_REQUIRE(ws.ok(), "clip_grad_norm: workspace too small (%zu needed, %zu given)", ws.used, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HMMC_CHECK_CUDA(cudaMemsetAsync(hyper, 0, size_t(n) * 8 * sizeof(float), st));
-  int rc = clip_coefs(g_ptrs, numels, block_offsets, n, total_blocks, hyper, max_norm, norms_out, w, st);
+  int rc = clip_coefs(g_ptrs, numels, block_offsets, n, total_blocks, hyper, max_norm, nullptr, norms_out, w, st);
   if (rc) return rc;
   grad_scale_kernel<<<unsigned(total_blocks), OPT_THREADS, 0, st>>>(g_ptrs, numels, block_offsets, n, w.coefs);
   HMMC_CHECK_LAUNCH();

@@ -187,30 +187,38 @@ struct LossFinal {
   int use_frame_fea;
 };
 
-// Called by every thread of a block at the end of the finish kernel.  The block that arrives last sums
-// row_loss[3][total_rows] (each thread a fixed strided subset, then a fixed tree) and writes the result.
-__device__ __forceinline__ void finish_losses(const float* __restrict__ row_loss, int total_rows, const LossFinal& f,
-                                              unsigned* counter) {
+// Called by every thread of a block at the end of the finish kernel with its row's loss shares (warp-uniform;
+// zeros for warps beyond the last row).  Each block adds its eight rows in warp order and publishes one partial
+// per loss slot; the block that arrives last adds the partials (each thread a fixed strided subset, then a
+// fixed tree) and writes the scalars.  The order never depends on which block is last.
+__device__ __forceinline__ void finish_losses(const float (&loss_kind)[3], float* __restrict__ block_loss /* [3][gridDim.x] */,
+                                              const LossFinal& f, unsigned* counter) {
+  __shared__ float wl[3][8];
   __shared__ float red[32];
   __shared__ float kinds[3];
   __shared__ bool last;
-  __threadfence();                          // this block's row_loss stores before its arrival
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wl[k][warp] = loss_kind[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += wl[threadIdx.x][w];
+    block_loss[int64_t(threadIdx.x) * gridDim.x + blockIdx.x] = acc;
+    __threadfence();                        // the partial before this block's arrival
+  }
   __syncthreads();
   if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
   for (int k = 0; k < 3; ++k) {
-    const volatile float* v = row_loss + int64_t(k) * total_rows;
+    const float* v = block_loss + int64_t(k) * gridDim.x;
     float acc = 0.f;
-    for (int i = threadIdx.x; i < total_rows; i += 4 * blockDim.x) {
-      const int i1 = i + blockDim.x, i2 = i + 2 * blockDim.x, i3 = i + 3 * blockDim.x;
-      const float a0 = v[i];
-      const float a1 = i1 < total_rows ? v[i1] : 0.f;
-      const float a2 = i2 < total_rows ? v[i2] : 0.f;
-      const float a3 = i3 < total_rows ? v[i3] : 0.f;
-      acc += (a0 + a1) + (a2 + a3);
-    }
+    for (int i = threadIdx.x; i < int(gridDim.x); i += blockDim.x) acc += __ldcg(v + i);
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) kinds[k] = acc;
     __syncthreads();
@@ -241,16 +249,20 @@ __device__ __forceinline__ void axpy4(float w, const float4& x, float4& y) {
 // (tensor-core path: the GEMM epilogue stores 2^{l log2 e} without the constant max, kexp = e^{-cmax}; fp32 path: 1).
 // Vector version: D == 128 * V, every row is V float4 per lane; all of a row's independent loads (query, two
 // key rows, two split-K partials of U) are issued together, 16 warps per SM.
+#ifndef HMMC_FIN_OCC
+#define HMMC_FIN_OCC 2      // resident blocks per SM the vector finish kernel is compiled for (measured: see profiles/)
+#endif
 template <int V>
-__global__ void __launch_bounds__(256, (V <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(256, (V <= 4 ? HMMC_FIN_OCC : 1))
 infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, float cmax, float kexp,
-                          float* __restrict__ row_loss /* [3][total_rows] */, const LossFinal fin, unsigned* counter) {
+                          float* __restrict__ row_loss /* [3][blocks] */, const LossFinal fin, unsigned* counter) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
   constexpr int D = 128 * V;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int total_rows = a.row_begin[a.n];
+  float loss_kind[3] = {0.f, 0.f, 0.f};
   if (row < total_rows) {
     int gi = 0;
 #pragma unroll
@@ -275,42 +287,19 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
     ss = warp_sum(ss);
     const float nq_raw = sqrtf(ss);
     const float nq = fmaxf(nq_raw, 1e-12f);
+    const float inq = 1.0f / nq;              // x * (1/n): within 1 ulp of F.normalize's x / n
 #pragma unroll
-    for (int i = 0; i < V; ++i) { qv[i].x /= nq; qv[i].y /= nq; qv[i].z /= nq; qv[i].w /= nq; }   // q_hat
+    for (int i = 0; i < V; ++i) { qv[i].x *= inq; qv[i].y *= inq; qv[i].z *= inq; qv[i].w *= inq; }   // q_hat
 
-    float loss_kind[3] = {0.f, 0.f, 0.f};
     for (int ci = 0; ci < G.ncontrib; ++ci) {
       const Contribution& C = G.c[ci];
-      // ---- issue the independent loads of this contribution: row-sum partials, U partials
+      // ---- row-sum partials of this contribution
       float S = 0.f, S1 = 0.f;
       for (int p = lane; p < C.n_parts; p += 64) {
         const float a0 = __ldg(C.rowsum_part + int64_t(p) * G.rows + r);
         const float a1 = (p + 32 < C.n_parts) ? __ldg(C.rowsum_part + int64_t(p + 32) * G.rows + r) : 0.f;
         S += a0;
         S1 += a1;
-      }
-      float4 us[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) us[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (G.dq != nullptr) {
-        // U_r = sum over the split-K partials, two partials in flight, added in split order
-        for (int s0 = 0; s0 < C.n_splits; s0 += 2) {
-          float4 t[2][V];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const bool on = s0 + k < C.n_splits;
-            const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(on ? s0 + k : s0) * C.split_stride +
-                                                               int64_t(r) * D) + lane;
-#pragma unroll
-            for (int i = 0; i < V; ++i) t[k][i] = on ? __ldg(up + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-              us[i].x += t[k][i].x; us[i].y += t[k][i].y; us[i].z += t[k][i].z; us[i].w += t[k][i].w;
-            }
-        }
       }
       S = warp_sum(S + S1) * kexp;
       int nterm, kbase, kstep;
@@ -366,14 +355,25 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
         }
       }
       loss_kind[C.kind] += C.coef * loss;
-      // g_hat += coef/T * (sum_t 1/Z_t) U_r
-      const float wu = scale * sum_invZ * kexp;
+      if (G.dq != nullptr) {
+        // g_hat += coef/T * (sum_t 1/Z_t) U_r ;  U_r = the split-K partials, streamed in split order, two in flight
+        const float wu = scale * sum_invZ * kexp;
+        for (int s0 = 0; s0 < C.n_splits; s0 += 2) {
+          float4 t[2][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) axpy4(wu, us[i], g[i]);
-    }
-    if (lane == 0) {
+          for (int k = 0; k < 2; ++k) {
+            const bool on = s0 + k < C.n_splits;
+            const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(on ? s0 + k : s0) * C.split_stride +
+                                                               int64_t(r) * D) + lane;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) row_loss[int64_t(k) * total_rows + row] = loss_kind[k];
+            for (int i = 0; i < V; ++i) t[k][i] = on ? __ldg(up + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int i = 0; i < V; ++i) axpy4(wu, t[k][i], g[i]);
+        }
+      }
     }
     if (G.dq != nullptr) {
       // dq = (g_hat - q_hat (q_hat . g_hat)) / ||q||
@@ -387,28 +387,29 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
       for (int i = 0; i < V; ++i) {
         float4 o;
         if (clamped) {
-          o = make_float4(g[i].x / nq, g[i].y / nq, g[i].z / nq, g[i].w / nq);
+          o = make_float4(g[i].x * inq, g[i].y * inq, g[i].z * inq, g[i].w * inq);
         } else {
-          o = make_float4((g[i].x - qv[i].x * qg) / nq, (g[i].y - qv[i].y * qg) / nq, (g[i].z - qv[i].z * qg) / nq,
-                          (g[i].w - qv[i].w * qg) / nq);
+          o = make_float4((g[i].x - qv[i].x * qg) * inq, (g[i].y - qv[i].y * qg) * inq, (g[i].z - qv[i].z * qg) * inq,
+                          (g[i].w - qv[i].w * qg) * inq);
         }
         op[32 * i] = o;
       }
     }
   }
-  finish_losses(row_loss, total_rows, fin, counter);
+  finish_losses(loss_kind, row_loss, fin, counter);
 }
 
 // Generic version (any D <= FIN_MAXD, scalar accesses).
 template <int NE>   // NE = elements per lane = D / 32 rounded up
 __global__ void __launch_bounds__(256, (NE <= 16 ? 2 : 1))
 infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax, float kexp,
-                      float* __restrict__ row_loss /* [3][total_rows] */, const LossFinal fin, unsigned* counter) {
+                      float* __restrict__ row_loss /* [3][blocks] */, const LossFinal fin, unsigned* counter) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int total_rows = a.row_begin[a.n];
+  float loss_kind[3] = {0.f, 0.f, 0.f};
   if (row < total_rows) {
     int gi = 0;
 #pragma unroll
@@ -433,7 +434,6 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
 #pragma unroll
     for (int i = 0; i < NE; ++i) qv[i] = qv[i] / nq;   // q_hat
 
-    float loss_kind[3] = {0.f, 0.f, 0.f};
     for (int ci = 0; ci < G.ncontrib; ++ci) {
       const Contribution& C = G.c[ci];
       // S_r: negatives' sum of exp(l - cmax)
@@ -503,10 +503,6 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
         for (int i = 0; i < NE; ++i) g[i] = fmaf(wu, us[i], g[i]);
       }
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) row_loss[int64_t(k) * total_rows + row] = loss_kind[k];
-    }
     if (G.dq != nullptr) {
       // dq = (g_hat - q_hat (q_hat . g_hat)) / ||q||
       float qg = 0.f;
@@ -521,7 +517,7 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
       }
     }
   }
-  finish_losses(row_loss, total_rows, fin, counter);
+  finish_losses(loss_kind, row_loss, fin, counter);
 }
 
 // ------------------------------------------------------------------ EMA
@@ -917,10 +913,12 @@ struct InfoNCELayout {       // workspace carving shared by the size query and t
 };
 
 // Split-K of the U-GEMMs (U = E.Q^T: a small output, a long contraction).  The launch is a single wave of
-// units (output tile x K slice) placed longest-first on the CTA pairs; the slice length is chosen so that the
-// wave ends everywhere at about the same time, with a charge for every extra partial tile the finish kernel
-// has to read back.  Costs are in k-block steps of one CTA pair (64 contraction elements of a 256 x 256 tile).
-struct SplitChoice { int splits[MAX_BLOCKS]; };
+// units (output tile x K slice) placed longest-first on the CTA pairs.  Every tile is cut into slices of `unit`
+// k-block steps plus a shorter remainder: the mix of long and short units packs the pairs far more evenly than
+// equal slices do (b = 256: makespan 85 steps against a mean of 82, where three equal slices give 128 and two
+// give 102), with a charge for every extra partial tile the finish kernel has to read back.
+// Costs are in k-block steps of one CTA pair (64 contraction elements of a 256 x 256 tile).
+struct SplitChoice { int unit[MAX_BLOCKS]; };     // k-block steps per slice, per problem
 
 static SplitChoice choose_u_splits(const int* rows, const int* Kq, int nb, int D, int planes, int bn2) {
   typedef std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int> Key;
@@ -945,29 +943,30 @@ static SplitChoice choose_u_splits(const int* rows, const int* Kq, int nb, int D
   }
   SplitChoice best;
   double best_cost = 1e30;
-  for (int unit = 4; unit <= max_kb; unit += (unit < 48 ? 1 : 4)) {
-    SplitChoice c;
+  for (int unit = 8; unit <= max_kb; ++unit) {
     std::vector<int> cost;
     int units = 0;
-    for (int k = 0; k < nb; ++k) {
-      int sp = std::min(32, std::max(1, (total_kb[k] + unit - 1) / unit));
-      const int per = (total_kb[k] + sp - 1) / sp;
-      sp = (total_kb[k] + per - 1) / per;
-      c.splits[k] = sp;
-      for (int s = 0; s < sp; ++s) {
-        const int len = std::min(per, total_kb[k] - s * per);
+    bool ok = true;
+    for (int k = 0; k < nb && ok; ++k) {
+      const int u = std::min(unit, total_kb[k]);
+      const int n_slices = (total_kb[k] + u - 1) / u;
+      ok = n_slices <= 32;
+      for (int s = 0; s < n_slices; ++s) {
+        const int len = std::min(u, total_kb[k] - s * u);
         for (int t = 0; t < tiles[k]; ++t) cost.push_back(len + UMMA_UNIT_FIXED_COST);
       }
-      units += sp * tiles[k];
+      units += n_slices * tiles[k];
     }
-    if (units > UMMA_MAX_UNITS) continue;
+    if (!ok || units > UMMA_MAX_UNITS) continue;
     // every partial tile is written once and read once more by the finish kernel: ~0.25 steps of chip time each
     const double total = double(lpt_makespan(cost, workers)) + 0.25 * units;
-    if (total < best_cost) { best_cost = total; best = c; }
+    if (total < best_cost) {
+      best_cost = total;
+      for (int k = 0; k < MAX_BLOCKS; ++k) best.unit[k] = k < nb ? std::min(unit, total_kb[k]) : 1;
+    }
   }
   if (best_cost > 1e29)
-    for (int k = 0; k < nb; ++k) best.splits[k] = 1;
-  for (int k = nb; k < MAX_BLOCKS; ++k) best.splits[k] = 1;
+    for (int k = 0; k < MAX_BLOCKS; ++k) best.unit[k] = k < nb ? total_kb[k] : 1;
   std::lock_guard<std::mutex> lk(mu);
   cache[key] = best;
   return best;
@@ -988,8 +987,9 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   for (int k = 0; k < nb; ++k)
     if (blk_Kq[k] % 256 != 0) L.bn1 = 128;
   L.bn2 = (D % 256 == 0) ? 256 : 128;
+  const int nseg_layout = (planes == 2) ? 3 : 1;
   SplitChoice sc;
-  for (int k = 0; k < MAX_BLOCKS; ++k) sc.splits[k] = 1;
+  for (int k = 0; k < MAX_BLOCKS; ++k) sc.unit[k] = k < nb ? nseg_layout * (blk_Kq[k] / UMMA_BK) : 1;
   if (prec != HMMC_PREC_FP32 && need_grad) {
     int rows[MAX_BLOCKS];
     for (int k = 0; k < nb; ++k) rows[k] = groups[blk_group[k]].rows;
@@ -1004,9 +1004,15 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
       L.rowsum_part[k] = ws.take<float>(size_t(R));
       L.E[k] = ws.take<float>(size_t(R) * Kq);
     } else {
-      L.nparts[k] = 2 * ((Kq + L.bn1 - 1) / L.bn1);     // two epilogue halves per tile
-      L.splits[k] = sc.splits[k];
-      L.nsplits_eff[k] = effective_splits(Kq, planes, sc.splits[k]);
+      // one partial per epilogue warp column range: the CTA-pair kernel runs four warps per TMEM lane quadrant
+      // for the single-plane epilogues, two otherwise (EpiInfoNCE::PARTS_PER_TILE_PAIR)
+      const int parts_per_tile = (L.bn1 == 256) ? ((need_grad && planes == 2) ? EpiInfoNCE<2>::PARTS_PER_TILE_PAIR
+                                                                              : EpiInfoNCE<1>::PARTS_PER_TILE_PAIR)
+                                                : 2;
+      L.nparts[k] = parts_per_tile * ((Kq + L.bn1 - 1) / L.bn1);
+      const int total_kb = nseg_layout * (Kq / UMMA_BK);
+      L.splits[k] = sc.unit[k] > 0 ? sc.unit[k] : total_kb;           // k-block steps per split-K slice
+      L.nsplits_eff[k] = (total_kb + L.splits[k] - 1) / L.splits[k];
       L.rowsum_part[k] = ws.take<float>(size_t(L.nparts[k]) * R);
       L.E[k] = need_grad ? ws.take<__nv_bfloat16>(size_t(R) * planes * Kq) : nullptr;
     }
@@ -1097,25 +1103,46 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
         if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
       }
     } else {
-      GemmProblem<EpiInfoNCE> p1[MAX_BLOCKS];
       GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
       for (int k = 0; k < nb; ++k) {
         const GroupDesc& G = groups[blocks[k].group];
         const int Kq = blk_Kq[k];
-        EpiInfoNCE::Params e1;
-        e1.rowsum_part = L.rowsum_part[k];
-        e1.e_planes = need_grad ? planes : 0;
-        e1.lo_col0 = Kq;
-        p1[k] = GemmProblem<EpiInfoNCE>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
-                                        int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1,
-                                        L.E[k], int64_t(planes) * Kq, int64_t(planes) * Kq};
         EpiStoreF32::Params e2{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
         p2[k] = GemmProblem<EpiStoreF32>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
-                                         G.rows, D, Kq, planes, L.splits[k], e2};
+                                         G.rows, D, Kq, planes, 1, e2};
+        p2[k].kb_per_split = L.splits[k];
       }
-      // CTA-pair kernels (256 x 256 tiles) whenever the tile width divides the problem
-      if (L.bn1 == 256) rc = launch_umma_grouped_pair<EpiInfoNCE>(p1, nb, st, reserved_sms);
-      else rc = launch_umma_grouped<128, EpiInfoNCE>(p1, nb, st, reserved_sms);
+      // S-GEMM, epilogue specialised on the number of E planes it writes (0 = forward only).
+      // CTA-pair kernels (256 x 256 tiles) whenever the tile width divides the problem.
+      auto launch_s = [&](auto epi_tag, bool pair) -> int {
+        using Epi = decltype(epi_tag);
+        GemmProblem<Epi> p1[MAX_BLOCKS];
+        for (int k = 0; k < nb; ++k) {
+          const GroupDesc& G = groups[blocks[k].group];
+          const int Kq = blk_Kq[k];
+          typename Epi::Params e1;
+          e1.rowsum_part = L.rowsum_part[k];
+          e1.lo_col0 = Kq;
+          p1[k] = GemmProblem<Epi>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
+                                   int64_t(planes) * D, G.rows, Kq, D, planes, 1, e1,
+                                   L.E[k], int64_t(planes) * Kq, int64_t(planes) * Kq};
+        }
+        if constexpr (Epi::PAIR_WARPS == 8 && Epi::STORE_COLS == 32) {
+          if (!pair) return launch_umma_grouped<128, Epi>(p1, nb, st, reserved_sms);
+        }
+        return launch_umma_grouped_pair<Epi>(p1, nb, st, reserved_sms);
+      };
+      const int ep_planes = need_grad ? planes : 0;
+      if (L.bn1 == 256) {
+        if (ep_planes == 0) rc = launch_s(EpiInfoNCE<0>(), true);
+        else if (ep_planes == 2) rc = launch_s(EpiInfoNCE<2>(), true);
+        else rc = launch_s(EpiInfoNCE<1>(), true);
+      } else {
+        // 128-wide single-CTA tiles (Kq not a multiple of 256): eight epilogue warps, one chunk per store
+        if (ep_planes == 0) rc = launch_s(EpiInfoNCE<0, 8, 6, 1, 2>(), false);
+        else if (ep_planes == 2) rc = launch_s(EpiInfoNCE<2, 8, 6, 1, 2>(), false);
+        else rc = launch_s(EpiInfoNCE<1, 8, 6, 1, 2>(), false);
+      }
       if (rc) return rc;
       if (need_grad) {
         if (L.bn2 == 256) rc = launch_umma_grouped_pair<EpiStoreF32>(p2, nb, st, reserved_sms);
@@ -1128,21 +1155,34 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
   if (release != nullptr) HMMC_CHECK_CUDA(cudaEventRecord(release, st));
   if (phase == 1) return HMMC_OK;
   // 4. positives, loss, gradient, loss sums
+  // Row order of the finish kernel: one warp per row, rows of a query tensor that owns a ONE_TO_FRAMES block
+  // first.  Those rows walk Fk key rows each (12 dependent rounds of loads) and set the kernel's duration unless
+  // they start with the first wave of blocks.
+  int slot_of[MAX_GROUPS], group_at[MAX_GROUPS];
+  {
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < ng; ++i) {
+        bool heavy = false;
+        for (int k = 0; k < nb; ++k) heavy = heavy || (blocks[k].group == i && blocks[k].pos_mode == HMMC_POS_ONE_TO_FRAMES);
+        if (heavy == (pass == 0)) { slot_of[i] = n; group_at[n] = i; ++n; }
+      }
+  }
   FinishArgs fa;
   fa.n = ng;
   fa.row_begin[0] = 0;
   for (int i = 0; i < MAX_GROUPS; ++i) {
-    const int gi = i < ng ? i : 0;
+    const int gi = i < ng ? group_at[i] : group_at[0];
     RowGroup& R = fa.g[i];
     R.q = groups[gi].q;
     R.dq = groups[gi].dq;
     R.rows = groups[gi].rows;
     R.Fq = groups[gi].Fq;
     R.ncontrib = 0;
-    fa.row_begin[i + 1] = fa.row_begin[i] + (i < ng ? groups[i].rows : 0);
+    fa.row_begin[i + 1] = fa.row_begin[i] + (i < ng ? groups[gi].rows : 0);
   }
   for (int k = 0; k < nb; ++k) {
-    RowGroup& R = fa.g[blocks[k].group];
+    RowGroup& R = fa.g[slot_of[blocks[k].group]];
     HMMC_REQUIRE(R.ncontrib < 2, "infonce: a query tensor may feed at most two queues");
     Contribution& C = R.c[R.ncontrib++];
     C.keys = blocks[k].keys;

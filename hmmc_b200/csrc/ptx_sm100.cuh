@@ -236,6 +236,13 @@ __device__ __forceinline__ void bulk_wait_group_read() {
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// two fp32 -> one register of two bf16 (round to nearest even): `first` in the low half (lower address)
+__device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+  return d;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

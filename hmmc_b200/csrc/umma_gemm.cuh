@@ -47,10 +47,14 @@ constexpr int UMMA_THREADS = (4 + UMMA_EPI_WARPS) * 32;
 
 template <int BN, class Epi>
 struct UmmaCfg {
-  static constexpr int STAGES = (BN > 128) ? 4 : 6;
   static constexpr uint32_t A_BYTES = UMMA_BM * UMMA_BK * 2;
   static constexpr uint32_t B_BYTES = BN * UMMA_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  // ring depth: 6 stages of 32 KB / 4 of 48 KB, fewer when the epilogue's staging area needs the room
+  static constexpr int WANT_STAGES = (BN > 128) ? 4 : 6;
+  static constexpr int FIT_STAGES = int((232448 - 2048 - UMMA_EPI_WARPS * Epi::STAGE_BYTES) / STAGE_BYTES);
+  static constexpr int STAGES = WANT_STAGES < FIT_STAGES ? WANT_STAGES : FIT_STAGES;
+  static_assert(STAGES >= 3, "TMA ring too shallow");
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128 : 256;
   static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;               // 256 B of mbarriers + the TMEM slot
@@ -105,6 +109,18 @@ __device__ __forceinline__ int find_problem(const GroupedArgs<Epi>& g, int t) {
   for (int i = 1; i < UMMA_MAX_PROBLEMS; ++i)
     if (i < g.num_problems && t >= g.tile_begin[i]) p = i;
   return p;
+}
+
+// The epilogue's walk over the 32-column chunks of its half tile, unrolled with the chunk index as a
+// compile-time constant (epilogues pick staging buffers by it): the TMEM load of chunk C+1 is in flight while
+// chunk C is processed.
+template <int C, int NC, class Epi>
+__device__ __forceinline__ void epi_chunks(Epi& epi, const typename Epi::Params& ep, const GemmShape& s, int row,
+                                           int col_base, uint32_t taddr, float (&v)[2][32]) {
+  ptx::tmem_ld_wait();
+  if constexpr (C + 1 < NC) ptx::tmem_ld_x32(taddr + (C + 1) * 32, v[(C + 1) & 1]);
+  epi.template chunk<C, NC>(ep, s, row, col_base + C * 32, v[C & 1]);
+  if constexpr (C + 1 < NC) epi_chunks<C + 1, NC>(epi, ep, s, row, col_base, taddr, v);
 }
 
 template <int BN, class Epi>
@@ -252,15 +268,9 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * HALF_N;
       epi.begin_tile(ep, s, row, n_blk, split, &tm.c[p]);
       {
-        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
         ptx::tmem_ld_x32(taddr, v[0]);
-#pragma unroll
-        for (int c = 0; c < HALF_N / 32; ++c) {
-          ptx::tmem_ld_wait();
-          if (c + 1 < HALF_N / 32) ptx::tmem_ld_x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-          epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v[c & 1]);
-        }
+        epi_chunks<0, HALF_N / 32>(epi, ep, s, row, n_blk * BN + half * HALF_N, taddr, v);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -285,27 +295,35 @@ umma_gemm_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ Gro
 // tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs, and each CTA's epilogue
 // warps drain their own 128 accumulator rows.  A stage is 32 KB instead of 48 KB, so six stages fit:
 // half the L2 -> SM bytes per FLOP and 1.5x more latency tolerance for the TMA ring.
+// The number of epilogue warps (8, or 16 = four per TMEM lane quadrant for epilogues that are latency-bound at
+// two warps per scheduler) and the depth of the TMA ring are properties of the epilogue (Epi::PAIR_WARPS,
+// Epi::PAIR_STAGES): a deeper ring or a larger store staging area, whichever the 227 KB pay for best.
 constexpr int UMMA_PAIR_BN = 256;
-constexpr int UMMA_PAIR_STAGES = 6;
 constexpr uint32_t UMMA_PAIR_A_BYTES = UMMA_BM * UMMA_BK * 2;               // 16 KB
 constexpr uint32_t UMMA_PAIR_B_BYTES = (UMMA_PAIR_BN / 2) * UMMA_BK * 2;    // 16 KB
 constexpr uint32_t UMMA_PAIR_STAGE_BYTES = UMMA_PAIR_A_BYTES + UMMA_PAIR_B_BYTES;
-constexpr uint32_t UMMA_PAIR_BAR_OFF = UMMA_PAIR_STAGES * UMMA_PAIR_STAGE_BYTES;
-constexpr uint32_t UMMA_PAIR_EPI_OFF = UMMA_PAIR_BAR_OFF + 1024;
 template <class Epi>
-constexpr size_t umma_pair_smem_bytes() {
-  return size_t(UMMA_PAIR_EPI_OFF) + 1024 + UMMA_EPI_WARPS * Epi::STAGE_BYTES;
-}
+struct UmmaPairCfg {
+  static constexpr int STAGES = Epi::PAIR_STAGES;
+  static constexpr int EPI_WARPS = Epi::PAIR_WARPS;
+  static constexpr int THREADS = (4 + EPI_WARPS) * 32;
+  static constexpr uint32_t BAR_OFF = STAGES * UMMA_PAIR_STAGE_BYTES;
+  static constexpr uint32_t EPI_OFF = BAR_OFF + 1024;
+  static constexpr size_t SMEM_BYTES = size_t(EPI_OFF) + 1024 + EPI_WARPS * Epi::STAGE_BYTES;
+  static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "two or four epilogue warps per TMEM lane quadrant");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
+};
 
 template <class Epi>
-__global__ void __launch_bounds__(UMMA_THREADS, 1)
+__global__ void __launch_bounds__(UmmaPairCfg<Epi>::THREADS, 1)
 umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ GroupedArgs<Epi> g) {
+  using Cfg = UmmaPairCfg<Epi>;
   constexpr int BN = UMMA_PAIR_BN;
-  constexpr int STAGES = UMMA_PAIR_STAGES;
-  static_assert(umma_pair_smem_bytes<Epi>() <= 232448, "shared memory budget of one CTA");
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int EPI_WARPS = Cfg::EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UMMA_PAIR_BAR_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t bar_base = ptx::smem_u32(bars);
   auto full_bar = [&](int i) { return bar_base + 8u * i; };
@@ -335,7 +353,7 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar(i), 1);
-      ptx::mbar_init(tempty_bar(i), 2 * UMMA_EPI_WARPS);   // epilogue warps of both CTAs (leader's copy is used)
+      ptx::mbar_init(tempty_bar(i), 2 * EPI_WARPS);        // epilogue warps of both CTAs (leader's copy is used)
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -417,13 +435,14 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
-    constexpr int HALF_N = BN / 2;
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    constexpr int PARTS = EPI_WARPS / 4;        // warps per quadrant: each takes BN / PARTS columns
+    const int part = (warp - 4) >> 2;
+    constexpr int PART_N = BN / PARTS;
     int acc = 0;
     uint32_t acc_phase = 0;
     Epi epi;
-    epi.stage = smem + UMMA_PAIR_EPI_OFF + size_t(warp - 4) * Epi::STAGE_BYTES;
+    epi.stage = smem + Cfg::EPI_OFF + size_t(warp - 4) * Epi::STAGE_BYTES;
     epi.lane = lane;
     epi.init();
     for (int u = 0; u < my_units; ++u) {
@@ -439,23 +458,17 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
       const int row = (m2 * 2 + int(cta)) * UMMA_BM + quad * 32 + lane;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * HALF_N;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + part * PART_N;
       epi.begin_tile(ep, s, row, n_blk, split, &tm.c[p]);
       {
-        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
         ptx::tmem_ld_x32(taddr, v[0]);
-#pragma unroll
-        for (int c = 0; c < HALF_N / 32; ++c) {
-          ptx::tmem_ld_wait();
-          if (c + 1 < HALF_N / 32) ptx::tmem_ld_x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-          epi.chunk(ep, s, row, n_blk * BN + half * HALF_N + c * 32, v[c & 1]);
-        }
+        epi_chunks<0, PART_N / 32>(epi, ep, s, row, n_blk * BN + part * PART_N, taddr, v);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
-      epi.end_tile(ep, s, row, n_blk * 2 + half, split);
+      epi.end_tile(ep, s, row, n_blk * PARTS + part, split);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     epi.finish();
@@ -481,6 +494,9 @@ struct EpiStoreF32 {
   };
   static constexpr uint32_t STAGE_BYTES = 32 * 80;    // per warp: 32 rows x (64 + 16 pad) bytes
   static constexpr bool USES_CMAP = false;
+  static constexpr int PAIR_WARPS = 8, PAIR_STAGES = 6;
+  static constexpr int PARTS_PER_TILE_PAIR = 2;       // partial results per 256-wide tile (CTA-pair kernel)
+  static constexpr int STORE_COLS = 64;               // (no TMA stores)
   uint8_t* stage;
   int lane;
   float* tile_out;   // &C[split][row of lane 0 of this warp, 0]
@@ -494,6 +510,7 @@ struct EpiStoreF32 {
     tile_out = p.C + int64_t(split) * p.split_stride + int64_t(row0) * p.ldc;
     vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.split_stride & 3) == 0);
   }
+  template <int C, int NC>
   __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
     // two 16-column halves: rows staged at an 80-byte pitch, then each instruction stores eight
     // 64-byte row segments
@@ -533,58 +550,91 @@ struct EpiStoreF32 {
 // the accumulator is the logit in base-2 units and e = 2^acc needs one MUFU per element and nothing else; the
 // constant maximum of the log-sum-exp (all logits <= 1/T) is applied by the finish kernel as one factor
 // 2^(-c2) on the row sums and on U (2^(2/T log2 e) still fits fp32 and bf16 comfortably for T >= 0.025).
-// Per-row partial sums -> rowsum_part[2*n_blk + half][row]; bf16 hi(/lo) planes of e -> E through TMA
-// stores: each warp writes its 32 x 32 chunk into a 64B-swizzled staging tile (conflict-free 16-byte stores,
-// two tiles in flight) and one lane hands it to the copy engine, which also clips rows beyond M.
-// No logits are written.  Requires N % 32 == 0 (checked by the host).
+// Per-row partial sums -> rowsum_part[part][row]; bf16 hi(/lo) planes of e -> E through TMA stores: a warp
+// packs GROUP 32-column chunks into a 32-row staging tile (64B / 128B swizzle, conflict-free 16-byte stores,
+// NBUF tiles in flight) and one lane hands it to the copy engine, which also clips rows beyond M.
+// No logits are written.  Requires N % 64 == 0 (checked by the host).
+// PLANES: 0 = forward only (no E), 1 = bf16, 2 = bf16x3 (hi and lo planes).
+// Shape of the epilogue in the CTA-pair kernel (measured on B200 at b = 256, profiles/r2_epilogue_sweep.md):
+// WARPS epilogue warps, STAGES TMA ring stages, GROUP chunks per store, NBUF staging tiles per warp.
+#ifndef HMMC_S_WARPS
+#define HMMC_S_WARPS 8
+#define HMMC_S_STAGES 6
+#define HMMC_S_GROUP 1
+#define HMMC_S_NBUF 2
+#endif
+template <int PLANES, int WARPS = (PLANES == 2 ? 8 : HMMC_S_WARPS), int STAGES = (PLANES == 2 ? 5 : HMMC_S_STAGES),
+          int GROUP = (PLANES == 2 ? 1 : HMMC_S_GROUP), int NBUF = (PLANES == 2 ? 2 : HMMC_S_NBUF)>
 struct EpiInfoNCE {
   struct Params {
-    float* rowsum_part;       // [2 * num_n_blk, M]: one partial per epilogue half-tile
-    int e_planes;             // 0 = forward only (no E), 1, 2
+    float* rowsum_part;       // [parts per tile * num_n_blk, M]: one partial per epilogue warp column range
     int lo_col0;              // column offset of the lo plane inside the E tensor map (= N)
   };
-  static constexpr uint32_t STAGE_BYTES = 2 * 2048;   // per warp: two 32-row x 64-byte TMA store sources
-  static constexpr bool USES_CMAP = true;
+  static constexpr int PAIR_WARPS = WARPS;
+  static constexpr int PAIR_STAGES = STAGES;
+  static constexpr int PARTS_PER_TILE_PAIR = WARPS / 4;
+  static constexpr int STORE_COLS = 32 * GROUP;                  // columns per TMA store (tensor-map box)
+  static constexpr uint32_t TILE_BYTES = 32 * STORE_COLS * 2;    // 32 rows of 64 / 128 bytes
+  static constexpr uint32_t STAGE_BYTES = NBUF * TILE_BYTES;     // per warp
+  static constexpr bool USES_CMAP = PLANES != 0;
+  static_assert(GROUP == 1 || GROUP == 2, "one or two chunks per store");
   uint8_t* stage;
   int lane;
   float s0, s1, s2, s3;
   int row0;
-  uint32_t nbuf;
-  uint32_t sw_off[4];         // this lane's four 16-byte slots inside a staging tile (64B swizzle)
+  uint32_t stage_addr;
+  uint32_t slot0;             // this lane's 16-byte slot 0 of a staging tile; slot c is at slot0 ^ (c << 4)
+  uint32_t hold_hi[16], hold_lo[16];      // first chunk of a two-chunk group (dead unless GROUP == 2)
   const CUtensorMap* cmap;
   __device__ __forceinline__ void init() {
-    nbuf = 0;
-    const uint32_t base = ptx::smem_u32(stage) + uint32_t(lane) * 64u;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sw_off[c] = base + (uint32_t(c ^ ((lane >> 1) & 3)) << 4);
+    stage_addr = ptx::smem_u32(stage);
+    // swizzle: the 16-byte chunk index is XORed with the row index (64B rows: bits 1..2 of the row; 128B rows: bits 0..2)
+    slot0 = (GROUP == 1) ? stage_addr + uint32_t(lane) * 64u + (uint32_t((lane >> 1) & 3) << 4)
+                         : stage_addr + uint32_t(lane) * 128u + (uint32_t(lane & 7) << 4);
   }
   __device__ __forceinline__ void finish() {
-    if (lane == 0) ptx::bulk_wait_group_read<0>();     // the copy engine still reads this CTA's shared memory
-    __syncwarp();
+    if (PLANES != 0) {
+      if (lane == 0) ptx::bulk_wait_group_read<0>();   // the copy engine still reads this CTA's shared memory
+      __syncwarp();
+    }
   }
   __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int row, int, int, const CUtensorMap* c) {
     s0 = s1 = s2 = s3 = 0.f;
     row0 = row - lane;
     cmap = c;
   }
-  __device__ __forceinline__ void store_plane(const uint32_t (&w)[16], int gcol) {
-    const uint32_t boff = (nbuf & 1u) * 2048u;
-    ++nbuf;
-    if (lane == 0) ptx::bulk_wait_group_read<1>();     // the store issued two chunks ago has read this tile
-    __syncwarp();
+  template <int SLOT>      // 16-byte slots SLOT .. SLOT+3 of this lane's row in staging tile BUF
+  __device__ __forceinline__ void stage4(const uint32_t (&w)[16], uint32_t buf_off) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw_off[c] + boff), "r"(w[4 * c]), "r"(w[4 * c + 1]),
-                   "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((slot0 ^ uint32_t((SLOT + c) << 4)) + buf_off),
+                   "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
                    : "memory");
+  }
+  // one plane of a group: a = the held first chunk (GROUP == 2 only), b = the current chunk; BUF = staging tile
+  template <int BUF>
+  __device__ __forceinline__ void store_group(const uint32_t (&a)[16], const uint32_t (&b)[16], int gcol) {
+    // the store that last used this staging tile (NBUF stores ago) must have been read by the copy engine
+    if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
+    __syncwarp();
+    if (GROUP == 2) {
+      stage4<0>(a, BUF * TILE_BYTES);
+      stage4<4>(b, BUF * TILE_BYTES);
+    } else {
+      stage4<0>(b, BUF * TILE_BYTES);
+    }
     ptx::fence_proxy_async();                          // generic-proxy writes -> visible to the copy engine
     __syncwarp();
     if (lane == 0) {
-      ptx::tma_store_2d(cmap, ptx::smem_u32(stage) + boff, gcol, row0);
+      ptx::tma_store_2d(cmap, stage_addr + BUF * TILE_BYTES, gcol, row0);
       ptx::bulk_commit_group();
     }
   }
+  template <int C, int NC>      // chunk C of the NC chunks this warp handles per tile
   __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
+    // staging tiles are reused round-robin across tiles: the stores of one tile must fill whole rounds
+    static_assert(PLANES == 0 || NBUF == 1 || ((PLANES * NC / GROUP) % NBUF == 0 && NC % GROUP == 0),
+                  "stores per tile must be a multiple of the staging tiles");
     float e[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) e[j] = ptx::ex2_approx(v[j]);
@@ -595,36 +645,42 @@ struct EpiInfoNCE {
       s2 += e[j + 2];
       s3 += e[j + 3];
     }
-    if (p.e_planes != 0) {
+    if constexpr (PLANES != 0) {
       uint32_t hi[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
-        hi[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      store_plane(hi, col0);
-      if (p.e_planes == 2) {
-        uint32_t lo[16];
+      for (int j = 0; j < 16; ++j) hi[j] = ptx::pack_bf16x2(e[2 * j], e[2 * j + 1]);
+      uint32_t lo[16];
+      if constexpr (PLANES == 2) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&hi[j]);
-          __nv_bfloat162 l = __floats2bfloat162_rn(e[2 * j] - __low2float(h), e[2 * j + 1] - __high2float(h));
-          lo[j] = *reinterpret_cast<uint32_t*>(&l);
+        for (int j = 0; j < 16; ++j)
+          lo[j] = ptx::pack_bf16x2(e[2 * j] - __uint_as_float(hi[j] << 16), e[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u));
+      }
+      if constexpr (GROUP == 2 && (C & 1) == 0) {
+        // first half of a 64-column group: keep it until the second half arrives
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hold_hi[j] = hi[j];
+        if constexpr (PLANES == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hold_lo[j] = lo[j];
         }
-        store_plane(lo, p.lo_col0 + col0);
+      } else {
+        constexpr int S = C / GROUP;                           // store index of this warp within the tile
+        const int gcol = col0 - 32 * (GROUP - 1);
+        store_group<(PLANES * S) % NBUF>(hold_hi, hi, gcol);
+        if constexpr (PLANES == 2) store_group<(PLANES * S + 1) % NBUF>(hold_lo, lo, p.lo_col0 + gcol);
       }
     }
   }
-  __device__ __forceinline__ void end_tile(const Params& p, const GemmShape& s, int row, int n_blk, int) {
-    if (row < s.M) p.rowsum_part[int64_t(n_blk) * s.M + row] = (s0 + s1) + (s2 + s3);
+  __device__ __forceinline__ void end_tile(const Params& p, const GemmShape& s, int row, int part, int) {
+    if (row < s.M) p.rowsum_part[int64_t(part) * s.M + row] = (s0 + s1) + (s2 + s3);
   }
 };
 
 // ------------------------------------------------------------------ host side
 
 // bf16 row-major [rows, cols] (leading dimension ld elements) -> 2-D tensor map with a
-// [box_rows x 64] box and the 128-byte swizzle (operand loads), or a [box_rows x 32] box with the 64-byte
-// swizzle (the epilogue's store tiles).
+// [box_rows x 64] box and the 128-byte swizzle (operand loads and the epilogue's 32-row store tiles);
+// box_cols = 32 selects the 64-byte swizzle.
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                    uint32_t box_cols = UMMA_BK);
 
@@ -651,6 +707,7 @@ struct GemmProblem {
   int M, N, K, planes, splits;
   typename Epi::Params ep;
   void* out = nullptr; int64_t out_cols = 0; int64_t out_ld = 0;
+  int kb_per_split = 0;      // > 0: k-block steps per split-K slice (the last slice may be shorter); overrides splits
 };
 
 // reserved_sms: SMs this launch leaves free (a bandwidth-bound kernel or a collective running beside the
@@ -745,15 +802,16 @@ static inline int fill_problems(const GemmProblem<Epi>* probs, int n, int m_tile
     const int total_kb = s.num_seg * s.kb_per_seg;
     int splits = pr.splits < 1 ? 1 : (pr.splits > total_kb ? total_kb : pr.splits);
     s.kb_per_split = (total_kb + splits - 1) / splits;
+    if (pr.kb_per_split > 0) s.kb_per_split = pr.kb_per_split < total_kb ? pr.kb_per_split : total_kb;
     s.num_splits = (total_kb + s.kb_per_split - 1) / s.kb_per_split;   // every split gets >= 1 k-block
     int rc = make_tmap_bf16(&tm.a[k], pr.A, uint64_t(pr.M), uint64_t(pr.planes) * pr.K, uint64_t(pr.lda), UMMA_BM);
     if (rc) return rc;
     rc = make_tmap_bf16(&tm.b[k], pr.B, uint64_t(pr.N), uint64_t(pr.planes) * pr.K, uint64_t(pr.ldb), b_box_rows);
     if (rc) return rc;
     if (Epi::USES_CMAP && pr.out != nullptr) {
-      HMMC_REQUIRE(pr.N % 32 == 0 && pr.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(pr.out) & 15) == 0,
-                   "umma gemm: TMA-store epilogue needs N %% 32 == 0 and a 16-byte aligned output");
-      rc = make_tmap_bf16(&tm.c[k], pr.out, uint64_t(pr.M), uint64_t(pr.out_cols), uint64_t(pr.out_ld), 32, 32);
+      HMMC_REQUIRE(pr.N % 64 == 0 && pr.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(pr.out) & 15) == 0,
+                   "umma gemm: TMA-store epilogue needs N %% 64 == 0 and a 16-byte aligned output");
+      rc = make_tmap_bf16(&tm.c[k], pr.out, uint64_t(pr.M), uint64_t(pr.out_cols), uint64_t(pr.out_ld), 32, Epi::STORE_COLS);
       if (rc) return rc;
     } else {
       tm.c[k] = tm.a[k];
@@ -774,12 +832,12 @@ static inline int fill_problems(const GemmProblem<Epi>* probs, int n, int m_tile
 }
 
 template <class Kern, class Epi>
-static inline int launch_gemm(Kern kern, int grid, int cluster, size_t smem, cudaStream_t stream, const TmapSet& tm,
-                              const GroupedArgs<Epi>& g) {
+static inline int launch_gemm(Kern kern, int grid, int cluster, size_t smem, int threads, cudaStream_t stream,
+                              const TmapSet& tm, const GroupedArgs<Epi>& g) {
   HMMC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(UMMA_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -813,7 +871,7 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
   const int budget = gemm_sm_budget(reserved_sms);
   const int grid = tiles < budget ? tiles : budget;
   build_schedule(g, grid);
-  return launch_gemm(umma_gemm_kernel<BN, Epi>, grid, 1, Cfg::SMEM_BYTES, stream, tm, g);
+  return launch_gemm(umma_gemm_kernel<BN, Epi>, grid, 1, Cfg::SMEM_BYTES, UMMA_THREADS, stream, tm, g);
 }
 
 // CTA-pair launch of a grouped GEMM (BN = 256).  GemmShape::num_m_blk counts 256-row super tiles;
@@ -830,7 +888,8 @@ int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t 
   int pairs = gemm_sm_budget(reserved_sms) / 2;
   if (pairs > tiles) pairs = tiles;
   build_schedule(g, pairs);
-  return launch_gemm(umma_gemm_pair_kernel<Epi>, 2 * pairs, 2, umma_pair_smem_bytes<Epi>(), stream, tm, g);
+  return launch_gemm(umma_gemm_pair_kernel<Epi>, 2 * pairs, 2, UmmaPairCfg<Epi>::SMEM_BYTES, UmmaPairCfg<Epi>::THREADS,
+                     stream, tm, g);
 }
 
 // number of split-K partials launch_umma_grouped will produce for a request of `splits`

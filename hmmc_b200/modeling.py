@@ -34,19 +34,24 @@ DEFAULT_CROSS_CONFIG = dict(temporal_hidden_size=512, weight_FAM=0.05, weight_VT
 
 # Schedule constants (measured on B200; these were environment knobs while being tuned):
 # * the enqueue of a single-rank step runs on a side stream next to the tail of the loss;
-# * on one rank the query-side GEMMs of the loss run beside the momentum update (head_loss_begin / head_loss_end)
-#   with their persistent grids kept on 148 - LOSS_GEMM_RESERVED SMs, because the EMA is HBM-bound and needs the
-#   other SMs to saturate the memory system (tools/overlap_probe.py);
+# * the query-side GEMMs of the loss CAN run beside the momentum update (head_loss_begin / head_loss_end) with
+#   their persistent grids kept on 148 - LOSS_GEMM_RESERVED SMs (the EMA is HBM-bound and needs the other SMs
+#   to saturate the memory system, tools/overlap_probe.py).  With round 2's loss kernels the plain sequence is
+#   faster (0.388 ms vs 0.400 ms per step on one B200), so forward() no longer splits by default;
 # * with several ranks the key exchange and the enqueue of step i are deferred to run beside step i+1's momentum
 #   update (nothing reads the queues before step i+1's loss), see ContrastiveHeadMixin.start_pending_exchange.
 LOSS_GEMM_RESERVED = 120
 _side_streams = {}
 
 
+SPLIT_SCHEDULE = False
+
+
 def use_split_schedule():
-    """The two-half schedule pays on a single rank (0.408 -> 0.399 ms per step); with several ranks the side
+    """Whether forward() issues the query-side half of the loss beside the momentum update.  Off: measured
+    slower than the plain sequence since the loss kernels shrank (see above); with several ranks the side
     stream beside the EMA carries the deferred key exchange instead."""
-    return parallel.world()[0] == 1
+    return SPLIT_SCHEDULE and parallel.world()[0] == 1
 
 
 def _side_stream(device, name="enqueue", priority=0):

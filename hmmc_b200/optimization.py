@@ -114,7 +114,14 @@ class BertAdam(Optimizer):
         reference's in-place clipping does (the training loops zero them right after, so the default
         skips that write).
     After a step, ``last_grad_norm`` is a 0-d device tensor with the total gradient norm.
+
+    --enable_amp (main_pretrain.py:267-284): ``scaler.step(optimizer)`` of torch.cuda.amp.GradScaler finds
+    ``_step_supports_amp_scaling`` and hands the step its ``grad_scale`` / ``found_inf`` tensors instead of
+    unscaling the gradients itself.  The step is skipped when an inf / NaN was found (one host read, as the
+    reference's unfused GradScaler path does) and otherwise multiplies every gradient by 1/scale inside the norm
+    and update kernels: the arithmetic equals unscale_ followed by step(), without the extra pass.
     """
+    _step_supports_amp_scaling = True
 
     def __init__(self, params, lr=required, warmup=-1, t_total=-1, schedule='warmup_linear',
                  b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01, max_grad_norm=1.0):
@@ -185,6 +192,14 @@ class BertAdam(Optimizer):
         if not live:
             return loss
         dev = live[0][1].device
+        # torch.cuda.amp.GradScaler protocol (set on the optimizer around scaler.step())
+        grad_scale = getattr(self, "grad_scale", None)
+        found_inf = getattr(self, "found_inf", None)
+        if found_inf is not None and float(found_inf) > 0:
+            return loss                       # GradScaler skips the step; scaler.update() lowers the scale
+        inv_scale = None
+        if grad_scale is not None:
+            inv_scale = grad_scale.detach().to(device=dev, dtype=torch.float64).reciprocal().to(torch.float32).reshape(1)
         p_ptrs = [p.data_ptr() for _, p, _ in live]
         g_ptrs = [p.grad.data_ptr() for _, p, _ in live]
         m_ptrs = [s['next_m'].data_ptr() for _, _, s in live]
@@ -234,7 +249,7 @@ class BertAdam(Optimizer):
         _lib.check(_lib.load().hmmc_bert_adam_multi(
             _p(tab.cols[0]), _p(tab.cols[1]), _p(tab.cols[2]), _p(tab.cols[3]), _p(tab.numels), _p(tab.dtypes),
             _p(tab.offs), tab.n, tab.total_blocks, _p(self._hyper_dev), gmax, 1 if write_back_grads else 0,
-            _p(self._norms), _p(ws), ws.numel(), _stream()), "hmmc_bert_adam_multi")
+            _p(inv_scale), _p(self._norms), _p(ws), ws.numel(), _stream()), "hmmc_bert_adam_multi")
         self.last_grad_norm = self._norms[tab.n]
         for _, _, state in live:
             state['step'] += 1

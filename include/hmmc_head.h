@@ -193,14 +193,18 @@ int hmmc_ema_block_elems(void);
  *   u <- m/(sqrt(v)+e) [+ wd*p];  p <- p - lr*u
  * with cg = min(1, G/(||g_all|| + 1e-6)), ct = min(1, max_grad_norm/(||g_t||*cg + 1e-6)).
  * write_back_grads != 0 also stores the clipped gradients (the reference clips p.grad in
- * place and zeroes it right after).  norms_out: NULL or device fp32 [n+1] receiving the
- * per-tensor gradient norms and, last, the total norm clip_grad_norm_ returns. */
+ * place and zeroes it right after).  inv_scale: NULL or a device fp32 scalar 1/scale of
+ * torch.cuda.amp.GradScaler (--enable_amp, main_pretrain.py:267-284): every gradient element is first
+ * replaced by fl(g * inv_scale), the value GradScaler.unscale_ would have stored, so the norms, both clips
+ * and the update see the unscaled gradients without a separate pass over them.  norms_out: NULL or
+ * device fp32 [n+1] receiving the per-tensor gradient norms and, last, the total norm
+ * clip_grad_norm_ returns. */
 size_t hmmc_bert_adam_workspace_bytes(int n, int64_t total_blocks);
 int hmmc_bert_adam_multi(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs,
                          const uint64_t* v_ptrs, const int64_t* numels, const int32_t* dtypes,
                          const int64_t* block_offsets, int n, int64_t total_blocks, const float* hyper,
-                         float global_max_norm, int write_back_grads, float* norms_out, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         float global_max_norm, int write_back_grads, const float* inv_scale, float* norms_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* clip_grad_norm_ on its own: gradients scaled in place by min(1, max_norm/(total + 1e-6));
  * workspace sized by hmmc_bert_adam_workspace_bytes. */
 int hmmc_clip_grad_norm_multi(const uint64_t* g_ptrs, const int64_t* numels, const int64_t* block_offsets, int n,

@@ -178,3 +178,40 @@ def test_large_table_many_blocks():
     for i, p in enumerate(params):
         torch.testing.assert_close(p.detach(), ref_p[i], rtol=2e-6, atol=1e-8)
         torch.testing.assert_close(opt.state[p]['next_m'], ref_m[i], rtol=2e-6, atol=1e-10)
+
+
+def test_grad_scaler_step_equals_unscaled_step():
+    """--enable_amp (main_pretrain.py:258-284): scaler.scale(loss).backward(); clip_grad_norm_; scaler.step(opt);
+    scaler.update().  GradScaler hands BertAdam its scale (`_step_supports_amp_scaling`); the unscale happens inside
+    the norm and update kernels.  With a power-of-two scale the result equals the fp32 run bit for bit; a step that
+    saw an inf is skipped (parameters, moments and step counters untouched) and the scale is halved."""
+    _, pa, opt_a = _make("pretrain")
+    _, pb, opt_b = _make("pretrain")
+    scaler = torch.amp.GradScaler("cuda", init_scale=65536.0, growth_interval=1000)
+    for st in range(3):
+        grads = [cu(g) for g in syn.optim_grads(st)]
+        for p, g in zip(pa, grads):
+            p.grad = g.clone()
+        opt_a.step()
+        loss = sum((p * g).sum() for p, g in zip(pb, grads))      # d loss / d p = g
+        scaler.scale(loss).backward()
+        assert float(pb[0].grad.abs().max()) > 100 * float(grads[0].abs().max())      # gradients really are scaled
+        scaler.step(opt_b)
+        scaler.update()
+        opt_b.zero_grad()
+        for a, b in zip(pa, pb):
+            assert torch.equal(a.detach(), b.detach()), st
+            assert torch.equal(opt_a.state[a]['next_v'], opt_b.state[b]['next_v']), st
+    assert float(scaler.get_scale()) == 65536.0
+    # an overflowing gradient: the step is skipped and the scale backs off
+    before = [p.detach().clone() for p in pb]
+    steps_before = [opt_b.state[p]['step'] for p in pb]
+    grads = [cu(g) for g in syn.optim_grads(5)]
+    loss = sum((p * g).sum() for p, g in zip(pb, grads))
+    scaler.scale(loss).backward()
+    pb[1].grad.view(-1)[0] = float("inf")
+    scaler.step(opt_b)
+    scaler.update()
+    assert float(scaler.get_scale()) == 32768.0
+    for p, b0, s0 in zip(pb, before, steps_before):
+        assert torch.equal(p.detach(), b0) and opt_b.state[p]['step'] == s0

@@ -354,3 +354,27 @@ def test_split_head_equals_fused_call(prec):
     for a, c in zip(res[0][2], res[1][2]):
         assert torch.equal(a, c)
     assert res[0][3] == res[1][3] == 32
+
+
+def test_head_accepts_fp16_autocast_embeddings():
+    """--enable_amp (main_pretrain.py:82,258): whatever the autocast region hands the head in fp16 is widened once,
+    the arithmetic stays the fp32-parity path, and the gradients come back in the inputs' dtype.  Checked against the
+    float64 oracle evaluated on the SAME fp16-rounded embeddings (1e-5 on the loss; the fp16 rounding of the returned
+    gradients bounds their error at ~1e-3)."""
+    b, F, D, K = 32, 12, 512, 1024
+    inp = {n: x.astype(np.float16).astype(np.float32) for n, x in syn.pretrain_inputs(b, F=F, D=D, seed=2).items()}
+    qs = syn.queues(K, F=F, D=D, seed=3)
+    ref_loss, ref_g = O.pretrain_loss_and_grads(inp, qs, 0.07)
+    m = _model(K, F, D, "bf16x3")
+    _load_queues(m, qs)
+    names = ("v_fea", "title_fea", "frame_fea", "frame_pred")
+    t = {n: torch.from_numpy(x).cuda().half().requires_grad_(n in names) for n, x in inp.items()}
+    with torch.autocast("cuda", dtype=torch.float16):
+        loss = m.head_loss(t["v_fea"], t["frame_fea"], t["title_fea"], t["frame_pred"], t["v_fea_k"], t["frame_fea_k"],
+                           t["title_fea_k"], t["tag_fea_k"], t["frame_proj_k"])
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    scaler.scale(loss).backward()
+    assert loss.dtype == torch.float32 and abs(float(loss.detach()) - ref_loss) / ref_loss < 1e-5
+    for n in names:
+        assert t[n].grad.dtype == torch.float16
+        assert rel(t[n].grad.float().cpu().numpy() / 1024.0, ref_g[n]) < 2e-3, n
