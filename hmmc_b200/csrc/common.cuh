@@ -156,4 +156,11 @@ int umma_effective_splits(int K, int planes, int splits);
 // src [rows, cols] fp32 -> straight [rows, planes*cols] and transposed [cols, planes*rows] bf16 plane
 // packs (either output may be null); defined in pretrain.cu
 int pack_dual(const float* src, int rows, int cols, int planes, void* straight, void* transposed, cudaStream_t st);
+// fused-tile eval (eval_fused.cu): gallery pack (1 + 12 rows per video, 208-row tiles) and the materialising
+// sweep that writes sim / fsim (or their sum) from the register top-k, no [Nt, Nv*F] intermediate
+size_t eval_gallery_pack_rows(int64_t Nv);
+int eval_pack_gallery(const float* video, const float* frames, int64_t Nv, int F, int D, int planes, void* out,
+                      cudaStream_t st);
+int eval_sim_write(const void* text_packed, const void* gallery_packed, int64_t Nt, int64_t Nv, int D, int prec,
+                   float scale, int top_k, float* sim, float* fsim, int64_t ld_out, int combine, cudaStream_t st);
 }  // namespace hmmc

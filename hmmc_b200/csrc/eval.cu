@@ -42,6 +42,8 @@ __global__ void topk_frames_kernel(const float* __restrict__ SF, int64_t Nt, int
 // t2v: one warp per text row.
 __global__ void rank_t2v_kernel(const float* __restrict__ sim, int64_t lds, int Nt, int Nv,
                                 const int32_t* __restrict__ gt, int32_t* __restrict__ t2v) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= Nt) return;
@@ -54,10 +56,15 @@ __global__ void rank_t2v_kernel(const float* __restrict__ sim, int64_t lds, int 
 }
 
 // theta[j] = max over the captions of video j of sim[s,j]   (NaN -> -inf, metrics.py:83)
+// also clears the v2t counters the next kernel accumulates into
 __global__ void rank_theta_kernel(const float* __restrict__ sim, int64_t lds, int Nv,
-                                  const int32_t* __restrict__ group_start, float* __restrict__ theta) {
+                                  const int32_t* __restrict__ group_start, float* __restrict__ theta,
+                                  int32_t* __restrict__ v2t) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Nv) return;
+  v2t[j] = 0;
   float m = -INFINITY;
   for (int s = group_start[j]; s < group_start[j + 1]; ++s) {
     float v = sim[int64_t(s) * lds + j];
@@ -72,6 +79,8 @@ __global__ void __launch_bounds__(256)
 rank_v2t_kernel(const float* __restrict__ sim, int64_t lds, int Nv, const int32_t* __restrict__ group_start,
                 const float* __restrict__ theta, int groups_per_block, int32_t* __restrict__ v2t) {
   __shared__ int cnts[8][32];
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   const int g0 = blockIdx.y * groups_per_block;
@@ -112,6 +121,17 @@ size_t hmmc_sim_topk_workspace_bytes(int64_t Nt, int64_t Nv, int F, int D, int p
     ws.take<float>(size_t(Nt) * D);
     ws.take<float>(size_t(Nv) * D);
     ws.take<float>(size_t(Nv) * F * D);
+  } else if (hmmc_eval_fused_supported(F, D, 1)) {
+    // fused tiles: packed text + packed gallery only (top_k is checked at call time; sized for either path)
+    ws.take<__nv_bfloat16>(size_t(Nt) * planes * D);
+    ws.take<__nv_bfloat16>(eval_gallery_pack_rows(Nv) * planes * D);
+    Workspace alt(nullptr, 0);
+    alt.take<__nv_bfloat16>(size_t(Nt) * planes * D);
+    alt.take<__nv_bfloat16>(size_t(Nv) * planes * D);
+    alt.take<__nv_bfloat16>(size_t(Nv) * F * planes * D);
+    alt.take<float>(size_t(Nt) * Nv * F);
+    (void)alt;
+    return ws.used + 256;
   } else {
     ws.take<__nv_bfloat16>(size_t(Nt) * planes * D);
     ws.take<__nv_bfloat16>(size_t(Nv) * planes * D);
@@ -152,6 +172,18 @@ int hmmc_sim_topk_fwd(const float* text, int64_t Nt, const float* video, const f
       if ((rc = rownorm_pack(frames, Nv * F, D, D, 0.f, 1, fh, nullptr, nullptr, 0, st))) return rc;
       if ((rc = gemm_f32(th, D, 1, fh, D, 1, SF, Nv * F, int(Nt), int(Nv * F), D, scale, st))) return rc;
     }
+  } else if (frames != nullptr && video != nullptr && hmmc_eval_fused_supported(F, D, top_k) && (sim != nullptr || fsim != nullptr)) {
+    // fused tiles (F = 12, top_k <= 4): one GEMM sweep over [video | 12 frames] column groups, top-k pooling in
+    // registers, scores written once - no [Nt, Nv*F] frame-similarity matrix, three launches in all
+    __nv_bfloat16* tp = ws.take<__nv_bfloat16>(size_t(Nt) * planes * D);
+    __nv_bfloat16* gp = ws.take<__nv_bfloat16>(eval_gallery_pack_rows(Nv) * planes * D);
+    if (!ws.ok()) { set_error("sim_topk: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
+    const int64_t ldp = int64_t(planes) * D;
+    if ((rc = rownorm_pack(text, Nt, D, D, 0.f, planes, nullptr, nullptr, tp, ldp, st))) return rc;
+    if ((rc = eval_pack_gallery(video, frames, Nv, F, D, planes, gp, st))) return rc;
+    // sim == fsim (one buffer): the caller wants the sum (main_task_retrieval.py:512-513)
+    const int combine = (sim != nullptr && sim == fsim) ? 1 : 0;
+    return eval_sim_write(tp, gp, Nt, Nv, D, prec, scale, top_k, sim, combine ? nullptr : fsim, ld_out, combine, st);
   } else {
     HMMC_REQUIRE(D % 64 == 0, "sim_topk: tensor-core path needs D %% 64 == 0 (D=%d)", D);
     __nv_bfloat16* tp = ws.take<__nv_bfloat16>(size_t(Nt) * planes * D);
@@ -184,14 +216,14 @@ int hmmc_rank_count(const float* sim, int64_t lds, int Nt, int Nv, const int32_t
   HMMC_REQUIRE(sim && Nt > 0 && Nv > 0 && lds >= Nv, "rank_count: bad arguments");
   if (t2v != nullptr) {
     HMMC_REQUIRE(gt != nullptr, "rank_count: t2v needs gt");
-    rank_t2v_kernel<<<unsigned((Nt + 7) / 8), 256, 0, st>>>(sim, lds, Nt, Nv, gt, t2v);
-    HMMC_CHECK_LAUNCH();
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(rank_t2v_kernel, dim3(unsigned((Nt + 7) / 8)), dim3(256), 0, st, sim, lds, Nt, Nv, gt, t2v));
   }
   if (v2t != nullptr) {
     HMMC_REQUIRE(group_start != nullptr && theta_scratch != nullptr, "rank_count: v2t needs group_start and theta_scratch");
-    rank_theta_kernel<<<unsigned((Nv + 255) / 256), 256, 0, st>>>(sim, lds, Nv, group_start, theta_scratch);
-    HMMC_CHECK_LAUNCH();
-    HMMC_CHECK_CUDA(cudaMemsetAsync(v2t, 0, sizeof(int32_t) * size_t(Nv), st));
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(rank_theta_kernel, dim3(unsigned((Nv + 255) / 256)), dim3(256), 0, st, sim, lds, Nv,
+                               group_start, theta_scratch, v2t));
     const int col_blocks = (Nv + 31) / 32;
     int gy = (4 * sm_count() + col_blocks - 1) / col_blocks;   // enough blocks to fill the machine
     if (gy < 1) gy = 1;
@@ -199,8 +231,8 @@ int hmmc_rank_count(const float* sim, int64_t lds, int Nt, int Nv, const int32_t
     if (gpb < 8) gpb = 8;
     gy = (Nv + gpb - 1) / gpb;
     dim3 grid(col_blocks, gy);
-    rank_v2t_kernel<<<grid, 256, 0, st>>>(sim, lds, Nv, group_start, theta_scratch, gpb, v2t);
-    HMMC_CHECK_LAUNCH();
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(rank_v2t_kernel, grid, dim3(256), 0, st, sim, lds, Nv, group_start, theta_scratch, gpb, v2t));
   }
   return HMMC_OK;
 }

@@ -45,6 +45,13 @@ struct EvalArgs {
   const int2* diag_tiles;         // mode 0: (m_blk, n_blk) pairs
   int n_diag_tiles;
   int panel_n_blk;                // mode 1: gallery tiles per L2-resident panel
+  // mode 2 (materialise): scores written out instead of counted.  sim = s * t.v, fsim = mean of the top-k frame
+  // similarities (either may be NULL); combine != 0: sim receives the sum (main_task_retrieval.py:512-513)
+  float* sim_out;
+  float* fsim_out;
+  int64_t ld_out;
+  int Nt;                         // valid text rows (rows beyond are padding of the last tile)
+  int combine;
 };
 
 // OR-reduction of a predicate over the 256 epilogue threads (named barrier 1); also a barrier.
@@ -81,12 +88,13 @@ struct VideoAcc {
     }
   }
   // scale > 0 commutes with max and mean: one multiply per video instead of one per column
-  __device__ __forceinline__ float score(float scale) const {
+  __device__ __forceinline__ float frame_score(float scale) const {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < K; ++i) s += best[i] * scale;        // descending order, like torch.topk(...).mean
-    return vsim * scale + s / float(K);
+    return s / float(K);
   }
+  __device__ __forceinline__ float score(float scale) const { return vsim * scale + frame_score(scale); }
 };
 
 constexpr int EV_EPI_WARPS = 8;
@@ -97,7 +105,9 @@ constexpr int EV_HALF_VID = EV_VPT / 2;
 // One epilogue warp's share of a tile: walk its 104 accumulator columns (8 videos x 13) in order,
 // pool each video (video sim + mean of the top-K frame sims), update the caption's t2v count and
 // return the bit mask of videos whose score beats theta (v2t candidates).
-template <int K>
+// WRITE (mode 2): the eight pooled scores of this thread's caption are kept in registers and written as two
+// 16-byte stores per output matrix (one full 32-byte sector per row and tile half).
+template <int K, bool WRITE>
 __device__ __forceinline__ uint32_t eval_tile_columns(const EvalArgs& a, uint32_t taddr, int row, int n_blk, int half,
                                                       int my_grp, float my_gt, int& my_cnt) {
   const int v0 = n_blk * EV_VPT + half * EV_HALF_VID;     // first local video of this warp's columns
@@ -105,12 +115,18 @@ __device__ __forceinline__ uint32_t eval_tile_columns(const EvalArgs& a, uint32_
   VideoAcc<K> va;
   va.reset();
   va.vsim = 0.f;
+  float o_sim[WRITE ? EV_HALF_VID : 1], o_fs[WRITE ? EV_HALF_VID : 1];
   auto consume = [&](float x, int c) {
     const int mem = c % EV_COLS;
     if (mem == 0) { va.reset(); va.vsim = x; } else { va.push(x); }
     if (mem == EV_COLS - 1) {
       const int vl = c / EV_COLS;             // video inside this warp's half
       const int vloc = v0 + vl;               // local video index
+      if (WRITE) {
+        o_sim[WRITE ? vl : 0] = va.vsim * a.scale;
+        o_fs[WRITE ? vl : 0] = va.frame_score(a.scale);
+        return;
+      }
       const float sc = va.score(a.scale);
       const bool own = (my_grp == a.video_base + vloc);
       if (a.mode == 0) {
@@ -135,6 +151,26 @@ __device__ __forceinline__ uint32_t eval_tile_columns(const EvalArgs& a, uint32_
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) consume(v[j], (EV_HALF_COLS / 32) * 32 + j);
+  }
+  if (WRITE && row < a.Nt) {
+    if (a.combine) {
+#pragma unroll
+      for (int i = 0; i < EV_HALF_VID; ++i) o_sim[WRITE ? i : 0] += o_fs[WRITE ? i : 0];
+    }
+    auto put = [&](float* out, const float (&o)[WRITE ? EV_HALF_VID : 1]) {
+      if (out == nullptr) return;
+      float* dst = out + int64_t(row) * a.ld_out + v0;
+      if (v0 + EV_HALF_VID <= a.Nv_local && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[WRITE ? 1 : 0], o[WRITE ? 2 : 0], o[WRITE ? 3 : 0]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(o[WRITE ? 4 : 0], o[WRITE ? 5 : 0], o[WRITE ? 6 : 0], o[WRITE ? 7 : 0]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EV_HALF_VID; ++i)
+          if (v0 + i < a.Nv_local) dst[i] = o[WRITE ? i : 0];
+      }
+    };
+    put(a.sim_out, o_sim);
+    if (!a.combine) put(a.fsim_out, o_fs);
   }
   return mask;
 }
@@ -168,7 +204,7 @@ __device__ __forceinline__ void eval_tile_v2t(const EvalArgs& a, uint32_t mask, 
   }
 }
 
-template <int K>
+template <int K, bool WRITE = false>
 __global__ void __launch_bounds__(EV_THREADS, 1)
 eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ EvalArgs a) {
@@ -223,10 +259,12 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   //           of its caption tiles against the panel:
   //             for (panel) for (m = blockIdx.x; m < num_m_blk; m += gridDim.x) for (n in panel)
   //   mode 0: for (t = blockIdx.x; t < n_diag_tiles; t += gridDim.x) (m, n) = diag_tiles[t]
+  //   mode 2: for (t = blockIdx.x; t < num_m_blk * num_n_blk; t += gridDim.x) (m, n) = (t % num_m_blk, t / num_m_blk)
   const int my_m = (a.num_m_blk - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int list_tiles = WRITE ? a.num_m_blk * a.num_n_blk : a.n_diag_tiles;
   const long long tiles_per_cta =
       (a.mode == 1) ? (long long)my_m * a.num_n_blk
-                    : (long long)((a.n_diag_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x));
+                    : (long long)((list_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x));
   const int NP = a.panel_n_blk;
   const long long full_span = (long long)my_m * NP * (a.num_n_blk / (NP > 0 ? NP : 1));
   const int rem_n = (NP > 0) ? a.num_n_blk % NP : 0;
@@ -246,6 +284,10 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       m_blk = int(blockIdx.x) + mi * int(gridDim.x);
       n_blk = nj;
+    } else if (WRITE) {
+      const int t = int(blockIdx.x) + int(i) * int(gridDim.x);
+      m_blk = t % a.num_m_blk;
+      n_blk = t / a.num_m_blk;
     } else {
       const int2 t = a.diag_tiles[int(blockIdx.x) + int(i) * int(gridDim.x)];
       m_blk = t.x;
@@ -319,7 +361,7 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (a.mode == 1 && cur_m >= 0 && my_cnt != 0) atomicAdd(&a.t2v_cnt[cur_m * UMMA_BM + trow], my_cnt);
         cur_m = m_blk;
         my_cnt = 0;
-        my_grp = a.grp[row];
+        my_grp = WRITE ? -1 : a.grp[row];
         if (a.mode == 1) {
           my_gt = a.gt_score[row];
           // publish the tile's group ids for the cross-row reduction (all 256 epilogue threads)
@@ -331,7 +373,7 @@ eval_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * Cfg::ACC_STRIDE + half * EV_HALF_COLS;
-      const uint32_t mask = eval_tile_columns<K>(a, taddr, row, n_blk, half, my_grp, my_gt, my_cnt);
+      const uint32_t mask = eval_tile_columns<K, WRITE>(a, taddr, row, n_blk, half, my_grp, my_gt, my_cnt);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -513,7 +555,7 @@ eval_rank_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           ptx::mbar_wait(tfull_bar(acc), acc_phase);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + half * EV_HALF_COLS;
-          const uint32_t mask = eval_tile_columns<K>(a, taddr, row, n, half, my_grp, my_gt, my_cnt);
+          const uint32_t mask = eval_tile_columns<K, false>(a, taddr, row, n, half, my_grp, my_gt, my_cnt);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA thread waits on it
@@ -631,7 +673,7 @@ int hmmc_eval_pack_gallery(const float* video, const float* frames, int64_t Nv, 
 }
 
 static int eval_launch(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
-                       int prec, EvalArgs& a, cudaStream_t st) {
+                       int prec, EvalArgs& a, cudaStream_t st, int64_t text_rows = 0) {
   HMMC_REQUIRE(text_packed && gallery_packed, "eval: null operand");
   HMMC_REQUIRE(Nt_pad > 0 && Nt_pad % UMMA_BM == 0, "eval: Nt_pad must be a positive multiple of %d", UMMA_BM);
   HMMC_REQUIRE(D % UMMA_BK == 0, "eval: D %% 64 != 0");
@@ -647,12 +689,14 @@ static int eval_launch(const void* text_packed, const void* gallery_packed, int6
   a.kb_per_seg = s.kb_per_seg;
   for (int i = 0; i < 3; ++i) { a.a_k0[i] = s.a_k0[i]; a.b_k0[i] = s.b_k0[i]; }
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16(&tmA, text_packed, uint64_t(Nt_pad), uint64_t(planes) * D, uint64_t(planes) * D, UMMA_BM);
+  // text_rows > 0: the operand has fewer rows than the tile grid covers, TMA zero-fills the rest
+  int rc = make_tmap_bf16(&tmA, text_packed, uint64_t(text_rows > 0 ? text_rows : Nt_pad), uint64_t(planes) * D,
+                          uint64_t(planes) * D, UMMA_BM);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, gallery_packed, uint64_t(a.num_n_blk) * EV_BN, uint64_t(planes) * D, uint64_t(planes) * D, EV_BN);
   if (rc) return rc;
   using Cfg = UmmaCfg<EV_BN, EpiStoreF32>;   // ring geometry only; this kernel has its own epilogue
-  const int work = (a.mode == 1) ? a.num_m_blk : a.n_diag_tiles;
+  const int work = (a.mode == 1) ? a.num_m_blk : (a.mode == 2 ? a.num_m_blk * a.num_n_blk : a.n_diag_tiles);
   if (work <= 0) return HMMC_OK;
   // counting sweep in one bf16 plane: CTA pairs with the caption tile resident in shared memory
   if (a.mode == 1 && planes == 1 && D / UMMA_BK <= EVP_MAX_KB) {
@@ -694,6 +738,14 @@ static int eval_launch(const void* text_packed, const void* gallery_packed, int6
     HMMC_CHECK_LAUNCH();
     return HMMC_OK;
   };
+  if (a.mode == 2) {
+    switch (a.top_k) {
+      case 1: return launch(eval_rank_kernel<1, true>);
+      case 2: return launch(eval_rank_kernel<2, true>);
+      case 3: return launch(eval_rank_kernel<3, true>);
+      default: return launch(eval_rank_kernel<4, true>);
+    }
+  }
   switch (a.top_k) {
     case 1: return launch(eval_rank_kernel<1>);
     case 2: return launch(eval_rank_kernel<2>);
@@ -701,6 +753,41 @@ static int eval_launch(const void* text_packed, const void* gallery_packed, int6
     default: return launch(eval_rank_kernel<4>);
   }
 }
+
+}  // extern "C"
+
+namespace hmmc {
+// Materialised scores through the same tiles: sim / fsim [Nt, Nv] from packed operands (text: straight
+// [Nt, planes*D] rows, tensor map clipped at Nt; gallery: hmmc_eval_pack_gallery layout).  Internal: called by
+// hmmc_sim_topk_fwd (eval.cu) for the shapes the fused tiles cover.
+int eval_sim_write(const void* text_packed, const void* gallery_packed, int64_t Nt, int64_t Nv, int D, int prec,
+                   float scale, int top_k, float* sim, float* fsim, int64_t ld_out, int combine, cudaStream_t st) {
+  EvalArgs a{};
+  a.scale = scale;
+  a.top_k = top_k;
+  a.mode = 2;
+  a.sim_out = sim;
+  a.fsim_out = fsim;
+  a.ld_out = ld_out;
+  a.Nt = int(Nt);
+  a.combine = combine;
+  const int64_t Nt_pad = (Nt + UMMA_BM - 1) / UMMA_BM * UMMA_BM;
+  return eval_launch(text_packed, gallery_packed, Nt_pad, Nv, D, prec, a, st, Nt);
+}
+
+size_t eval_gallery_pack_rows(int64_t Nv) { return size_t((Nv + EV_VPT - 1) / EV_VPT) * EV_BN; }
+
+int eval_pack_gallery(const float* video, const float* frames, int64_t Nv, int F, int D, int planes, void* out,
+                      cudaStream_t st) {
+  const int64_t rows_pad = int64_t(eval_gallery_pack_rows(Nv));
+  eval_pack_gallery_kernel<<<unsigned((rows_pad + 7) / 8), 256, 0, st>>>(video, frames, Nv, rows_pad, F, D, planes,
+                                                                        static_cast<__nv_bfloat16*>(out));
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+}  // namespace hmmc
+
+extern "C" {
 
 int hmmc_eval_gt_scores(const void* text_packed, const void* gallery_packed, int64_t Nt_pad, int64_t Nv_local, int D,
                         int prec, float scale, int top_k, int video_base, const int32_t* grp,

@@ -1,7 +1,7 @@
 // Fine-tune (hierarchical matching) head: loose_similarity, CrossEn and the fused
 // symmetric-CE loss over the text x video and the F text x frame similarity matrices.
 #include "common.cuh"
-#include <stdlib.h>
+#include "ptx_sm100.cuh"
 
 namespace hmmc {
 
@@ -179,8 +179,12 @@ __device__ __forceinline__ const float* symce_src_row(const SymOperands& o, int 
 __global__ void __launch_bounds__(1024)
 symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, int Bk, int NGk,
                   __nv_bfloat16* __restrict__ Tp,
-                  __nv_bfloat16* __restrict__ TTp, __nv_bfloat16* __restrict__ Gp, __nv_bfloat16* __restrict__ GTp) {
+                  __nv_bfloat16* __restrict__ TTp, __nv_bfloat16* __restrict__ Gp, __nv_bfloat16* __restrict__ GTp,
+                  unsigned* __restrict__ lse_counter) {
   extern __shared__ float tile[];                 // [32][D + 1]
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *lse_counter = 0u;
   const int ld = D + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 32;
@@ -217,64 +221,73 @@ symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, in
   }
 }
 
-// Row and column log-sum-exp of S_all in one launch.  Blocks [0, row_blocks): one warp per (text row,
-// similarity block) pair, 8 pairs per block; the remaining blocks take 32 columns each.
+// Row and column log-sum-exp of S_all in one launch, and the loss: blocks [0, row_blocks) take one warp per
+// (text row, similarity block) pair, 8 pairs per block; the remaining blocks take 32 columns each.  The block
+// that finishes last adds  loss = sum_fp w_fp/B sum_i (lse_row + lse_col - 2 S_ii)  in a fixed order.
 __global__ void __launch_bounds__(256)
 symce_lse_kernel(const float* __restrict__ S, int B, int NB, int row_blocks, float* __restrict__ lse_row,
-                 float* __restrict__ lse_col) {
+                 float* __restrict__ lse_col, int voff, float w0, float wf, float* __restrict__ loss_out,
+                 unsigned* __restrict__ counter) {
   __shared__ float sm[8][32], ss[8][32];
+  __shared__ float red[32];
+  __shared__ bool last;
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ncol = int64_t(NB) * B;
   if (int(blockIdx.x) < row_blocks) {
     const int pair = blockIdx.x * 8 + warp;          // = i * NB + fp: consecutive warps read consecutive memory
-    if (pair >= B * NB) return;
-    const int i = pair / NB, fp = pair - i * NB;
-    const float* row = S + int64_t(i) * ncol + int64_t(fp) * B;
-    float m = -INFINITY;
-    for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int j = lane; j < B; j += 32) s += expf(row[j] - m);
-    s = warp_sum(s);
-    if (lane == 0) lse_row[fp * B + i] = m + logf(s);
-    return;
-  }
-  const int64_t col = int64_t(blockIdx.x - row_blocks) * 32 + lane;
-  float m = -INFINITY, s = 0.f;
-  if (col < ncol) {
-    for (int i = warp; i < B; i += 8) {
-      const float v = S[int64_t(i) * ncol + col];
-      if (v > m) { s = s * expf(m - v) + 1.f; m = v; } else { s += expf(v - m); }
+    if (pair < B * NB) {
+      const int i = pair / NB, fp = pair - i * NB;
+      const float* row = S + int64_t(i) * ncol + int64_t(fp) * B;
+      float m = -INFINITY;
+      for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < B; j += 32) s += expf(row[j] - m);
+      s = warp_sum(s);
+      if (lane == 0) lse_row[fp * B + i] = m + logf(s);
+    }
+  } else {
+    const int64_t col = int64_t(blockIdx.x - row_blocks) * 32 + lane;
+    float m = -INFINITY, s = 0.f;
+    if (col < ncol) {
+      for (int i = warp; i < B; i += 8) {
+        const float v = S[int64_t(i) * ncol + col];
+        if (v > m) { s = s * expf(m - v) + 1.f; m = v; } else { s += expf(v - m); }
+      }
+    }
+    sm[warp][lane] = m;
+    ss[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && col < ncol) {
+      float Mx = sm[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) Mx = fmaxf(Mx, sm[w][lane]);
+      float Ssum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) Ssum += (sm[w][lane] == -INFINITY) ? 0.f : ss[w][lane] * expf(sm[w][lane] - Mx);
+      lse_col[col] = Mx + logf(Ssum);
     }
   }
-  sm[warp][lane] = m;
-  ss[warp][lane] = s;
+  // ---- the last block to arrive adds the loss
+  __threadfence();
   __syncthreads();
-  if (warp == 0 && col < ncol) {
-    float Mx = sm[0][lane];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) Mx = fmaxf(Mx, sm[w][lane]);
-    float Ssum = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) Ssum += (sm[w][lane] == -INFINITY) ? 0.f : ss[w][lane] * expf(sm[w][lane] - Mx);
-    lse_col[col] = Mx + logf(Ssum);
-  }
-}
-
-// loss = sum_fp w_fp/B sum_i (lse_row + lse_col - 2 S_ii)   (one block, fixed order)
-__global__ void symce_loss_kernel(const float* __restrict__ S, int B, int NB, const float* __restrict__ lse_row,
-                                  const float* __restrict__ lse_col, int voff, float w0, float wf,
-                                  float* __restrict__ loss_out) {
-  __shared__ float red[32];
-  const int64_t ncol = int64_t(NB) * B;
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   float acc = 0.f;
   for (int k = threadIdx.x; k < NB * B; k += blockDim.x) {
     const int fp = k / B, i = k - fp * B;
     const float w = ((fp < voff) ? w0 : wf) / float(B);
-    acc += w * (lse_row[k] + lse_col[k] - 2.f * S[int64_t(i) * ncol + k]);
+    acc += w * (__ldcg(lse_row + k) + __ldcg(lse_col + k) - 2.f * S[int64_t(i) * ncol + k]);
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) loss_out[0] = acc;
+  if (threadIdx.x == 0) {
+    loss_out[0] = acc;
+    *counter = 0u;
+  }
 }
 
 // G = dL/dS computed on the fly from S and the two LSE vectors and written straight as the bf16
@@ -284,6 +297,8 @@ symce_gradpack_kernel(const float* __restrict__ S, int B, int NB, const float* _
                       const float* __restrict__ lse_col, int voff, float w0, float wf, int planes, int Bk, int NGk,
                       __nv_bfloat16* __restrict__ Sp, __nv_bfloat16* __restrict__ STp) {
   __shared__ float tile[32][33];
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NG = NB * B;
   const int c0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
@@ -323,6 +338,8 @@ template <int NV>
 __global__ void symce_unnorm_kernel(SymOperands src, int B, int F, int voff, int D,
                                     const float* __restrict__ gt_parts, int n_splits, int64_t split_stride,
                                     const float* __restrict__ gg, SymGrads out) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int NG = (voff + F) * B;
@@ -469,6 +486,7 @@ int hmmc_cross_en_fwd_bwd(const float* S, int64_t lds, int B, float* loss_out, f
 
 struct SymCeWs {
   float *that, *ghat, *S, *lse_row, *lse_col, *row_loss, *gt, *gg;
+  unsigned* counter;
   // tensor-core path: plane-packed operands (straight and transposed) and split-K partials
   __nv_bfloat16 *Tp, *TTp, *Gp, *GTp, *Sp, *STp;
   float* parts;
@@ -492,6 +510,7 @@ static void symce_carve(Workspace& ws, SymCeWs& w, int B, int F, int D, int prec
   w.lse_row = ws.take<float>(NB * B);
   w.lse_col = ws.take<float>(NB * B);
   w.row_loss = ws.take<float>(size_t(B));
+  w.counter = ws.take<unsigned>(4);
   w.gt = ws.take<float>(size_t(B) * D);
   w.gg = ws.take<float>(NB * B * D);
   w.Tp = w.TTp = w.Gp = w.GTp = w.Sp = w.STp = nullptr;
@@ -537,7 +556,8 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
   const bool need_grad = dtext || dvideo || dframes;
   int rc;
   if (symce_tensor_ok(B, D, prec)) {
-    // tensor-core path: 7 launches (4 without gradients)
+    // tensor-core path: 6 launches (3 without gradients)
+    HMMC_REQUIRE(D <= 1024, "sym_ce: D=%d above the tensor-core path's limit of 1024", D);
     const int NG = NB * B, P = planes_of(prec);
     const int Bk = int(align_up(size_t(B), 64)), NGk = int(align_up(size_t(NG), 64));
     const float wf = (F > 0) ? w_ftm / float(F) : 0.f;
@@ -555,20 +575,23 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
       HMMC_CHECK_CUDA(cudaFuncSetAttribute(symce_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prep_smem)));
       prep_smem_set = int(prep_smem);
     }
-    symce_prep_kernel<<<unsigned((B + NG) / 32), 1024, prep_smem, st>>>(src, B, F, voff, D, P, Bk, NGk, w.Tp,
-                                                                need_grad ? w.TTp : nullptr, w.Gp,
-                                                                need_grad ? w.GTp : nullptr);
-    HMMC_CHECK_LAUNCH();
-    if ((rc = umma_gemm_store(w.Tp, int64_t(P) * D, w.Gp, int64_t(P) * D, w.S, NG, 0, B, NG, D, P, 1, scale, st))) return rc;
+    // every launch of the chain is programmatically serialised: a kernel's blocks become resident (and run their
+    // prologue) while the previous kernel drains, and wait for its results with griddepcontrol.wait
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(symce_prep_kernel, dim3(unsigned((B + NG) / 32)), dim3(1024), prep_smem, st, src, B, F, voff,
+                               D, P, Bk, NGk, w.Tp, need_grad ? w.TTp : nullptr, w.Gp, need_grad ? w.GTp : nullptr,
+                               w.counter));
+    // 128-wide tiles: at these sizes the GEMMs are a fraction of a wave, narrower tiles put twice the SMs to work
+    if ((rc = umma_gemm_store(w.Tp, int64_t(P) * D, w.Gp, int64_t(P) * D, w.S, NG, 0, B, NG, D, P, 1, scale, st,
+                              (int64_t(B) * NG <= int64_t(148) * 128 * 256) ? 128 : 0))) return rc;
     const int row_blocks = (B * NB + 7) / 8;
-    symce_lse_kernel<<<unsigned(row_blocks + (NG + 31) / 32), 256, 0, st>>>(w.S, B, NB, row_blocks, w.lse_row, w.lse_col);
-    HMMC_CHECK_LAUNCH();
-    symce_loss_kernel<<<1, 1024, 0, st>>>(w.S, B, NB, w.lse_row, w.lse_col, voff, w_vtm, wf, loss_out);
-    HMMC_CHECK_LAUNCH();
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(symce_lse_kernel, dim3(unsigned(row_blocks + (NG + 31) / 32)), dim3(256), 0, st, w.S, B, NB,
+                               row_blocks, w.lse_row, w.lse_col, voff, w_vtm, wf, loss_out, w.counter));
     if (!need_grad) return HMMC_OK;
-    symce_gradpack_kernel<<<dim3(NG / 32, B / 32), 256, 0, st>>>(w.S, B, NB, w.lse_row, w.lse_col, voff, w_vtm, wf, P,
-                                                                  Bk, NGk, w.Sp, w.STp);
-    HMMC_CHECK_LAUNCH();
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(symce_gradpack_kernel, dim3(NG / 32, B / 32), dim3(256), 0, st, w.S, B, NB, w.lse_row,
+                               w.lse_col, voff, w_vtm, wf, P, Bk, NGk, w.Sp, w.STp));
     // backward contractions in one grouped launch:
     //   g_that[i,d] = scale * sum_g G[i,g] ghat[g,d]   long K (= NG), few output tiles: split-K partials
     //   g_ghat[g,d] = scale * sum_i G[i,g] that[i,d]
@@ -586,14 +609,13 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
     if (dvideo != nullptr || dframes != nullptr)
       gm[ng++] = StoreGemm{w.STp, int64_t(P) * Bk, w.TTp, int64_t(P) * Bk, w.gg, D, 0, NG, D, Bk, 1};
     if ((rc = umma_gemm_store_grouped(gm, ng, P, scale, st))) return rc;
-    HMMC_REQUIRE(D <= 1024, "sym_ce: D=%d above the tensor-core path's limit of 1024", D);
+    count_launch();
     if (D <= 512)
-      symce_unnorm_kernel<16><<<unsigned((B + NG + 7) / 8), 256, 0, st>>>(src, B, F, voff, D, w.parts, eff,
-                                                                          int64_t(B) * D, w.gg, grads);
+      HMMC_CHECK_CUDA(launch_pdl(symce_unnorm_kernel<16>, dim3(unsigned((B + NG + 7) / 8)), dim3(256), 0, st, src, B, F, voff,
+                                 D, w.parts, eff, int64_t(B) * D, w.gg, grads));
     else
-      symce_unnorm_kernel<32><<<unsigned((B + NG + 7) / 8), 256, 0, st>>>(src, B, F, voff, D, w.parts, eff,
-                                                                          int64_t(B) * D, w.gg, grads);
-    HMMC_CHECK_LAUNCH();
+      HMMC_CHECK_CUDA(launch_pdl(symce_unnorm_kernel<32>, dim3(unsigned((B + NG + 7) / 8)), dim3(256), 0, st, src, B, F, voff,
+                                 D, w.parts, eff, int64_t(B) * D, w.gg, grads));
     return HMMC_OK;
   }
   HMMC_REQUIRE(src.ldt == D && (video == nullptr || src.ldv == D) && (F == 0 || src.ldf == int64_t(F) * D) &&
@@ -690,7 +712,7 @@ int hmmc_sym_ce_packed_fwd_bwd(const float* packed, int B, int F, int D, float s
                         workspace_bytes - align_up(ws.used, 256), st))) return rc;
   if (dpacked != nullptr) {
     const uint64_t g_ptrs[3] = {reinterpret_cast<uint64_t>(dt), reinterpret_cast<uint64_t>(dv), reinterpret_cast<uint64_t>(df)};
-    if ((rc = hmmc_pack_rows(g_ptrs, widths, n, B, dpacked, stream))) return rc;
+    if ((rc = hmmc_pack_rows(g_ptrs, widths, n, B, dpacked, nullptr, stream))) return rc;
   }
   return HMMC_OK;
 }

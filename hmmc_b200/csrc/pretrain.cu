@@ -278,6 +278,43 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
 #pragma unroll
       for (int i = 0; i < V; ++i) qv[i] = __ldg(qp + 32 * i);
     }
+    // Everything a contribution needs first is independent of the query: its row-sum partials and its first two
+    // key rows are requested together with the query row, one round trip instead of three.
+    float sp[3];
+    float4 kv[2][V];
+    bool on[2];
+    auto key_row = [&](const Contribution& C, int t, int& kr) -> bool {
+      int nterm;
+      if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kr = r; }
+      else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
+        nterm = 2;
+        const int fk = (t == 0) ? f + 1 : f - 1;          // pairs (i, i+1) and (i+1, i) of frame_self_loss
+        kr = n * C.Fk + fk;
+        return t < nterm && fk >= 0 && fk < C.Fk;         // warp-uniform
+      }
+      else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kr = n * C.Fk + t; }
+      else { nterm = 1; kr = n; }
+      return t < nterm;
+    };
+    auto load_keys = [&](const Contribution& C, int t0) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        int kr = 0;
+        on[k] = key_row(C, t0 + k, kr);
+        const float4* kp = reinterpret_cast<const float4*>(C.keys + int64_t(on[k] ? kr : 0) * D) + lane;
+#pragma unroll
+        for (int i = 0; i < V; ++i) kv[k][i] = on[k] ? __ldg(kp + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto prefetch = [&](const Contribution& C) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int p = lane + 32 * j;
+        sp[j] = (p < C.n_parts) ? __ldg(C.rowsum_part + int64_t(p) * G.rows + r) : 0.f;
+      }
+      load_keys(C, 0);
+    };
+    prefetch(G.c[0]);
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -293,63 +330,48 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
 
     for (int ci = 0; ci < G.ncontrib; ++ci) {
       const Contribution& C = G.c[ci];
-      // ---- row-sum partials of this contribution
-      float S = 0.f, S1 = 0.f;
-      for (int p = lane; p < C.n_parts; p += 64) {
-        const float a0 = __ldg(C.rowsum_part + int64_t(p) * G.rows + r);
-        const float a1 = (p + 32 < C.n_parts) ? __ldg(C.rowsum_part + int64_t(p + 32) * G.rows + r) : 0.f;
-        S += a0;
-        S1 += a1;
-      }
-      S = warp_sum(S + S1) * kexp;
-      int nterm, kbase, kstep;
-      if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kbase = r; kstep = 0; }
-      else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) { nterm = 2; kbase = 0; kstep = 0; }
-      else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kbase = n * C.Fk; kstep = 1; }
-      else { nterm = 1; kbase = n; kstep = 0; }
+      if (ci > 0) prefetch(C);
+      // ---- S_r: the negatives' sum, from the row-sum partials
+      float S = (sp[0] + sp[1]) + sp[2];
+      for (int p = lane + 96; p < C.n_parts; p += 32) S += __ldg(C.rowsum_part + int64_t(p) * G.rows + r);
+      S = warp_sum(S) * kexp;
+      const int nterm = (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) ? 2 : (C.pos_mode == HMMC_POS_ONE_TO_FRAMES ? C.Fk : 1);
       float loss = 0.f, sum_invZ = 0.f;
       const float scale = C.coef * invT;
-      // positive terms, two key rows in flight per iteration
+      // positive terms, two key rows in flight per iteration (the first pair is already on its way)
       for (int t0 = 0; t0 < nterm; t0 += 2) {
-        int kr[2];
-        bool on[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int t = t0 + k;
-          on[k] = t < nterm;
-          kr[k] = kbase + t * kstep;
-          if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
-            const int fk = (t == 0) ? f + 1 : f - 1;      // pairs (i, i+1) and (i+1, i) of frame_self_loss
-            on[k] = on[k] && fk >= 0 && fk < C.Fk;        // warp-uniform
-            kr[k] = n * C.Fk + fk;
-          }
-        }
-        float4 kv[2][V];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const float4* kp = reinterpret_cast<const float4*>(C.keys + int64_t(on[k] ? kr[k] : 0) * D) + lane;
-#pragma unroll
-          for (int i = 0; i < V; ++i) kv[k][i] = on[k] ? __ldg(kp + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (t0 > 0) load_keys(C, t0);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           if (!on[k]) continue;
-          float kk = 0.f, qk = 0.f;
+          // ||k||^2 and q_hat.k: two accumulators each (short dependency chains), both reduced in one butterfly
+          float kk0 = 0.f, kk1 = 0.f, qk0 = 0.f, qk1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < V; ++i) {
-            kk = dot4(kv[k][i], kv[k][i], kk);
-            qk = dot4(kv[k][i], qv[i], qk);
+          for (int i = 0; i < V; i += 2) {
+            kk0 = dot4(kv[k][i], kv[k][i], kk0);
+            qk0 = dot4(kv[k][i], qv[i], qk0);
+            if (i + 1 < V) {
+              kk1 = dot4(kv[k][i + 1], kv[k][i + 1], kk1);
+              qk1 = dot4(kv[k][i + 1], qv[i + 1], qk1);
+            }
           }
-          kk = warp_sum(kk);
-          qk = warp_sum(qk);
-          const float nk = fmaxf(sqrtf(kk), 1e-12f);
-          const float lpos = (qk / nk) * invT;
-          const float epos = expf(lpos - cmax);
+          float kk = kk0 + kk1, qk = qk0 + qk1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            kk += __shfl_xor_sync(0xffffffffu, kk, o);
+            qk += __shfl_xor_sync(0xffffffffu, qk, o);
+          }
+          // fast-math intrinsics (2^-21 relative): the row's loss share and weights are O(1) scalars whose error
+          // averages over b*F rows; measured against the float64 oracle in tests/test_gpu_pretrain.py
+          const float ink = (kk > 1e-24f) ? rsqrtf(kk) : 1e12f;          // 1 / max(||k||, 1e-12)
+          const float lpos = qk * ink * invT;
+          const float epos = __expf(lpos - cmax);
           const float Z = epos + S;
-          loss += logf(Z) + cmax - lpos;
-          sum_invZ += 1.0f / Z;
+          const float iZ = __fdividef(1.0f, Z);
+          loss += __logf(Z) + cmax - lpos;
+          sum_invZ += iZ;
           // g_hat += coef/T * (p+ - 1) k_hat_t
-          const float w = scale * (epos / Z - 1.0f) / nk;
+          const float w = scale * (epos * iZ - 1.0f) * ink;
 #pragma unroll
           for (int i = 0; i < V; ++i) axpy4(w, kv[k][i], g[i]);
         }
@@ -362,11 +384,11 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
           float4 t[2][V];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const bool on = s0 + k < C.n_splits;
-            const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(on ? s0 + k : s0) * C.split_stride +
+            const bool uon = s0 + k < C.n_splits;
+            const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(uon ? s0 + k : s0) * C.split_stride +
                                                                int64_t(r) * D) + lane;
 #pragma unroll
-            for (int i = 0; i < V; ++i) t[k][i] = on ? __ldg(up + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < V; ++i) t[k][i] = uon ? __ldg(up + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int k = 0; k < 2; ++k)
@@ -612,7 +634,9 @@ constexpr int ENQ_DCHUNK = 128;
 // advance to advance_ptr_kernel.
 // max(||x||, 1e-12) of every key vector of the five queues, one warp per vector;
 // norms[qi][c] with c = sample*mult + f, queue qi starting at norm_off[qi]
-__global__ void key_norms_kernel(int nsamples, int D, EnqueueArgs a, float* __restrict__ norms) {
+__global__ void key_norms_kernel(int nsamples, int D, EnqueueArgs a, float* __restrict__ norms,
+                                 const int32_t* __restrict__ staged) {
+  if (staged != nullptr && *staged == 0) return;      // nothing staged: these keys were enqueued already
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.y;
   const int mult = a.mult[qi];
@@ -629,7 +653,8 @@ __global__ void key_norms_kernel(int nsamples, int D, EnqueueArgs a, float* __re
 template <int CB>
 __global__ void __launch_bounds__(256)
 enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __restrict__ norms,
-               int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
+               int64_t* __restrict__ queue_ptr, int ptr, int new_ptr, const int32_t* __restrict__ staged) {
+  if (staged != nullptr && *staged == 0) return;
   __shared__ float inv[CB];            // 1 / max(||x||, 1e-12) of the block's key vectors
   __shared__ int64_t soff[CB];         // element offset of each key vector in its source tensor
   __shared__ float tile[CB][33];
@@ -722,7 +747,8 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __re
 // Needs the norms pre-pass.  Falls back to scalar stores when the first destination column is odd.
 __global__ void __launch_bounds__(256)
 enqueue_vec_kernel(int nsamples, int D, EnqueueArgs a, const float* __restrict__ norms,
-                   int64_t* __restrict__ queue_ptr, int ptr, int new_ptr) {
+                   int64_t* __restrict__ queue_ptr, int ptr, int new_ptr, const int32_t* __restrict__ staged) {
+  if (staged != nullptr && *staged == 0) return;
   constexpr int CB = 64, DB = 64;
   __shared__ float inv[CB];
   __shared__ int64_t soff[CB];
@@ -813,10 +839,13 @@ struct RowPackArgs {
   int total;
 };
 
+// staged (PACK only): NULL or a device flag set to 1 once the rows are packed: the deferred key exchange marks
+// its send buffer "keys staged", the enqueue consumes the mark (hmmc_enqueue_norm)
 template <bool PACK>
-__global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_t rows) {
+__global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_t rows, int32_t* staged) {
   const int64_t row = blockIdx.x;
   const int t = blockIdx.y;
+  if (PACK && staged != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *staged = 1;
   float* x = reinterpret_cast<float*>(a.ptrs[t]) + row * a.widths[t];
   float* y = packed + row * a.total + a.offs[t];
   for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
@@ -831,7 +860,8 @@ struct ScaleArgs {
 };
 // x_t *= scale[0] for up to 8 tensors (backward of the fused heads: the gradients were produced
 // with the loss, the upstream gradient arrives later)
-__global__ void scale_tensors_kernel(ScaleArgs a, const float* __restrict__ scale) {
+__global__ void scale_tensors_kernel(const ScaleArgs a, const float* __restrict__ scale) {
+  ptx::grid_dependency_wait();
   const float s = scale[0];
   if (s == 1.0f) return;               // loss.backward() with no upstream scaling: nothing to do
   float* x = a.ptrs[blockIdx.y];
@@ -1328,11 +1358,18 @@ int hmmc_ema_multi(const uint64_t* pk_ptrs, const uint64_t* p_ptrs, const int64_
   return HMMC_OK;
 }
 
-__global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K) { queue_ptr[0] = (queue_ptr[0] + B) % K; }
+// after the scatter: advance the device-side pointer (advance != 0) and consume the "keys staged" mark
+__global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K, int advance, int32_t* staged) {
+  if (staged != nullptr) {
+    if (*staged == 0) return;
+    *staged = 0;
+  }
+  if (advance) queue_ptr[0] = (queue_ptr[0] + B) % K;
+}
 
 static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
                           const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch,
-                          cudaStream_t st) {
+                          int32_t* staged, cudaStream_t st) {
   HMMC_REQUIRE(queues5 && queue_ptr, "enqueue: null argument");
   // the reference's slice assignment raises when the batch does not fit (modules/modeling.py:273-280)
   const bool device_ptr = ptr_host < 0;     // pointer lives on the device only (graph replay)
@@ -1360,7 +1397,7 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   }
   if (scratch != nullptr) {
     // norms once (one warp per key vector) so the transposing kernel can use small, numerous blocks
-    key_norms_kernel<<<dim3((B * F + 7) / 8, 5), 256, 0, st>>>(B, D, a, scratch);
+    key_norms_kernel<<<dim3((B * F + 7) / 8, 5), 256, 0, st>>>(B, D, a, scratch, staged);
     HMMC_CHECK_LAUNCH();
   }
   const int dchunk = scratch != nullptr ? 64 : ENQ_DCHUNK;
@@ -1374,26 +1411,27 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   }
   if (vec_ok) {
     dim3 grid((B * F + 63) / 64, (D + 63) / 64, 5);
-    enqueue_vec_kernel<<<grid, 256, 0, st>>>(B, D, a, scratch, queue_ptr, p_arg, np_arg);
+    enqueue_vec_kernel<<<grid, 256, 0, st>>>(B, D, a, scratch, queue_ptr, p_arg, np_arg, staged);
   } else {
     dim3 grid((B * F + 31) / 32, dchunks, 5);
-    enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg);
+    enqueue_kernel<32><<<grid, 256, 0, st>>>(B, D, dchunk, a, scratch, queue_ptr, p_arg, np_arg, staged);
   }
   HMMC_CHECK_LAUNCH();
-  if (device_ptr) {
-    advance_ptr_kernel<<<1, 1, 0, st>>>(queue_ptr, B, K);
+  if (device_ptr || staged != nullptr) {
+    advance_ptr_kernel<<<1, 1, 0, st>>>(queue_ptr, B, K, device_ptr ? 1 : 0, staged);
     HMMC_CHECK_LAUNCH();
   }
   return HMMC_OK;
 }
 
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5, int64_t* queue_ptr,
-                      int64_t ptr_host, int K, float* scratch, void* stream) {
+                      int64_t ptr_host, int K, float* scratch, int32_t* staged, void* stream) {
   HMMC_REQUIRE(gathered != nullptr, "enqueue: null gathered buffer");
   const int64_t row = int64_t(3 + 2 * F) * D;
   const float* src[5] = {gathered, gathered + D, gathered + 2 * D, gathered + 3 * D, gathered + 3 * D + int64_t(F) * D};
   const int64_t stride[5] = {row, row, row, row, row};
-  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, scratch,
+  HMMC_REQUIRE(staged == nullptr || ptr_host < 0, "enqueue: the staged mark needs the device-side queue pointer (ptr_host < 0)");
+  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, scratch, staged,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -1402,7 +1440,8 @@ int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* 
                              int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch, void* stream) {
   const float* src[5] = {v_k, tag_k, title_k, frame_fea_k, frame_proj_k};
   const int64_t stride[5] = {D, D, D, int64_t(F) * D, int64_t(F) * D};
-  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, static_cast<cudaStream_t>(stream));
+  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, nullptr,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, int n, const float* scale, void* stream) {
@@ -1419,18 +1458,18 @@ int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, in
   int gx = int((mx / 4 + 255) / 256);
   if (gx < 1) gx = 1;
   if (gx > 4 * sm_count()) gx = 4 * sm_count();
-  scale_tensors_kernel<<<dim3(gx, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, scale);
-  HMMC_CHECK_LAUNCH();
+  count_launch();
+  HMMC_CHECK_CUDA(launch_pdl(scale_tensors_kernel, dim3(gx, n), dim3(256), 0, static_cast<cudaStream_t>(stream), a, scale));
   return HMMC_OK;
 }
 
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows, float* dst,
-                   void* stream) {
+                   int32_t* staged, void* stream) {
   RowPackArgs a;
   int rc = build_rowpack(a, src_ptrs_host, widths_host, n);
   if (rc) return rc;
   if (rows <= 0) return HMMC_OK;
-  rowpack_kernel<true><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, rows);
+  rowpack_kernel<true><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, rows, staged);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -1441,7 +1480,8 @@ int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int3
   int rc = build_rowpack(a, dst_ptrs_host, widths_host, n);
   if (rc) return rc;
   if (rows <= 0) return HMMC_OK;
-  rowpack_kernel<false><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, const_cast<float*>(src), rows);
+  rowpack_kernel<false><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, const_cast<float*>(src), rows,
+                                                                                                   nullptr);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }

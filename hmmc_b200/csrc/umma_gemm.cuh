@@ -586,8 +586,10 @@ struct EpiInfoNCE {
   uint32_t slot0;             // this lane's 16-byte slot 0 of a staging tile; slot c is at slot0 ^ (c << 4)
   uint32_t hold_hi[16], hold_lo[16];      // first chunk of a two-chunk group (dead unless GROUP == 2)
   const CUtensorMap* cmap;
+  uint64_t keep;              // L2 policy of the E stores: the U-GEMM reads E right back, keep it out of HBM if possible
   __device__ __forceinline__ void init() {
     stage_addr = ptx::smem_u32(stage);
+    keep = ptx::l2_policy_evict_last();
     // swizzle: the 16-byte chunk index is XORed with the row index (64B rows: bits 1..2 of the row; 128B rows: bits 0..2)
     slot0 = (GROUP == 1) ? stage_addr + uint32_t(lane) * 64u + (uint32_t((lane >> 1) & 3) << 4)
                          : stage_addr + uint32_t(lane) * 128u + (uint32_t(lane & 7) << 4);
@@ -626,7 +628,7 @@ struct EpiInfoNCE {
     ptx::fence_proxy_async();                          // generic-proxy writes -> visible to the copy engine
     __syncwarp();
     if (lane == 0) {
-      ptx::tma_store_2d(cmap, stage_addr + BUF * TILE_BYTES, gcol, row0);
+      ptx::tma_store_2d_hint(cmap, stage_addr + BUF * TILE_BYTES, gcol, row0, keep);
       ptx::bulk_commit_group();
     }
   }

@@ -13,7 +13,10 @@ the step again.
 The warm-up calls are REAL steps: each one updates the momentum parameters, enqueues the step's keys and
 advances queue_ptr, exactly like a call outside the graph (the capture pass itself executes nothing).  A
 training loop that must not take extra steps passes ``warmup=0`` after having run its first steps eagerly
-(those already sized the workspaces and built the operand copies the capture relies on).
+(those already sized the workspaces and built the operand copies the capture relies on).  Drop every reference
+to the eager steps' loss tensors before capturing: a live loss keeps its autograd graph alive, whose AccumulateGrad
+nodes belong to the stream of that eager step, and the capture's backward would have to synchronise with it -
+which invalidates the capture.
 """
 import gc
 
@@ -34,7 +37,9 @@ class GraphedStep:
             torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process keep making CUDA calls while this one captures - the NCCL
+        # watchdog polls the events of earlier collectives - and must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.outputs = fn()
 
     def replay(self):

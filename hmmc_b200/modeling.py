@@ -204,9 +204,10 @@ class ContrastiveHeadMixin:
         return int(self.queue_ptr)
 
     @torch.no_grad()
-    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None):
+    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None, staged=None):
         ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, self._enqueue_ptr_mode(W * b),
-                    self.contrast_num_negative, ops.resolve_precision(self.head_precision), direct=direct)
+                    self.contrast_num_negative, ops.resolve_precision(self.head_precision), direct=direct,
+                    staged=staged)
 
     def _defer_enqueue(self):
         v = getattr(self.task_config, "defer_enqueue", None)
@@ -215,18 +216,25 @@ class ContrastiveHeadMixin:
     @torch.no_grad()
     def _stage_keys(self, v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k):
         """Deferred schedule, end of step i: copy the step's keys into the persistent send buffer.  Their
-        exchange and enqueue are issued by start_pending_exchange() of step i+1 (or flush_pending_enqueue())."""
+        exchange and enqueue are issued by start_pending_exchange() of step i+1 (or flush_pending_enqueue()).
+        A device-side mark travels with the buffer: the packing kernel sets it, the enqueue consumes it, so an
+        eager flush followed by the replay of a captured step (whose graph carries the same enqueue) writes the
+        keys once."""
         self._join_pending()
         b, F, D, keys = self._key_blocks(v_fea_k, tag_fea_k, title_fea_k, frame_fea_k, frame_proj_k)
         W, _ = parallel.world()
+        if self.contrast_num_negative % (W * b) != 0:
+            raise ValueError("the deferred enqueue needs K %% (world*batch) == 0 (K=%d, B=%d): the queue pointer "
+                             "lives on the device" % (self.contrast_num_negative, W * b))
         dev = keys[0].device
         width = (3 + 2 * F) * D
         bufs = getattr(self, "_hmmc_xchg", None)
         if bufs is None or bufs[0].shape != (b, width) or bufs[1].shape[0] != W * b or bufs[0].device != dev:
             send = torch.empty(b, width, dtype=torch.float32, device=dev)
-            bufs = (send, send if W == 1 else torch.empty(W * b, width, dtype=torch.float32, device=dev))
+            bufs = (send, send if W == 1 else torch.empty(W * b, width, dtype=torch.float32, device=dev),
+                    torch.zeros(1, dtype=torch.int32, device=dev))
             self._hmmc_xchg = bufs
-        ops.pack_rows(keys, out=bufs[0])
+        ops.pack_rows(keys, out=bufs[0], staged=bufs[2])
         self._hmmc_pending = {"dims": (W, b, F, D), "done": None}
         if not getattr(self, "_hmmc_hooked", False) and isinstance(self, nn.Module):
             # checkpoints must see the queues with every staged key in place
@@ -235,16 +243,19 @@ class ContrastiveHeadMixin:
             self._hmmc_hooked = True
 
     @torch.no_grad()
-    def start_pending_exchange(self):
+    def start_pending_exchange(self, force=False):
         """Deferred schedule, start of step i+1: issue the all-gather and the enqueue of step i's keys on a side
         stream and return at once.  Call it before `_momentum_update()` (forward() does): the exchange then
         runs beside the HBM-bound parameter update and is joined right before the loss reads the queues.
-        Safe to call at any time; does nothing when no keys are staged."""
+        Safe to call at any time; does nothing when no keys are staged (the enqueue itself is guarded by the
+        device-side mark, so even a redundant issue writes nothing)."""
         p = getattr(self, "_hmmc_pending", None)
-        if p is None or p["done"] is not None:
+        if getattr(self, "_hmmc_xchg", None) is None or p is None:
+            return
+        if p["done"] is not None and not force:
             return
         W, b, F, D = p["dims"]
-        send, gathered = self._hmmc_xchg
+        send, gathered, staged = self._hmmc_xchg
         main = torch.cuda.current_stream()
         side = _side_stream(main.device)
         fork = torch.cuda.Event()
@@ -253,23 +264,30 @@ class ContrastiveHeadMixin:
         with torch.cuda.stream(side):
             if W > 1:
                 parallel.all_gather_rows_into(gathered, send)
-            self._enqueue_rows(W, b, F, D, gathered=gathered)
+            self._enqueue_rows(W, b, F, D, gathered=gathered, staged=staged)
             done = torch.cuda.Event()
             done.record(side)
         p["done"] = done
 
     def _join_pending(self):
         p = getattr(self, "_hmmc_pending", None)
-        if p is None:
-            return
+        if p is None or p.get("joined"):
+            return                  # nothing staged, or already ordered before the current stream's work
         if p["done"] is None:
             self.start_pending_exchange()
         torch.cuda.current_stream().wait_event(p["done"])
-        self._hmmc_pending = None
+        p["joined"] = True          # (a capture starting later inherits this order; it must not wait on this event)
 
     def flush_pending_enqueue(self):
         """Make the queue buffers current (stream-ordered on the current stream): call before reading
-        queue_*_ng / queue_ptr directly.  state_dict() and load_state_dict() do it themselves."""
+        queue_*_ng / queue_ptr directly, and after replaying a captured step before issuing eager ones (a replay
+        stages keys without this object noticing).  state_dict() and load_state_dict() do it themselves.
+        Always issues the exchange: the device-side mark decides whether anything is written."""
+        if getattr(self, "_hmmc_pending", None) is None:
+            return
+        p = self._hmmc_pending
+        p["joined"] = False
+        self.start_pending_exchange(force=True)
         self._join_pending()
 
     @torch.no_grad()

@@ -443,8 +443,9 @@ class EmaTable:
                    "hmmc_ema_multi")
 
 
-def pack_rows(tensors, out=None):
-    """[rows, w_i] blocks -> one [rows, sum w_i] fp32 buffer (send buffer of the all-gather)."""
+def pack_rows(tensors, out=None, staged=None):
+    """[rows, w_i] blocks -> one [rows, sum w_i] fp32 buffer (send buffer of the all-gather).
+    staged: optional int32[1] device tensor the kernel sets to 1 ("keys staged", consumed by enqueue)."""
     lib = _lib.load()
     ts = [_f32c(t, "block").reshape(t.shape[0], -1) for t in tensors]
     rows = ts[0].shape[0]
@@ -454,7 +455,7 @@ def pack_rows(tensors, out=None):
     n = len(ts)
     ptrs = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in ts])
     ws = (ctypes.c_int32 * n)(*widths)
-    _lib.check(lib.hmmc_pack_rows(ptrs, ws, n, rows, _p(out), _stream()), "hmmc_pack_rows")
+    _lib.check(lib.hmmc_pack_rows(ptrs, ws, n, rows, _p(out), _p(staged), _stream()), "hmmc_pack_rows")
     return out
 
 
@@ -469,9 +470,10 @@ def unpack_rows(packed, widths):
     return outs
 
 
-def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None):
+def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None, staged=None):
     """queue_bufs5 order: v, tag, title, frame_cross, frame_proj.  ``direct`` = the five key
-    tensors themselves (single process: no gather, no packed copy)."""
+    tensors themselves (single process: no gather, no packed copy).  staged: the mark pack_rows set
+    (deferred schedule): the enqueue happens only while it is set, and clears it."""
     lib = _lib.load()
     arr = (hmmc_queue * 5)()
     keep = []
@@ -486,7 +488,7 @@ def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, dir
                                                 int(ptr_host), K, _p(scratch), _stream()), "hmmc_enqueue_norm_direct")
     else:
         _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _p(scratch),
-                                         _stream()), "hmmc_enqueue_norm")
+                                         _p(staged), _stream()), "hmmc_enqueue_norm")
     planes = None if prec == PREC_FP32 else (2 if prec == PREC_BF16X3 else 1)
     for st, buf in zip(keep, queue_bufs5):
         st.wrote(buf, planes)               # the kernel kept the copies of this plane count in step
@@ -660,8 +662,10 @@ def sym_ce_packed(packed, F, D, scale, w_vtm, w_ftm, precision=None):
 
 # ----------------------------------------------------------------------------- eval
 
-def sim_topk(text, video, frames, scale, top_k, precision=None, want_sim=True, want_fsim=True):
-    """(sim [Nt,Nv], fsim [Nt,Nv]) of one text block against one gallery block."""
+def sim_topk(text, video, frames, scale, top_k, precision=None, want_sim=True, want_fsim=True, combine=False):
+    """(sim [Nt,Nv], fsim [Nt,Nv]) of one text block against one gallery block.
+    combine=True: returns (sim + fsim, None), the sum formed inside the kernel where the fused tiles apply
+    (main_task_retrieval.py:512-513)."""
     lib = _lib.load()
     prec = resolve_precision(precision)
     text = _f32c(text, "text")
@@ -674,8 +678,15 @@ def sim_topk(text, video, frames, scale, top_k, precision=None, want_sim=True, w
     fsim = torch.empty(Nt, Nv, dtype=torch.float32, device=text.device) if (want_fsim and frames is not None) else None
     nbytes = lib.hmmc_sim_topk_workspace_bytes(Nt, Nv, F, D, prec)
     ws = workspace(text.device, nbytes)
+    fused_sum = (combine and sim is not None and fsim is not None and prec != PREC_FP32
+                 and lib.hmmc_eval_fused_supported(F, D, int(top_k)))
     _lib.check(lib.hmmc_sim_topk_fwd(_p(text), Nt, _p(video), _p(frames), Nv, F, D, float(scale), int(top_k), prec,
-                                     _p(sim), _p(fsim), Nv, _p(ws), ws.numel(), _stream()), "hmmc_sim_topk_fwd")
+                                     _p(sim), _p(sim if fused_sum else fsim), Nv, _p(ws), ws.numel(), _stream()),
+               "hmmc_sim_topk_fwd")
+    if combine:
+        if fused_sum or fsim is None:
+            return sim, None
+        return sim + fsim, None
     return sim, fsim
 
 

@@ -47,10 +47,10 @@ def similarity_matrix(model, text, video, frames, use_frame_fea=True, text_tile=
     prec = getattr(model, "head_precision", None)
     out = []
     for i in range(0, text.shape[0], text_tile):
-        sim, fsim = ops.sim_topk(text[i:i + text_tile], video, frames if use_frame_fea else None, scale,
-                                 model.top_frames, prec)
-        out.append(sim + fsim if fsim is not None else sim)
-    return torch.cat(out, dim=0)
+        sim, _ = ops.sim_topk(text[i:i + text_tile], video, frames if use_frame_fea else None, scale,
+                              model.top_frames, prec, combine=True)
+        out.append(sim)
+    return out[0] if len(out) == 1 else torch.cat(out, dim=0)
 
 
 def eval_metrics(model, text, video, frames, multi_sentence_=False, cut_off_points_=None, use_frame_fea=True):

@@ -226,7 +226,11 @@ int hmmc_clip_grad_norm_multi(const uint64_t* g_ptrs, const int64_t* numels, con
  * is a multiple of B, like the reference's own no-wrap condition. */
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
                       int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch /* (3+2F)*W*b floats, or NULL */,
-                      void* stream);
+                      int32_t* staged, void* stream);
+/* staged: NULL, or the device mark hmmc_pack_rows set when it filled `gathered`'s send buffer (deferred
+ * schedule: the keys of step i are exchanged and enqueued beside step i+1).  The enqueue then happens only if
+ * the mark is set and clears it, so issuing it twice for the same keys - an eager flush followed by the replay
+ * of a captured step that carries the same enqueue - writes them once.  Needs ptr_host < 0. */
 
 /* Same, reading the five key tensors in place ([B,D] x3, [B,F,D] x2, contiguous): the
  * single-process case needs no gather and no packed copy. */
@@ -242,7 +246,7 @@ int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, in
 /* gather n row-blocks src_i[rows, width_i] into dst[rows, sum width_i] (the packed
  * send buffer of the key / embedding all-gather) and the inverse. */
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows,
-                   float* dst, void* stream);
+                   float* dst, int32_t* staged /* NULL, or a device mark set to 1 */, void* stream);
 int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int32_t* widths_host, int n,
                      int64_t rows, void* stream);
 
@@ -328,7 +332,11 @@ int hmmc_sym_ce_packed_fwd_bwd(const float* packed, int B, int F, int D, float s
 /* One (text tile x gallery tile) of _run_on_single_gpu (main_task_retrieval.py:321-357):
  *   sim  [Nt,Nv] = s * t_hat . v_hat
  *   fsim [Nt,Nv] = mean over the top_k frames of s * t_hat . f_hat   (torch.topk + mean)
- * video [Nv,D], frames [Nv,F,D].  Either output may be NULL. */
+ * video [Nv,D], frames [Nv,F,D].  Either output may be NULL.  sim == fsim (one buffer): that buffer receives
+ * sim + fsim, the sum eval_epoch forms on the host (main_task_retrieval.py:512-513).
+ * With 12 frames, top_k <= 4 and a tensor-core precision the call is three launches: normalise + pack the
+ * captions, pack the gallery as [video | 12 frames] column groups, one GEMM sweep whose epilogue pools the
+ * top-k frames in registers and writes each score once (no [Nt, Nv*F] frame-similarity matrix). */
 size_t hmmc_sim_topk_workspace_bytes(int64_t Nt, int64_t Nv, int F, int D, int prec);
 int hmmc_sim_topk_fwd(const float* text, int64_t Nt, const float* video, const float* frames, int64_t Nv,
                       int F, int D, float scale, int top_k, int prec, float* sim, float* fsim, int64_t ld_out,

@@ -122,11 +122,13 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
                 for n in order:
                     static[n].copy_(torch.from_numpy(inps[s][rank][n]))
             if mode == "graph" and s == 1:
-                # capture on step 1 (GraphedStep restores the state its warm-up calls touch), replay from then on
+                # step 0 ran eagerly (it sized the workspaces and left its keys staged); capture without further
+                # warm-up steps and replay from here on
                 from hmmc_b200.graphs import GraphedStep
-                graphed = GraphedStep(step, state=m.head_state_tensors())
+                graphed = GraphedStep(step, warmup=0)
             loss = graphed.replay() if graphed is not None else step()
             lerr = abs(float(loss) - ref_losses[s]) / ref_losses[s]
+            del loss        # a live loss keeps the step's autograd graph (and its AccumulateGrad streams): see graphs.py
             assert lerr < 1e-5, (mode, s, lerr)
             m.flush_pending_enqueue()
             want, want_ptr = ref_queues[s]
@@ -136,7 +138,8 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
                 worst = max(worst, err)
                 assert err <= 2e-7, (mode, s, n, err)
         out["enqueue_%s_max_abs_vs_oracle_concat" % mode] = worst
-        del graphed
+        if graphed is not None:
+            graphed.release()
     out["enqueue_steps"] = steps
     out["enqueue_global_batch"] = W * b
     return out
