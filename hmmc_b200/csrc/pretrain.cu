@@ -82,13 +82,17 @@ struct PrepArgs {
 // One warp per row, all query tensors of the call in one launch (F.normalize, eps 1e-12).
 // The bf16 operand copy carries the factor pack_scale = log2(e)/T, so that the S-GEMM's accumulators are
 // logits in base-2 units (see EpiInfoNCE); the fp32 copy stays the plain unit vector.
-// Block 0 also clears the finish kernel's arrival counter.
+// Block 0 also clears the finish kernel's arrival counter and the S -> U hand-over counters.
 template <int V>   // float4 per lane (D == 128 * V), 0 = any D (scalar accesses)
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(const __grid_constant__ PrepArgs a, int D, int planes, float pack_scale, unsigned* finish_counter) {
+prep_rows_kernel(const __grid_constant__ PrepArgs a, int D, int planes, float pack_scale, unsigned* finish_counter,
+                 unsigned* dep_counters, int n_dep) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
   if (blockIdx.x == 0 && threadIdx.x == 0 && finish_counter != nullptr) *finish_counter = 0u;
+  // arrival counters of the fused S/U launch (EpiPipe): cleared here, one kernel boundary before they are used
+  if (blockIdx.x == 0 && dep_counters != nullptr)
+    for (int i = threadIdx.x; i < n_dep; i += blockDim.x) dep_counters[i] = 0u;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= a.row_begin[a.n]) return;
@@ -930,9 +934,13 @@ struct GroupDesc {
   int rows, Fq;
 };
 
+constexpr int DEP_PER_BLOCK = 32;     // 256-row query tiles per block the fused launch can track (rows <= 8192)
+
 struct InfoNCELayout {       // workspace carving shared by the size query and the run
   float* row_loss;
   unsigned* counter;
+  unsigned* dep;             // [MAX_BLOCKS][DEP_PER_BLOCK] arrival counters of the fused S/U launch
+  bool fused;                // S- and U-GEMM in one persistent launch (EpiPipe)
   float* xhat[MAX_GROUPS];
   __nv_bfloat16* packed[MAX_GROUPS];
   float* rowsum_part[MAX_BLOCKS];
@@ -1002,6 +1010,110 @@ static SplitChoice choose_u_splits(const int* rows, const int* Kq, int nb, int D
   return best;
 }
 
+// ---- fused S/U launch (EpiPipe): the order of the units and the length of the U slices
+// Query tiles ("groups" = block k, 256-row tile m2) sorted by work; the global order is
+//   S(g0) S(g1) U(g0) S(g2) U(g1) ... : a group's U slices come PIPE_LAG groups after its S tiles, late enough
+// for the S tiles to be done when a pair reaches them, early enough for E to be read back from L2.
+constexpr int PIPE_LAG = 2;
+constexpr float PIPE_S_FIXED = 1.5f, PIPE_U_FIXED = 3.0f;    // cost of a unit beyond its k-block steps
+
+struct PipeGroup { int k, m2, n_tiles, total_kb; };
+
+static std::vector<PipeGroup> pipe_groups(const int* rows, const int* Kq, int nb, int nseg) {
+  std::vector<PipeGroup> gs;
+  std::vector<int> order(nb);
+  for (int k = 0; k < nb; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return Kq[a] != Kq[b] ? Kq[a] > Kq[b] : rows[a] > rows[b];
+  });
+  for (int k : order)
+    for (int m2 = 0; m2 < (rows[k] + 2 * UMMA_BM - 1) / (2 * UMMA_BM); ++m2)
+      gs.push_back(PipeGroup{k, m2, Kq[k] / UMMA_PAIR_BN, nseg * (Kq[k] / UMMA_BK)});
+  return gs;
+}
+
+// makespan (k-block steps) of the ordered, dependency-aware schedule for U slices of `unit` steps
+static double pipe_makespan(const std::vector<PipeGroup>& gs, int unit, int nseg, int workers, int* n_units) {
+  struct U { int kind, g; float cost; };
+  std::vector<U> seq;
+  const int G = int(gs.size());
+  const float s_cost = float(nseg * 8) + PIPE_S_FIXED;
+  int units = 0;
+  for (int i = 0; i < G + PIPE_LAG; ++i) {
+    if (i < G)
+      for (int n = 0; n < gs[i].n_tiles; ++n) seq.push_back(U{0, i, s_cost});
+    const int j = i - PIPE_LAG;
+    if (j >= 0) {
+      const int u = std::min(unit, gs[j].total_kb);
+      for (int k0 = 0; k0 < gs[j].total_kb; k0 += u)
+        for (int n2 = 0; n2 < 2; ++n2) {
+          seq.push_back(U{1, j, float(std::min(u, gs[j].total_kb - k0)) + PIPE_U_FIXED});
+          ++units;
+        }
+    }
+  }
+  std::vector<double> load(workers, 0.0);
+  std::vector<std::vector<int>> mine(workers);
+  for (int i = 0; i < int(seq.size()); ++i) {
+    int best = 0;
+    for (int w = 1; w < workers; ++w)
+      if (load[w] < load[best]) best = w;
+    load[best] += seq[i].cost;
+    mine[best].push_back(i);
+  }
+  std::vector<double> t(workers, 0.0), s_done(G, 0.0);
+  std::vector<int> idx(workers, 0), s_left(G);
+  for (int i = 0; i < G; ++i) s_left[i] = gs[i].n_tiles;
+  size_t remaining = seq.size();
+  while (remaining) {
+    int pick = -1;
+    for (int w = 0; w < workers; ++w) {
+      if (idx[w] >= int(mine[w].size())) continue;
+      const U& u = seq[mine[w][idx[w]]];
+      if (u.kind == 1 && s_left[u.g] > 0) continue;
+      if (pick < 0 || t[w] < t[pick]) pick = w;
+    }
+    if (pick < 0) return 1e30;              // cannot happen: the order is acyclic
+    const U& u = seq[mine[pick][idx[pick]]];
+    double start = t[pick];
+    if (u.kind == 1) start = std::max(start, s_done[u.g]);
+    t[pick] = start + u.cost;
+    ++idx[pick];
+    --remaining;
+    if (u.kind == 0) { --s_left[u.g]; s_done[u.g] = std::max(s_done[u.g], t[pick]); }
+  }
+  if (n_units) *n_units = units;
+  return *std::max_element(t.begin(), t.end());
+}
+
+static int choose_pipe_unit(const int* rows, const int* Kq, int nb, int planes) {
+  typedef std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int> Key;
+  static std::mutex mu;
+  static std::map<Key, int> cache;
+  int kr[MAX_BLOCKS] = {0}, kk[MAX_BLOCKS] = {0};
+  for (int k = 0; k < nb; ++k) { kr[k] = rows[k]; kk[k] = Kq[k]; }
+  const Key key(nb, planes, kr[0], kr[1], kr[2], kr[3], kr[4], kr[5], kk[0], kk[1], kk[2], kk[3], kk[4], kk[5]);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  const int nseg = (planes == 2) ? 3 : 1;
+  const std::vector<PipeGroup> gs = pipe_groups(rows, Kq, nb, nseg);
+  const int workers = sm_count() / 2;
+  int best = 48 * nseg;
+  double best_cost = 1e30;
+  for (int unit : {16, 24, 32, 40, 48, 64, 80, 96, 128, 192}) {
+    int units = 0;
+    const double mk = pipe_makespan(gs, unit * nseg, nseg, workers, &units);
+    const double cost = mk + 0.25 * units;      // every partial tile is read back once by the finish kernel
+    if (cost < best_cost) { best_cost = cost; best = unit * nseg; }
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  cache[key] = best;
+  return best;
+}
+
 static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* groups, int ng, const int* blk_group,
                            const int* blk_Kq, int nb, int D, int prec, bool need_grad) {
   const int planes = planes_of(prec);
@@ -1009,6 +1121,7 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   for (int i = 0; i < ng; ++i) total_rows += groups[i].rows;
   L.row_loss = ws.take<float>(size_t(3) * total_rows);
   L.counter = ws.take<unsigned>(4);
+  L.dep = ws.take<unsigned>(size_t(MAX_BLOCKS) * DEP_PER_BLOCK);
   for (int i = 0; i < ng; ++i) {
     L.xhat[i] = (prec == HMMC_PREC_FP32) ? ws.take<float>(size_t(groups[i].rows) * D) : nullptr;
     L.packed[i] = (prec != HMMC_PREC_FP32) ? ws.take<__nv_bfloat16>(size_t(groups[i].rows) * planes * D) : nullptr;
@@ -1020,10 +1133,22 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   const int nseg_layout = (planes == 2) ? 3 : 1;
   SplitChoice sc;
   for (int k = 0; k < MAX_BLOCKS; ++k) sc.unit[k] = k < nb ? nseg_layout * (blk_Kq[k] / UMMA_BK) : 1;
+  L.fused = false;
   if (prec != HMMC_PREC_FP32 && need_grad) {
     int rows[MAX_BLOCKS];
-    for (int k = 0; k < nb; ++k) rows[k] = groups[blk_group[k]].rows;
-    sc = choose_u_splits(rows, blk_Kq, nb, D, planes, L.bn2);
+    bool fits = (L.bn1 == 256 && L.bn2 == 256 && D == 2 * UMMA_PAIR_BN);
+    for (int k = 0; k < nb; ++k) {
+      rows[k] = groups[blk_group[k]].rows;
+      fits = fits && rows[k] <= DEP_PER_BLOCK * 2 * UMMA_BM;
+    }
+    if (fits) {
+      // one persistent launch for both GEMMs: U slices of one length for every block
+      L.fused = true;
+      const int unit = choose_pipe_unit(rows, blk_Kq, nb, planes);
+      for (int k = 0; k < nb; ++k) sc.unit[k] = std::min(unit, nseg_layout * (blk_Kq[k] / UMMA_BK));
+    } else {
+      sc = choose_u_splits(rows, blk_Kq, nb, D, planes, L.bn2);
+    }
   }
   for (int k = 0; k < nb; ++k) {
     const int R = groups[blk_group[k]].rows;
@@ -1115,11 +1240,11 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
   if (phase != 2) {
     const dim3 pgrid((total_rows + 7) / 8), pblock(256);
     cudaError_t e;
-    if (vec_q && D == 512) e = launch_pdl(prep_rows_kernel<4>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
-    else if (vec_q && D == 256) e = launch_pdl(prep_rows_kernel<2>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
-    else if (vec_q && D == 128) e = launch_pdl(prep_rows_kernel<1>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
-    else if (vec_q && D == 1024) e = launch_pdl(prep_rows_kernel<8>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
-    else e = launch_pdl(prep_rows_kernel<0>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter);
+    if (vec_q && D == 512) e = launch_pdl(prep_rows_kernel<4>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
+    else if (vec_q && D == 256) e = launch_pdl(prep_rows_kernel<2>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
+    else if (vec_q && D == 128) e = launch_pdl(prep_rows_kernel<1>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
+    else if (vec_q && D == 1024) e = launch_pdl(prep_rows_kernel<8>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
+    else e = launch_pdl(prep_rows_kernel<0>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
     count_launch();
     HMMC_CHECK_CUDA(e);
     if (prec == HMMC_PREC_FP32) {
@@ -1133,6 +1258,66 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
         if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
       }
     } else {
+      if (L.fused) {
+        // ONE persistent launch: S tiles and U slices of all blocks, ordered and handed over through counters
+        auto launch_pipe = [&](auto epi_tag) -> int {
+          using Epi = decltype(epi_tag);
+          GemmProblem<Epi> pp[2 * MAX_BLOCKS];
+          int rows[MAX_BLOCKS];
+          float fixed[2 * MAX_BLOCKS];
+          for (int k = 0; k < nb; ++k) {
+            const GroupDesc& G = groups[blocks[k].group];
+            const int Kq = blk_Kq[k];
+            rows[k] = G.rows;
+            typename Epi::Params e{};
+            e.kind = 0;
+            e.nce.rowsum_part = L.rowsum_part[k];
+            e.nce.lo_col0 = Kq;
+            e.dep = L.dep + k * DEP_PER_BLOCK;
+            e.dep_expected = 0;
+            pp[k] = GemmProblem<Epi>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
+                                     int64_t(planes) * D, G.rows, Kq, D, planes, 1, e,
+                                     L.E[k], int64_t(planes) * Kq, int64_t(planes) * Kq};
+            fixed[k] = PIPE_S_FIXED;
+            typename Epi::Params u{};
+            u.kind = 1;
+            u.st = EpiStoreF32::Params{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
+            u.dep = L.dep + k * DEP_PER_BLOCK;
+            u.dep_expected = unsigned(2 * Epi::PAIR_WARPS * (Kq / UMMA_PAIR_BN));     // epilogue warps of both CTAs x S tiles
+            pp[nb + k] = GemmProblem<Epi>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
+                                          G.rows, D, Kq, planes, 1, u};
+            pp[nb + k].kb_per_split = L.splits[k];
+            fixed[nb + k] = PIPE_U_FIXED;
+          }
+          // unit numbers as the launcher assigns them: problem after problem, split-major, then n * m-tiles + m
+          int tile_begin[2 * MAX_BLOCKS + 1];
+          tile_begin[0] = 0;
+          for (int k = 0; k < nb; ++k)
+            tile_begin[k + 1] = tile_begin[k] + ((rows[k] + 255) / 256) * (blk_Kq[k] / UMMA_PAIR_BN);
+          for (int k = 0; k < nb; ++k)
+            tile_begin[nb + k + 1] = tile_begin[nb + k] + ((rows[k] + 255) / 256) * 2 * L.nsplits_eff[k];
+          const std::vector<PipeGroup> gs = pipe_groups(rows, blk_Kq, nb, planes == 2 ? 3 : 1);
+          std::vector<int> seq;
+          const int Gn = int(gs.size());
+          for (int i = 0; i < Gn + PIPE_LAG; ++i) {
+            if (i < Gn) {
+              const PipeGroup& g = gs[i];
+              const int num_m = (rows[g.k] + 255) / 256;
+              for (int n = 0; n < g.n_tiles; ++n) seq.push_back(tile_begin[g.k] + n * num_m + g.m2);
+            }
+            const int j = i - PIPE_LAG;
+            if (j >= 0) {
+              const PipeGroup& g = gs[j];
+              const int num_m = (rows[g.k] + 255) / 256;
+              for (int sp = 0; sp < L.nsplits_eff[g.k]; ++sp)
+                for (int n2 = 0; n2 < 2; ++n2) seq.push_back(tile_begin[nb + g.k] + sp * (num_m * 2) + n2 * num_m + g.m2);
+            }
+          }
+          return launch_umma_grouped_pair<Epi>(pp, 2 * nb, st, reserved_sms, &seq, fixed);
+        };
+        rc = (planes == 2) ? launch_pipe(EpiPipe<2>()) : launch_pipe(EpiPipe<1>());
+        if (rc) return rc;
+      } else {
       GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
       for (int k = 0; k < nb; ++k) {
         const GroupDesc& G = groups[blocks[k].group];
@@ -1179,6 +1364,7 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
         else rc = launch_umma_grouped<128, EpiStoreF32>(p2, nb, st, reserved_sms);
         if (rc) return rc;
       }
+      }   // two launches
     }
     // every kernel that reads the queues has been issued: let the enqueue start on another stream
   }

@@ -109,6 +109,28 @@ def multi_sentence_ranks(sim_matrix, cut_off_points_):
     return t2v.cpu().numpy(), v2t.cpu().numpy()
 
 
+def logging_rank_from_ranks(t2v, v2t, multi_sentence_, logger, shape=None):
+    """The logging half of logging_rank for ranks that were counted without a matrix (fused / sharded eval):
+    same scalars, same log lines; returns tv_metrics."""
+    t2v, v2t = np.asarray(t2v), np.asarray(v2t)
+    tv_metrics = t2v_metrics_from_ranks(t2v) if multi_sentence_ else metrics_from_ranks(t2v)
+    vt_metrics = metrics_from_ranks(v2t)
+    if shape is not None and not multi_sentence_:
+        logger.info('\t Length-T: {}, Length-V:{}'.format(shape[0], shape[1]))
+    _log_both(tv_metrics, vt_metrics, logger)
+    return tv_metrics
+
+
+def _log_both(tv_metrics, vt_metrics, logger):
+    logger.info("Text-to-Video:")
+    logger.info('\t>>>  R@1: {:.1f} - R@5: {:.1f} - R@10: {:.1f} - Median R: {:.1f} - Mean R: {:.1f}'.
+                format(tv_metrics['R1'], tv_metrics['R5'], tv_metrics['R10'], tv_metrics['MR'], tv_metrics['MeanR']))
+    logger.info("Video-to-Text:")
+    logger.info(
+        '\t>>>  V2T$R@1: {:.1f} - V2T$R@5: {:.1f} - V2T$R@10: {:.1f} - V2T$Median R: {:.1f} - V2T$Mean R: {:.1f}'.format(
+            vt_metrics['R1'], vt_metrics['R5'], vt_metrics['R10'], vt_metrics['MR'], vt_metrics['MeanR']))
+
+
 def logging_rank(sim_matrix, multi_sentence_, cut_off_points_, logger):
     """run similarity in one single gpu (metrics.py:89-143); returns tv_metrics."""
     if multi_sentence_:

@@ -244,15 +244,44 @@ def cache_eval_features(args, model, test_dataloader, device, multi_sentence_=Fa
     return flat(texts), flat(videos), fr, (flat(titles) if titles else None)
 
 
+# an [Nt, Nv] fp32 matrix above this size is not materialised: the ranks are counted tile by tile instead
+MATRIX_BYTES_LIMIT = 2 << 30
+
+
+def choose_eval_path(Nt, Nv, F, D, top_k, per_video, precision, task="retrieval", sharded=False):
+    """Which similarity + ranking path an eval set takes:
+      "matrix"  - materialise sim (+ sim_frame) [Nt, Nv] on this GPU, rank it (small sets; any shape);
+      "fused"   - fused similarity + top-k + rank counting on this GPU, no matrix;
+      "sharded" - the same with the gallery split over the ranks of the process group (every rank must call).
+    The fused tiles need 12 frames, top_frames <= 4, D % 64 == 0, <= 128 captions per video, a tensor-core
+    precision and the plain retrieval task."""
+    from . import _lib
+    prec = ops.resolve_precision(precision)
+    per = np.asarray(per_video)
+    fused_ok = (task == "retrieval" and prec != ops.PREC_FP32 and per.size == Nv and (per.size == 0 or per.max() <= 128)
+                and bool(_lib.load().hmmc_eval_fused_supported(int(F), int(D), int(top_k))))
+    if sharded and parallel.world()[0] > 1:
+        if not fused_ok:
+            raise ops.HmmcError("sharded eval needs the fused tiles (12 frames, top_frames <= 4, D %% 64 == 0, <= 128 "
+                                "captions per video, bf16 / bf16x3, task retrieval)")
+        return "sharded"
+    if fused_ok and 4 * int(Nt) * int(Nv) > MATRIX_BYTES_LIMIT:
+        return "fused"
+    return "matrix"
+
+
 def eval_epoch(args, model, test_dataloader, device, n_gpu, logger=None):
     """Drop-in for main_task_retrieval.py:358-524: cache the features, build the similarity matrix
     (sim + sim_frame when --use_frame_fea, + weight_title * sim_title for retrieval_VT), log and return
     the text-to-video metrics of `logging_rank`.
 
-    The reference fans text tiles out over `n_gpu` devices of one process with threads and peer copies
-    (:447-488); here a process owns one GPU and everything stays in one gallery tensor on it — `n_gpu`
-    is accepted for signature compatibility.  Galleries too large for an [Nt, Nv] matrix go through
-    `fused_eval_ranks` (sharded over the ranks of the process group) instead."""
+    The reference fans text tiles out over `n_gpu` devices of ONE process with threads and peer copies of the
+    whole gallery (:447-488).  Here a process owns one GPU (`n_gpu` is accepted for signature compatibility)
+    and the path is picked from the size (`choose_eval_path`): small sets materialise the matrix on this GPU;
+    sets whose matrix would exceed MATRIX_BYTES_LIMIT count the ranks tile by tile without one; and with
+    ``args.eval_sharded`` set - every rank of the process group then has to call eval_epoch, not rank 0 alone
+    as main_task_retrieval.py:620-622 does - the gallery is split over the ranks (two small
+    all-reduces and one all-gather of integer ranks)."""
     logger = logger or _NullLogger()
     if hasattr(model, 'module'):
         model = model.module
@@ -270,6 +299,25 @@ def eval_epoch(args, model, test_dataloader, device, n_gpu, logger=None):
         text, video, frames, title = cache_eval_features(args, model, test_dataloader, device, multi_sentence_,
                                                          cut_off_points_)
         use_frame = bool(getattr(args, "use_frame_fea", True))
+        task = getattr(args, "task", "retrieval")
+        Nt, Nv = text.shape[0], video.shape[0]
+        if multi_sentence_:
+            ends = np.asarray([c + 1 for c in cut_off_points_], dtype=np.int64)
+            per = np.diff(np.concatenate([[0], ends]))
+        else:
+            per = np.ones(Nv, dtype=np.int64) if Nt == Nv else np.zeros(0, dtype=np.int64)
+        path = choose_eval_path(Nt, Nv, frames.shape[1], text.shape[1], model.top_frames, per,
+                                getattr(model, "head_precision", None), task if use_frame else "no-frames",
+                                sharded=bool(getattr(args, "eval_sharded", False)))
+        logger.info("eval path: {}".format(path))
+        if path != "matrix":
+            W, rank = parallel.world() if path == "sharded" else (1, 0)
+            lo, hi = parallel.shard_range(Nv, W, rank)
+            prec = getattr(model, "head_precision", None) or ops.DEFAULT_PRECISION
+            t2v, v2t = fused_eval_ranks(text, video[lo:hi], frames[lo:hi], per, _scale_of(model), model.top_frames, prec,
+                                        video_range=None if path == "sharded" else (0, Nv))
+            logger.info("sim matrix size:  {}".format((Nt, Nv)))
+            return M.logging_rank_from_ranks(t2v.cpu().numpy(), v2t.cpu().numpy(), multi_sentence_, logger, (Nt, Nv))
         sim = similarity_matrix(model, text, video, frames, use_frame_fea=use_frame)
         if getattr(args, "task", "retrieval") == "retrieval_VT":
             tsim = ops.loose_similarity_raw(ops._f32c(text, "text"), ops._f32c(title, "title"), _scale_of(model),

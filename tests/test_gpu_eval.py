@@ -187,3 +187,45 @@ def test_eval_epoch_matches_reference(golden, tag, multi, batch, prec):
     assert sorted(tv.keys()) == list(g[tag + "_keys"])
     got = np.array([tv[k] for k in sorted(tv.keys())], dtype=np.float64)
     np.testing.assert_allclose(got, g[tag + "_vals"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("tag,multi,batch", [("square", False, 64), ("multi", True, 32)])
+def test_eval_epoch_fused_path_matches_matrix_path(golden, tag, multi, batch, monkeypatch):
+    """eval_epoch picks the path from the size (retrieval.choose_eval_path): with the matrix budget forced to zero
+    the same fake dataloader goes through the fused rank counting (no [Nt, Nv] matrix) and must return the metrics
+    the reference's eval_epoch returned (tests/golden/eval_epoch.npz)."""
+    g = golden("eval_epoch")
+    T, V, Fr, batches, cut = syn.eval_epoch_case(multi, batch)
+    Tc, Vc, Fc = cu(T), cu(V), cu(Fr)
+
+    class Txt:
+        logit_scale = torch.tensor(4.6052)
+
+        def __call__(self, ids, mask):
+            return Tc[ids[:, 0]]
+    task = types.SimpleNamespace(local_rank=0, top_frames=2, use_frame_fea=True, head_precision="bf16x3")
+    m = modeling.BirdModel(modeling.default_cross_config(), task, text_encoder=Txt(),
+                           visual_encoder=lambda video, video_frame: (Vc[video[:, 0]], Fc[video[:, 0]]))
+
+    class DS:
+        multi_sentence_per_video = multi
+        cut_off_points = cut
+
+    class DL(list):
+        dataset = DS()
+    dl = DL([(torch.from_numpy(ci)[:, None], torch.ones(len(ci), 1, dtype=torch.long),
+              torch.from_numpy(vi)[:, None], torch.full((len(ci),), 12)) for ci, vi in batches])
+    lines = []
+
+    class Log:
+        def info(self, *a):
+            lines.append(a[0] if a else "")
+    monkeypatch.setattr(retrieval, "MATRIX_BYTES_LIMIT", 0)
+    tv = retrieval.eval_epoch(types.SimpleNamespace(task="retrieval", use_frame_fea=True), m, dl, torch.device("cuda"), 1, Log())
+    assert any("eval path: fused" in str(x) for x in lines)
+    assert sorted(tv.keys()) == list(g[tag + "_keys"])
+    got = np.array([tv[k] for k in sorted(tv.keys())], dtype=np.float64)
+    np.testing.assert_allclose(got, g[tag + "_vals"], rtol=1e-6)
+    assert retrieval.choose_eval_path(1000, 1000, 12, 512, 2, np.ones(1000), "bf16") == "matrix"
+    assert retrieval.choose_eval_path(10 ** 6, 10 ** 5, 12, 512, 3, np.full(10 ** 5, 10), "bf16") == "fused"
+    assert retrieval.choose_eval_path(10 ** 6, 10 ** 5, 8, 512, 3, np.full(10 ** 5, 10), "bf16") == "matrix"
