@@ -71,6 +71,11 @@ __global__ void exp_rowsum_kernel(float* __restrict__ S, int64_t lds, int Kq, fl
 constexpr int MAX_GROUPS = 4;   // distinct query tensors of one fused call
 constexpr int MAX_BLOCKS = 6;   // (query tensor, queue) pairs = GEMM problems
 
+struct LossAcc {
+  unsigned long long sum[3];      // loss slots (FAM, VTM, FTM) in units of 2^-40
+  unsigned arrived;
+  unsigned pad;
+};
 struct PrepArgs {
   const float* x[MAX_GROUPS];
   float* xhat[MAX_GROUPS];              // fp32 normalised copy (FP32 path) or nullptr
@@ -82,17 +87,13 @@ struct PrepArgs {
 // One warp per row, all query tensors of the call in one launch (F.normalize, eps 1e-12).
 // The bf16 operand copy carries the factor pack_scale = log2(e)/T, so that the S-GEMM's accumulators are
 // logits in base-2 units (see EpiInfoNCE); the fp32 copy stays the plain unit vector.
-// Block 0 also clears the finish kernel's arrival counter and the S -> U hand-over counters.
+// Block 0 also clears the finish kernel's loss accumulators.
 template <int V>   // float4 per lane (D == 128 * V), 0 = any D (scalar accesses)
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(const __grid_constant__ PrepArgs a, int D, int planes, float pack_scale, unsigned* finish_counter,
-                 unsigned* dep_counters, int n_dep) {
+prep_rows_kernel(const __grid_constant__ PrepArgs a, int D, int planes, float pack_scale, LossAcc* loss_acc) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
-  if (blockIdx.x == 0 && threadIdx.x == 0 && finish_counter != nullptr) *finish_counter = 0u;
-  // arrival counters of the fused S/U launch (EpiPipe): cleared here, one kernel boundary before they are used
-  if (blockIdx.x == 0 && dep_counters != nullptr)
-    for (int i = threadIdx.x; i < n_dep; i += blockDim.x) dep_counters[i] = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_acc != nullptr) *loss_acc = LossAcc{{0ull, 0ull, 0ull}, 0u, 0u};
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= a.row_begin[a.n]) return;
@@ -178,6 +179,7 @@ struct FinishArgs {
   RowGroup g[MAX_GROUPS];
   int row_begin[MAX_GROUPS + 1];
   int n;
+  int heavy_rows;             // vector kernel: the first heavy_rows rows get a whole block each (finish_row_block)
 };
 
 // Per-kind sums in a fixed order (deterministic) and the final scalars:
@@ -191,44 +193,42 @@ struct LossFinal {
   int use_frame_fea;
 };
 
-// Called by every thread of a block at the end of the finish kernel with its row's loss shares (warp-uniform;
-// zeros for warps beyond the last row).  Each block adds its eight rows in warp order and publishes one partial
-// per loss slot; the block that arrives last adds the partials (each thread a fixed strided subset, then a
-// fixed tree) and writes the scalars.  The order never depends on which block is last.
-__device__ __forceinline__ void finish_losses(const float (&loss_kind)[3], float* __restrict__ block_loss /* [3][gridDim.x] */,
-                                              const LossFinal& f, unsigned* counter) {
-  __shared__ float wl[3][8];
-  __shared__ float red[32];
-  __shared__ float kinds[3];
-  __shared__ bool last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Loss sums without a hand-over on the critical path.  Every block adds its three shares to 64-bit fixed-point
+// accumulators with fire-and-forget reductions (integer addition commutes: the sums are identical from run to run
+// whatever the order) and signals its arrival with a release reduction; nobody waits for an answer, so the block
+// retires at once.  (Measured: the former "publish a partial, fence, returning atomic, last block adds" sequence
+// kept every block resident for two more round trips, 7 us of a 26 us kernel at b = 256, profiles/r2_finish_kernel.md.)
+// The block with the highest index then waits for the arrival count (all other blocks are resident or done by the
+// time it runs, so this cannot deadlock), converts the sums and re-arms the accumulators for the next call.
+constexpr float LOSS_FIX_SCALE = 1099511627776.0f;            // 2^40
+
+__device__ __forceinline__ void finish_losses(const float (&loss_kind)[3], LossAcc* acc, const LossFinal& f) {
+  __shared__ float wl[3][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;       // nw <= 16
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) wl[k][warp] = loss_kind[k];
   }
   __syncthreads();
-  if (threadIdx.x < 3) {
-    float acc = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) acc += wl[threadIdx.x][w];
-    block_loss[int64_t(threadIdx.x) * gridDim.x + blockIdx.x] = acc;
-    __threadfence();                        // the partial before this block's arrival
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  for (int k = 0; k < 3; ++k) {
-    const float* v = block_loss + int64_t(k) * gridDim.x;
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < int(gridDim.x); i += blockDim.x) acc += __ldcg(v + i);
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) kinds[k] = acc;
-    __syncthreads();
-  }
   if (threadIdx.x != 0) return;
-  *counter = 0u;                            // ready for the next call on this workspace
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = 0.f;
+    for (int w = 0; w < nw; ++w) v += wl[k][w];
+    atomicAdd(&acc->sum[k], static_cast<unsigned long long>(__float2ll_rn(v * LOSS_FIX_SCALE)));
+  }
+  ptx::red_release_add(&acc->arrived, 1u);
+  if (blockIdx.x != gridDim.x - 1) return;
+  const long long t0 = clock64();
+  while (ptx::ld_acquire(&acc->arrived) != gridDim.x)
+    if (clock64() - t0 > (1ll << 33)) __trap();            // seconds: a lost arrival is a bug, not a wait
+  float kinds[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    kinds[k] = float(double(static_cast<long long>(__ldcg(&acc->sum[k]))) * (1.0 / double(LOSS_FIX_SCALE)));
+    acc->sum[k] = 0ull;                     // ready for the next call on this workspace
+  }
+  acc->arrived = 0u;
   if (f.mode == 0) {
     f.out[0] += kinds[0] + kinds[1] + kinds[2];
   } else {
@@ -249,33 +249,212 @@ __device__ __forceinline__ void axpy4(float w, const float4& x, float4& y) {
   y.x = fmaf(w, x.x, y.x); y.y = fmaf(w, x.y, y.y); y.z = fmaf(w, x.z, y.z); y.w = fmaf(w, x.w, y.w);
 }
 
+#ifndef HMMC_FIN_OCC
+#define HMMC_FIN_OCC 2      // resident blocks per SM the vector finish kernel is compiled for (measured: see profiles/)
+#endif
+#ifndef HMMC_FIN_WARPS
+#define HMMC_FIN_WARPS 8    // warps (= rows) per block of the vector finish kernel
+#endif
+constexpr int FIN_WARPS = HMMC_FIN_WARPS;
+#ifndef HMMC_FIN_HEAVY
+#define HMMC_FIN_HEAVY 1    // rows with a ONE_TO_FRAMES contribution get a whole block each: 0 never, 1 small grids, 2 always
+#endif
+// number of positive terms of a contribution and the key row of term t (false: the term does not exist)
+__device__ __forceinline__ int contrib_terms(const Contribution& C) {
+  return (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) ? 2 : (C.pos_mode == HMMC_POS_ONE_TO_FRAMES ? C.Fk : 1);
+}
+__device__ __forceinline__ bool contrib_key_row(const Contribution& C, int r, int n, int f, int t, int& kr) {
+  if (C.pos_mode == HMMC_POS_PAIR) { kr = r; return t < 1; }
+  if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
+    const int fk = (t == 0) ? f + 1 : f - 1;            // pairs (i, i+1) and (i+1, i) of frame_self_loss
+    kr = n * C.Fk + fk;
+    return t < 2 && fk >= 0 && fk < C.Fk;
+  }
+  if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { kr = n * C.Fk + t; return t < C.Fk; }
+  kr = n;
+  return t < 1;
+}
+
+// One row handled by a whole block.  A row with a ONE_TO_FRAMES contribution walks Fk key rows and several split-K
+// partials: with one warp that is 8-10 dependent round trips and those rows set the kernel's duration (SMs 42 %
+// idle, profiles/r2_ncu_kernels.md).  Here the positive terms and then the U partials are dealt to the eight warps
+// (one or two each, all loads of a phase in flight together); the partial gradients meet in shared memory and are
+// added in warp order, so the result does not depend on timing.
+template <int V>
+__device__ __forceinline__ void finish_row_block(const RowGroup& G, int r, float invT, float cmax, float kexp,
+                                                 float (&loss_kind)[3]) {
+  constexpr int D = 128 * V;
+  __shared__ float4 gs[FIN_WARPS][32 * V];            // the warps' partial gradients
+  __shared__ float invz[2][FIN_WARPS];
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = r / G.Fq, f = r - n * G.Fq;
+  // terms of all contributions in one list; warp w takes the terms w, w + FIN_WARPS, ... (two key rows in flight)
+  const int nt0 = contrib_terms(G.c[0]);
+  const int T = nt0 + (G.ncontrib > 1 ? contrib_terms(G.c[1]) : 0);
+  float4 qv[V], g[V];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(G.q + int64_t(r) * D) + lane;
+#pragma unroll
+    for (int i = 0; i < V; ++i) qv[i] = __ldg(qp + 32 * i);
+  }
+  float4 kv[2][V];
+  bool on[2];
+  int cix[2];
+  auto load_terms = [&](int t0) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int tt = t0 + FIN_WARPS * k;
+      cix[k] = (tt >= nt0) ? 1 : 0;
+      int kr = 0;
+      on[k] = tt < T && contrib_key_row(G.c[cix[k]], r, n, f, tt - (cix[k] ? nt0 : 0), kr);
+      const float4* kp = reinterpret_cast<const float4*>(G.c[cix[k]].keys + int64_t(on[k] ? kr : 0) * D) + lane;
+#pragma unroll
+      for (int i = 0; i < V; ++i) kv[k][i] = on[k] ? __ldg(kp + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load_terms(warp);
+  // the negatives' sums of both contributions (every warp: a few hundred bytes from L2)
+  float S0 = 0.f, S1 = 0.f;
+  {
+    float acc = 0.f;
+    for (int p = lane; p < G.c[0].n_parts; p += 32) acc += __ldg(G.c[0].rowsum_part + int64_t(p) * G.rows + r);
+    S0 = warp_sum(acc) * kexp;
+    if (G.ncontrib > 1) {
+      acc = 0.f;
+      for (int p = lane; p < G.c[1].n_parts; p += 32) acc += __ldg(G.c[1].rowsum_part + int64_t(p) * G.rows + r);
+      S1 = warp_sum(acc) * kexp;
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    ss = dot4(qv[i], qv[i], ss);
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  ss = warp_sum(ss);
+  const float nq_raw = sqrtf(ss);
+  const float inq = 1.0f / fmaxf(nq_raw, 1e-12f);
+#pragma unroll
+  for (int i = 0; i < V; ++i) { qv[i].x *= inq; qv[i].y *= inq; qv[i].z *= inq; qv[i].w *= inq; }   // q_hat
+  float sum_invZ0 = 0.f, sum_invZ1 = 0.f;
+  for (int t0 = warp; t0 < T; t0 += 2 * FIN_WARPS) {
+    if (t0 != warp) load_terms(t0);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!on[k]) continue;
+      const Contribution& C = G.c[cix[k]];
+      float kk0 = 0.f, kk1 = 0.f, qk0 = 0.f, qk1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; i += 2) {
+        kk0 = dot4(kv[k][i], kv[k][i], kk0);
+        qk0 = dot4(kv[k][i], qv[i], qk0);
+        if (i + 1 < V) {
+          kk1 = dot4(kv[k][i + 1], kv[k][i + 1], kk1);
+          qk1 = dot4(kv[k][i + 1], qv[i + 1], qk1);
+        }
+      }
+      float kk = kk0 + kk1, qk = qk0 + qk1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        kk += __shfl_xor_sync(0xffffffffu, kk, o);
+        qk += __shfl_xor_sync(0xffffffffu, qk, o);
+      }
+      const float ink = (kk > 1e-24f) ? rsqrtf(kk) : 1e12f;
+      const float lpos = qk * ink * invT;
+      const float epos = __expf(lpos - cmax);
+      const float Z = epos + (cix[k] ? S1 : S0);
+      const float iZ = __fdividef(1.0f, Z);
+      loss_kind[C.kind] += C.coef * (__logf(Z) + cmax - lpos);
+      if (cix[k]) sum_invZ1 += iZ; else sum_invZ0 += iZ;
+      const float w = C.coef * invT * (epos * iZ - 1.0f) * ink;
+#pragma unroll
+      for (int i = 0; i < V; ++i) axpy4(w, kv[k][i], g[i]);
+    }
+  }
+  if (G.dq == nullptr) return;
+  if (lane == 0) { invz[0][warp] = sum_invZ0; invz[1][warp] = sum_invZ1; }
+  __syncthreads();
+  // U partials of all contributions in one list, dealt from the last warp down (the first warps had two terms)
+  {
+    float tot0 = 0.f, tot1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < FIN_WARPS; ++w) { tot0 += invz[0][w]; tot1 += invz[1][w]; }
+    const int ns0 = G.c[0].n_splits;
+    const int NU = ns0 + (G.ncontrib > 1 ? G.c[1].n_splits : 0);
+    for (int u = FIN_WARPS - 1 - warp; u < NU; u += FIN_WARPS) {
+      const int ci = (u >= ns0) ? 1 : 0;
+      const Contribution& C = G.c[ci];
+      const float wu = C.coef * invT * (ci ? tot1 : tot0) * kexp;
+      const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(u - (ci ? ns0 : 0)) * C.split_stride +
+                                                         int64_t(r) * D) + lane;
+      float4 t[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) t[i] = __ldg(up + 32 * i);
+#pragma unroll
+      for (int i = 0; i < V; ++i) axpy4(wu, t[i], g[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) gs[warp][32 * i + lane] = g[i];
+  __syncthreads();
+  // every thread owns D / blockDim columns: add the partials in warp order, project through the normalisation
+  constexpr int FIN_COLS = (D + 32 * FIN_WARPS - 1) / (32 * FIN_WARPS);
+  const float* gflat = reinterpret_cast<const float*>(&gs[0][0]);
+  float gsum[FIN_COLS], qh[FIN_COLS];
+  float part = 0.f;
+#pragma unroll
+  for (int j = 0; j < FIN_COLS; ++j) {
+    const int c = threadIdx.x + 32 * FIN_WARPS * j;
+    gsum[j] = 0.f;
+    qh[j] = 0.f;
+    if (c < D) {
+      // column c of the row lives in float4 number c / 4 = 32 * i + lane  ->  same slot in every warp's partial
+#pragma unroll
+      for (int w = 0; w < FIN_WARPS; ++w) gsum[j] += gflat[w * D + c];
+      qh[j] = __ldg(G.q + int64_t(r) * D + c) * inq;
+      part = fmaf(gsum[j], qh[j], part);
+    }
+  }
+  const float qg = block_sum(part, red);
+  const bool clamped = nq_raw < 1e-12f;
+#pragma unroll
+  for (int j = 0; j < FIN_COLS; ++j) {
+    const int c = threadIdx.x + 32 * FIN_WARPS * j;
+    if (c < D) G.dq[int64_t(r) * D + c] = clamped ? gsum[j] * inq : (gsum[j] - qh[j] * qg) * inq;
+  }
+}
+
 // kexp: factor that brings the negatives' sums (row sums and U) to the e^{l - cmax} scale the positives use
 // (tensor-core path: the GEMM epilogue stores 2^{l log2 e} without the constant max, kexp = e^{-cmax}; fp32 path: 1).
 // Vector version: D == 128 * V, every row is V float4 per lane; all of a row's independent loads (query, two
 // key rows, two split-K partials of U) are issued together, 16 warps per SM.
-#ifndef HMMC_FIN_OCC
-#define HMMC_FIN_OCC 2      // resident blocks per SM the vector finish kernel is compiled for (measured: see profiles/)
-#endif
 template <int V>
-__global__ void __launch_bounds__(256, (V <= 4 ? HMMC_FIN_OCC : 1))
+__global__ void __launch_bounds__(32 * FIN_WARPS, (V <= 4 ? HMMC_FIN_OCC * 8 / FIN_WARPS : 1))
 infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, float cmax, float kexp,
-                          float* __restrict__ row_loss /* [3][blocks] */, const LossFinal fin, unsigned* counter) {
+                          const LossFinal fin, LossAcc* acc) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
   constexpr int D = 128 * V;
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int total_rows = a.row_begin[a.n];
   float loss_kind[3] = {0.f, 0.f, 0.f};
-  if (row < total_rows) {
-    int gi = 0;
+  // Blocks [0, heavy_rows): one row each (finish_row_block).  The others: FIN_WARPS consecutive rows of ONE query
+  // tensor (the host checks the row counts), so the tensor, its contributions and every loop bound below depend on
+  // blockIdx only: the compiler keeps the control flow on the uniform path, without convergence barriers around
+  // the warp shuffles.  What differs between the warps of a block (a frame without a left or right neighbour) is
+  // handled with a 0/1 factor instead of a branch.
+  const bool whole_block = int(blockIdx.x) < a.heavy_rows;
+  const int row0 = whole_block ? int(blockIdx.x) : a.heavy_rows + (int(blockIdx.x) - a.heavy_rows) * FIN_WARPS;
+  int gi = 0;
 #pragma unroll
-    for (int i = 1; i < MAX_GROUPS; ++i)
-      if (i < a.n && row >= a.row_begin[i]) gi = i;
-    const RowGroup& G = a.g[gi];
-    const int r = row - a.row_begin[gi];
+  for (int i = 1; i < MAX_GROUPS; ++i)
+    if (i < a.n && row0 >= a.row_begin[i]) gi = i;
+  const RowGroup& G = a.g[gi];
+  if (whole_block) {
+    finish_row_block<V>(G, row0 - a.row_begin[gi], invT, cmax, kexp, loss_kind);
+  } else {
+    const int r = row0 - a.row_begin[gi] + int(threadIdx.x >> 5);
     const int n = r / G.Fq, f = r - n * G.Fq;
-
     float4 qv[V], g[V];
     {
       const float4* qp = reinterpret_cast<const float4*>(G.q + int64_t(r) * D) + lane;
@@ -286,28 +465,26 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
     // key rows are requested together with the query row, one round trip instead of three.
     float sp[3];
     float4 kv[2][V];
-    bool on[2];
-    auto key_row = [&](const Contribution& C, int t, int& kr) -> bool {
-      int nterm;
-      if (C.pos_mode == HMMC_POS_PAIR) { nterm = 1; kr = r; }
-      else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
-        nterm = 2;
-        const int fk = (t == 0) ? f + 1 : f - 1;          // pairs (i, i+1) and (i+1, i) of frame_self_loss
-        kr = n * C.Fk + fk;
-        return t < nterm && fk >= 0 && fk < C.Fk;         // warp-uniform
-      }
-      else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) { nterm = C.Fk; kr = n * C.Fk + t; }
-      else { nterm = 1; kr = n; }
-      return t < nterm;
-    };
-    auto load_keys = [&](const Contribution& C, int t0) {
+    float on[2];                       // 1: the term exists for this row, 0: it does not (its key row is a dummy)
+    auto load_keys = [&](const Contribution& C, int t0, int nterm) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        int kr = 0;
-        on[k] = key_row(C, t0 + k, kr);
-        const float4* kp = reinterpret_cast<const float4*>(C.keys + int64_t(on[k] ? kr : 0) * D) + lane;
+        on[k] = 0.f;
+        if (t0 + k < nterm) {          // uniform
+          int kr;
+          on[k] = 1.f;
+          if (C.pos_mode == HMMC_POS_PAIR) kr = r;
+          else if (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) {
+            const int fk = (t0 + k == 0) ? f + 1 : f - 1;       // pairs (i, i+1) and (i+1, i) of frame_self_loss
+            on[k] = (fk >= 0 && fk < C.Fk) ? 1.f : 0.f;
+            kr = n * C.Fk + min(max(fk, 0), C.Fk - 1);
+          }
+          else if (C.pos_mode == HMMC_POS_ONE_TO_FRAMES) kr = n * C.Fk + t0 + k;
+          else kr = n;
+          const float4* kp = reinterpret_cast<const float4*>(C.keys + int64_t(kr) * D) + lane;
 #pragma unroll
-        for (int i = 0; i < V; ++i) kv[k][i] = on[k] ? __ldg(kp + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < V; ++i) kv[k][i] = __ldg(kp + 32 * i);
+        }
       }
     };
     auto prefetch = [&](const Contribution& C) {
@@ -316,7 +493,7 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
         const int p = lane + 32 * j;
         sp[j] = (p < C.n_parts) ? __ldg(C.rowsum_part + int64_t(p) * G.rows + r) : 0.f;
       }
-      load_keys(C, 0);
+      load_keys(C, 0, contrib_terms(C));
     };
     prefetch(G.c[0]);
     float ss = 0.f;
@@ -339,43 +516,60 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
       float S = (sp[0] + sp[1]) + sp[2];
       for (int p = lane + 96; p < C.n_parts; p += 32) S += __ldg(C.rowsum_part + int64_t(p) * G.rows + r);
       S = warp_sum(S) * kexp;
-      const int nterm = (C.pos_mode == HMMC_POS_FRAME_NEIGHBOUR) ? 2 : (C.pos_mode == HMMC_POS_ONE_TO_FRAMES ? C.Fk : 1);
+      const int nterm = contrib_terms(C);
       float loss = 0.f, sum_invZ = 0.f;
       const float scale = C.coef * invT;
       // positive terms, two key rows in flight per iteration (the first pair is already on its way)
       for (int t0 = 0; t0 < nterm; t0 += 2) {
-        if (t0 > 0) load_keys(C, t0);
+        if (t0 > 0) load_keys(C, t0, nterm);
+        const bool two = t0 + 1 < nterm;        // uniform
+        // ||k||^2 and q_hat.k of both rows, reduced in one butterfly
+        float kk[2] = {0.f, 0.f}, qk[2] = {0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          if (!on[k]) continue;
-          // ||k||^2 and q_hat.k: two accumulators each (short dependency chains), both reduced in one butterfly
-          float kk0 = 0.f, kk1 = 0.f, qk0 = 0.f, qk1 = 0.f;
+          if (k == 1 && !two) break;
+          float kk1 = 0.f, qk1 = 0.f;
 #pragma unroll
           for (int i = 0; i < V; i += 2) {
-            kk0 = dot4(kv[k][i], kv[k][i], kk0);
-            qk0 = dot4(kv[k][i], qv[i], qk0);
+            kk[k] = dot4(kv[k][i], kv[k][i], kk[k]);
+            qk[k] = dot4(kv[k][i], qv[i], qk[k]);
             if (i + 1 < V) {
               kk1 = dot4(kv[k][i + 1], kv[k][i + 1], kk1);
               qk1 = dot4(kv[k][i + 1], qv[i + 1], qk1);
             }
           }
-          float kk = kk0 + kk1, qk = qk0 + qk1;
+          kk[k] += kk1;
+          qk[k] += qk1;
+        }
+        if (two) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            kk += __shfl_xor_sync(0xffffffffu, kk, o);
-            qk += __shfl_xor_sync(0xffffffffu, qk, o);
+            kk[0] += __shfl_xor_sync(0xffffffffu, kk[0], o);
+            qk[0] += __shfl_xor_sync(0xffffffffu, qk[0], o);
+            kk[1] += __shfl_xor_sync(0xffffffffu, kk[1], o);
+            qk[1] += __shfl_xor_sync(0xffffffffu, qk[1], o);
           }
+        } else {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            kk[0] += __shfl_xor_sync(0xffffffffu, kk[0], o);
+            qk[0] += __shfl_xor_sync(0xffffffffu, qk[0], o);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k == 1 && !two) break;
           // fast-math intrinsics (2^-21 relative): the row's loss share and weights are O(1) scalars whose error
           // averages over b*F rows; measured against the float64 oracle in tests/test_gpu_pretrain.py
-          const float ink = (kk > 1e-24f) ? rsqrtf(kk) : 1e12f;          // 1 / max(||k||, 1e-12)
-          const float lpos = qk * ink * invT;
+          const float ink = (kk[k] > 1e-24f) ? rsqrtf(kk[k]) : 1e12f;          // 1 / max(||k||, 1e-12)
+          const float lpos = qk[k] * ink * invT;
           const float epos = __expf(lpos - cmax);
           const float Z = epos + S;
           const float iZ = __fdividef(1.0f, Z);
-          loss += __logf(Z) + cmax - lpos;
-          sum_invZ += iZ;
+          loss = fmaf(on[k], __logf(Z) + cmax - lpos, loss);
+          sum_invZ = fmaf(on[k], iZ, sum_invZ);
           // g_hat += coef/T * (p+ - 1) k_hat_t
-          const float w = scale * (epos * iZ - 1.0f) * ink;
+          const float w = on[k] * scale * (epos * iZ - 1.0f) * ink;
 #pragma unroll
           for (int i = 0; i < V; ++i) axpy4(w, kv[k][i], g[i]);
         }
@@ -385,19 +579,22 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
         // g_hat += coef/T * (sum_t 1/Z_t) U_r ;  U_r = the split-K partials, streamed in split order, two in flight
         const float wu = scale * sum_invZ * kexp;
         for (int s0 = 0; s0 < C.n_splits; s0 += 2) {
+          const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(s0) * C.split_stride + int64_t(r) * D) + lane;
           float4 t[2][V];
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const bool uon = s0 + k < C.n_splits;
-            const float4* up = reinterpret_cast<const float4*>(C.U_part + int64_t(uon ? s0 + k : s0) * C.split_stride +
-                                                               int64_t(r) * D) + lane;
+          for (int i = 0; i < V; ++i) t[0][i] = __ldg(up + 32 * i);
+          if (s0 + 1 < C.n_splits) {       // uniform
+            const float4* up1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(up) + C.split_stride);
 #pragma unroll
-            for (int i = 0; i < V; ++i) t[k][i] = uon ? __ldg(up + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < V; ++i) t[1][i] = __ldg(up1 + 32 * i);
+#pragma unroll
+            for (int i = 0; i < V; ++i) axpy4(wu, t[0][i], g[i]);
+#pragma unroll
+            for (int i = 0; i < V; ++i) axpy4(wu, t[1][i], g[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) axpy4(wu, t[0][i], g[i]);
           }
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int i = 0; i < V; ++i) axpy4(wu, t[k][i], g[i]);
         }
       }
     }
@@ -407,29 +604,23 @@ infonce_finish_vec_kernel(const __grid_constant__ FinishArgs a, float invT, floa
 #pragma unroll
       for (int i = 0; i < V; ++i) qg = dot4(qv[i], g[i], qg);
       qg = warp_sum(qg);
-      const bool clamped = nq_raw < 1e-12f;   // F.normalize clamps: q_hat = q/eps is then linear in q
+      // F.normalize clamps: q_hat = q/eps is then linear in q and the projection term drops out
+      const float proj = (nq_raw < 1e-12f) ? 0.f : qg;
       float4* op = reinterpret_cast<float4*>(G.dq + int64_t(r) * D) + lane;
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float4 o;
-        if (clamped) {
-          o = make_float4(g[i].x * inq, g[i].y * inq, g[i].z * inq, g[i].w * inq);
-        } else {
-          o = make_float4((g[i].x - qv[i].x * qg) * inq, (g[i].y - qv[i].y * qg) * inq, (g[i].z - qv[i].z * qg) * inq,
-                          (g[i].w - qv[i].w * qg) * inq);
-        }
-        op[32 * i] = o;
-      }
+      for (int i = 0; i < V; ++i)
+        op[32 * i] = make_float4((g[i].x - qv[i].x * proj) * inq, (g[i].y - qv[i].y * proj) * inq,
+                                 (g[i].z - qv[i].z * proj) * inq, (g[i].w - qv[i].w * proj) * inq);
     }
   }
-  finish_losses(loss_kind, row_loss, fin, counter);
+  finish_losses(loss_kind, acc, fin);
 }
 
 // Generic version (any D <= FIN_MAXD, scalar accesses).
 template <int NE>   // NE = elements per lane = D / 32 rounded up
 __global__ void __launch_bounds__(256, (NE <= 16 ? 2 : 1))
 infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, float cmax, float kexp,
-                      float* __restrict__ row_loss /* [3][blocks] */, const LossFinal fin, unsigned* counter) {
+                      const LossFinal fin, LossAcc* acc) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31;
@@ -543,7 +734,7 @@ infonce_finish_kernel(const __grid_constant__ FinishArgs a, int D, float invT, f
       }
     }
   }
-  finish_losses(loss_kind, row_loss, fin, counter);
+  finish_losses(loss_kind, acc, fin);
 }
 
 // ------------------------------------------------------------------ EMA
@@ -934,13 +1125,8 @@ struct GroupDesc {
   int rows, Fq;
 };
 
-constexpr int DEP_PER_BLOCK = 32;     // 256-row query tiles per block the fused launch can track (rows <= 8192)
-
 struct InfoNCELayout {       // workspace carving shared by the size query and the run
-  float* row_loss;
-  unsigned* counter;
-  unsigned* dep;             // [MAX_BLOCKS][DEP_PER_BLOCK] arrival counters of the fused S/U launch
-  bool fused;                // S- and U-GEMM in one persistent launch (EpiPipe)
+  LossAcc* acc;
   float* xhat[MAX_GROUPS];
   __nv_bfloat16* packed[MAX_GROUPS];
   float* rowsum_part[MAX_BLOCKS];
@@ -1010,118 +1196,12 @@ static SplitChoice choose_u_splits(const int* rows, const int* Kq, int nb, int D
   return best;
 }
 
-// ---- fused S/U launch (EpiPipe): the order of the units and the length of the U slices
-// Query tiles ("groups" = block k, 256-row tile m2) sorted by work; the global order is
-//   S(g0) S(g1) U(g0) S(g2) U(g1) ... : a group's U slices come PIPE_LAG groups after its S tiles, late enough
-// for the S tiles to be done when a pair reaches them, early enough for E to be read back from L2.
-constexpr int PIPE_LAG = 2;
-constexpr float PIPE_S_FIXED = 1.5f, PIPE_U_FIXED = 3.0f;    // cost of a unit beyond its k-block steps
-
-struct PipeGroup { int k, m2, n_tiles, total_kb; };
-
-static std::vector<PipeGroup> pipe_groups(const int* rows, const int* Kq, int nb, int nseg) {
-  std::vector<PipeGroup> gs;
-  std::vector<int> order(nb);
-  for (int k = 0; k < nb; ++k) order[k] = k;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    return Kq[a] != Kq[b] ? Kq[a] > Kq[b] : rows[a] > rows[b];
-  });
-  for (int k : order)
-    for (int m2 = 0; m2 < (rows[k] + 2 * UMMA_BM - 1) / (2 * UMMA_BM); ++m2)
-      gs.push_back(PipeGroup{k, m2, Kq[k] / UMMA_PAIR_BN, nseg * (Kq[k] / UMMA_BK)});
-  return gs;
-}
-
-// makespan (k-block steps) of the ordered, dependency-aware schedule for U slices of `unit` steps
-static double pipe_makespan(const std::vector<PipeGroup>& gs, int unit, int nseg, int workers, int* n_units) {
-  struct U { int kind, g; float cost; };
-  std::vector<U> seq;
-  const int G = int(gs.size());
-  const float s_cost = float(nseg * 8) + PIPE_S_FIXED;
-  int units = 0;
-  for (int i = 0; i < G + PIPE_LAG; ++i) {
-    if (i < G)
-      for (int n = 0; n < gs[i].n_tiles; ++n) seq.push_back(U{0, i, s_cost});
-    const int j = i - PIPE_LAG;
-    if (j >= 0) {
-      const int u = std::min(unit, gs[j].total_kb);
-      for (int k0 = 0; k0 < gs[j].total_kb; k0 += u)
-        for (int n2 = 0; n2 < 2; ++n2) {
-          seq.push_back(U{1, j, float(std::min(u, gs[j].total_kb - k0)) + PIPE_U_FIXED});
-          ++units;
-        }
-    }
-  }
-  std::vector<double> load(workers, 0.0);
-  std::vector<std::vector<int>> mine(workers);
-  for (int i = 0; i < int(seq.size()); ++i) {
-    int best = 0;
-    for (int w = 1; w < workers; ++w)
-      if (load[w] < load[best]) best = w;
-    load[best] += seq[i].cost;
-    mine[best].push_back(i);
-  }
-  std::vector<double> t(workers, 0.0), s_done(G, 0.0);
-  std::vector<int> idx(workers, 0), s_left(G);
-  for (int i = 0; i < G; ++i) s_left[i] = gs[i].n_tiles;
-  size_t remaining = seq.size();
-  while (remaining) {
-    int pick = -1;
-    for (int w = 0; w < workers; ++w) {
-      if (idx[w] >= int(mine[w].size())) continue;
-      const U& u = seq[mine[w][idx[w]]];
-      if (u.kind == 1 && s_left[u.g] > 0) continue;
-      if (pick < 0 || t[w] < t[pick]) pick = w;
-    }
-    if (pick < 0) return 1e30;              // cannot happen: the order is acyclic
-    const U& u = seq[mine[pick][idx[pick]]];
-    double start = t[pick];
-    if (u.kind == 1) start = std::max(start, s_done[u.g]);
-    t[pick] = start + u.cost;
-    ++idx[pick];
-    --remaining;
-    if (u.kind == 0) { --s_left[u.g]; s_done[u.g] = std::max(s_done[u.g], t[pick]); }
-  }
-  if (n_units) *n_units = units;
-  return *std::max_element(t.begin(), t.end());
-}
-
-static int choose_pipe_unit(const int* rows, const int* Kq, int nb, int planes) {
-  typedef std::tuple<int, int, int, int, int, int, int, int, int, int, int, int, int, int> Key;
-  static std::mutex mu;
-  static std::map<Key, int> cache;
-  int kr[MAX_BLOCKS] = {0}, kk[MAX_BLOCKS] = {0};
-  for (int k = 0; k < nb; ++k) { kr[k] = rows[k]; kk[k] = Kq[k]; }
-  const Key key(nb, planes, kr[0], kr[1], kr[2], kr[3], kr[4], kr[5], kk[0], kk[1], kk[2], kk[3], kk[4], kk[5]);
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) return it->second;
-  }
-  const int nseg = (planes == 2) ? 3 : 1;
-  const std::vector<PipeGroup> gs = pipe_groups(rows, Kq, nb, nseg);
-  const int workers = sm_count() / 2;
-  int best = 48 * nseg;
-  double best_cost = 1e30;
-  for (int unit : {16, 24, 32, 40, 48, 64, 80, 96, 128, 192}) {
-    int units = 0;
-    const double mk = pipe_makespan(gs, unit * nseg, nseg, workers, &units);
-    const double cost = mk + 0.25 * units;      // every partial tile is read back once by the finish kernel
-    if (cost < best_cost) { best_cost = cost; best = unit * nseg; }
-  }
-  std::lock_guard<std::mutex> lk(mu);
-  cache[key] = best;
-  return best;
-}
-
 static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* groups, int ng, const int* blk_group,
                            const int* blk_Kq, int nb, int D, int prec, bool need_grad) {
   const int planes = planes_of(prec);
   int total_rows = 0;
   for (int i = 0; i < ng; ++i) total_rows += groups[i].rows;
-  L.row_loss = ws.take<float>(size_t(3) * total_rows);
-  L.counter = ws.take<unsigned>(4);
-  L.dep = ws.take<unsigned>(size_t(MAX_BLOCKS) * DEP_PER_BLOCK);
+  L.acc = ws.take<LossAcc>(1);
   for (int i = 0; i < ng; ++i) {
     L.xhat[i] = (prec == HMMC_PREC_FP32) ? ws.take<float>(size_t(groups[i].rows) * D) : nullptr;
     L.packed[i] = (prec != HMMC_PREC_FP32) ? ws.take<__nv_bfloat16>(size_t(groups[i].rows) * planes * D) : nullptr;
@@ -1133,22 +1213,10 @@ static void infonce_layout(Workspace& ws, InfoNCELayout& L, const GroupDesc* gro
   const int nseg_layout = (planes == 2) ? 3 : 1;
   SplitChoice sc;
   for (int k = 0; k < MAX_BLOCKS; ++k) sc.unit[k] = k < nb ? nseg_layout * (blk_Kq[k] / UMMA_BK) : 1;
-  L.fused = false;
   if (prec != HMMC_PREC_FP32 && need_grad) {
     int rows[MAX_BLOCKS];
-    bool fits = (L.bn1 == 256 && L.bn2 == 256 && D == 2 * UMMA_PAIR_BN);
-    for (int k = 0; k < nb; ++k) {
-      rows[k] = groups[blk_group[k]].rows;
-      fits = fits && rows[k] <= DEP_PER_BLOCK * 2 * UMMA_BM;
-    }
-    if (fits) {
-      // one persistent launch for both GEMMs: U slices of one length for every block
-      L.fused = true;
-      const int unit = choose_pipe_unit(rows, blk_Kq, nb, planes);
-      for (int k = 0; k < nb; ++k) sc.unit[k] = std::min(unit, nseg_layout * (blk_Kq[k] / UMMA_BK));
-    } else {
-      sc = choose_u_splits(rows, blk_Kq, nb, D, planes, L.bn2);
-    }
+    for (int k = 0; k < nb; ++k) rows[k] = groups[blk_group[k]].rows;
+    sc = choose_u_splits(rows, blk_Kq, nb, D, planes, L.bn2);
   }
   for (int k = 0; k < nb; ++k) {
     const int R = groups[blk_group[k]].rows;
@@ -1240,11 +1308,11 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
   if (phase != 2) {
     const dim3 pgrid((total_rows + 7) / 8), pblock(256);
     cudaError_t e;
-    if (vec_q && D == 512) e = launch_pdl(prep_rows_kernel<4>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
-    else if (vec_q && D == 256) e = launch_pdl(prep_rows_kernel<2>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
-    else if (vec_q && D == 128) e = launch_pdl(prep_rows_kernel<1>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
-    else if (vec_q && D == 1024) e = launch_pdl(prep_rows_kernel<8>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
-    else e = launch_pdl(prep_rows_kernel<0>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.counter, L.dep, MAX_BLOCKS * DEP_PER_BLOCK);
+    if (vec_q && D == 512) e = launch_pdl(prep_rows_kernel<4>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.acc);
+    else if (vec_q && D == 256) e = launch_pdl(prep_rows_kernel<2>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.acc);
+    else if (vec_q && D == 128) e = launch_pdl(prep_rows_kernel<1>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.acc);
+    else if (vec_q && D == 1024) e = launch_pdl(prep_rows_kernel<8>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.acc);
+    else e = launch_pdl(prep_rows_kernel<0>, pgrid, pblock, 0, st, pa, D, planes, pack_scale, L.acc);
     count_launch();
     HMMC_CHECK_CUDA(e);
     if (prec == HMMC_PREC_FP32) {
@@ -1258,66 +1326,6 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
         if (need_grad && (rc = gemm_f32(S, Kq, 1, blocks[k].queue->dk, Kq, 1, L.U_part[k], D, G.rows, D, Kq, 1.0f, st))) return rc;
       }
     } else {
-      if (L.fused) {
-        // ONE persistent launch: S tiles and U slices of all blocks, ordered and handed over through counters
-        auto launch_pipe = [&](auto epi_tag) -> int {
-          using Epi = decltype(epi_tag);
-          GemmProblem<Epi> pp[2 * MAX_BLOCKS];
-          int rows[MAX_BLOCKS];
-          float fixed[2 * MAX_BLOCKS];
-          for (int k = 0; k < nb; ++k) {
-            const GroupDesc& G = groups[blocks[k].group];
-            const int Kq = blk_Kq[k];
-            rows[k] = G.rows;
-            typename Epi::Params e{};
-            e.kind = 0;
-            e.nce.rowsum_part = L.rowsum_part[k];
-            e.nce.lo_col0 = Kq;
-            e.dep = L.dep + k * DEP_PER_BLOCK;
-            e.dep_expected = 0;
-            pp[k] = GemmProblem<Epi>{L.packed[blocks[k].group], int64_t(planes) * D, blocks[k].queue->pack_kd,
-                                     int64_t(planes) * D, G.rows, Kq, D, planes, 1, e,
-                                     L.E[k], int64_t(planes) * Kq, int64_t(planes) * Kq};
-            fixed[k] = PIPE_S_FIXED;
-            typename Epi::Params u{};
-            u.kind = 1;
-            u.st = EpiStoreF32::Params{L.U_part[k], int64_t(D), int64_t(G.rows) * D, 1.0f};
-            u.dep = L.dep + k * DEP_PER_BLOCK;
-            u.dep_expected = unsigned(2 * Epi::PAIR_WARPS * (Kq / UMMA_PAIR_BN));     // epilogue warps of both CTAs x S tiles
-            pp[nb + k] = GemmProblem<Epi>{L.E[k], int64_t(planes) * Kq, blocks[k].queue->pack_dk, int64_t(planes) * Kq,
-                                          G.rows, D, Kq, planes, 1, u};
-            pp[nb + k].kb_per_split = L.splits[k];
-            fixed[nb + k] = PIPE_U_FIXED;
-          }
-          // unit numbers as the launcher assigns them: problem after problem, split-major, then n * m-tiles + m
-          int tile_begin[2 * MAX_BLOCKS + 1];
-          tile_begin[0] = 0;
-          for (int k = 0; k < nb; ++k)
-            tile_begin[k + 1] = tile_begin[k] + ((rows[k] + 255) / 256) * (blk_Kq[k] / UMMA_PAIR_BN);
-          for (int k = 0; k < nb; ++k)
-            tile_begin[nb + k + 1] = tile_begin[nb + k] + ((rows[k] + 255) / 256) * 2 * L.nsplits_eff[k];
-          const std::vector<PipeGroup> gs = pipe_groups(rows, blk_Kq, nb, planes == 2 ? 3 : 1);
-          std::vector<int> seq;
-          const int Gn = int(gs.size());
-          for (int i = 0; i < Gn + PIPE_LAG; ++i) {
-            if (i < Gn) {
-              const PipeGroup& g = gs[i];
-              const int num_m = (rows[g.k] + 255) / 256;
-              for (int n = 0; n < g.n_tiles; ++n) seq.push_back(tile_begin[g.k] + n * num_m + g.m2);
-            }
-            const int j = i - PIPE_LAG;
-            if (j >= 0) {
-              const PipeGroup& g = gs[j];
-              const int num_m = (rows[g.k] + 255) / 256;
-              for (int sp = 0; sp < L.nsplits_eff[g.k]; ++sp)
-                for (int n2 = 0; n2 < 2; ++n2) seq.push_back(tile_begin[nb + g.k] + sp * (num_m * 2) + n2 * num_m + g.m2);
-            }
-          }
-          return launch_umma_grouped_pair<Epi>(pp, 2 * nb, st, reserved_sms, &seq, fixed);
-        };
-        rc = (planes == 2) ? launch_pipe(EpiPipe<2>()) : launch_pipe(EpiPipe<1>());
-        if (rc) return rc;
-      } else {
       GemmProblem<EpiStoreF32> p2[MAX_BLOCKS];
       for (int k = 0; k < nb; ++k) {
         const GroupDesc& G = groups[blocks[k].group];
@@ -1364,7 +1372,6 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
         else rc = launch_umma_grouped<128, EpiStoreF32>(p2, nb, st, reserved_sms);
         if (rc) return rc;
       }
-      }   // two launches
     }
     // every kernel that reads the queues has been issued: let the enqueue start on another stream
   }
@@ -1415,17 +1422,39 @@ static int run_infonce(const GroupDesc* groups, int ng, const BlockDesc* blocks,
   }
   for (int i = 0; i < MAX_GROUPS; ++i)
     if (fa.g[i].ncontrib < 2) fa.g[i].c[1] = fa.g[i].c[0];
-  const dim3 fgrid((total_rows + 7) / 8), fblock(256);
+  // vector kernel: the rows of the leading (ONE_TO_FRAMES) tensors get a whole block each (finish_row_block)
+  bool vec_kernel = vec_q && (D == 128 || D == 256 || D == 512 || D == 1024);
+  for (int i = 0; i < ng; ++i) vec_kernel = vec_kernel && (groups[i].rows % FIN_WARPS == 0);   // a block = one tensor
+  // Worth it while the grid stays within two waves: then the kernel lasts as long as its slowest row.  Beyond
+  // that it is bound by block slots and the extra blocks cost more than they save (b = 128: -2.9 us, b = 256:
+  // +4.4 us, profiles/r2_finish_kernel.md).
+  fa.heavy_rows = 0;
+  if (vec_kernel && HMMC_FIN_HEAVY) {
+    int heavy_rows = 0;
+    for (int i = 0; i < ng; ++i) {
+      bool heavy = false;
+      for (int k = 0; k < nb; ++k)
+        heavy = heavy || (blocks[k].group == group_at[i] && blocks[k].pos_mode == HMMC_POS_ONE_TO_FRAMES);
+      if (!heavy) break;
+      heavy_rows = fa.row_begin[i + 1];
+    }
+    const int grid_blocks = heavy_rows + (total_rows - heavy_rows + FIN_WARPS - 1) / FIN_WARPS;
+    const int slots = sm_count() * HMMC_FIN_OCC * 8 / FIN_WARPS;
+    if (HMMC_FIN_HEAVY == 2 || grid_blocks <= 2 * slots) fa.heavy_rows = heavy_rows;
+  }
+  const int fin_warps = vec_kernel ? FIN_WARPS : 8;
+  const int fin_blocks = fa.heavy_rows + (total_rows - fa.heavy_rows + fin_warps - 1) / fin_warps;
+  const dim3 fgrid(fin_blocks), fblock(32 * fin_warps);
   const int ne = (D + 31) / 32;
   cudaError_t e;
-  if (vec_q && D == 512) e = launch_pdl(infonce_finish_vec_kernel<4>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else if (vec_q && D == 256) e = launch_pdl(infonce_finish_vec_kernel<2>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else if (vec_q && D == 128) e = launch_pdl(infonce_finish_vec_kernel<1>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else if (vec_q && D == 1024) e = launch_pdl(infonce_finish_vec_kernel<8>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else if (ne <= 4) e = launch_pdl(infonce_finish_kernel<4>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else if (ne <= 16) e = launch_pdl(infonce_finish_kernel<16>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else if (ne <= 32) e = launch_pdl(infonce_finish_kernel<32>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
-  else e = launch_pdl(infonce_finish_kernel<FIN_MAXE>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, L.row_loss, fin, L.counter);
+  if (vec_kernel && D == 512) e = launch_pdl(infonce_finish_vec_kernel<4>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, fin, L.acc);
+  else if (vec_kernel && D == 256) e = launch_pdl(infonce_finish_vec_kernel<2>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, fin, L.acc);
+  else if (vec_kernel && D == 128) e = launch_pdl(infonce_finish_vec_kernel<1>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, fin, L.acc);
+  else if (vec_kernel && D == 1024) e = launch_pdl(infonce_finish_vec_kernel<8>, fgrid, fblock, 0, st, fa, invT, cmax, kexp, fin, L.acc);
+  else if (ne <= 4) e = launch_pdl(infonce_finish_kernel<4>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, fin, L.acc);
+  else if (ne <= 16) e = launch_pdl(infonce_finish_kernel<16>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, fin, L.acc);
+  else if (ne <= 32) e = launch_pdl(infonce_finish_kernel<32>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, fin, L.acc);
+  else e = launch_pdl(infonce_finish_kernel<FIN_MAXE>, fgrid, fblock, 0, st, fa, D, invT, cmax, kexp, fin, L.acc);
   count_launch();
   HMMC_CHECK_CUDA(e);
   return HMMC_OK;
@@ -1641,9 +1670,12 @@ int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, in
     mx = numels_host[i] > mx ? numels_host[i] : mx;
   }
   if (mx <= 0) return HMMC_OK;
+  // two blocks per SM over all tensors: in the usual case (upstream gradient 1) every block reads the scalar and
+  // exits, and a grid of thousands of blocks costs microseconds just to drain
   int gx = int((mx / 4 + 255) / 256);
+  const int cap = (2 * sm_count() + n - 1) / n;
+  if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  if (gx > 4 * sm_count()) gx = 4 * sm_count();
   count_launch();
   HMMC_CHECK_CUDA(launch_pdl(scale_tensors_kernel, dim3(gx, n), dim3(256), 0, static_cast<cudaStream_t>(stream), a, scale));
   return HMMC_OK;

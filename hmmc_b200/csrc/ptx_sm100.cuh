@@ -249,14 +249,7 @@ __device__ __forceinline__ void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// wait until at most N of this thread's bulk groups are still in flight (their global writes are complete)
-template <int N>
-__device__ __forceinline__ void bulk_wait_group() {
-  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-// ordering between the async proxy (TMA) and the generic proxy, all state spaces
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// device-scope release / acquire on a counter in global memory (producer -> consumer hand-over between CTAs)
+// device-scope release / acquire on a counter in global memory (hand-over between CTAs)
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -65,7 +65,7 @@ struct UmmaCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
 };
 
-constexpr int UMMA_MAX_PROBLEMS = 12;
+constexpr int UMMA_MAX_PROBLEMS = 6;
 constexpr int UMMA_MAX_UNITS = 2048;      // units a launch can place explicitly; larger launches go round-robin
 constexpr int UMMA_MAX_WORKERS = 160;     // CTAs (single-CTA kernel) or CTA pairs of a launch
 
@@ -388,7 +388,6 @@ umma_gemm_pair_kernel(const __grid_constant__ TmapSet tm, const __grid_constant_
         const int m2 = mn % s.num_m_blk, n_blk = mn / s.num_m_blk;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, s.num_seg * s.kb_per_seg);
-        Epi::producer_wait(g.ep[p], m2);      // units whose A operand another unit of this launch produces
         for (int i = kb0; i < kb1; ++i) {
           const int seg = i / s.kb_per_seg, kb = i - seg * s.kb_per_seg;
           const int ak = (seg == 0 ? s.a_k0[0] : (seg == 1 ? s.a_k0[1] : s.a_k0[2])) + kb * UMMA_BK;
@@ -505,7 +504,6 @@ struct EpiStoreF32 {
   bool vec_ok;
   __device__ __forceinline__ void init() {}
   __device__ __forceinline__ void finish() {}
-  __device__ static __forceinline__ void producer_wait(const Params&, int) {}
   __device__ __forceinline__ void begin_tile(const Params& p, const GemmShape& s, int row, int n_blk, int split,
                                              const CUtensorMap*) {
     row0 = row - lane;
@@ -602,7 +600,6 @@ struct EpiInfoNCE {
       __syncwarp();
     }
   }
-  __device__ static __forceinline__ void producer_wait(const Params&, int) {}
   __device__ __forceinline__ void begin_tile(const Params&, const GemmShape&, int row, int, int, const CUtensorMap* c) {
     s0 = s1 = s2 = s3 = 0.f;
     row0 = row - lane;
@@ -678,73 +675,6 @@ struct EpiInfoNCE {
   }
   __device__ __forceinline__ void end_tile(const Params& p, const GemmShape& s, int row, int part, int) {
     if (row < s.M) p.rowsum_part[int64_t(part) * s.M + row] = (s0 + s1) + (s2 + s3);
-  }
-};
-
-// Both GEMMs of the InfoNCE backward in ONE persistent launch.  kind 0 = an S tile (EpiInfoNCE: exponentials, row
-// sums, E stored through TMA), kind 1 = a split-K slice of U = E.Q^T (EpiStoreF32).  A U unit reads the E rows that
-// the S tiles of the same 256-row query tile wrote: those tiles publish their stores on a counter in global
-// memory (one release-add per epilogue warp, after its bulk stores have completed), and the TMA producer of the U
-// unit acquires it before its first load.  The host orders the units so that every pair walks its list in one
-// global order in which a U unit comes after all the S tiles it waits for (no cycles), a query tile's U units
-// follow its S tiles closely (E is read back from L2, not from HBM), and S tiles (bound by their epilogue) and U
-// slices (bound by the MMAs) alternate on a pair so that each hides behind the other.
-template <int PLANES>
-struct EpiPipe {
-  using NCE = EpiInfoNCE<PLANES, 8, 6, 1, 2>;
-  struct Params {
-    int kind;                         // 0: S tile, 1: U slice
-    typename NCE::Params nce;
-    EpiStoreF32::Params st;
-    unsigned* dep;                    // counters of this block's query tiles (index = 256-row tile)
-    unsigned dep_expected;            // kind 1: arrivals that make the query tile's E complete
-  };
-  static constexpr int PAIR_WARPS = 8, PAIR_STAGES = 6;
-  static constexpr int PARTS_PER_TILE_PAIR = 2;
-  static constexpr int STORE_COLS = NCE::STORE_COLS;
-  static constexpr uint32_t STAGE_BYTES = NCE::STAGE_BYTES > EpiStoreF32::STAGE_BYTES ? NCE::STAGE_BYTES : EpiStoreF32::STAGE_BYTES;
-  static constexpr bool USES_CMAP = true;
-  uint8_t* stage;
-  int lane;
-  NCE nce;
-  EpiStoreF32 st;
-  __device__ __forceinline__ void init() {
-    nce.stage = stage; nce.lane = lane; nce.init();
-    st.stage = stage; st.lane = lane; st.init();
-  }
-  __device__ __forceinline__ void finish() { nce.finish(); }
-  // The copy engine's reads of E must come after the S tiles' stores: spin (with a time limit that turns a
-  // scheduling bug into a trap instead of a hang) until every epilogue warp of every S tile has arrived.
-  __device__ static __forceinline__ void producer_wait(const Params& p, int m2) {
-    if (p.kind != 1) return;
-    const unsigned* c = p.dep + m2;
-    const long long t0 = clock64();
-    while (ptx::ld_acquire(c) < p.dep_expected) {
-      __nanosleep(100);
-      if (clock64() - t0 > (1ll << 33)) __trap();       // ~4 s
-    }
-    ptx::fence_proxy_async_all();
-  }
-  __device__ __forceinline__ void begin_tile(const Params& p, const GemmShape& s, int row, int n_blk, int split,
-                                             const CUtensorMap* c) {
-    if (p.kind == 0) nce.begin_tile(p.nce, s, row, n_blk, split, c);
-    else st.begin_tile(p.st, s, row, n_blk, split, c);
-  }
-  template <int C, int NC>
-  __device__ __forceinline__ void chunk(const Params& p, const GemmShape& s, int row, int col0, float (&v)[32]) {
-    if (p.kind == 0) nce.template chunk<C, NC>(p.nce, s, row, col0, v);
-    else st.template chunk<C, NC>(p.st, s, row, col0, v);
-  }
-  __device__ __forceinline__ void end_tile(const Params& p, const GemmShape& s, int row, int part, int split) {
-    if (p.kind == 0) {
-      nce.end_tile(p.nce, s, row, part, split);
-      if (lane == 0) {
-        ptx::bulk_wait_group<0>();                      // this warp's E stores of the tile have landed
-        ptx::fence_proxy_async_all();
-        ptx::red_release_add(p.dep + (row >> 8), 1u);
-      }
-      __syncwarp();
-    }
   }
 };
 
@@ -948,12 +878,8 @@ int launch_umma_grouped(const GemmProblem<Epi>* probs, int n, cudaStream_t strea
 
 // CTA-pair launch of a grouped GEMM (BN = 256).  GemmShape::num_m_blk counts 256-row super tiles;
 // everything else (segments, split-K, epilogue parameters) is identical to launch_umma_grouped.
-// sequence (optional): the units in the global order every pair has to respect (a unit may wait for units that
-// come earlier in it, see EpiPipe); they are dealt in that order, each to the pair with the least work so far.
-// unit_cost(p, k-block steps) prices a unit of problem p.
 template <class Epi>
-int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t stream, int reserved_sms = 0,
-                             const std::vector<int>* sequence = nullptr, const float* fixed_cost = nullptr) {
+int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t stream, int reserved_sms = 0) {
   constexpr int BN = UMMA_PAIR_BN;
   TmapSet tm;
   GroupedArgs<Epi> g;
@@ -963,38 +889,7 @@ int launch_umma_grouped_pair(const GemmProblem<Epi>* probs, int n, cudaStream_t 
   const int tiles = g.tile_begin[g.num_problems];
   int pairs = gemm_sm_budget(reserved_sms) / 2;
   if (pairs > tiles) pairs = tiles;
-  if (sequence != nullptr) {
-    HMMC_REQUIRE(int(sequence->size()) == tiles && tiles <= UMMA_MAX_UNITS && pairs <= UMMA_MAX_WORKERS,
-                 "umma gemm: ordered launch of %d units (sequence %d, max %d)", tiles, int(sequence->size()), UMMA_MAX_UNITS);
-    HMMC_REQUIRE(g.num_problems == n, "umma gemm: ordered launch with empty problems");
-    UnitSchedule& sc = g.sched;
-    sc.num_units = tiles;
-    sc.explicit_order = 1;
-    std::vector<double> load(pairs, 0.0);
-    std::vector<std::vector<uint16_t>> mine(pairs);
-    for (int t : *sequence) {
-      int p = 0;
-      for (int i = 1; i < g.num_problems; ++i)
-        if (t >= g.tile_begin[i]) p = i;
-      const GemmShape& s = g.shape[p];
-      const int split = (t - g.tile_begin[p]) / (s.num_m_blk * s.num_n_blk);
-      const int kb0 = split * s.kb_per_split;
-      const int kb1 = std::min(kb0 + s.kb_per_split, s.num_seg * s.kb_per_seg);
-      int best = 0;
-      for (int w = 1; w < pairs; ++w)
-        if (load[w] < load[best]) best = w;
-      load[best] += double(kb1 - kb0) + (fixed_cost ? double(fixed_cost[p]) : double(UMMA_UNIT_FIXED_COST));
-      mine[best].push_back(uint16_t(t));
-    }
-    int pos = 0;
-    for (int w = 0; w < pairs; ++w) {
-      sc.begin[w] = uint16_t(pos);
-      for (uint16_t u : mine[w]) sc.order[pos++] = u;
-    }
-    for (int w = pairs; w <= UMMA_MAX_WORKERS; ++w) sc.begin[w] = uint16_t(pos);
-  } else {
-    build_schedule(g, pairs);
-  }
+  build_schedule(g, pairs);
   return launch_gemm(umma_gemm_pair_kernel<Epi>, 2 * pairs, 2, UmmaPairCfg<Epi>::SMEM_BYTES, UmmaPairCfg<Epi>::THREADS,
                      stream, tm, g);
 }
