@@ -253,7 +253,7 @@ __device__ __forceinline__ void axpy4(float w, const float4& x, float4& y) {
 #define HMMC_FIN_OCC 2      // resident blocks per SM the vector finish kernel is compiled for (measured: see profiles/)
 #endif
 #ifndef HMMC_FIN_WARPS
-#define HMMC_FIN_WARPS 8    // warps (= rows) per block of the vector finish kernel
+#define HMMC_FIN_WARPS 4    // warps (= rows) per block of the vector finish kernel (measured: profiles/r2_finish_kernel.md)
 #endif
 constexpr int FIN_WARPS = HMMC_FIN_WARPS;
 #ifndef HMMC_FIN_HEAVY
