@@ -816,7 +816,14 @@ struct EnqueueArgs {
   int mult[5];              // columns per sample: 1 or F
   int norm_off[5];          // offset of each queue's norms in the scratch array
   int planes;
+  // peer exchange (hmmc_peer_push_rows): the keys sit in one of two slots of the receive buffer, chosen on the
+  // device by the exchange counter (NULL: no slots)
+  const int32_t* slot_epoch;
+  int64_t slot_stride;      // elements between the two slots
 };
+__device__ __forceinline__ int64_t enqueue_slot_offset(const EnqueueArgs& a) {
+  return a.slot_epoch != nullptr ? int64_t((*a.slot_epoch - 1) & 1) * a.slot_stride : 0;
+}
 
 constexpr int ENQ_DCHUNK = 128;
 
@@ -838,7 +845,7 @@ __global__ void key_norms_kernel(int nsamples, int D, EnqueueArgs a, float* __re
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= nsamples * mult) return;
   const int smp = c / mult, f = c - smp * mult;
-  const float* x = a.src[qi] + int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
+  const float* x = a.src[qi] + enqueue_slot_offset(a) + int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
   float ss = 0.f;
   for (int d = lane; d < D; d += 32) { const float v = x[d]; ss = fmaf(v, v, ss); }
   ss = warp_sum(ss);
@@ -866,7 +873,7 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __re
   const int Kq = a.Kq[qi];
   const int col_base = ptr * mult;       // first destination column
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* src = a.src[qi];
+  const float* src = a.src[qi] + enqueue_slot_offset(a);
   for (int cc = threadIdx.x; cc < CB; cc += blockDim.x) {
     const int c = min(c0 + cc, ncols - 1);         // c = local column = sample*mult + f
     const int smp = c / mult, f = c - smp * mult;
@@ -961,7 +968,7 @@ enqueue_vec_kernel(int nsamples, int D, EnqueueArgs a, const float* __restrict__
   const int Kq = a.Kq[qi];
   const int col_base = ptr * mult;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* src = a.src[qi];
+  const float* src = a.src[qi] + enqueue_slot_offset(a);
   if (threadIdx.x < CB) {
     const int c = min(c0 + threadIdx.x, ncols - 1);
     const int smp = c / mult, f = c - smp * mult;
@@ -1046,6 +1053,51 @@ __global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_
   for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
     if (PACK) y[i] = x[i]; else x[i] = y[i];
   }
+}
+
+// ---------------------------------------------------------------- key exchange over peer memory (NVLink)
+// The ranks of one node map each other's receive buffers (symmetric memory).  Every rank PUSHES its block of rows
+// into all receive buffers with plain 16-byte stores (posted writes: no round trip per access), then raises its
+// flag in every peer; a rank's enqueue starts once all flags have reached the current exchange number.  Two slots
+// alternate so that a fast rank's next push never lands in a buffer a slow rank still reads (a rank pushes
+// exchange e+2 only after it has seen every peer's flag e+1, which that peer raised after its enqueue e).
+// All counters live on the device: a captured step replays unchanged.
+struct PeerPtrs { uint64_t p[HMMC_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const float4* __restrict__ send, int64_t n4, PeerPtrs bufs, PeerPtrs flags, int W, int rank,
+                 int64_t slot_stride, const int32_t* __restrict__ epoch, unsigned* done) {
+  const int e = *epoch;                                         // exchanges completed so far
+  const int peer = (rank + int(blockIdx.y)) % W;                // staggered: no two ranks start on the same peer
+  float4* dst = reinterpret_cast<float4*>(bufs.p[peer]) + (int64_t(e & 1) * slot_stride + int64_t(rank) * n4 * 4) / 4;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x)
+    dst[i] = send[i];
+  // last block: every block's stores are ordered before its arrival (system-scope fence), the flags after all arrivals
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x < W) {
+    volatile int32_t* f = reinterpret_cast<volatile int32_t*>(flags.p[threadIdx.x]) + rank;
+    *f = e + 1;
+  }
+  if (threadIdx.x == 0) *done = 0u;
+}
+
+// Waits until every rank's rows of the current exchange have landed here, then counts the exchange.
+__global__ void peer_wait_kernel(const volatile int32_t* my_flags, int W, int32_t* epoch) {
+  const int e = *epoch + 1;
+  if (threadIdx.x < W) {
+    const long long t0 = clock64();
+    while (my_flags[threadIdx.x] < e)
+      if (clock64() - t0 > (1ll << 34)) __trap();             // ~9 s: a rank that never pushes is an error, not a hang
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch = e;
 }
 
 struct ScaleArgs {
@@ -1584,7 +1636,7 @@ __global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K, int advance
 
 static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
                           const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch,
-                          int32_t* staged, cudaStream_t st) {
+                          int32_t* staged, const int32_t* slot_epoch, int64_t slot_stride, cudaStream_t st) {
   HMMC_REQUIRE(queues5 && queue_ptr, "enqueue: null argument");
   // the reference's slice assignment raises when the batch does not fit (modules/modeling.py:273-280)
   const bool device_ptr = ptr_host < 0;     // pointer lives on the device only (graph replay)
@@ -1595,6 +1647,8 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   EnqueueArgs a;
   const int mult[5] = {1, 1, 1, F, F};
   a.planes = queues5[0].planes;
+  a.slot_epoch = slot_epoch;
+  a.slot_stride = slot_stride;
   for (int i = 0; i < 5; ++i) {
     const hmmc_queue& q = queues5[i];
     HMMC_REQUIRE(q.dk != nullptr && q.D == D && q.Kq == K * mult[i], "enqueue: queue %d has shape [%d,%d], expected [%d,%d]",
@@ -1640,14 +1694,16 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
 }
 
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5, int64_t* queue_ptr,
-                      int64_t ptr_host, int K, float* scratch, int32_t* staged, void* stream) {
+                      int64_t ptr_host, int K, float* scratch, int32_t* staged, const int32_t* slot_epoch,
+                      int64_t slot_stride, void* stream) {
   HMMC_REQUIRE(gathered != nullptr, "enqueue: null gathered buffer");
   const int64_t row = int64_t(3 + 2 * F) * D;
   const float* src[5] = {gathered, gathered + D, gathered + 2 * D, gathered + 3 * D, gathered + 3 * D + int64_t(F) * D};
   const int64_t stride[5] = {row, row, row, row, row};
   HMMC_REQUIRE(staged == nullptr || ptr_host < 0, "enqueue: the staged mark needs the device-side queue pointer (ptr_host < 0)");
-  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, scratch, staged,
-                        static_cast<cudaStream_t>(stream));
+  HMMC_REQUIRE(slot_epoch == nullptr || slot_stride >= int64_t(W) * b * row, "enqueue: slot stride smaller than a slot");
+  return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, scratch, staged, slot_epoch,
+                        slot_stride, static_cast<cudaStream_t>(stream));
 }
 
 int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
@@ -1655,7 +1711,7 @@ int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* 
                              int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch, void* stream) {
   const float* src[5] = {v_k, tag_k, title_k, frame_fea_k, frame_proj_k};
   const int64_t stride[5] = {D, D, D, int64_t(F) * D, int64_t(F) * D};
-  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, nullptr,
+  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, nullptr, nullptr, 0,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -1700,6 +1756,39 @@ int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int3
   if (rows <= 0) return HMMC_OK;
   rowpack_kernel<false><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, const_cast<float*>(src), rows,
                                                                                                    nullptr);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_peer_push_rows(const float* send, int64_t elems, const uint64_t* peer_bufs_host, const uint64_t* peer_flags_host,
+                        int W, int rank, int64_t slot_stride, const int32_t* epoch, uint32_t* done_counter,
+                        void* stream) {
+  HMMC_REQUIRE(send && peer_bufs_host && peer_flags_host && epoch && done_counter, "peer_push: null argument");
+  HMMC_REQUIRE(W >= 1 && W <= HMMC_MAX_PEERS && rank >= 0 && rank < W, "peer_push: world %d (max %d), rank %d", W,
+               HMMC_MAX_PEERS, rank);
+  HMMC_REQUIRE(elems > 0 && elems % 4 == 0 && slot_stride % 4 == 0 && slot_stride >= int64_t(W) * elems,
+               "peer_push: %lld elements per rank, slot stride %lld", (long long)elems, (long long)slot_stride);
+  HMMC_REQUIRE(reinterpret_cast<uintptr_t>(send) % 16 == 0, "peer_push: send buffer not 16-byte aligned");
+  PeerPtrs bufs, flags;
+  for (int i = 0; i < HMMC_MAX_PEERS; ++i) {
+    bufs.p[i] = i < W ? peer_bufs_host[i] : 0;
+    flags.p[i] = i < W ? peer_flags_host[i] : 0;
+    HMMC_REQUIRE(i >= W || (bufs.p[i] % 16 == 0 && flags.p[i] != 0), "peer_push: bad peer pointer %d", i);
+  }
+  const int64_t n4 = elems / 4;
+  // a few blocks per destination: the copy is bound by the links, not by the SMs it leaves to the momentum update
+  const int gx = int(std::min<int64_t>((n4 + 255) / 256, 16));
+  count_launch();
+  peer_push_kernel<<<dim3(gx, W), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(send), n4, bufs, flags, W, rank, slot_stride, epoch, done_counter);
+  HMMC_CHECK_LAUNCH();
+  return HMMC_OK;
+}
+
+int hmmc_peer_wait(const int32_t* my_flags, int W, int32_t* epoch, void* stream) {
+  HMMC_REQUIRE(my_flags && epoch && W >= 1 && W <= HMMC_MAX_PEERS, "peer_wait: bad arguments");
+  count_launch();
+  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(my_flags, W, epoch);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }

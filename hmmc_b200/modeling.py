@@ -204,10 +204,16 @@ class ContrastiveHeadMixin:
         return int(self.queue_ptr)
 
     @torch.no_grad()
-    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None, staged=None):
+    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None, staged=None, slot=None):
         ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, self._enqueue_ptr_mode(W * b),
                     self.contrast_num_negative, ops.resolve_precision(self.head_precision), direct=direct,
-                    staged=staged)
+                    staged=staged, slot=slot)
+
+    def _use_peer_exchange(self):
+        """Exchange the keys over peer memory (parallel.PeerExchange) rather than with an NCCL all-gather:
+        default whenever the ranks can map each other's memory; task_config.peer_exchange = False forces NCCL."""
+        v = getattr(self.task_config, "peer_exchange", None)
+        return True if v is None else bool(v)
 
     def _defer_enqueue(self):
         v = getattr(self.task_config, "defer_enqueue", None)
@@ -229,10 +235,18 @@ class ContrastiveHeadMixin:
         dev = keys[0].device
         width = (3 + 2 * F) * D
         bufs = getattr(self, "_hmmc_xchg", None)
-        if bufs is None or bufs[0].shape != (b, width) or bufs[1].shape[0] != W * b or bufs[0].device != dev:
+        if bufs is None or bufs[0].shape != (b, width) or bufs[3] != W or bufs[0].device != dev:
+            # (collective when W > 1: every rank builds its buffers at the same first deferred step, outside a
+            # graph capture)
             send = torch.empty(b, width, dtype=torch.float32, device=dev)
-            bufs = (send, send if W == 1 else torch.empty(W * b, width, dtype=torch.float32, device=dev),
-                    torch.zeros(1, dtype=torch.int32, device=dev))
+            peer = parallel.make_peer_exchange(b, width, dev) if (W > 1 and self._use_peer_exchange()) else None
+            if W == 1:
+                gathered = send
+            elif peer is not None:
+                gathered = peer.recv
+            else:
+                gathered = torch.empty(W * b, width, dtype=torch.float32, device=dev)
+            bufs = (send, gathered, torch.zeros(1, dtype=torch.int32, device=dev), W, peer)
             self._hmmc_xchg = bufs
         ops.pack_rows(keys, out=bufs[0], staged=bufs[2])
         self._hmmc_pending = {"dims": (W, b, F, D), "done": None}
@@ -255,16 +269,19 @@ class ContrastiveHeadMixin:
         if p["done"] is not None and not force:
             return
         W, b, F, D = p["dims"]
-        send, gathered, staged = self._hmmc_xchg
+        send, gathered, staged, _, peer = self._hmmc_xchg
         main = torch.cuda.current_stream()
-        side = _side_stream(main.device)
+        side = _side_stream(main.device, "exchange", priority=-1)
         fork = torch.cuda.Event()
         fork.record(main)                  # after step i's kernels (they read the queues) and the staging copy
         side.wait_event(fork)
         with torch.cuda.stream(side):
-            if W > 1:
-                parallel.all_gather_rows_into(gathered, send)
-            self._enqueue_rows(W, b, F, D, gathered=gathered, staged=staged)
+            if W > 1 and peer is not None:
+                peer.exchange(send)
+            elif W > 1:
+                parallel.all_gather_rows_into(gathered, send, group=parallel.overlap_group())
+            self._enqueue_rows(W, b, F, D, gathered=gathered, staged=staged,
+                               slot=(peer.epoch, peer.slot_stride) if peer is not None else None)
             done = torch.cuda.Event()
             done.record(side)
         p["done"] = done

@@ -470,10 +470,11 @@ def unpack_rows(packed, widths):
     return outs
 
 
-def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None, staged=None):
+def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None, staged=None, slot=None):
     """queue_bufs5 order: v, tag, title, frame_cross, frame_proj.  ``direct`` = the five key
     tensors themselves (single process: no gather, no packed copy).  staged: the mark pack_rows set
-    (deferred schedule): the enqueue happens only while it is set, and clears it."""
+    (deferred schedule): the enqueue happens only while it is set, and clears it.  slot = (epoch, stride):
+    ``gathered`` is the two-slot receive buffer of the peer exchange, the slot is chosen on the device."""
     lib = _lib.load()
     arr = (hmmc_queue * 5)()
     keep = []
@@ -487,11 +488,29 @@ def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, dir
         _lib.check(lib.hmmc_enqueue_norm_direct(*[_p(t) for t in direct], W * b, F, D, arr, _p(queue_ptr),
                                                 int(ptr_host), K, _p(scratch), _stream()), "hmmc_enqueue_norm_direct")
     else:
+        epoch, stride = slot if slot is not None else (None, 0)
         _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _p(scratch),
-                                         _p(staged), _stream()), "hmmc_enqueue_norm")
+                                         _p(staged), _p(epoch), int(stride), _stream()), "hmmc_enqueue_norm")
     planes = None if prec == PREC_FP32 else (2 if prec == PREC_BF16X3 else 1)
     for st, buf in zip(keep, queue_bufs5):
         st.wrote(buf, planes)               # the kernel kept the copies of this plane count in step
+
+
+def peer_push_rows(send, peer_bufs, peer_flags, rank, slot_stride, epoch, done_counter):
+    """Copy this rank's packed rows into block `rank` of the current slot of every rank's receive buffer and raise
+    this rank's flag everywhere (hmmc_peer_push_rows).  peer_bufs / peer_flags: the W base addresses (ints)."""
+    lib = _lib.load()
+    W = len(peer_bufs)
+    bufs = (ctypes.c_uint64 * W)(*[int(x) for x in peer_bufs])
+    flags = (ctypes.c_uint64 * W)(*[int(x) for x in peer_flags])
+    _lib.check(lib.hmmc_peer_push_rows(_p(send), send.numel(), bufs, flags, W, int(rank), int(slot_stride), _p(epoch),
+                                       _p(done_counter), _stream()), "hmmc_peer_push_rows")
+
+
+def peer_wait(my_flags, W, epoch):
+    """Block the current stream until every rank's rows of the current exchange have landed, then count it."""
+    lib = _lib.load()
+    _lib.check(lib.hmmc_peer_wait(_p(my_flags), int(W), _p(epoch), _stream()), "hmmc_peer_wait")
 
 
 # ----------------------------------------------------------------------------- fine-tune head

@@ -226,17 +226,34 @@ int hmmc_clip_grad_norm_multi(const uint64_t* g_ptrs, const int64_t* numels, con
  * is a multiple of B, like the reference's own no-wrap condition. */
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
                       int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch /* (3+2F)*W*b floats, or NULL */,
-                      int32_t* staged, void* stream);
+                      int32_t* staged, const int32_t* slot_epoch, int64_t slot_stride, void* stream);
 /* staged: NULL, or the device mark hmmc_pack_rows set when it filled `gathered`'s send buffer (deferred
  * schedule: the keys of step i are exchanged and enqueued beside step i+1).  The enqueue then happens only if
  * the mark is set and clears it, so issuing it twice for the same keys - an eager flush followed by the replay
- * of a captured step that carries the same enqueue - writes them once.  Needs ptr_host < 0. */
+ * of a captured step that carries the same enqueue - writes them once.  Needs ptr_host < 0.
+ * slot_epoch: NULL, or the exchange counter of hmmc_peer_wait: `gathered` is then the base of a two-slot
+ * receive buffer and the keys are read from slot (*slot_epoch - 1) & 1, slot_stride elements apart. */
 
 /* Same, reading the five key tensors in place ([B,D] x3, [B,F,D] x2, contiguous): the
  * single-process case needs no gather and no packed copy. */
 int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
                              const float* frame_proj_k, int B, int F, int D, const hmmc_queue* queues5,
                              int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch, void* stream);
+
+/* Key exchange over peer memory (replaces the all-gather of dist_collect for the deferred enqueue; the reference
+ * gathers with torch.distributed, modules/modeling.py:25-36 and :249-262).  Every rank of the node owns a receive
+ * buffer of two slots [2][W][elems] fp32 and W int32 flags, both mapped into its peers (symmetric memory; the host
+ * passes the W base addresses as this process sees them).  hmmc_peer_push_rows copies this rank's `elems` floats
+ * into block `rank` of slot (*epoch & 1) of EVERY rank's buffer with plain stores over NVLink and then sets
+ * flag[rank] = *epoch + 1 in every rank.  hmmc_peer_wait blocks the stream until all W flags of this rank have
+ * reached *epoch + 1 and then increments *epoch.  epoch and done_counter are device words owned by the caller,
+ * zero before the first exchange; nothing here depends on host state, so a captured step replays unchanged.
+ * Every rank must issue the same sequence of exchanges. */
+#define HMMC_MAX_PEERS 16
+int hmmc_peer_push_rows(const float* send, int64_t elems, const uint64_t* peer_bufs_host,
+                        const uint64_t* peer_flags_host, int W, int rank, int64_t slot_stride, const int32_t* epoch,
+                        uint32_t* done_counter, void* stream);
+int hmmc_peer_wait(const int32_t* my_flags, int W, int32_t* epoch, void* stream);
 
 /* x_t *= scale[0] (device scalar) for up to 8 fp32 tensors in one launch: applies the upstream
  * gradient to the gradients the fused heads produced together with the loss. */

@@ -83,7 +83,7 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
     cu = _cu(dev)
     assert K % (W * b) == 0
     qs0 = syn.queues(K, F=F, D=D, seed=3)
-    steps = 3
+    steps = 4
     inps = [[syn.pretrain_inputs(b, F=F, D=D, seed=70 + 10 * s + r) for r in range(W)] for s in range(steps)]
     # oracle: enqueue of the rank-major concatenation, step after step; the loss of step s reads the queues
     # as they are before that step's enqueue
@@ -99,10 +99,14 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
     out = {}
     order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k",
              "frame_proj_k"]
-    for mode in ("eager", "deferred", "graph"):
+    # eager: the reference's immediate gather + enqueue.  deferred / graph: the staged keys travel over peer memory
+    # (parallel.PeerExchange) at the start of the next step; *_nccl: the same schedule with the NCCL all-gather;
+    # graph_noflush: replays back to back (both receive slots in use), queues compared after the last step only.
+    for mode in ("eager", "deferred", "graph", "deferred_nccl", "graph_nccl", "graph_noflush"):
         task = types.SimpleNamespace(local_rank=local, top_frames=3, contrast_momentum=0.99, contrast_temperature=0.07,
                                      contrast_num_negative=K, max_frames=F, use_frame_fea=True, head_precision="fp32",
-                                     defer_enqueue=(mode != "eager"))
+                                     defer_enqueue=(mode != "eager"),
+                                     peer_exchange=(False if mode.endswith("_nccl") else None))
         m = modeling.BirdPreTrainedModel(modeling.default_cross_config(temporal_hidden_size=D), task).to(dev)
         with torch.no_grad():
             for n, x in qs0.items():
@@ -121,7 +125,7 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
             with torch.no_grad():
                 for n in order:
                     static[n].copy_(torch.from_numpy(inps[s][rank][n]))
-            if mode == "graph" and s == 1:
+            if mode.startswith("graph") and s == 1:
                 # step 0 ran eagerly (it sized the workspaces and left its keys staged); capture without further
                 # warm-up steps and replay from here on
                 from hmmc_b200.graphs import GraphedStep
@@ -130,6 +134,8 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
             lerr = abs(float(loss) - ref_losses[s]) / ref_losses[s]
             del loss        # a live loss keeps the step's autograd graph (and its AccumulateGrad streams): see graphs.py
             assert lerr < 1e-5, (mode, s, lerr)
+            if mode == "graph_noflush" and s < steps - 1:
+                continue
             m.flush_pending_enqueue()
             want, want_ptr = ref_queues[s]
             assert int(m.queue_ptr) == want_ptr, (mode, s, int(m.queue_ptr), want_ptr)

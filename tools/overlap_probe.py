@@ -1,86 +1,72 @@
-"""Does the loss (tensor-bound GEMMs) hide under the EMA (HBM-bound) when both run at once?
-Times EMA + loss sequentially and concurrently on two streams, for several SM budgets of the GEMM grids
-and both issue orders."""
+"""Does a small kernel on a side stream run BESIDE the momentum update (a kernel that fills the GPU), or after it?
+Eager and graph replay, default and high stream priority.   python tools/overlap_probe.py"""
 import os, sys, types
-import numpy as np, torch
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from hmmc_b200 import ops, synthetic as syn
+from hmmc_b200 import modeling, synthetic as syn
+dev = torch.device("cuda", 0)
 
-dev = torch.device("cuda")
+class Params(torch.nn.Module):
+    def __init__(self, flat, sizes):
+        super().__init__()
+        self.ps = torch.nn.ParameterList([torch.nn.Parameter(x, requires_grad=False) for x in torch.split(flat, sizes)])
 sizes = syn.ema_param_numels()
-flat = torch.randn(sum(sizes), device=dev)
-flat_k = torch.randn(sum(sizes), device=dev)
-tab = ops.EmaTable(list(zip(torch.split(flat, sizes), torch.split(flat_k, sizes))))
-b, F, D, K = 128, 12, 512, 1024
-inp = {n: torch.from_numpy(x).to(dev) for n, x in syn.pretrain_inputs(b, F=F, D=D, seed=2).items()}
-qs = {n: torch.from_numpy(x).to(dev) for n, x in syn.queues(K, F=F, D=D, seed=3).items()}
-qn = ("v_fea", "title_fea", "frame_fea", "frame_pred")
-for n in qn:
-    inp[n].requires_grad_(True)
+enc = Params(torch.randn(sum(sizes), device=dev), sizes); enc_k = Params(torch.randn(sum(sizes), device=dev), sizes)
+task = types.SimpleNamespace(local_rank=0, top_frames=3, contrast_momentum=0.99, contrast_temperature=0.07,
+                             contrast_num_negative=1024, max_frames=12, use_frame_fea=True, head_precision="bf16")
+m = modeling.BirdPreTrainedModel(modeling.default_cross_config(), task).to(dev)
+m.model_pairs = [[enc, enc_k]]
+B = int(os.environ.get("B", 1024))
+keys = [torch.randn(B, 512, device=dev), torch.randn(B, 512, device=dev), torch.randn(B, 512, device=dev),
+        torch.randn(B, 12, 512, device=dev), torch.randn(B, 12, 512, device=dev)]
 
-
-def loss():
-    total, _ = ops.pretrain_head(inp["v_fea"], inp["title_fea"], inp["frame_fea"], inp["frame_pred"], inp["v_fea_k"],
-                                 inp["title_fea_k"], inp["frame_fea_k"], inp["frame_proj_k"], qs["queue_v_cross_ng"],
-                                 qs["queue_title_cross_ng"], qs["queue_frame_proj_ng"], qs["queue_frame_cross_ng"],
-                                 0.07, 0.05, 0.45, 0.45, True, "bf16")
-    return total
-
-
-def ema():
-    tab.run(0.99)
-
-
-A = torch.cuda.Stream()
-B = torch.cuda.Stream(priority=-1)
-main = torch.cuda.current_stream()
-
-
-def timeit(fn, reps=40):
+def timeit(fn, n=50):
     for _ in range(5):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
+    for _ in range(n):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3
+    return e0.elapsed_time(e1) / n
 
-
-def seq():
+def ema():
     with torch.no_grad():
-        ema()
-        loss()
+        m._momentum_update()
+def small_op():
+    with torch.no_grad():
+        m._dequeue_and_enqueue(*keys)          # the real enqueue of B keys (W = 1: no gather)
+print("ema alone %.4f ms   small alone %.4f ms" % (timeit(ema), timeit(small_op)), flush=True)
 
-
-def par(order):
-    def run():
-        e = torch.cuda.Event()
-        e.record(main)
-        A.wait_event(e)
-        B.wait_event(e)
-        with torch.no_grad():
-            for who in order:
-                if who == "loss":
-                    with torch.cuda.stream(B):
-                        loss()
-                else:
-                    with torch.cuda.stream(A):
-                        ema()
-        main.wait_stream(A)
-        main.wait_stream(B)
-    return run
-
-
-with torch.no_grad():
-    print("ema alone   %.1f us" % timeit(ema))
-    print("loss alone  %.1f us (forward + fused backward kernels, no autograd)" % timeit(loss))
-    print("sequential  %.1f us" % timeit(seq))
-    for reserved in (0, 48, 74, 100, 120):
-        ops.set_reserved_sms(reserved)
-        for order in (("loss", "ema"), ("ema", "loss")):
-            print("concurrent  reserved=%3d  issue order %s: %.1f us" % (reserved, "+".join(order), timeit(par(order))))
-    ops.set_reserved_sms(0)
+for prio in (0, -1):
+    side = torch.cuda.Stream(device=dev, priority=prio)
+    for first in ("side", "main"):
+        def both():
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event(); fork.record(main); side.wait_event(fork)
+            if first == "side":
+                with torch.cuda.stream(side):
+                    small_op()
+                    done = torch.cuda.Event(); done.record(side)
+                ema()
+            else:
+                ema()
+                with torch.cuda.stream(side):
+                    small_op()
+                    done = torch.cuda.Event(); done.record(side)
+            main.wait_event(done)
+        t_eager = timeit(both)
+        g = torch.cuda.CUDAGraph()
+        cs = torch.cuda.Stream(device=dev)
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            both()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=cs, capture_error_mode="thread_local"):
+                both()
+        torch.cuda.synchronize()
+        t_graph = timeit(g.replay)
+        print("priority %2d, %s issued first: eager %.4f ms   graph %.4f ms" % (prio, first, t_eager, t_graph), flush=True)
