@@ -1050,7 +1050,16 @@ __global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_
   if (PACK && staged != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *staged = 1;
   float* x = reinterpret_cast<float*>(a.ptrs[t]) + row * a.widths[t];
   float* y = packed + row * a.total + a.offs[t];
-  for (int i = threadIdx.x; i < a.widths[t]; i += blockDim.x) {
+  const int w = a.widths[t];
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (w & 3) == 0) {
+    float4* x4 = reinterpret_cast<float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (int i = threadIdx.x; i < w / 4; i += blockDim.x) {
+      if (PACK) y4[i] = x4[i]; else x4[i] = y4[i];
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < w; i += blockDim.x) {
     if (PACK) y[i] = x[i]; else x[i] = y[i];
   }
 }
@@ -1070,8 +1079,14 @@ peer_push_kernel(const float4* __restrict__ send, int64_t n4, PeerPtrs bufs, Pee
   const int e = *epoch;                                         // exchanges completed so far
   const int peer = (rank + int(blockIdx.y)) % W;                // staggered: no two ranks start on the same peer
   float4* dst = reinterpret_cast<float4*>(bufs.p[peer]) + (int64_t(e & 1) * slot_stride + int64_t(rank) * n4 * 4) / 4;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x)
-    dst[i] = send[i];
+  // four independent 16-byte loads in flight per thread before the posted stores
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 v0 = send[i], v1 = send[i + stride], v2 = send[i + 2 * stride], v3 = send[i + 3 * stride];
+    dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+  }
+  for (; i < n4; i += stride) dst[i] = send[i];
   // last block: every block's stores are ordered before its arrival (system-scope fence), the flags after all arrivals
   __shared__ bool last;
   __threadfence_system();
@@ -1777,7 +1792,7 @@ int hmmc_peer_push_rows(const float* send, int64_t elems, const uint64_t* peer_b
   }
   const int64_t n4 = elems / 4;
   // a few blocks per destination: the copy is bound by the links, not by the SMs it leaves to the momentum update
-  const int gx = int(std::min<int64_t>((n4 + 255) / 256, 16));
+  const int gx = int(std::min<int64_t>((n4 + 1023) / 1024, 32));
   count_launch();
   peer_push_kernel<<<dim3(gx, W), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(send), n4, bufs, flags, W, rank, slot_stride, epoch, done_counter);

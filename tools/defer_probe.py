@@ -25,10 +25,13 @@ enc = Params(torch.randn(sum(sizes), device=dev), sizes); enc_k = Params(torch.r
 order = ["v_fea", "frame_fea", "title_fea", "frame_pred", "v_fea_k", "frame_fea_k", "title_fea_k", "tag_fea_k", "frame_proj_k"]
 inp = syn.pretrain_inputs(b, F=F, D=D, seed=100 + rank)
 
+PEER = None
+
+
 def run(defer, graph, ema=True):
     task = types.SimpleNamespace(local_rank=local, top_frames=3, contrast_momentum=0.99, contrast_temperature=0.07,
                                  contrast_num_negative=K, max_frames=F, use_frame_fea=True, head_precision="bf16",
-                                 defer_enqueue=defer)
+                                 defer_enqueue=defer, peer_exchange=PEER)
     m = modeling.BirdPreTrainedModel(modeling.default_cross_config(temporal_hidden_size=D), task).to(dev)
     m.model_pairs = [[enc, enc_k]]
     with torch.no_grad():
@@ -63,6 +66,22 @@ def run(defer, graph, ema=True):
         fn()
     e1.record()
     torch.cuda.synchronize()
+    if os.environ.get("TRACE") and defer and ema:        # every rank replays (the exchange is collective)
+        # kernel timeline of a few replays (CUPTI through torch.profiler): stream, start, duration
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(4):
+                fn()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda e: e.time_range.start)
+        emas = [e for e in evs if "ema_multi" in e.name]
+        if len(emas) >= 3 and rank == 0:
+            t0, t1 = emas[1].time_range.start, emas[2].time_range.start
+            print("---- timeline of one replay (us from the start of the momentum update), peer=%s" % (PEER,))
+            for e in evs:
+                if t0 - 50 <= e.time_range.start < t1 - 50:
+                    print("%8.1f  +%7.1f  %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:90]), flush=True)
     ms = torch.tensor([e0.elapsed_time(e1) / 100], device=dev)
     if W > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -72,13 +91,19 @@ def run(defer, graph, ema=True):
         g.release()
     return float(ms)
 
-ms = run(False, True)
-if rank == 0:
-    print("W=%d immediate enqueue, graph replay: %.4f ms/step" % (W, ms), flush=True)
-for reserve in (0, 8, 16, 32, 48):
-    modeling.EXCHANGE_RESERVED_SMS = reserve
-    ms = run(True, True)
-    if rank == 0:
-        print("W=%d deferred, momentum update leaves %2d SMs free, graph replay: %.4f ms/step" % (W, reserve, ms), flush=True)
+def run_cfg(defer, peer, ema=True):
+    global PEER
+    PEER = peer
+    return run(defer, True, ema)
+
+for ema in (True, False):
+    for name, defer, peer in (("immediate (gather + enqueue at the end of the step)", False, None),
+                              ("deferred, exchange over peer memory", True, None),
+                              ("deferred, NCCL all-gather", True, False)):
+        if W == 1 and peer is False:
+            continue
+        ms = run_cfg(defer, peer, ema)
+        if rank == 0:
+            print("W=%d %s momentum update, %s: %.4f ms/step" % (W, "with" if ema else "WITHOUT", name, ms), flush=True)
 if W > 1:
     dist.destroy_process_group()

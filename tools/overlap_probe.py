@@ -36,7 +36,13 @@ def timeit(fn, n=50):
 def ema():
     with torch.no_grad():
         m._momentum_update()
+CHAIN = int(os.environ.get("CHAIN", 0))
+tiny = torch.zeros(1 << 18, device=dev)
 def small_op():
+    if CHAIN:                                   # a chain of CHAIN dependent tiny kernels (~2-3 us each alone)
+        for _ in range(CHAIN):
+            tiny.add_(1.0)
+        return
     with torch.no_grad():
         m._dequeue_and_enqueue(*keys)          # the real enqueue of B keys (W = 1: no gather)
 print("ema alone %.4f ms   small alone %.4f ms" % (timeit(ema), timeit(small_op)), flush=True)
