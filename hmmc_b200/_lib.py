@@ -90,12 +90,13 @@ SIGNATURES = {
     "hmmc_clip_grad_norm_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p,
                                           c_size_t, c_void_p]),
     "hmmc_enqueue_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(hmmc_queue), c_void_p, c_int64,
-                                  c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+                                  c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "hmmc_peer_push_rows": (c_int, [c_void_p, c_int64, POINTER(c_uint64), POINTER(c_uint64), c_int, c_int, c_int64,
                                     c_void_p, c_void_p, c_void_p]),
     "hmmc_peer_wait": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hmmc_scale_tensors": (c_int, [POINTER(c_uint64), POINTER(c_int64), c_int, c_void_p, c_void_p]),
-    "hmmc_pack_rows": (c_int, [POINTER(c_uint64), POINTER(c_int32), c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "hmmc_pack_rows": (c_int, [POINTER(c_uint64), POINTER(c_int32), c_int, c_int64, c_void_p, c_void_p, c_int,
+                               c_void_p]),
     "hmmc_unpack_rows": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_int32), c_int, c_int64, c_void_p]),
     "hmmc_similarity_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "hmmc_loose_similarity_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_int,

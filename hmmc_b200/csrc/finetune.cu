@@ -712,7 +712,7 @@ int hmmc_sym_ce_packed_fwd_bwd(const float* packed, int B, int F, int D, float s
                         workspace_bytes - align_up(ws.used, 256), st))) return rc;
   if (dpacked != nullptr) {
     const uint64_t g_ptrs[3] = {reinterpret_cast<uint64_t>(dt), reinterpret_cast<uint64_t>(dv), reinterpret_cast<uint64_t>(df)};
-    if ((rc = hmmc_pack_rows(g_ptrs, widths, n, B, dpacked, nullptr, stream))) return rc;
+    if ((rc = hmmc_pack_rows(g_ptrs, widths, n, B, dpacked, nullptr, 0, stream))) return rc;
   }
   return HMMC_OK;
 }

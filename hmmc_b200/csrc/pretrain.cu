@@ -820,6 +820,7 @@ struct EnqueueArgs {
   // device by the exchange counter (NULL: no slots)
   const int32_t* slot_epoch;
   int64_t slot_stride;      // elements between the two slots
+  int prenormalised;        // the keys arrive as unit vectors (hmmc_pack_rows normalised them): written as they are
 };
 __device__ __forceinline__ int64_t enqueue_slot_offset(const EnqueueArgs& a) {
   return a.slot_epoch != nullptr ? int64_t((*a.slot_epoch - 1) & 1) * a.slot_stride : 0;
@@ -880,7 +881,9 @@ enqueue_kernel(int nsamples, int D, int dchunk, EnqueueArgs a, const float* __re
     soff[cc] = int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
   }
   __syncthreads();
-  if (norms != nullptr) {
+  if (a.prenormalised) {
+    for (int cc = threadIdx.x; cc < CB; cc += blockDim.x) inv[cc] = (c0 + cc < ncols) ? 1.0f : 0.f;
+  } else if (norms != nullptr) {
     for (int cc = threadIdx.x; cc < CB; cc += blockDim.x)
       inv[cc] = (c0 + cc < ncols) ? 1.0f / norms[a.norm_off[qi] + c0 + cc] : 0.f;
   } else {
@@ -973,7 +976,7 @@ enqueue_vec_kernel(int nsamples, int D, EnqueueArgs a, const float* __restrict__
     const int c = min(c0 + threadIdx.x, ncols - 1);
     const int smp = c / mult, f = c - smp * mult;
     soff[threadIdx.x] = int64_t(smp) * a.src_stride[qi] + int64_t(f) * D;
-    inv[threadIdx.x] = (c0 + threadIdx.x < ncols) ? 1.0f / norms[a.norm_off[qi] + c0 + threadIdx.x] : 0.f;
+    inv[threadIdx.x] = (c0 + threadIdx.x < ncols) ? (a.prenormalised ? 1.0f : 1.0f / norms[a.norm_off[qi] + c0 + threadIdx.x]) : 0.f;
   }
   __syncthreads();
   const int planes = a.planes;
@@ -1072,6 +1075,28 @@ __global__ void rowpack_kernel(RowPackArgs a, float* __restrict__ packed, int64_
 // exchange e+2 only after it has seen every peer's flag e+1, which that peer raised after its enqueue e).
 // All counters live on the device: a captured step replays unchanged.
 struct PeerPtrs { uint64_t p[HMMC_MAX_PEERS]; };
+
+// Packing with the enqueue's normalisation folded in: every D-vector of every block is written as
+// x * (1 / max(||x||, 1e-12)), the sum of squares accumulated exactly as key_norms_kernel does, so the values are
+// bit-identical to what the enqueue would have computed from the raw keys.  Each rank then normalises only its own
+// keys (not all W*b of them after the exchange) and the enqueue reads the received rows once.
+__global__ void __launch_bounds__(256)
+rowpack_norm_kernel(RowPackArgs a, float* __restrict__ packed, int D, int32_t* staged) {
+  const int64_t row = blockIdx.x;
+  const int t = blockIdx.y;
+  if (staged != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *staged = 1;
+  const float* x = reinterpret_cast<const float*>(a.ptrs[t]) + row * a.widths[t];
+  float* y = packed + row * a.total + a.offs[t];
+  const int lane = threadIdx.x & 31;
+  for (int v = threadIdx.x >> 5; v < a.widths[t] / D; v += blockDim.x >> 5) {
+    const float* xv = x + int64_t(v) * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float e = xv[d]; ss = fmaf(e, e, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int d = lane; d < D; d += 32) y[int64_t(v) * D + d] = xv[d] * inv;
+  }
+}
 
 __global__ void __launch_bounds__(256)
 peer_push_kernel(const float4* __restrict__ send, int64_t n4, PeerPtrs bufs, PeerPtrs flags, int W, int rank,
@@ -1651,7 +1676,8 @@ __global__ void advance_ptr_kernel(int64_t* queue_ptr, int B, int K, int advance
 
 static int enqueue_common(const float* const* src5, const int64_t* stride5, int B, int F, int D,
                           const hmmc_queue* queues5, int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch,
-                          int32_t* staged, const int32_t* slot_epoch, int64_t slot_stride, cudaStream_t st) {
+                          int32_t* staged, const int32_t* slot_epoch, int64_t slot_stride, int prenormalised,
+                          cudaStream_t st) {
   HMMC_REQUIRE(queues5 && queue_ptr, "enqueue: null argument");
   // the reference's slice assignment raises when the batch does not fit (modules/modeling.py:273-280)
   const bool device_ptr = ptr_host < 0;     // pointer lives on the device only (graph replay)
@@ -1664,6 +1690,7 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
   a.planes = queues5[0].planes;
   a.slot_epoch = slot_epoch;
   a.slot_stride = slot_stride;
+  a.prenormalised = prenormalised;
   for (int i = 0; i < 5; ++i) {
     const hmmc_queue& q = queues5[i];
     HMMC_REQUIRE(q.dk != nullptr && q.D == D && q.Kq == K * mult[i], "enqueue: queue %d has shape [%d,%d], expected [%d,%d]",
@@ -1679,15 +1706,16 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
     a.src_stride[i] = stride5[i];
     a.norm_off[i] = (i == 0) ? 0 : a.norm_off[i - 1] + B * mult[i - 1];
   }
-  if (scratch != nullptr) {
+  if (scratch != nullptr && !prenormalised) {
     // norms once (one warp per key vector) so the transposing kernel can use small, numerous blocks
     key_norms_kernel<<<dim3((B * F + 7) / 8, 5), 256, 0, st>>>(B, D, a, scratch, staged);
     HMMC_CHECK_LAUNCH();
   }
-  const int dchunk = scratch != nullptr ? 64 : ENQ_DCHUNK;
+  const bool have_norms = scratch != nullptr || prenormalised;
+  const int dchunk = have_norms ? 64 : ENQ_DCHUNK;
   const int dchunks = (D + dchunk - 1) / dchunk;
   const int p_arg = device_ptr ? -1 : int(ptr_host), np_arg = device_ptr ? 0 : int((ptr_host + B) % K);
-  bool vec_ok = scratch != nullptr && (D % 2) == 0;
+  bool vec_ok = have_norms && (D % 2) == 0;
   for (int i = 0; i < 5 && vec_ok; ++i) {
     vec_ok = (reinterpret_cast<uintptr_t>(a.src[i]) % 8 == 0) && (a.src_stride[i] % 2 == 0) && (a.Kq[i] % 2 == 0) &&
              (reinterpret_cast<uintptr_t>(a.dk[i]) % 8 == 0) && (reinterpret_cast<uintptr_t>(a.pack_kd[i]) % 4 == 0) &&
@@ -1710,7 +1738,7 @@ static int enqueue_common(const float* const* src5, const int64_t* stride5, int 
 
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5, int64_t* queue_ptr,
                       int64_t ptr_host, int K, float* scratch, int32_t* staged, const int32_t* slot_epoch,
-                      int64_t slot_stride, void* stream) {
+                      int64_t slot_stride, int prenormalised, void* stream) {
   HMMC_REQUIRE(gathered != nullptr, "enqueue: null gathered buffer");
   const int64_t row = int64_t(3 + 2 * F) * D;
   const float* src[5] = {gathered, gathered + D, gathered + 2 * D, gathered + 3 * D, gathered + 3 * D + int64_t(F) * D};
@@ -1718,7 +1746,7 @@ int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const h
   HMMC_REQUIRE(staged == nullptr || ptr_host < 0, "enqueue: the staged mark needs the device-side queue pointer (ptr_host < 0)");
   HMMC_REQUIRE(slot_epoch == nullptr || slot_stride >= int64_t(W) * b * row, "enqueue: slot stride smaller than a slot");
   return enqueue_common(src, stride, W * b, F, D, queues5, queue_ptr, ptr_host, K, scratch, staged, slot_epoch,
-                        slot_stride, static_cast<cudaStream_t>(stream));
+                        slot_stride, prenormalised, static_cast<cudaStream_t>(stream));
 }
 
 int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* title_k, const float* frame_fea_k,
@@ -1726,7 +1754,7 @@ int hmmc_enqueue_norm_direct(const float* v_k, const float* tag_k, const float* 
                              int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch, void* stream) {
   const float* src[5] = {v_k, tag_k, title_k, frame_fea_k, frame_proj_k};
   const int64_t stride[5] = {D, D, D, int64_t(F) * D, int64_t(F) * D};
-  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, nullptr, nullptr, 0,
+  return enqueue_common(src, stride, B, F, D, queues5, queue_ptr, ptr_host, K, scratch, nullptr, nullptr, 0, 0,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -1753,11 +1781,19 @@ int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, in
 }
 
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows, float* dst,
-                   int32_t* staged, void* stream) {
+                   int32_t* staged, int norm_dim, void* stream) {
   RowPackArgs a;
   int rc = build_rowpack(a, src_ptrs_host, widths_host, n);
   if (rc) return rc;
   if (rows <= 0) return HMMC_OK;
+  if (norm_dim > 0) {
+    for (int i = 0; i < n; ++i)
+      HMMC_REQUIRE(widths_host[i] % norm_dim == 0, "pack_rows: width %d is not a multiple of the vector length %d",
+                   widths_host[i], norm_dim);
+    rowpack_norm_kernel<<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, norm_dim, staged);
+    HMMC_CHECK_LAUNCH();
+    return HMMC_OK;
+  }
   rowpack_kernel<true><<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, rows, staged);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;

@@ -204,10 +204,10 @@ class ContrastiveHeadMixin:
         return int(self.queue_ptr)
 
     @torch.no_grad()
-    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None, staged=None, slot=None):
+    def _enqueue_rows(self, W, b, F, D, gathered=None, direct=None, staged=None, slot=None, prenormalised=False):
         ops.enqueue(gathered, W, b, F, D, self._queue_buffers(), self.queue_ptr, self._enqueue_ptr_mode(W * b),
                     self.contrast_num_negative, ops.resolve_precision(self.head_precision), direct=direct,
-                    staged=staged, slot=slot)
+                    staged=staged, slot=slot, prenormalised=prenormalised)
 
     def _use_peer_exchange(self):
         """Exchange the keys over peer memory (parallel.PeerExchange) rather than with an NCCL all-gather:
@@ -248,7 +248,8 @@ class ContrastiveHeadMixin:
                 gathered = torch.empty(W * b, width, dtype=torch.float32, device=dev)
             bufs = (send, gathered, torch.zeros(1, dtype=torch.int32, device=dev), W, peer)
             self._hmmc_xchg = bufs
-        ops.pack_rows(keys, out=bufs[0], staged=bufs[2])
+        # normalised at the source: each rank normalises its own b keys, the enqueue reads the W*b received rows once
+        ops.pack_rows(keys, out=bufs[0], staged=bufs[2], norm_dim=D)
         self._hmmc_pending = {"dims": (W, b, F, D), "done": None}
         if not getattr(self, "_hmmc_hooked", False) and isinstance(self, nn.Module):
             # checkpoints must see the queues with every staged key in place
@@ -280,7 +281,7 @@ class ContrastiveHeadMixin:
                 peer.exchange(send)
             elif W > 1:
                 parallel.all_gather_rows_into(gathered, send, group=parallel.overlap_group())
-            self._enqueue_rows(W, b, F, D, gathered=gathered, staged=staged,
+            self._enqueue_rows(W, b, F, D, gathered=gathered, staged=staged, prenormalised=True,
                                slot=(peer.epoch, peer.slot_stride) if peer is not None else None)
             done = torch.cuda.Event()
             done.record(side)

@@ -443,9 +443,10 @@ class EmaTable:
                    "hmmc_ema_multi")
 
 
-def pack_rows(tensors, out=None, staged=None):
+def pack_rows(tensors, out=None, staged=None, norm_dim=0):
     """[rows, w_i] blocks -> one [rows, sum w_i] fp32 buffer (send buffer of the all-gather).
-    staged: optional int32[1] device tensor the kernel sets to 1 ("keys staged", consumed by enqueue)."""
+    staged: optional int32[1] device tensor the kernel sets to 1 ("keys staged", consumed by enqueue).
+    norm_dim = D: every D-vector is written L2-normalised (the enqueue's normalisation, done at the source)."""
     lib = _lib.load()
     ts = [_f32c(t, "block").reshape(t.shape[0], -1) for t in tensors]
     rows = ts[0].shape[0]
@@ -455,7 +456,7 @@ def pack_rows(tensors, out=None, staged=None):
     n = len(ts)
     ptrs = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in ts])
     ws = (ctypes.c_int32 * n)(*widths)
-    _lib.check(lib.hmmc_pack_rows(ptrs, ws, n, rows, _p(out), _p(staged), _stream()), "hmmc_pack_rows")
+    _lib.check(lib.hmmc_pack_rows(ptrs, ws, n, rows, _p(out), _p(staged), int(norm_dim), _stream()), "hmmc_pack_rows")
     return out
 
 
@@ -470,11 +471,13 @@ def unpack_rows(packed, widths):
     return outs
 
 
-def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None, staged=None, slot=None):
+def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, direct=None, staged=None, slot=None,
+            prenormalised=False):
     """queue_bufs5 order: v, tag, title, frame_cross, frame_proj.  ``direct`` = the five key
     tensors themselves (single process: no gather, no packed copy).  staged: the mark pack_rows set
     (deferred schedule): the enqueue happens only while it is set, and clears it.  slot = (epoch, stride):
-    ``gathered`` is the two-slot receive buffer of the peer exchange, the slot is chosen on the device."""
+    ``gathered`` is the two-slot receive buffer of the peer exchange, the slot is chosen on the device.
+    prenormalised: the gathered rows are unit vectors already (pack_rows(norm_dim=D))."""
     lib = _lib.load()
     arr = (hmmc_queue * 5)()
     keep = []
@@ -490,7 +493,8 @@ def enqueue(gathered, W, b, F, D, queue_bufs5, queue_ptr, ptr_host, K, prec, dir
     else:
         epoch, stride = slot if slot is not None else (None, 0)
         _lib.check(lib.hmmc_enqueue_norm(_p(gathered), W, b, F, D, arr, _p(queue_ptr), int(ptr_host), K, _p(scratch),
-                                         _p(staged), _p(epoch), int(stride), _stream()), "hmmc_enqueue_norm")
+                                         _p(staged), _p(epoch), int(stride), int(bool(prenormalised)), _stream()),
+                   "hmmc_enqueue_norm")
     planes = None if prec == PREC_FP32 else (2 if prec == PREC_BF16X3 else 1)
     for st, buf in zip(keep, queue_bufs5):
         st.wrote(buf, planes)               # the kernel kept the copies of this plane count in step

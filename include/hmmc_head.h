@@ -226,13 +226,15 @@ int hmmc_clip_grad_norm_multi(const uint64_t* g_ptrs, const int64_t* numels, con
  * is a multiple of B, like the reference's own no-wrap condition. */
 int hmmc_enqueue_norm(const float* gathered, int W, int b, int F, int D, const hmmc_queue* queues5,
                       int64_t* queue_ptr, int64_t ptr_host, int K, float* scratch /* (3+2F)*W*b floats, or NULL */,
-                      int32_t* staged, const int32_t* slot_epoch, int64_t slot_stride, void* stream);
+                      int32_t* staged, const int32_t* slot_epoch, int64_t slot_stride, int prenormalised,
+                      void* stream);
 /* staged: NULL, or the device mark hmmc_pack_rows set when it filled `gathered`'s send buffer (deferred
  * schedule: the keys of step i are exchanged and enqueued beside step i+1).  The enqueue then happens only if
  * the mark is set and clears it, so issuing it twice for the same keys - an eager flush followed by the replay
  * of a captured step that carries the same enqueue - writes them once.  Needs ptr_host < 0.
  * slot_epoch: NULL, or the exchange counter of hmmc_peer_wait: `gathered` is then the base of a two-slot
- * receive buffer and the keys are read from slot (*slot_epoch - 1) & 1, slot_stride elements apart. */
+ * receive buffer and the keys are read from slot (*slot_epoch - 1) & 1, slot_stride elements apart.
+ * prenormalised != 0: `gathered` holds unit vectors already (hmmc_pack_rows with norm_dim = D on every rank). */
 
 /* Same, reading the five key tensors in place ([B,D] x3, [B,F,D] x2, contiguous): the
  * single-process case needs no gather and no packed copy. */
@@ -261,9 +263,11 @@ int hmmc_scale_tensors(const uint64_t* ptrs_host, const int64_t* numels_host, in
                        void* stream);
 
 /* gather n row-blocks src_i[rows, width_i] into dst[rows, sum width_i] (the packed
- * send buffer of the key / embedding all-gather) and the inverse. */
+ * send buffer of the key / embedding all-gather) and the inverse.
+ * norm_dim > 0: every norm_dim-vector is written L2-normalised (eps 1e-12), bit-identical to what
+ * hmmc_enqueue_norm computes from the raw keys; the enqueue is then told `prenormalised`. */
 int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, int n, int64_t rows,
-                   float* dst, int32_t* staged /* NULL, or a device mark set to 1 */, void* stream);
+                   float* dst, int32_t* staged /* NULL, or a device mark set to 1 */, int norm_dim, void* stream);
 int hmmc_unpack_rows(const float* src, const uint64_t* dst_ptrs_host, const int32_t* widths_host, int n,
                      int64_t rows, void* stream);
 

@@ -12,7 +12,8 @@ concatenation of all ranks' inputs (the oracle is the checker here, nothing of i
 
   1. fine-tune head (modules/modeling.py:698-709): every rank's loss equals the global loss; each rank's
      gradient equals W x its slice of the single-loss gradient (the reference's dist_collect contract);
-     the replicated backward (no exchange) equals the SUM reduce-scatter backward bit for bit;
+     the replicated backward (no exchange) equals the SUM reduce-scatter backward (bit for bit at W = 2,
+     within the rounding of an 8-term sum otherwise);
   2. pre-train head (modules/modeling.py:244-284): loss is rank-local; after the key all-gather + enqueue
      all ranks hold the same queues, equal to the oracle's enqueue of the rank-major concatenation --
      through the eager call, the deferred schedule and a CUDA-graph replay;
@@ -72,9 +73,14 @@ def check_finetune(W, rank, local, dev, b=16, F=12, D=512):
                 loss2.backward()
             finally:
                 parallel.REPLICATED_GATHER_BWD = saved
-            same = all(torch.equal(x.grad, y.grad) for x, y in zip(a, a2)) and torch.equal(loss.detach(), loss2.detach())
-            assert same, "replicated backward differs from the reduce-scatter backward"
+            # W identical summands: W * x is exact, a ring that adds x eight times rounds at 3x, 5x, 6x, 7x --
+            # bit-identical for W = 2, within summation rounding (a few ulp) beyond
+            assert torch.equal(loss.detach(), loss2.detach())
+            rel = max(float((x.grad - y.grad).abs().max() / y.grad.abs().max().clamp_min(1e-30)) for x, y in zip(a, a2))
+            same = all(torch.equal(x.grad, y.grad) for x, y in zip(a, a2))
+            assert same if W == 2 else rel < 1e-6, ("replicated backward differs from the reduce-scatter backward", rel)
             out["replicated_bwd_equals_reduce_scatter"] = bool(same)
+            out["replicated_bwd_vs_reduce_scatter_max_rel"] = rel
     out["finetune_global_batch"] = W * b
     return out
 
