@@ -76,11 +76,11 @@ def check_finetune(W, rank, local, dev, b=16, F=12, D=512):
             # W identical summands: W * x is exact, a ring that adds x eight times rounds at 3x, 5x, 6x, 7x --
             # bit-identical for W = 2, within summation rounding (a few ulp) beyond
             assert torch.equal(loss.detach(), loss2.detach())
-            rel = max(float((x.grad - y.grad).abs().max() / y.grad.abs().max().clamp_min(1e-30)) for x, y in zip(a, a2))
+            rs_rel = max(float((x.grad - y.grad).abs().max() / y.grad.abs().max().clamp_min(1e-30)) for x, y in zip(a, a2))
             same = all(torch.equal(x.grad, y.grad) for x, y in zip(a, a2))
-            assert same if W == 2 else rel < 1e-6, ("replicated backward differs from the reduce-scatter backward", rel)
+            assert same if W == 2 else rs_rel < 1e-6, ("replicated backward differs from the reduce-scatter backward", rs_rel)
             out["replicated_bwd_equals_reduce_scatter"] = bool(same)
-            out["replicated_bwd_vs_reduce_scatter_max_rel"] = rel
+            out["replicated_bwd_vs_reduce_scatter_max_rel"] = rs_rel
     out["finetune_global_batch"] = W * b
     return out
 

@@ -10,7 +10,7 @@ from hmmc_b200.mlp import MLP
 from hmmc_b200.optimization import BertAdam
 dev = torch.device("cuda", 0)
 cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-REP = 2
+REP = int(os.environ.get("REP", 2))        # under ncu: REP=1 (every launch is replayed ~40 times)
 
 # ---- pre-train step at BASELINE config 4 (b=128) and the north-star loss (b=256)
 class Params(torch.nn.Module):
@@ -56,7 +56,7 @@ g = torch.Generator(device=dev).manual_seed(5)
 Tb = torch.randn(Nv * cap, 512, device=dev, generator=g)
 Vb = torch.randn(Nv, 512, device=dev, generator=g) + Tb.view(Nv, cap, 512).sum(1) / cap ** 0.5
 Fb = torch.randn(Nv, 12, 512, device=dev, generator=g) + 0.7 * (Tb.view(Nv, cap, 512).sum(1) / cap ** 0.5)[:, None, :]
-for prec in ("bf16", "bf16x3"):
+for prec in ("bf16",):
     for _ in range(REP):
         retrieval.fused_eval_ranks(Tb, Vb, Fb, per, 100.0, 3, prec)
 torch.cuda.synchronize()
