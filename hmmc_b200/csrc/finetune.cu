@@ -156,6 +156,11 @@ __global__ void gallery_scatter_kernel(const float* __restrict__ dG, int B, int 
 // Row r of the stacked operand matrix: r < B -> text row r; else gallery row g = r - B = fp*B + j.
 // The three operands with their row strides (elements): contiguous tensors have ldt = ldv = D,
 // ldf = F*D; the packed layout [text | video | frames] of the all-gather has all three = (2+F)*D.
+struct SymLossAcc {
+  unsigned long long sum;       // units of 2^-36
+  unsigned arrived;
+  unsigned pad;
+};
 struct SymOperands {
   const float* text; int64_t ldt;
   const float* video; int64_t ldv;
@@ -180,11 +185,11 @@ __global__ void __launch_bounds__(1024)
 symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, int Bk, int NGk,
                   __nv_bfloat16* __restrict__ Tp,
                   __nv_bfloat16* __restrict__ TTp, __nv_bfloat16* __restrict__ Gp, __nv_bfloat16* __restrict__ GTp,
-                  unsigned* __restrict__ lse_counter) {
+                  SymLossAcc* __restrict__ loss_acc) {
   extern __shared__ float tile[];                 // [32][D + 1]
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
-  if (blockIdx.x == 0 && threadIdx.x == 0) *lse_counter = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *loss_acc = SymLossAcc{0ull, 0u, 0u};
   const int ld = D + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 32;
@@ -221,20 +226,26 @@ symce_prep_kernel(SymOperands src, int B, int F, int voff, int D, int planes, in
   }
 }
 
-// Row and column log-sum-exp of S_all in one launch, and the loss: blocks [0, row_blocks) take one warp per
-// (text row, similarity block) pair, 8 pairs per block; the remaining blocks take 32 columns each.  The block
-// that finishes last adds  loss = sum_fp w_fp/B sum_i (lse_row + lse_col - 2 S_ii)  in a fixed order.
+// Row and column log-sum-exp of S_all in one launch, and the loss
+//   loss = sum_fp w_fp/B sum_i (lse_row + lse_col - 2 S_ii).
+// Blocks [0, row_blocks) take one warp per (text row, similarity block) pair, 8 pairs per block; the remaining
+// blocks take 32 columns each.  Every block adds its share of the loss to a 64-bit fixed-point accumulator with a
+// fire-and-forget reduction (integer sums: the same from run to run) and signals with a release reduction; nobody
+// waits for an answer.  The highest block waits for the arrival count and converts (see finish_losses in
+// pretrain.cu: the publish / fence / returning-atomic hand-over kept every block resident for two round trips).
+constexpr float SYM_FIX_SCALE = 68719476736.0f;          // 2^36: |loss| < 2^27
+
 __global__ void __launch_bounds__(256)
 symce_lse_kernel(const float* __restrict__ S, int B, int NB, int row_blocks, float* __restrict__ lse_row,
                  float* __restrict__ lse_col, int voff, float w0, float wf, float* __restrict__ loss_out,
-                 unsigned* __restrict__ counter) {
-  __shared__ float sm[8][32], ss[8][32];
-  __shared__ float red[32];
-  __shared__ bool last;
+                 SymLossAcc* __restrict__ acc) {
+  __shared__ float sm[8][32], ss[8][32], sd[32];
+  __shared__ float wsum[8];
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ncol = int64_t(NB) * B;
+  float share = 0.f;                                 // this thread's part of the loss (lane 0 / warp 0 only)
   if (int(blockIdx.x) < row_blocks) {
     const int pair = blockIdx.x * 8 + warp;          // = i * NB + fp: consecutive warps read consecutive memory
     if (pair < B * NB) {
@@ -246,19 +257,37 @@ symce_lse_kernel(const float* __restrict__ S, int B, int NB, int row_blocks, flo
       float s = 0.f;
       for (int j = lane; j < B; j += 32) s += expf(row[j] - m);
       s = warp_sum(s);
-      if (lane == 0) lse_row[fp * B + i] = m + logf(s);
+      if (lane == 0) {
+        const float l = m + logf(s);
+        lse_row[fp * B + i] = l;
+        share = (((fp < voff) ? w0 : wf) / float(B)) * (l - row[i]);
+      }
     }
   } else {
     const int64_t col = int64_t(blockIdx.x - row_blocks) * 32 + lane;
-    float m = -INFINITY, s = 0.f;
+    const int fp = int(col / B), j = int(col - int64_t(fp) * B);       // the column's own text row
+    // four independent running (max, sum) pairs per thread: rows warp, warp+8, .. dealt round-robin to them
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, s[4] = {0.f, 0.f, 0.f, 0.f};
+    float diag = 0.f;
     if (col < ncol) {
-      for (int i = warp; i < B; i += 8) {
-        const float v = S[int64_t(i) * ncol + col];
-        if (v > m) { s = s * expf(m - v) + 1.f; m = v; } else { s += expf(v - m); }
+      for (int i0 = warp; i0 < B; i0 += 32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 8 * u;
+          if (i < B) {
+            const float v = S[int64_t(i) * ncol + col];
+            if (i == j) diag = v;
+            if (v > m[u]) { s[u] = s[u] * expf(m[u] - v) + 1.f; m[u] = v; } else { s[u] += expf(v - m[u]); }
+          }
+        }
       }
     }
-    sm[warp][lane] = m;
-    ss[warp][lane] = s;
+    float M = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), Sx = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Sx += (m[u] == -INFINITY) ? 0.f : s[u] * expf(m[u] - M);
+    sm[warp][lane] = M;
+    ss[warp][lane] = Sx;
+    if ((j & 7) == warp && col < ncol) sd[lane] = diag;                // the warp that read row j holds S_jj
     __syncthreads();
     if (warp == 0 && col < ncol) {
       float Mx = sm[0][lane];
@@ -267,27 +296,33 @@ symce_lse_kernel(const float* __restrict__ S, int B, int NB, int row_blocks, flo
       float Ssum = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) Ssum += (sm[w][lane] == -INFINITY) ? 0.f : ss[w][lane] * expf(sm[w][lane] - Mx);
-      lse_col[col] = Mx + logf(Ssum);
+      const float l = Mx + logf(Ssum);
+      lse_col[col] = l;
+      share = warp_sum((((fp < voff) ? w0 : wf) / float(B)) * (l - sd[lane]));
+    } else if (warp == 0) {
+      share = warp_sum(0.f);
     }
   }
-  // ---- the last block to arrive adds the loss
-  __threadfence();
+  // ---- the block's share of the loss: warp order, then one fixed-point reduction
+  if (lane == 0) wsum[warp] = share;
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  float acc = 0.f;
-  for (int k = threadIdx.x; k < NB * B; k += blockDim.x) {
-    const int fp = k / B, i = k - fp * B;
-    const float w = ((fp < voff) ? w0 : wf) / float(B);
-    acc += w * (__ldcg(lse_row + k) + __ldcg(lse_col + k) - 2.f * S[int64_t(i) * ncol + k]);
+  if (threadIdx.x != 0) return;
+  float v = 0.f;
+  if (int(blockIdx.x) < row_blocks) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += wsum[w];
+  } else {
+    v = wsum[0];
   }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) {
-    loss_out[0] = acc;
-    *counter = 0u;
-  }
+  atomicAdd(&acc->sum, static_cast<unsigned long long>(__float2ll_rn(v * SYM_FIX_SCALE)));
+  ptx::red_release_add(&acc->arrived, 1u);
+  if (blockIdx.x != gridDim.x - 1) return;
+  const long long t0 = clock64();
+  while (ptx::ld_acquire(&acc->arrived) != gridDim.x)
+    if (clock64() - t0 > (1ll << 33)) __trap();
+  loss_out[0] = float(double(static_cast<long long>(__ldcg(&acc->sum))) * (1.0 / double(SYM_FIX_SCALE)));
+  acc->sum = 0ull;
+  acc->arrived = 0u;
 }
 
 // G = dL/dS computed on the fly from S and the two LSE vectors and written straight as the bf16
@@ -389,6 +424,70 @@ __global__ void symce_unnorm_kernel(SymOperands src, int B, int F, int voff, int
   }
 }
 
+// The same with 16-byte accesses: D == 128 * V, every row is V float4 per lane (rows and leading dimensions
+// 16-byte aligned, checked by the host).
+template <int V>
+__global__ void __launch_bounds__(256)
+symce_unnorm_vec_kernel(SymOperands src, int B, int F, int voff, const float* __restrict__ gt_parts, int n_splits,
+                        int64_t split_stride, const float* __restrict__ gg, SymGrads out) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
+  constexpr int D = 128 * V;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int NG = (voff + F) * B;
+  if (r >= B + NG) return;
+  const float4* x = reinterpret_cast<const float4*>(symce_src_row(src, B, voff, D, r)) + lane;
+  float* dst;
+  const float* grow;
+  int ns = 1;
+  if (r < B) {
+    dst = out.text ? out.text + int64_t(r) * out.ldt : nullptr;
+    grow = gt_parts + int64_t(r) * D;
+    ns = n_splits;
+  } else {
+    const int g = r - B, fp = g / B, j = g - fp * B;
+    dst = (fp < voff) ? (out.video ? out.video + int64_t(j) * out.ldv : nullptr)
+                      : (out.frames ? out.frames + int64_t(j) * out.ldf + int64_t(fp - voff) * D : nullptr);
+    grow = gg + int64_t(g) * D;
+  }
+  if (dst == nullptr) return;
+  float4 xv[V], gv[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    xv[k] = __ldg(x + 32 * k);
+    gv[k] = __ldg(reinterpret_cast<const float4*>(grow) + lane + 32 * k);
+  }
+  for (int s0 = 1; s0 < ns; ++s0) {                     // split-K partials in split order
+    const float4* gs = reinterpret_cast<const float4*>(grow + int64_t(s0) * split_stride) + lane;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float4 t = __ldg(gs + 32 * k);
+      gv[k].x += t.x; gv[k].y += t.y; gv[k].z += t.z; gv[k].w += t.w;
+    }
+  }
+  float ss = 0.f, xg = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    ss = fmaf(xv[k].x, xv[k].x, ss); ss = fmaf(xv[k].y, xv[k].y, ss);
+    ss = fmaf(xv[k].z, xv[k].z, ss); ss = fmaf(xv[k].w, xv[k].w, ss);
+    xg = fmaf(xv[k].x, gv[k].x, xg); xg = fmaf(xv[k].y, gv[k].y, xg);
+    xg = fmaf(xv[k].z, gv[k].z, xg); xg = fmaf(xv[k].w, gv[k].w, xg);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    xg += __shfl_xor_sync(0xffffffffu, xg, o);
+  }
+  const float n = sqrtf(ss);
+  const float proj = xg / (n * n);
+  float4* o4 = reinterpret_cast<float4*>(dst) + lane;
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    o4[32 * k] = make_float4((gv[k].x - xv[k].x * proj) / n, (gv[k].y - xv[k].y * proj) / n,
+                             (gv[k].z - xv[k].z * proj) / n, (gv[k].w - xv[k].w * proj) / n);
+}
+
 }  // namespace hmmc
 
 using namespace hmmc;
@@ -486,7 +585,7 @@ int hmmc_cross_en_fwd_bwd(const float* S, int64_t lds, int B, float* loss_out, f
 
 struct SymCeWs {
   float *that, *ghat, *S, *lse_row, *lse_col, *row_loss, *gt, *gg;
-  unsigned* counter;
+  SymLossAcc* counter;
   // tensor-core path: plane-packed operands (straight and transposed) and split-K partials
   __nv_bfloat16 *Tp, *TTp, *Gp, *GTp, *Sp, *STp;
   float* parts;
@@ -510,7 +609,7 @@ static void symce_carve(Workspace& ws, SymCeWs& w, int B, int F, int D, int prec
   w.lse_row = ws.take<float>(NB * B);
   w.lse_col = ws.take<float>(NB * B);
   w.row_loss = ws.take<float>(size_t(B));
-  w.counter = ws.take<unsigned>(4);
+  w.counter = ws.take<SymLossAcc>(1);
   w.gt = ws.take<float>(size_t(B) * D);
   w.gg = ws.take<float>(NB * B * D);
   w.Tp = w.TTp = w.Gp = w.GTp = w.Sp = w.STp = nullptr;
@@ -610,7 +709,18 @@ static int sym_ce_impl(const SymOperands& src, int B, int F, int D, float scale,
       gm[ng++] = StoreGemm{w.STp, int64_t(P) * Bk, w.TTp, int64_t(P) * Bk, w.gg, D, 0, NG, D, Bk, 1};
     if ((rc = umma_gemm_store_grouped(gm, ng, P, scale, st))) return rc;
     count_launch();
-    if (D <= 512)
+    auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec = a16(src.text) && a16(src.video) && a16(src.frames) && a16(grads.text) && a16(grads.video) &&
+                     a16(grads.frames) && src.ldt % 4 == 0 && src.ldv % 4 == 0 && src.ldf % 4 == 0 &&
+                     grads.ldt % 4 == 0 && grads.ldv % 4 == 0 && grads.ldf % 4 == 0;
+    const dim3 ugrid(unsigned((B + NG + 7) / 8));
+    if (vec && D == 512)
+      HMMC_CHECK_CUDA(launch_pdl(symce_unnorm_vec_kernel<4>, ugrid, dim3(256), 0, st, src, B, F, voff, w.parts, eff,
+                                 int64_t(B) * D, w.gg, grads));
+    else if (vec && D == 256)
+      HMMC_CHECK_CUDA(launch_pdl(symce_unnorm_vec_kernel<2>, ugrid, dim3(256), 0, st, src, B, F, voff, w.parts, eff,
+                                 int64_t(B) * D, w.gg, grads));
+    else if (D <= 512)
       HMMC_CHECK_CUDA(launch_pdl(symce_unnorm_kernel<16>, dim3(unsigned((B + NG + 7) / 8)), dim3(256), 0, st, src, B, F, voff,
                                  D, w.parts, eff, int64_t(B) * D, w.gg, grads));
     else

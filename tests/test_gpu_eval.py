@@ -226,6 +226,7 @@ def test_eval_epoch_fused_path_matches_matrix_path(golden, tag, multi, batch, mo
     assert sorted(tv.keys()) == list(g[tag + "_keys"])
     got = np.array([tv[k] for k in sorted(tv.keys())], dtype=np.float64)
     np.testing.assert_allclose(got, g[tag + "_vals"], rtol=1e-6)
+    monkeypatch.undo()                      # the default limit again
     assert retrieval.choose_eval_path(1000, 1000, 12, 512, 2, np.ones(1000), "bf16") == "matrix"
     assert retrieval.choose_eval_path(10 ** 6, 10 ** 5, 12, 512, 3, np.full(10 ** 5, 10), "bf16") == "fused"
     assert retrieval.choose_eval_path(10 ** 6, 10 ** 5, 8, 512, 3, np.full(10 ** 5, 10), "bf16") == "matrix"
