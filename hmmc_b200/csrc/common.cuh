@@ -160,7 +160,7 @@ int pack_dual(const float* src, int rows, int cols, int planes, void* straight, 
 // sweep that writes sim / fsim (or their sum) from the register top-k, no [Nt, Nv*F] intermediate
 size_t eval_gallery_pack_rows(int64_t Nv);
 int eval_pack_gallery(const float* video, const float* frames, int64_t Nv, int F, int D, int planes, void* out,
-                      cudaStream_t st);
+                      cudaStream_t st, const float* text = nullptr, int64_t Nt = 0, void* text_out = nullptr);
 int eval_sim_write(const void* text_packed, const void* gallery_packed, int64_t Nt, int64_t Nv, int D, int prec,
                    float scale, int top_k, float* sim, float* fsim, int64_t ld_out, int combine, cudaStream_t st);
 }  // namespace hmmc

@@ -74,6 +74,38 @@ __global__ void rank_theta_kernel(const float* __restrict__ sim, int64_t lds, in
   theta[j] = m;
 }
 
+// t2v counts and the v2t thresholds in one launch (they are independent): blocks [0, t2v_blocks) count, the rest
+// compute theta
+__global__ void rank_t2v_theta_kernel(const float* __restrict__ sim, int64_t lds, int Nt, int Nv,
+                                      const int32_t* __restrict__ gt, int32_t* __restrict__ t2v, int t2v_blocks,
+                                      const int32_t* __restrict__ group_start, float* __restrict__ theta,
+                                      int32_t* __restrict__ v2t) {
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
+  if (int(blockIdx.x) < t2v_blocks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= Nt) return;
+    const float* row = sim + s * lds;
+    const float ref = row[gt[s]];
+    int cnt = 0;
+    for (int j = lane; j < Nv; j += 32) cnt += (row[j] > ref) ? 1 : 0;
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) t2v[s] = cnt;
+    return;
+  }
+  const int j = (int(blockIdx.x) - t2v_blocks) * blockDim.x + threadIdx.x;
+  if (j >= Nv) return;
+  v2t[j] = 0;
+  float m = -INFINITY;
+  for (int s = group_start[j]; s < group_start[j + 1]; ++s) {
+    float v = sim[int64_t(s) * lds + j];
+    if (v != v) v = -INFINITY;
+    m = fmaxf(m, v);
+  }
+  theta[j] = m;
+}
+
 // v2t: block = 32 video columns x a slice of caption groups; warps stride the groups.
 __global__ void __launch_bounds__(256)
 rank_v2t_kernel(const float* __restrict__ sim, int64_t lds, int Nv, const int32_t* __restrict__ group_start,
@@ -179,8 +211,8 @@ int hmmc_sim_topk_fwd(const float* text, int64_t Nt, const float* video, const f
     __nv_bfloat16* gp = ws.take<__nv_bfloat16>(eval_gallery_pack_rows(Nv) * planes * D);
     if (!ws.ok()) { set_error("sim_topk: workspace too small (%zu > %zu)", ws.used, workspace_bytes); return HMMC_ERR_WORKSPACE; }
     const int64_t ldp = int64_t(planes) * D;
-    if ((rc = rownorm_pack(text, Nt, D, D, 0.f, planes, nullptr, nullptr, tp, ldp, st))) return rc;
-    if ((rc = eval_pack_gallery(video, frames, Nv, F, D, planes, gp, st))) return rc;
+    (void)ldp;
+    if ((rc = eval_pack_gallery(video, frames, Nv, F, D, planes, gp, st, text, Nt, tp))) return rc;   // both operands
     // sim == fsim (one buffer): the caller wants the sum (main_task_retrieval.py:512-513)
     const int combine = (sim != nullptr && sim == fsim) ? 1 : 0;
     return eval_sim_write(tp, gp, Nt, Nv, D, prec, scale, top_k, sim, combine ? nullptr : fsim, ld_out, combine, st);
@@ -214,16 +246,24 @@ int hmmc_rank_count(const float* sim, int64_t lds, int Nt, int Nv, const int32_t
                     int32_t* t2v, int32_t* v2t, float* theta_scratch, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HMMC_REQUIRE(sim && Nt > 0 && Nv > 0 && lds >= Nv, "rank_count: bad arguments");
-  if (t2v != nullptr) {
-    HMMC_REQUIRE(gt != nullptr, "rank_count: t2v needs gt");
+  HMMC_REQUIRE(t2v == nullptr || gt != nullptr, "rank_count: t2v needs gt");
+  HMMC_REQUIRE(v2t == nullptr || (group_start != nullptr && theta_scratch != nullptr),
+               "rank_count: v2t needs group_start and theta_scratch");
+  if (t2v != nullptr && v2t != nullptr) {
+    const int tb = (Nt + 7) / 8;
+    count_launch();
+    HMMC_CHECK_CUDA(launch_pdl(rank_t2v_theta_kernel, dim3(unsigned(tb + (Nv + 255) / 256)), dim3(256), 0, st, sim, lds, Nt,
+                               Nv, gt, t2v, tb, group_start, theta_scratch, v2t));
+  } else if (t2v != nullptr) {
     count_launch();
     HMMC_CHECK_CUDA(launch_pdl(rank_t2v_kernel, dim3(unsigned((Nt + 7) / 8)), dim3(256), 0, st, sim, lds, Nt, Nv, gt, t2v));
   }
   if (v2t != nullptr) {
-    HMMC_REQUIRE(group_start != nullptr && theta_scratch != nullptr, "rank_count: v2t needs group_start and theta_scratch");
-    count_launch();
-    HMMC_CHECK_CUDA(launch_pdl(rank_theta_kernel, dim3(unsigned((Nv + 255) / 256)), dim3(256), 0, st, sim, lds, Nv,
-                               group_start, theta_scratch, v2t));
+    if (t2v == nullptr) {
+      count_launch();
+      HMMC_CHECK_CUDA(launch_pdl(rank_theta_kernel, dim3(unsigned((Nv + 255) / 256)), dim3(256), 0, st, sim, lds, Nv,
+                                 group_start, theta_scratch, v2t));
+    }
     const int col_blocks = (Nv + 31) / 32;
     int gy = (4 * sm_count() + col_blocks - 1) / col_blocks;   // enough blocks to fill the machine
     if (gy < 1) gy = 1;

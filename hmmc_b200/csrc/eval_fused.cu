@@ -603,19 +603,29 @@ __global__ void eval_pack_text_kernel(const float* __restrict__ text, const int3
 }
 
 // gallery: row v*(1+F)+0 = video v, rows v*(1+F)+1+f = frame f of video v; rows beyond Nv are zeros
+// text (optional): Nt more rows after the gallery's, normalised and packed straight into text_out [Nt, planes*D]
+// (the same arithmetic as rownorm_pack_kernel) - one launch for both operands of the materialised eval
 __global__ void eval_pack_gallery_kernel(const float* __restrict__ video, const float* __restrict__ frames, int64_t Nv,
-                                         int64_t rows_pad, int F, int D, int planes, __nv_bfloat16* __restrict__ out) {
+                                         int64_t rows_pad, int F, int D, int planes, __nv_bfloat16* __restrict__ out,
+                                         const float* __restrict__ text, int64_t Nt, __nv_bfloat16* __restrict__ text_out) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows_pad) return;
+  int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows_pad + Nt) return;
   const int64_t ldp = int64_t(planes) * D;
-  const int64_t v = r / (1 + F);
-  const int mem = int(r - v * (1 + F));
-  if (v >= Nv) {
-    for (int d = lane; d < planes * D; d += 32) out[r * ldp + d] = __float2bfloat16_rn(0.f);
-    return;
+  const float* x;
+  if (r >= rows_pad) {
+    r -= rows_pad;
+    x = text + r * D;
+    out = text_out;
+  } else {
+    const int64_t v = r / (1 + F);
+    const int mem = int(r - v * (1 + F));
+    if (v >= Nv) {
+      for (int d = lane; d < planes * D; d += 32) out[r * ldp + d] = __float2bfloat16_rn(0.f);
+      return;
+    }
+    x = (mem == 0) ? video + v * D : frames + (v * F + (mem - 1)) * D;
   }
-  const float* x = (mem == 0) ? video + v * D : frames + (v * F + (mem - 1)) * D;
   float ss = 0.f;
   for (int d = lane; d < D; d += 32) { const float t = x[d]; ss = fmaf(t, t, ss); }
   ss = warp_sum(ss);
@@ -667,7 +677,7 @@ int hmmc_eval_pack_gallery(const float* video, const float* frames, int64_t Nv, 
   const int64_t nblk = (Nv + EV_VPT - 1) / EV_VPT;
   const int64_t rows_pad = nblk * EV_BN;
   eval_pack_gallery_kernel<<<unsigned((rows_pad + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      video, frames, Nv, rows_pad, F, D, planes_of(prec), static_cast<__nv_bfloat16*>(out));
+      video, frames, Nv, rows_pad, F, D, planes_of(prec), static_cast<__nv_bfloat16*>(out), nullptr, 0, nullptr);
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }
@@ -778,10 +788,12 @@ int eval_sim_write(const void* text_packed, const void* gallery_packed, int64_t 
 size_t eval_gallery_pack_rows(int64_t Nv) { return size_t((Nv + EV_VPT - 1) / EV_VPT) * EV_BN; }
 
 int eval_pack_gallery(const float* video, const float* frames, int64_t Nv, int F, int D, int planes, void* out,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* text, int64_t Nt, void* text_out) {
   const int64_t rows_pad = int64_t(eval_gallery_pack_rows(Nv));
-  eval_pack_gallery_kernel<<<unsigned((rows_pad + 7) / 8), 256, 0, st>>>(video, frames, Nv, rows_pad, F, D, planes,
-                                                                        static_cast<__nv_bfloat16*>(out));
+  if (text == nullptr) Nt = 0;
+  eval_pack_gallery_kernel<<<unsigned((rows_pad + Nt + 7) / 8), 256, 0, st>>>(video, frames, Nv, rows_pad, F, D, planes,
+                                                                             static_cast<__nv_bfloat16*>(out), text, Nt,
+                                                                             static_cast<__nv_bfloat16*>(text_out));
   HMMC_CHECK_LAUNCH();
   return HMMC_OK;
 }

@@ -713,6 +713,20 @@ def sim_topk(text, video, frames, scale, top_k, precision=None, want_sim=True, w
     return sim, fsim
 
 
+_diag_index = {}
+
+
+def _diagonal_index(n, dev):
+    """gt = 0..n-1 and group_start = 0..n of the square (one caption per video) case, built once per size and
+    device instead of two fill kernels per call."""
+    key = (n, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _diag_index:
+        if len(_diag_index) > 16:
+            _diag_index.clear()
+        _diag_index[key] = (torch.arange(n, dtype=torch.int32, device=dev), torch.arange(n + 1, dtype=torch.int32, device=dev))
+    return _diag_index[key]
+
+
 def rank_count(sim, gt=None, group_start=None, want_t2v=True, want_v2t=True):
     """Integer rank vectors (int32, on the device) of a materialised similarity matrix."""
     lib = _lib.load()
@@ -722,8 +736,7 @@ def rank_count(sim, gt=None, group_start=None, want_t2v=True, want_v2t=True):
     if gt is None:
         if Nt != Nv:
             raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,1)" % (Nt, Nv, Nt))
-        gt = torch.arange(Nt, dtype=torch.int32, device=dev)
-        group_start = torch.arange(Nv + 1, dtype=torch.int32, device=dev)
+        gt, group_start = _diagonal_index(Nt, dev)
     gt = gt.to(device=dev, dtype=torch.int32).contiguous()
     group_start = group_start.to(device=dev, dtype=torch.int32).contiguous()
     t2v = torch.empty(Nt, dtype=torch.int32, device=dev) if want_t2v else None
