@@ -67,6 +67,7 @@ NCU_TRAFFIC_FILE = "profiles/r2_ncu_traffic.json"
 def ncu_traffic(*kernels):
     try:
         tab = json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))["kernels"]
+        tab = {k.split("<")[0]: v for k, v in tab.items()}          # template arguments dropped: bert_adam_kernel<0>
         return int(sum(tab[k]["dram_bytes_read"] + tab[k]["dram_bytes_write"] for k in kernels))
     except Exception:   # noqa: BLE001
         return None

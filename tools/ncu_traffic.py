@@ -84,7 +84,15 @@ def main():
                    "kernels": {k: {kk: v[kk] for kk in ("time_us", "dram_bytes_read", "dram_bytes_write", "lts_bytes",
                                                         "tensor_pct_elapsed", "grid", "report")} for k, v in kernels.items()}},
                   open(a.json, "w"), indent=1)
-    md = ("| kernel | grid x block | time us | DRAM read / write MB | L2 MB | DRAM GB/s | tensor pipe % of elapsed | regs | issue % | SM GHz |\n"
+    md = ("# ncu --set full, one launch per shipped kernel\n\n"
+          "Captured with `tools/r2_profile.sh` (`ncu --set full --import-source on --clock-control none "
+          "--kernel-name-base demangled -k regex:hmmc:: python tools/profile_all.py`, after the same program exited 0 "
+          "without ncu), exported on the GPU box with `ncu -i ... --page raw --csv` (the report itself exceeds what "
+          "travels back; the raw page is committed beside this file) and tabulated by `tools/ncu_traffic.py`. Times are "
+          "ncu's: serialised launches, cold-ish caches, no clock control - shares of a step, not bench values. "
+          "Pre-train kernels: the last captured launch is the b = 256 loss; eval: config 2 (`eval_rank_kernel<2, 1>`) "
+          "and a 100k x 10k slice of config 5; optimizer and EMA: the full 172 M parameters.\n\n"
+          "| kernel | grid x block | time us | DRAM read / write MB | L2 MB | DRAM GB/s | tensor pipe % of elapsed | regs | issue % | SM GHz |\n"
           "|---|---|---|---|---|---|---|---|---|---|\n" + "\n".join(lines) + "\n")
     if a.md:
         open(a.md, "w").write(md)
