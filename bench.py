@@ -316,11 +316,20 @@ def gallery_data(Nv, cap, D, F, lo, hi, dev, signal=(1.0, 0.7)):
     return T, V, Fr
 
 
-def gallery_checks(T, V, Fr, cap, lo, hi, Nt, Nv, k, t2v, v2t, rank, dev, n_caps=128, n_vids=8):
+# A rank is an integer function of floating-point scores: two scores closer than the arithmetic's error may be
+# ordered either way.  Tolerance on a score (scale 100 x [sim + mean of the top-k frame sims], unit vectors,
+# D = 512): bf16 operands 2^-9 relative each -> a few 1e-4 on a dot product -> 0.08 on the score; bf16x3 (and the
+# fp32 oracle itself) a few 1e-6 -> 2e-3.  The check: the fused rank must lie between the oracle's counts taken
+# with thresholds gt + tol and gt - tol.
+RANK_SCORE_TOL = {"bf16": 0.08, "bf16x3": 2e-3, "fp32": 2e-3}
+
+
+def gallery_checks(T, V, Fr, cap, lo, hi, Nt, Nv, k, t2v, v2t, rank, dev, n_caps=128, n_vids=8, prec="bf16"):
     """Fused ranks against the numpy oracle (oracle/head_oracle.eval_scores, fp32, the checker -- nothing of it
     is timed): the t2v ranks of n_caps sampled captions over the WHOLE gallery (every rank scores its own shard
     on its host cores, counts are summed) and the grouped v2t ranks of n_vids sampled videos of rank 0's shard
-    over ALL captions.  Mismatches are near-ties that the run's precision resolved the other way."""
+    over ALL captions.  Mismatches are near-ties that the run's precision resolved the other way: every rank is
+    also checked against the oracle's band for the precision's score tolerance (RANK_SCORE_TOL)."""
     from hmmc_b200 import parallel
     from oracle import head_oracle as O
     Tn = None
@@ -334,11 +343,19 @@ def gallery_checks(T, V, Fr, cap, lo, hi, Nt, Nv, k, t2v, v2t, rank, dev, n_caps
     gts[own] = ref[own, gt[own] - lo]
     gts_t = torch.from_numpy(gts).to(dev)
     parallel.all_reduce_sum_(gts_t)                       # each caption's score comes from exactly one shard
-    cnt = torch.from_numpy((ref > gts_t.cpu().numpy()[:, None]).sum(1).astype(np.int32)).to(dev)
-    parallel.all_reduce_sum_(cnt)
-    t2v_mism = int((cnt != t2v[idx]).sum())
+    g_all = gts_t.cpu().numpy()[:, None]
+    tol = RANK_SCORE_TOL[prec]
+    cnt = torch.from_numpy((ref > g_all).sum(1).astype(np.int32)).to(dev)
+    cnt_lo = torch.from_numpy((ref > g_all + tol).sum(1).astype(np.int32)).to(dev)
+    cnt_hi = torch.from_numpy((ref > g_all - tol).sum(1).astype(np.int32)).to(dev)
+    for c in (cnt, cnt_lo, cnt_hi):
+        parallel.all_reduce_sum_(c)
+    got_t = t2v[idx]
+    t2v_mism = int((cnt != got_t).sum())
+    outside = int(((got_t < cnt_lo) | (got_t > cnt_hi)).sum())
     out = {"t2v_sampled_captions": int(idx.numel()), "t2v_mismatches_vs_fp32_oracle": t2v_mism,
-           "t2v_sample_rank_sum_oracle": int(cnt.long().sum())}
+           "t2v_max_abs_rank_diff": int((cnt - got_t).abs().max()), "score_tolerance": tol,
+           "t2v_outside_tolerance_band": outside, "t2v_sample_rank_sum_oracle": int(cnt.long().sum())}
     if rank == 0:
         vids = np.linspace(0, hi - lo - 1, n_vids).astype(np.int64)
         Tn = T.cpu().numpy()
@@ -399,7 +416,7 @@ def gallery_core(args, W, rank, local, dev, steps, warmup):
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    checks = gallery_checks(T, V, Fr, cap, lo, hi, Nt, Nv, k, t2v, v2t, rank, dev)
+    checks = gallery_checks(T, V, Fr, cap, lo, hi, Nt, Nv, k, t2v, v2t, rank, dev, prec=prec)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -1113,14 +1130,28 @@ def retrieval_leg(args, dev):
     for _ in range(3):
         dev_pass()
     torch.cuda.synchronize()
-    reps = 20
+    # device time: the pass is a fixed sequence of five launches, replayed from a CUDA graph like the other legs
+    run, mode = dev_pass, "eager"
+    if not args.no_graph:
+        try:
+            from hmmc_b200.graphs import GraphedStep
+            g = GraphedStep(lambda: dev_pass()[0])
+            GRAPHS.append(g)
+            run, mode = g.replay, "cuda graph replay"
+        except Exception:   # noqa: BLE001
+            torch.cuda.synchronize()
+    for _ in range(5):
+        run()
+    torch.cuda.synchronize()
+    reps = 100
     a, c = ev(), ev()
     a.record()
     for _ in range(reps):
-        dev_pass()
+        run()
     c.record()
     torch.cuda.synchronize()
     ms_dev = a.elapsed_time(c) / reps
+    reps = 20
     t0 = time.perf_counter()
     for _ in range(reps):
         sim = retrieval.similarity_matrix(m, hT.to(dev, non_blocking=True), hV.to(dev, non_blocking=True),
@@ -1132,7 +1163,7 @@ def retrieval_leg(args, dev):
     from hmmc_b200 import metrics as GM
     tv = GM.metrics_from_ranks(r[0].numpy())
     out = {"workload": "BASELINE config 2: 1000 x 1000 x 12, top_frames 2, sim + top-k + t2v/v2t ranks",
-           "value": 1000.0 / (ms_dev / 1e3), "unit": "queries/s", "ms": ms_dev,
+           "value": 1000.0 / (ms_dev / 1e3), "unit": "queries/s", "ms": ms_dev, "issue_mode": mode,
            "e2e": {"value": 1000.0 / (ms_e2e / 1e3), "unit": "queries/s", "ms": ms_e2e,
                    "h2d_bytes": int(4 * (T.size + V.size + Fr.size)), "d2h_bytes": 8000},
            "R1": tv["R1"], "MeanR": tv["MeanR"]}
