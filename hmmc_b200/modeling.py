@@ -520,9 +520,13 @@ class BirdModel(ContrastiveHeadMixin, nn.Module):
         b = query_output.shape[0]
         F = frame_output.shape[1]
         D = query_output.shape[-1]
-        # one packed exchange instead of the reference's three dist_collect calls
-        packed = torch.cat([query_output.reshape(b, D), visual_output.reshape(b, D),
-                            frame_output.reshape(b, F * D)], dim=1)
+        if parallel.world()[0] == 1:
+            # nothing to gather: the fused head reads the three tensors where they are
+            return self.finetune_head_loss(query_output.reshape(b, D), visual_output.reshape(b, D), frame_output)
+        # one packed exchange instead of the reference's three dist_collect calls (one launch to pack, one to
+        # unpack the gradient)
+        packed = ops.pack_rows_autograd([query_output.reshape(b, D), visual_output.reshape(b, D),
+                                         frame_output.reshape(b, F * D)])
         # every rank evaluates the same global loss on the same gathered rows: the gather's backward needs no
         # exchange (parallel.all_gather_cat_replicated); dist_collect keeps the general reduce-scatter
         full = parallel.all_gather_cat_replicated(packed)

@@ -460,6 +460,28 @@ def pack_rows(tensors, out=None, staged=None, norm_dim=0):
     return out
 
 
+class _PackRowsFn(torch.autograd.Function):
+    """pack_rows with a gradient: one launch forward, one launch (unpack_rows) backward."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        ctx.shapes = [tuple(t.shape) for t in tensors]
+        ctx.dtypes = [t.dtype for t in tensors]
+        return pack_rows(tensors)
+
+    @staticmethod
+    def backward(ctx, g):
+        rows = ctx.shapes[0][0]
+        widths = [int(torch.Size(s).numel() // rows) for s in ctx.shapes]
+        outs = unpack_rows(_f32c(g, "packed gradient"), widths)
+        return tuple(o.reshape(s).to(d) for o, s, d in zip(outs, ctx.shapes, ctx.dtypes))
+
+
+def pack_rows_autograd(tensors):
+    """[rows, ...] blocks -> [rows, sum of widths] fp32, differentiable (send buffer of a differentiable gather)."""
+    return _PackRowsFn.apply(*tensors)
+
+
 def unpack_rows(packed, widths):
     lib = _lib.load()
     rows = packed.shape[0]
@@ -632,9 +654,13 @@ class _SymCeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         saved = list(ctx.saved_tensors)
-        dt = saved.pop(0) * g
-        dv = saved.pop(0) * g if ctx.has[0] else None
-        df = saved.pop(0) * g if ctx.has[1] else None
+        if getattr(ctx, "consumed", False):
+            raise HmmcError("the fused head's gradients were already consumed (retain_graph is not supported)")
+        ctx.consumed = True
+        scale_inplace(saved, g)                   # one launch (a no-op for loss.backward()); the buffers are ours
+        dt = saved.pop(0)
+        dv = saved.pop(0) if ctx.has[0] else None
+        df = saved.pop(0) if ctx.has[1] else None
         return dt, dv, df, None, None, None, None
 
 
