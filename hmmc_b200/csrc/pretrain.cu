@@ -1081,22 +1081,40 @@ struct PeerPtrs { uint64_t p[HMMC_MAX_PEERS]; };
 // bit-identical to what the enqueue would have computed from the raw keys.  Each rank then normalises only its own
 // keys (not all W*b of them after the exchange) and the enqueue reads the received rows once.
 __global__ void __launch_bounds__(256)
-rowpack_norm_kernel(RowPackArgs a, float* __restrict__ packed, int D, int32_t* staged) {
-  const int64_t row = blockIdx.x;
-  const int t = blockIdx.y;
-  if (staged != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *staged = 1;
-  const float* x = reinterpret_cast<const float*>(a.ptrs[t]) + row * a.widths[t];
-  float* y = packed + row * a.total + a.offs[t];
+rowpack_norm_kernel(RowPackArgs a, float* __restrict__ packed, int D, int64_t rows, int32_t* staged) {
+  // one warp per D-vector, vectors numbered row-major over the packed row (total / D per row)
+  if (staged != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *staged = 1;
   const int lane = threadIdx.x & 31;
-  for (int v = threadIdx.x >> 5; v < a.widths[t] / D; v += blockDim.x >> 5) {
-    const float* xv = x + int64_t(v) * D;
-    float ss = 0.f;
-    for (int d = lane; d < D; d += 32) { const float e = xv[d]; ss = fmaf(e, e, ss); }
-    ss = warp_sum(ss);
-    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-    for (int d = lane; d < D; d += 32) y[int64_t(v) * D + d] = xv[d] * inv;
+  const int per_row = a.total / D;
+  const int64_t g = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= rows * per_row) return;
+  const int64_t row = g / per_row;
+  const int off = int(g - row * per_row) * D;          // element offset inside the packed row
+  int t = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < a.n && off >= a.offs[i]) t = i;
+  const float* xv = reinterpret_cast<const float*>(a.ptrs[t]) + row * a.widths[t] + (off - a.offs[t]);
+  float* y = packed + row * a.total + off;
+  // the row stays in registers between the two passes (D <= 1024: 32 values per lane); the sum of squares is
+  // accumulated in the same order as key_norms_kernel (lane-strided, then the shuffle tree)
+  float e[32];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int d = lane + 32 * k;
+    e[k] = (d < D) ? xv[d] : 0.f;
+    if (d < D) ss = fmaf(e[k], e[k], ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int d = lane + 32 * k;
+    if (d < D) y[d] = e[k] * inv;
   }
 }
+
 
 __global__ void __launch_bounds__(256)
 peer_push_kernel(const float4* __restrict__ send, int64_t n4, PeerPtrs bufs, PeerPtrs flags, int W, int rank,
@@ -1104,12 +1122,16 @@ peer_push_kernel(const float4* __restrict__ send, int64_t n4, PeerPtrs bufs, Pee
   const int e = *epoch;                                         // exchanges completed so far
   const int peer = (rank + int(blockIdx.y)) % W;                // staggered: no two ranks start on the same peer
   float4* dst = reinterpret_cast<float4*>(bufs.p[peer]) + (int64_t(e & 1) * slot_stride + int64_t(rank) * n4 * 4) / 4;
-  // four independent 16-byte loads in flight per thread before the posted stores
+  // eight independent 16-byte loads in flight per thread before the posted stores: beside the momentum update the
+  // memory system serves requests roughly in proportion to what each kernel has outstanding
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n4; i += 4 * stride) {
-    const float4 v0 = send[i], v1 = send[i + stride], v2 = send[i + 2 * stride], v3 = send[i + 3 * stride];
-    dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+  for (; i + 7 * stride < n4; i += 8 * stride) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = send[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dst[i + u * stride] = v[u];
   }
   for (; i < n4; i += stride) dst[i] = send[i];
   // last block: every block's stores are ordered before its arrival (system-scope fence), the flags after all arrivals
@@ -1790,7 +1812,9 @@ int hmmc_pack_rows(const uint64_t* src_ptrs_host, const int32_t* widths_host, in
     for (int i = 0; i < n; ++i)
       HMMC_REQUIRE(widths_host[i] % norm_dim == 0, "pack_rows: width %d is not a multiple of the vector length %d",
                    widths_host[i], norm_dim);
-    rowpack_norm_kernel<<<dim3(unsigned(rows), a.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, norm_dim, staged);
+    HMMC_REQUIRE(norm_dim <= 1024, "pack_rows: vectors longer than 1024 are not supported (got %d)", norm_dim);
+    const int64_t vectors = rows * (a.total / norm_dim);
+    rowpack_norm_kernel<<<unsigned((vectors + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dst, norm_dim, rows, staged);
     HMMC_CHECK_LAUNCH();
     return HMMC_OK;
   }
@@ -1827,8 +1851,7 @@ int hmmc_peer_push_rows(const float* send, int64_t elems, const uint64_t* peer_b
     HMMC_REQUIRE(i >= W || (bufs.p[i] % 16 == 0 && flags.p[i] != 0), "peer_push: bad peer pointer %d", i);
   }
   const int64_t n4 = elems / 4;
-  // a few blocks per destination: the copy is bound by the links, not by the SMs it leaves to the momentum update
-  const int gx = int(std::min<int64_t>((n4 + 1023) / 1024, 32));
+  const int gx = int(std::min<int64_t>((n4 + 2047) / 2048, std::max(8, 512 / W)));      // about 512 blocks in all
   count_launch();
   peer_push_kernel<<<dim3(gx, W), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(send), n4, bufs, flags, W, rank, slot_stride, epoch, done_counter);

@@ -13,7 +13,7 @@ W = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0));
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 if W > 1:
     dist.init_process_group("nccl", device_id=dev)
-b, F, D = 128, 12, 512
+b, F, D = int(os.environ.get("B_PER", 128)), 12, 512
 K = max(1024, b * W)
 
 class Params(torch.nn.Module):
