@@ -76,3 +76,39 @@ def test_umma_gemm_nt(M, N, K, planes):
     assert rel(C, ref) < 1e-5, rel(C, ref)   # tcgen05 accumulates in fp32 with truncation: ~5e-6 at K~1k
     if planes == 2:      # and the split product is fp32-grade w.r.t. the unsplit operands
         assert rel(C, 2.0 * f(A) @ f(B).T) < 2e-5
+
+
+def test_pack_rows_autograd_is_cat_with_slice_gradients():
+    """ops.pack_rows_autograd (send buffer of the fine-tune gather): forward == torch.cat, backward == the slices."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(24, 128, device="cuda", generator=g, requires_grad=True)
+    b = torch.randn(24, 128, device="cuda", generator=g, requires_grad=True)
+    c = torch.randn(24, 12, 128, device="cuda", generator=g, requires_grad=True)
+    packed = ops.pack_rows_autograd([a, b, c.reshape(24, -1)])
+    want = torch.cat([a, b, c.reshape(24, -1)], dim=1)
+    assert torch.equal(packed, want)
+    up = torch.randn_like(packed)
+    packed.backward(up)
+    assert torch.equal(a.grad, up[:, :128]) and torch.equal(b.grad, up[:, 128:256])
+    assert torch.equal(c.grad, up[:, 256:].reshape(24, 12, 128))
+
+
+@pytest.mark.parametrize("D", [128, 512])
+def test_pack_rows_normalised_matches_the_enqueue_arithmetic(D):
+    """pack_rows(norm_dim=D) (keys normalised at the source, before the exchange): every D-vector equals
+    x * (1 / max(||x||, 1e-12)) with the sum of squares taken lane-strided then by the shuffle tree -- compared with
+    F.normalize to 2 ulp, zero vectors stay zero, and the staged mark is set."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    v = torch.randn(16, D, device="cuda", generator=g)
+    f = torch.randn(16, 12, D, device="cuda", generator=g) * 3.0
+    v[3].zero_()
+    staged = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = ops.pack_rows([v, f], staged=staged, norm_dim=D)
+    assert int(staged) == 1 and out.shape == (16, 13 * D)
+    want = torch.cat([torch.nn.functional.normalize(v, dim=-1, eps=1e-12),
+                      torch.nn.functional.normalize(f, dim=-1, eps=1e-12).reshape(16, -1)], dim=1)
+    assert float((out - want).abs().max()) <= 2.5e-7
+    assert float(out[3, :D].abs().max()) == 0.0
+    norms = out.reshape(16, 13, D).norm(dim=-1)
+    norms[3, 0] = 1.0
+    assert float((norms - 1).abs().max()) < 1e-6
