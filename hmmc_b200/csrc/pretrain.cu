@@ -1151,7 +1151,8 @@ __global__ void peer_wait_kernel(const volatile int32_t* my_flags, int W, int32_
   if (threadIdx.x < W) {
     const long long t0 = clock64();
     while (my_flags[threadIdx.x] < e)
-      if (clock64() - t0 > (1ll << 34)) __trap();             // ~9 s: a rank that never pushes is an error, not a hang
+      if (clock64() - t0 > (1ll << 39)) __trap();             // minutes (a peer may be busy saving a checkpoint): a rank
+                                                              // that never pushes is an error in the end, not a hang
   }
   __threadfence_system();
   __syncthreads();

@@ -196,10 +196,22 @@ class PeerExchange:
         return self.recv[slot * self.W * self.b:(slot + 1) * self.W * self.b]
 
 
+def same_node():
+    """True when every rank of the default group runs on this host (collective): peer-mapped memory only exists
+    between the GPUs of one node."""
+    W, _ = world()
+    if W == 1:
+        return True
+    import socket
+    names = [None] * W
+    dist.all_gather_object(names, socket.gethostname())
+    return all(n == names[0] for n in names)
+
+
 def make_peer_exchange(b, width, device):
     """PeerExchange if every rank can build one, else None on every rank (collective)."""
     ok, px = 0, None
-    if PeerExchange.usable():
+    if PeerExchange.usable() and same_node():
         try:
             px = PeerExchange(b, width, device)
             ok = 1

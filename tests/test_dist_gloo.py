@@ -55,6 +55,11 @@ def _worker(rank, W, port, ret):
         v = torch.arange(hi - lo, dtype=torch.int32) + 100 * rank
         allv = parallel.all_gather_varlen(v, [6, 5])
         assert allv.tolist() == list(range(6)) + [100 + i for i in range(5)]
+        # the peer-memory key exchange is for NCCL ranks of one node: on gloo every rank gets None (and agrees)
+        assert parallel.same_node()
+        assert not parallel.PeerExchange.usable()
+        assert parallel.make_peer_exchange(4, 8, torch.device("cpu")) is None
+        assert parallel.overlap_group() is dist.group.WORLD
         ret[rank] = "ok"
     except Exception as e:  # noqa: BLE001
         ret[rank] = repr(e)
