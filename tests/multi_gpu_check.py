@@ -150,6 +150,11 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
                 worst = max(worst, err)
                 assert err <= 2e-7, (mode, s, n, err)
         out["enqueue_%s_max_abs_vs_oracle_concat" % mode] = worst
+        if mode != "eager":
+            # which exchange ran: the peer-memory push (default between NCCL ranks of one node) or the all-gather
+            peer_used = m._hmmc_xchg[4] is not None
+            assert peer_used == (not mode.endswith("_nccl") and parallel.PeerExchange.usable()), (mode, peer_used)
+            out["enqueue_%s_exchange" % mode] = "peer memory" if peer_used else "nccl all-gather"
         if graphed is not None:
             graphed.release()
     out["enqueue_steps"] = steps
