@@ -1107,7 +1107,7 @@ def finetune_leg(args, W, rank, local, dev):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         out["b%d_per_gpu" % b] = {"global_batch": b * W, "ms_per_step": ms, "samples_per_s": b * W / (ms / 1e3),
-                                  "loss": float(loss), "issue_mode": mode}
+                                  "loss": float(loss.detach()), "issue_mode": mode}
     out["workload"] = "BASELINE config 3: fine-tune head fwd+bwd (packed all-gather + 13 symmetric CrossEn matrices), bf16x3"
     return out
 

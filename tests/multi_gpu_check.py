@@ -58,7 +58,7 @@ def check_finetune(W, rank, local, dev, b=16, F=12, D=512):
         a = [cu(x, True) for x in parts[rank]]
         loss = m.head_loss(*a)
         loss.backward()
-        lerr = abs(float(loss) - ref_loss) / ref_loss
+        lerr = abs(float(loss.detach()) - ref_loss) / ref_loss
         gerr = max(rel(got.grad.cpu().numpy(), W * ref[sl]) for got, ref in zip(a, (dt, dv, dfr)))
         assert lerr < tol and gerr < 3 * tol, (prec, lerr, gerr)
         out["finetune_%s_loss_rel" % prec] = lerr
@@ -137,7 +137,7 @@ def check_pretrain_enqueue(W, rank, local, dev, b=8, F=12, D=128, K=64):
                 from hmmc_b200.graphs import GraphedStep
                 graphed = GraphedStep(step, warmup=0)
             loss = graphed.replay() if graphed is not None else step()
-            lerr = abs(float(loss) - ref_losses[s]) / ref_losses[s]
+            lerr = abs(float(loss.detach()) - ref_losses[s]) / ref_losses[s]
             del loss        # a live loss keeps the step's autograd graph (and its AccumulateGrad streams): see graphs.py
             assert lerr < 1e-5, (mode, s, lerr)
             if mode == "graph_noflush" and s < steps - 1:
