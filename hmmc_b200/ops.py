@@ -621,10 +621,29 @@ def cross_en(sim):
     return _CrossEnFn.apply(sim)
 
 
+_warned_slow_symce = set()
+
+
+def _warn_symce_path(B, D, prec):
+    """The tensor-core tiling of the fine-tune head takes global batches that are a multiple of 32 (bf16x3) or 64
+    (bf16) with D % 64 == 0 and D <= 1024 (symce_tensor_ok in csrc/finetune.cu); anything else runs the exact
+    CUDA-core path, correct but several times slower.  Say so once per shape instead of being silently slow."""
+    if prec == PREC_FP32:
+        return
+    ok = D % 64 == 0 and D <= 1024 and (B % 32 == 0 if prec == PREC_BF16X3 else B % 64 == 0)
+    if not ok and (B, D, prec) not in _warned_slow_symce:
+        _warned_slow_symce.add((B, D, prec))
+        import warnings
+        warnings.warn("hmmc_b200: fine-tune head with global batch %d, D %d takes the CUDA-core path (the tensor-core "
+                      "path needs batch %% %d == 0, D %% 64 == 0, D <= 1024): expect several times the step time"
+                      % (B, D, 32 if prec == PREC_BF16X3 else 64), RuntimeWarning, stacklevel=3)
+
+
 def sym_ce_raw(text, video, frames, scale, w_vtm, w_ftm, prec, need_grad):
     """Fused fine-tune head on gathered embeddings; returns (loss, dtext, dvideo, dframes)."""
     lib = _lib.load()
     B, D = text.shape
+    _warn_symce_path(B, D, prec)
     F = frames.shape[1] if frames is not None else 0
     nbytes = lib.hmmc_sym_ce_workspace_bytes(B, F, D, prec)
     ws = workspace(text.device, nbytes)
@@ -676,6 +695,7 @@ def sym_ce_packed_raw(packed, F, D, scale, w_vtm, w_ftm, prec, need_grad):
     B = packed.shape[0]
     if packed.shape[1] != (2 + F) * D:
         raise HmmcError("sym_ce_packed: row width %d is not (2+F)*D = %d" % (packed.shape[1], (2 + F) * D))
+    _warn_symce_path(B, D, prec)
     nbytes = lib.hmmc_sym_ce_packed_workspace_bytes(B, F, D, prec)
     ws = workspace(packed.device, nbytes)
     loss = torch.empty((), dtype=torch.float32, device=packed.device)

@@ -143,3 +143,22 @@ def test_cache_eval_features_filters_videos_at_cut_off_points():
     import pytest
     with pytest.raises(ValueError):
         retrieval.cache_eval_features(types.SimpleNamespace(task="caption"), model, dl, torch.device("cpu"))
+
+
+def test_fine_tune_head_warns_when_the_batch_leaves_the_tensor_path():
+    """batches the tensor-core tiling does not take must not be silently slow."""
+    import warnings
+    from hmmc_b200 import ops
+    ops._warned_slow_symce.clear()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ops._warn_symce_path(256, 512, ops.PREC_BF16X3)      # tensor path: silent
+        ops._warn_symce_path(64, 512, ops.PREC_BF16)
+        ops._warn_symce_path(40, 512, ops.PREC_FP32)         # fp32 is the CUDA-core path by choice: silent
+        assert not w
+        ops._warn_symce_path(40, 512, ops.PREC_BF16X3)
+        ops._warn_symce_path(40, 512, ops.PREC_BF16X3)       # once per shape
+        ops._warn_symce_path(96, 512, ops.PREC_BF16)         # 96 % 64 != 0
+        ops._warn_symce_path(64, 1536, ops.PREC_BF16X3)      # D > 1024
+    assert len(w) == 3 and all(issubclass(x.category, RuntimeWarning) for x in w)
+    assert "CUDA-core path" in str(w[0].message)
