@@ -767,8 +767,8 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
                          "traffic": ncu_traffic("ema_multi_kernel"), "traffic_source": NCU_TRAFFIC_FILE,
                          "algorithmic_bytes": ema_bytes, "ms": ms_ema, "peak_source": peak_src},
-            "roofline_head": {"kernels": "infonce fwd+bwd (5 query blocks: rownorm_pack, umma S-GEMM+exp epilogue, "
-                                         "umma U-GEMM, finish, reduce) + pack + enqueue",
+            "roofline_head": {"kernels": "infonce fwd+bwd (5 query blocks: prep_rows, umma S-GEMM+exp epilogue, "
+                                         "umma U-GEMM, finish, gradient scale) + enqueue",
                               "bound": "tensor", "achieved": head_tf, "peak": tf_peak, "unit": "TFLOP/s",
                               "frac": head_tf / tf_peak, "algorithmic_flops": head_flops, "ms": ms_head,
                               "peak_source": peak_src},
@@ -1130,7 +1130,7 @@ def retrieval_leg(args, dev):
     for _ in range(3):
         dev_pass()
     torch.cuda.synchronize()
-    # device time: the pass is a fixed sequence of five launches, replayed from a CUDA graph like the other legs
+    # device time: the pass is a fixed sequence of four launches, replayed from a CUDA graph like the other legs
     run, mode = dev_pass, "eager"
     if not args.no_graph:
         try:

@@ -241,7 +241,7 @@ def scale_inplace(tensors, g):
 
 class _PretrainHeadFn(torch.autograd.Function):
     """w_fam*FAM + w_vtm*VTM + w_ftm*FTM of the pre-train head, forward and backward in one C
-    call (five launches).  Returns (total, parts[3]); only ``total`` is differentiable."""
+    call (four launches).  Returns (total, parts[3]); only ``total`` is differentiable."""
 
     @staticmethod
     def forward(ctx, v_fea, title_fea, frame_fea, frame_pred, v_fea_k, title_fea_k, frame_fea_k, frame_proj_k,

@@ -117,7 +117,8 @@ int hmmc_infonce_queue_fwd_bwd(const float* q, const float* keys, int pos_mode, 
                                void* stream);
 
 /* The whole pre-train head loss of BirdPreTrainedModel.forward (modules/modeling.py:385-400,424;
- * dataset != "bird"), forward and backward in five launches:
+ * dataset != "bird"), forward and backward in four launches (normalise + pack, S-GEMM with the
+ * InfoNCE epilogue, U-GEMM, finish):
  *   losses_out[0] = w_fam*FAM + w_vtm*VTM + w_ftm*FTM,  losses_out[1..3] = FAM, VTM, FTM
  *   FAM = frame_self_loss(frame_pred, frame_proj_k, q_frame_proj)
  *   VTM = contrastive_loss(v_fea, title_fea_k, q_title) + contrastive_loss(title_fea, v_fea_k, q_v)
@@ -355,8 +356,8 @@ int hmmc_sym_ce_packed_fwd_bwd(const float* packed, int B, int F, int D, float s
  *   fsim [Nt,Nv] = mean over the top_k frames of s * t_hat . f_hat   (torch.topk + mean)
  * video [Nv,D], frames [Nv,F,D].  Either output may be NULL.  sim == fsim (one buffer): that buffer receives
  * sim + fsim, the sum eval_epoch forms on the host (main_task_retrieval.py:512-513).
- * With 12 frames, top_k <= 4 and a tensor-core precision the call is three launches: normalise + pack the
- * captions, pack the gallery as [video | 12 frames] column groups, one GEMM sweep whose epilogue pools the
+ * With 12 frames, top_k <= 4 and a tensor-core precision the call is two launches: one kernel normalises and
+ * packs the captions and the gallery ([video | 12 frames] column groups), one GEMM sweep whose epilogue pools the
  * top-k frames in registers and writes each score once (no [Nt, Nv*F] frame-similarity matrix). */
 size_t hmmc_sim_topk_workspace_bytes(int64_t Nt, int64_t Nv, int F, int D, int prec);
 int hmmc_sim_topk_fwd(const float* text, int64_t Nt, const float* video, const float* frames, int64_t Nv,
